@@ -1,0 +1,503 @@
+"""CPU oracle for the P3DFFT r2c/c2r hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy/scipy restatement of the reference algorithm (sdsc/p3dfft 2.7.x,
+Fortran + MPI + FFTW).  It is the *checker*: only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  Nothing
+under ``p3dfft_b200/`` (the product) imports or calls it.
+
+Why numpy and not the reference itself: the reference cannot be built in this image
+(no Fortran compiler, no MPI, no FFTW -- SURVEY.md section 0), and its 1D transforms live
+in an un-vendored, un-pinned third-party dependency (FFTW 3.x, ``build/fft_spec.F90:88``,
+``configure.ac:330-353``).  The published FFTW definitions restated here are
+  r2c / c2c forward : Y_k = sum_j X_j exp(-2 pi i jk/N)   (unnormalised)
+  c2r / c2c backward: Y_k = sum_j X_j exp(+2 pi i jk/N)   (unnormalised)
+  REDFT00 (DCT-I)   : Y_k = X_0 + (-1)^k X_{N-1} + 2 sum_{j=1}^{N-2} X_j cos(pi jk/(N-1))
+  RODFT00 (DST-I)   : Y_k = 2 sum_{j=0}^{N-1} X_j sin(pi (j+1)(k+1)/(N+1))
+computed with scipy's pocketfft.  PARITY PINNING: the reference ships no golden vectors;
+the oracle is pinned on the known-answer checks of the reference's own sample drivers
+(``sample/C/driver_inverse.c:222-240``, ``driver_sine.c:168-228``, ``driver_noop.c``,
+``sample/FORTRAN/driver_cheby.F90:258-285``, ``driver_sine_pruned.F90``) -- see
+``tests/test_oracle_known_answers.py``.  Bit-level parity with "the FFTW build" is
+therefore unpinned; the parity bar is relative L2 <= 1e-12 (double) / 1e-5 (single).
+
+Two restatements are provided:
+  * ``global_*``      -- the mathematical definition on the global array, sliced per rank.
+  * ``SimWorld``      -- P simulated ranks running the reference's actual stage sequence
+                         (FFT -> pack -> alltoallv -> unpack ...) with the reference's
+                         buffer layouts and byte counts, so that the exchange tables are
+                         exercised.  This is also what the CPU baseline times.
+
+All arrays are Fortran-ordered (column-major, x fastest) like the reference.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.fft as sfft
+
+__all__ = [
+    "map_data_to_proc", "Decomp", "global_forward", "global_backward", "global_cheby",
+    "local_forward", "local_backward", "SimWorld", "philox_field", "rel_l2",
+]
+
+
+# --------------------------------------------------------------------------------------
+# decomposition arithmetic
+# --------------------------------------------------------------------------------------
+def map_data_to_proc(data: int, proc: int):
+    """``MapDataToProc`` (build/setup.F90:608-635): the LAST ``data mod proc`` ranks get
+    one extra element.  Returns 1-based (st, en, sz) lists."""
+    size = data // proc
+    nu = data - size * proc
+    nl = proc - nu
+    st, en, sz = [0] * proc, [0] * proc, [0] * proc
+    st[0], sz[0], en[0] = 1, size, size
+    for i in range(1, nl):
+        st[i] = st[i - 1] + size
+        sz[i] = size
+        en[i] = en[i - 1] + size
+    size1 = size + 1
+    for i in range(max(nl, 1), proc):
+        st[i] = en[i - 1] + 1
+        sz[i] = size1
+        en[i] = en[i - 1] + size1
+    en[proc - 1] = data
+    sz[proc - 1] = data - st[proc - 1] + 1
+    return st, en, sz
+
+
+@dataclass
+class Decomp:
+    """Per-rank plan integers.  Follows build/setup.F90:148-176 (derived extents),
+    :192-219 (rank -> (ipid,jpid)), :279-312 (block maps), :382-398 (padi, nm),
+    :481-518 (alltoallv tables), :580-603 (memsize); build/module.F90:225-273 (get_dims)."""
+    nx: int
+    ny: int
+    nz: int
+    dims: tuple
+    rank: int = 0
+    nxc: int | None = None
+    nyc: int | None = None
+    nzc: int | None = None
+    dims_c: bool = False          # -DDIMS_C
+    stride1: bool = False         # -DSTRIDE1 (changes conf-2 layout only)
+    elem: int = 8                 # bytes per real (8 double, 4 single)
+
+    def __post_init__(self):
+        nx, ny, nz = self.nx, self.ny, self.nz
+        if nx <= 0 or ny <= 0 or nz <= 0:
+            raise ValueError(f"Invalid dimensions : {nx} {ny} {nz}")
+        self.nxc = nx if self.nxc is None else self.nxc
+        self.nyc = ny if self.nyc is None else self.nyc
+        self.nzc = nz if self.nzc is None else self.nzc
+        self.iproc, self.jproc = int(self.dims[0]), int(self.dims[1])
+        if self.iproc <= 0 or self.jproc <= 0:
+            raise ValueError("Invalid processor geometry")
+        self.numtasks = self.iproc * self.jproc
+        if not (0 <= self.rank < self.numtasks):
+            raise ValueError("rank outside processor grid")
+        self.nxh = nx // 2
+        self.nxhp = self.nxh + 1
+        self.nxhc = self.nxc // 2
+        self.nxhpc = self.nxhc + 1
+        self.nyh, self.nzh = ny // 2, nz // 2
+        self.nyhc, self.nzhc = self.nyc // 2, self.nzc // 2
+        self.nycph, self.nzcph = (self.nyc + 1) // 2, (self.nzc + 1) // 2
+        # rank -> grid coordinates (setup.F90:195-219; row-major MPI_Cart_create)
+        if self.dims_c:
+            self.ipid, self.jpid = self.rank // self.jproc, self.rank % self.jproc
+        else:
+            self.ipid, self.jpid = self.rank % self.iproc, self.rank // self.iproc
+        self.iist, self.iien, self.iisz = map_data_to_proc(self.nxhpc, self.iproc)
+        self.jist, self.jien, self.jisz = map_data_to_proc(ny, self.iproc)
+        self.jjst, self.jjen, self.jjsz = map_data_to_proc(self.nyc, self.jproc)
+        self.kjst, self.kjen, self.kjsz = map_data_to_proc(nz, self.jproc)
+        i, j = self.ipid, self.jpid
+        self.iistart, self.iiend, self.iisize = self.iist[i], self.iien[i], self.iisz[i]
+        self.jistart, self.jiend, self.jisize = self.jist[i], self.jien[i], self.jisz[i]
+        self.jjstart, self.jjend, self.jjsize = self.jjst[j], self.jjen[j], self.jjsz[j]
+        self.kjstart, self.kjend, self.kjsize = self.kjst[j], self.kjen[j], self.kjsz[j]
+        # work-buffer padding (setup.F90:382-398)
+        padd = max(self.iisize * self.jjsize * nz, self.iisize * ny * self.kjsize) \
+            - self.nxhp * self.jisize * self.kjsize
+        if padd <= 0:
+            padi = 0
+        else:
+            d = self.nxhp * self.jisize
+            padi = padd // d if padd % d == 0 else padd // d + 1
+        self.padi_work = padi
+        self.nm = self.nxhp * self.jisize * (self.kjsize + padi)
+        # alltoallv tables in BYTES (setup.F90:481-518); c = bytes per complex
+        c = 2 * self.elem
+        ii, ji, jj, kj = self.iisize, self.jisize, self.jjsize, self.kjsize
+        self.IfSndStrt = [(self.iist[p] - 1) * ji * kj * c for p in range(self.iproc)]
+        self.IfSndCnts = [self.iisz[p] * ji * kj * c for p in range(self.iproc)]
+        self.IfRcvStrt = [(self.jist[p] - 1) * ii * kj * c for p in range(self.iproc)]
+        self.IfRcvCnts = [self.jisz[p] * ii * kj * c for p in range(self.iproc)]
+        self.KfSndStrt = [(self.jjst[p] - 1) * ii * kj * c for p in range(self.jproc)]
+        self.KfSndCnts = [ii * kj * self.jjsz[p] * c for p in range(self.jproc)]
+        self.KfRcvStrt = [(self.kjst[p] - 1) * ii * jj * c for p in range(self.jproc)]
+        self.KfRcvCnts = [ii * jj * self.kjsz[p] * c for p in range(self.jproc)]
+        self.JrSndStrt, self.JrSndCnts = self.KfRcvStrt, self.KfRcvCnts
+        self.JrRcvStrt, self.JrRcvCnts = self.KfSndStrt, self.KfSndCnts
+        self.KrSndStrt, self.KrSndCnts = self.IfRcvStrt, self.IfRcvCnts
+        self.KrRcvStrt, self.KrRcvCnts = self.IfSndStrt, self.IfSndCnts
+        # memsize (setup.F90:580-603): real elements needed for an in-place array
+        pad1 = 2 * max(nz * jj * ii, ny * kj * ii) - nx * ji * kj
+        if pad1 <= 0:
+            pad1 = 0
+        d = nx * ji
+        padm = pad1 // d + (1 if pad1 % d else 0) if d > 0 else 0
+        self.padi = padm                      # public module variable after setup
+        self.memsize = (nx, ji, kj + padm)
+
+    # ---- communicators -------------------------------------------------------------
+    def rank_of(self, ipid: int, jpid: int) -> int:
+        return ipid * self.jproc + jpid if self.dims_c else jpid * self.iproc + ipid
+
+    def row_ranks(self):
+        """mpi_comm_row: same jpid, ordered by ipid (setup.F90:245-261)."""
+        return [self.rank_of(i, self.jpid) for i in range(self.iproc)]
+
+    def col_ranks(self):
+        """mpi_comm_col: same ipid, ordered by jpid."""
+        return [self.rank_of(self.ipid, j) for j in range(self.jproc)]
+
+    # ---- p3dfft_get_dims (module.F90:225-273) --------------------------------------
+    def get_dims(self, conf: int):
+        if conf == 1:
+            return ([1, self.jistart, self.kjstart], [self.nx, self.jiend, self.kjend],
+                    [self.nx, self.jisize, self.kjsize])
+        if conf == 2:
+            if self.stride1:
+                return ([1, self.jjstart, self.iistart], [self.nzc, self.jjend, self.iiend],
+                        [self.nzc, self.jjsize, self.iisize])
+            return ([self.iistart, self.jjstart, 1], [self.iiend, self.jjend, self.nzc],
+                    [self.iisize, self.jjsize, self.nzc])
+        if conf == 3:
+            m = list(self.memsize)
+            return ([0, 0, 0], m, list(m))
+        raise ValueError("conf must be 1, 2 or 3")
+
+    # ---- pruning index maps (0-based kept -> full index) -----------------------------
+    def kept_y(self):
+        """Kept Y modes: first nycph, last nyc-nycph (seg_copy_y calls, ftran.F90:756-757).
+        NOTE: for odd nyc and jproc>1 the reference's pack_fcomm2 splits at nyhc instead
+        (fcomm2.F90:339-381) and loses an element; even nyc (all reference tests) agree."""
+        h1 = self.nycph
+        return np.concatenate([np.arange(h1), np.arange(h1, self.nyc) + (self.ny - self.nyc)])
+
+    def kept_z(self):
+        """Kept Z modes: first nzcph, last nzc-nzcph (seg_copy_z, ftran.F90:645-646)."""
+        h1 = self.nzcph
+        return np.concatenate([np.arange(h1), np.arange(h1, self.nzc) + (self.nz - self.nzc)])
+
+
+# --------------------------------------------------------------------------------------
+# 1D transforms (FFTW definitions, unnormalised)
+# --------------------------------------------------------------------------------------
+_WORKERS = int(os.environ.get("P3DFFT_ORACLE_WORKERS", "0")) or None
+
+
+def _fft(a, axis, inverse=False):
+    if inverse:
+        return sfft.ifft(a, axis=axis, norm="forward", workers=_WORKERS)
+    return sfft.fft(a, axis=axis, workers=_WORKERS)
+
+
+def _ztrans(a, axis, ch, inverse):
+    """Third-dimension transform selected by the op letter (ftran.F90:613-643,
+    btran.F90:440-466): t/f = c2c FFT, c = DCT-I, s = DST-I on re and im separately
+    (fft_exec.F90:670-671, 890-891), n/0 = nothing."""
+    if ch in ("t", "f"):
+        return _fft(a, axis, inverse)
+    if ch == "c":
+        return sfft.dct(a.real, type=1, axis=axis, workers=_WORKERS) + \
+            1j * sfft.dct(a.imag, type=1, axis=axis, workers=_WORKERS)
+    if ch == "s":
+        return sfft.dst(a.real, type=1, axis=axis, workers=_WORKERS) + \
+            1j * sfft.dst(a.imag, type=1, axis=axis, workers=_WORKERS)
+    if ch in ("n", "0"):
+        return a
+    raise ValueError(f"Unknown transform type: {ch}")
+
+
+def _ctype(real_dtype):
+    return np.complex64 if np.dtype(real_dtype) == np.float32 else np.complex128
+
+
+# --------------------------------------------------------------------------------------
+# global definition
+# --------------------------------------------------------------------------------------
+def global_forward(A, d: Decomp, op="fft"):
+    """Whole-array forward transform: real A[nx,ny,nz] -> complex [nxhpc, nyc, nzc]
+    (x-pruned to the first nxhpc, y/z pruned to the outer modes).  ftran.F90:489-780."""
+    A = np.asfortranarray(A)
+    F = sfft.rfft(A, axis=0, workers=_WORKERS)[: d.nxhpc]
+    F = _fft(F, 1)[:, d.kept_y(), :]
+    F = _ztrans(F, 2, op[2], False)[:, :, d.kept_z()]
+    return np.asfortranarray(F.astype(_ctype(A.dtype), copy=False))
+
+
+def global_backward(F, d: Decomp, op="tff"):
+    """Whole-array backward transform: complex [nxhpc,nyc,nzc] -> real [nx,ny,nz];
+    pruned modes are zero-filled first (btran.F90:471-509, bcomm1.F90:367-374,
+    bcomm2.F90:307-313).  Unnormalised."""
+    ct = F.dtype
+    Z = np.zeros((d.nxhpc, d.nyc, d.nz), dtype=ct, order="F")
+    Z[:, :, d.kept_z()] = F
+    Z = _ztrans(Z, 2, op[0], True)
+    Y = np.zeros((d.nxhp, d.ny, d.nz), dtype=ct, order="F")
+    Y[: d.nxhpc, d.kept_y(), :] = Z
+    Y = _fft(Y, 1, inverse=True)
+    R = sfft.irfft(Y, n=d.nx, axis=0, norm="forward", workers=_WORKERS)
+    rt = np.float32 if ct == np.complex64 else np.float64
+    return np.asfortranarray(R.astype(rt, copy=False))
+
+
+def cheby_epilogue(out, d: Decomp, Lz):
+    """Scaling + Chebyshev derivative recurrence along z (ftran.F90:408-451); ``out`` is
+    the 'ffc' transform with z as LAST axis; returns a new array."""
+    nzc = d.nzc
+    a = out * (1.0 / (float(d.nx * d.ny) * float(nzc - 1)))
+    res = np.array(a, copy=True)
+    L = 4.0 / float(Lz)
+    # 1-based k in the reference; here z index k-1
+    res[..., nzc - 1] = 0
+    res[..., nzc - 2] = L * (nzc - 1) * a[..., nzc - 1] * 0.5
+    for k in range(nzc - 2, 0, -1):          # k = nzc-2 .. 1 (1-based)
+        res[..., k - 1] = L * k * a[..., k] + res[..., k + 1]
+    res[..., 0] = res[..., 0] * 0.5
+    return res
+
+
+def global_cheby(A, d: Decomp, Lz):
+    return np.asfortranarray(cheby_epilogue(global_forward(A, d, "ffc"), d, Lz))
+
+
+def local_in_slice(d: Decomp):
+    return (slice(None), slice(d.jistart - 1, d.jiend), slice(d.kjstart - 1, d.kjend))
+
+
+def local_out_slice(d: Decomp):
+    return (slice(d.iistart - 1, d.iiend), slice(d.jjstart - 1, d.jjend), slice(None))
+
+
+def local_forward(Aglobal, d: Decomp, op="fft"):
+    """Rank-local wavenumber block in the layout get_dims(conf=2) describes."""
+    F = global_forward(Aglobal, d, op)[local_out_slice(d)]
+    return np.asfortranarray(F.transpose(2, 1, 0)) if d.stride1 else np.asfortranarray(F)
+
+
+def local_backward(Fglobal, d: Decomp, op="tff"):
+    return np.asfortranarray(global_backward(Fglobal, d, op)[local_in_slice(d)])
+
+
+# --------------------------------------------------------------------------------------
+# structural restatement: P simulated ranks, the reference's stage sequence
+# --------------------------------------------------------------------------------------
+class SimWorld:
+    """All ranks of an iproc x jproc grid simulated in one process.  Each stage follows
+    the non-STRIDE1 single-variable code path: ftran.F90:489-780 / btran.F90:396-679 with
+    fcomm1.F90:209-327, fcomm2.F90:250-386, bcomm1.F90:250-380, bcomm2.F90:213-318.
+    The alltoallv is a python loop moving the byte ranges given by the If/Kf/Jr/Kr tables."""
+
+    def __init__(self, nx, ny, nz, dims, nxc=None, nyc=None, nzc=None, dtype=np.float64,
+                 dims_c=False):
+        self.rt = np.dtype(dtype)
+        self.ct = np.dtype(_ctype(dtype))
+        elem = self.rt.itemsize
+        P = dims[0] * dims[1]
+        self.d = [Decomp(nx, ny, nz, tuple(dims), r, nxc, nyc, nzc, dims_c=dims_c, elem=elem)
+                  for r in range(P)]
+        self.P = P
+
+    # ---- helpers -----------------------------------------------------------------
+    def scatter_real(self, Aglobal):
+        return [np.asfortranarray(Aglobal[local_in_slice(d)].astype(self.rt)) for d in self.d]
+
+    def gather_real(self, parts):
+        d0 = self.d[0]
+        G = np.zeros((d0.nx, d0.ny, d0.nz), dtype=self.rt, order="F")
+        for d, p in zip(self.d, parts):
+            G[local_in_slice(d)] = p
+        return G
+
+    def scatter_wave(self, Fglobal):
+        return [np.asfortranarray(Fglobal[local_out_slice(d)].astype(self.ct)) for d in self.d]
+
+    def gather_wave(self, parts):
+        d0 = self.d[0]
+        G = np.zeros((d0.nxhpc, d0.nyc, d0.nzc), dtype=self.ct, order="F")
+        for d, p in zip(self.d, parts):
+            G[local_out_slice(d)] = p
+        return G
+
+    def _alltoallv(self, sendbufs, group_of, snd_strt, snd_cnts, rcv_strt, rcv_cnts, recv_len):
+        """MPI_Alltoallv with counts in bytes over flat complex buffers."""
+        c = self.ct.itemsize
+        recv = [np.zeros(recv_len(d), dtype=self.ct) for d in self.d]
+        for d in self.d:
+            grp = group_of(d)
+            me = grp.index(d.rank)
+            for p, peer in enumerate(grp):
+                dp = self.d[peer]
+                s0, n = snd_strt(d)[p] // c, snd_cnts(d)[p] // c
+                r0, m = rcv_strt(dp)[me] // c, rcv_cnts(dp)[me] // c
+                assert n == m, "alltoallv count mismatch"
+                recv[peer][r0:r0 + n] = sendbufs[d.rank][s0:s0 + n]
+        return recv
+
+    # ---- forward -----------------------------------------------------------------
+    def forward(self, parts, op="fft"):
+        D = self.d
+        # 1. X r2c: (nx,ji,kj) -> (nxhp,ji,kj)              exec_f_r2c, ftran.F90:530
+        b2 = [np.asfortranarray(sfft.rfft(a, axis=0, workers=_WORKERS).astype(self.ct)) for a in parts]
+        # 2. row transpose                                   fcomm1 / seg_copy_x
+        ybuf = []
+        if D[0].iproc > 1:
+            send = []
+            for d, s in zip(D, b2):
+                buf1 = np.zeros(d.nxhpc * d.jisize * d.kjsize, dtype=self.ct)
+                for p in range(d.iproc):                     # fcomm1.F90:239-253
+                    pos = d.IfSndStrt[p] // self.ct.itemsize
+                    blk = s[d.iist[p] - 1:d.iien[p], :, :]
+                    buf1[pos:pos + blk.size] = blk.ravel(order="F")
+                send.append(buf1)
+            recv = self._alltoallv(send, lambda d: d.row_ranks(), lambda d: d.IfSndStrt,
+                                   lambda d: d.IfSndCnts, lambda d: d.IfRcvStrt,
+                                   lambda d: d.IfRcvCnts, lambda d: d.iisize * d.ny * d.kjsize)
+            for d, r in zip(D, recv):                        # fcomm1.F90:284-320
+                dest = np.zeros((d.iisize, d.ny, d.kjsize), dtype=self.ct, order="F")
+                for p in range(d.iproc):
+                    pos = d.IfRcvStrt[p] // self.ct.itemsize
+                    n = d.iisize * d.jisz[p] * d.kjsize
+                    dest[:, d.jist[p] - 1:d.jien[p], :] = \
+                        r[pos:pos + n].reshape((d.iisize, d.jisz[p], d.kjsize), order="F")
+                ybuf.append(dest)
+        else:
+            ybuf = [np.asfortranarray(s[: d.nxhpc]) for d, s in zip(D, b2)]   # ftran.F90:554
+        # 3. Y c2c per z-plane                               ftran.F90:581-583
+        ybuf = [_fft(b, 1) for b in ybuf]
+        # 4. column transpose with Y pruning                 fcomm2 / seg_copy_y
+        zbuf = []
+        if D[0].jproc > 1:
+            send = []
+            for d, s in zip(D, ybuf):
+                sp = s[:, d.kept_y(), :]                      # pack_fcomm2, fcomm2.F90:321-386
+                buf1 = np.zeros(d.iisize * d.nyc * d.kjsize, dtype=self.ct)
+                for p in range(d.jproc):
+                    pos = d.KfSndStrt[p] // self.ct.itemsize
+                    blk = sp[:, d.jjst[p] - 1:d.jjen[p], :]
+                    buf1[pos:pos + blk.size] = blk.ravel(order="F")
+                send.append(buf1)
+            recv = self._alltoallv(send, lambda d: d.col_ranks(), lambda d: d.KfSndStrt,
+                                   lambda d: d.KfSndCnts, lambda d: d.KfRcvStrt,
+                                   lambda d: d.KfRcvCnts, lambda d: d.iisize * d.jjsize * d.nz)
+            # lands directly as (iisize,jjsize,nz)            fcomm2.F90:313
+            zbuf = [r.reshape((d.iisize, d.jjsize, d.nz), order="F") for d, r in zip(D, recv)]
+        else:
+            zbuf = [np.asfortranarray(s[:, d.kept_y(), :]) for d, s in zip(D, ybuf)]
+        # 5. Z transform + Z pruning                         ftran.F90:605-683
+        out = []
+        for d, b in zip(D, zbuf):
+            t = _ztrans(b, 2, op[2], False)
+            out.append(np.asfortranarray(t[:, :, d.kept_z()].astype(self.ct)))
+        return out
+
+    # ---- backward ----------------------------------------------------------------
+    def backward(self, parts, op="tff"):
+        D = self.d
+        # 1. zero-pad in z + Z inverse                        btran.F90:437-509
+        zb = []
+        for d, f in zip(D, parts):
+            b = np.zeros((d.iisize, d.jjsize, d.nz), dtype=self.ct, order="F")
+            b[:, :, d.kept_z()] = f
+            zb.append(np.asfortranarray(_ztrans(b, 2, op[0], True).astype(self.ct)))
+        # 2. column transpose + Y zero fill                   bcomm1 / seg_copy_y+seg_zero_y
+        yb = []
+        if D[0].jproc > 1:
+            send = [b.ravel(order="F") for b in zb]           # sent from the array itself, bcomm1.F90:295
+            recv = self._alltoallv(send, lambda d: d.col_ranks(), lambda d: d.JrSndStrt,
+                                   lambda d: d.JrSndCnts, lambda d: d.JrRcvStrt,
+                                   lambda d: d.JrRcvCnts, lambda d: d.iisize * d.nyc * d.kjsize)
+            for d, r in zip(D, recv):                         # unpack_bcomm1, bcomm1.F90:309-380
+                dest = np.zeros((d.iisize, d.ny, d.kjsize), dtype=self.ct, order="F")
+                ky = d.kept_y()
+                for p in range(d.jproc):
+                    pos = d.JrRcvStrt[p] // self.ct.itemsize
+                    n = d.iisize * d.jjsz[p] * d.kjsize
+                    dest[:, ky[d.jjst[p] - 1:d.jjen[p]], :] = \
+                        r[pos:pos + n].reshape((d.iisize, d.jjsz[p], d.kjsize), order="F")
+                yb.append(dest)
+        else:
+            for d, b in zip(D, zb):
+                dest = np.zeros((d.iisize, d.ny, d.nz), dtype=self.ct, order="F")
+                dest[:, d.kept_y(), :] = b
+                yb.append(dest)
+        # 3. Y inverse                                       btran.F90:618-623
+        yb = [_fft(b, 1, inverse=True) for b in yb]
+        # 4. row transpose + X zero fill                      bcomm2 / seg_copy_x+seg_zero_x
+        xb = []
+        if D[0].iproc > 1:
+            send = []
+            for d, s in zip(D, yb):                           # bcomm2.F90:233-273
+                buf1 = np.zeros(d.iisize * d.ny * d.kjsize, dtype=self.ct)
+                for p in range(d.iproc):
+                    pos = d.KrSndStrt[p] // self.ct.itemsize
+                    blk = s[:, d.jist[p] - 1:d.jien[p], :]
+                    buf1[pos:pos + blk.size] = blk.ravel(order="F")
+                send.append(buf1)
+            recv = self._alltoallv(send, lambda d: d.row_ranks(), lambda d: d.KrSndStrt,
+                                   lambda d: d.KrSndCnts, lambda d: d.KrRcvStrt,
+                                   lambda d: d.KrRcvCnts, lambda d: d.nxhpc * d.jisize * d.kjsize)
+            for d, r in zip(D, recv):                         # bcomm2.F90:290-313
+                dest = np.zeros((d.nxhp, d.jisize, d.kjsize), dtype=self.ct, order="F")
+                for p in range(d.iproc):
+                    pos = d.KrRcvStrt[p] // self.ct.itemsize
+                    n = d.iisz[p] * d.jisize * d.kjsize
+                    dest[d.iist[p] - 1:d.iien[p], :, :] = \
+                        r[pos:pos + n].reshape((d.iisz[p], d.jisize, d.kjsize), order="F")
+                xb.append(dest)
+        else:
+            for d, s in zip(D, yb):
+                dest = np.zeros((d.nxhp, d.jisize, d.kjsize), dtype=self.ct, order="F")
+                dest[: d.nxhpc] = s
+                xb.append(dest)
+        # 5. X c2r                                           btran.F90:655
+        return [np.asfortranarray(
+            sfft.irfft(b, n=d.nx, axis=0, norm="forward", workers=_WORKERS).astype(self.rt))
+            for d, b in zip(D, xb)]
+
+    def cheby(self, parts, Lz):
+        out = self.forward(parts, "ffc")
+        return [np.asfortranarray(cheby_epilogue(o, d, Lz).astype(self.ct)) for d, o in zip(self.d, out)]
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs and metrics
+# --------------------------------------------------------------------------------------
+def philox_field(nx, ny, nz, seed=20240229, dtype=np.float64, sl=None):
+    """Uniform [0,1) field keyed by GLOBAL index, like
+    driver_rand.c:194's rand()/RAND_MAX but reproducible for any rank count.
+    ``sl`` = (yslice, zslice) restricts generation to an X-pencil."""
+    ys = range(ny)[sl[0]] if sl else range(ny)
+    zs = range(nz)[sl[1]] if sl else range(nz)
+    out = np.empty((nx, len(ys), len(zs)), dtype=dtype, order="F")
+    for kk, z in enumerate(zs):
+        # one Philox stream per z-plane: value = f(seed, z)[x + nx*y]
+        g = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, 0, z]))
+        plane = g.random(nx * ny).reshape((nx, ny), order="F")
+        out[:, :, kk] = plane[:, ys.start:ys.stop] if isinstance(ys, range) else plane[:, ys]
+    return out
+
+
+def rel_l2(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    den = np.linalg.norm(b.ravel().astype(np.complex128 if np.iscomplexobj(b) else np.float64))
+    num = np.linalg.norm((a.ravel() - b.ravel()).astype(
+        np.complex128 if np.iscomplexobj(b) else np.float64))
+    return float(num / den) if den > 0 else float(num)
