@@ -1,0 +1,83 @@
+/* p3dfft_b200.h -- non-breaking extensions of the B200 build of the P3DFFT C ABI.
+ *
+ * The reference library takes a Fortran MPI communicator handle in p3dfft_setup
+ * (build/setup.F90:83-107) and relies on MPI for process bootstrap.  The B200 build runs
+ * one process per GPU and moves data with NCCL / NVLink peer memory, so the `comm` integer
+ * passed to p3dfft_setup is a handle returned by p3dfft_b200_comm_create() (a process that
+ * never creates one gets a single-rank communicator whatever it passes).
+ *
+ * Everything here is plain C: pointers, ints and sizes only.
+ */
+#ifndef P3DFFT_B200_H
+#define P3DFFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3DFFT_B200_UNIQUE_ID_BYTES 128
+
+/* build facts: bit0 = SINGLE_PREC, bit1 = STRIDE1, bit2 = DIMS_C (configure.ac:171-329) */
+int p3dfft_b200_build_flags(void);
+/* run-time override of the STRIDE1 / DIMS_C build defaults; must precede p3dfft_setup */
+void p3dfft_b200_set_layout(int stride1, int dims_c);
+
+/* ---- process bootstrap (replaces MPI_Init/MPI_Comm_*) ------------- */
+/* rank 0 obtains an id and ships its 128 bytes to the other ranks by any side channel */
+int p3dfft_b200_get_unique_id(void* id128);
+/* collective over all ranks; binds this process to CUDA device `device` (<0: current).
+ * Returns a handle >= 1 to pass as `comm` to p3dfft_setup, or a negative error code. */
+int p3dfft_b200_comm_create(int rank, int size, const void* id128, int device);
+void p3dfft_b200_comm_destroy(int handle);
+
+/* ---- error reporting ---------------------------------------------------------------- */
+/* mode 0 (default) = the reference's behaviour: print and abort the process where the
+ * reference calls MPI_Abort (setup.F90:125-135,181-184; ftran.F90:640-643).
+ * mode 1 = record the message, return to the caller.                                      */
+void p3dfft_b200_set_error_mode(int mode);
+/* copies the last recorded message (empty string if none), clears it, returns its length */
+int p3dfft_b200_last_error(char* buf, int buflen);
+
+/* ---- execution control ---------------------------------------------------------------- */
+/* transforms are issued on this CUDA stream (cudaStream_t passed as void*; NULL = own)    */
+void p3dfft_b200_set_stream(void* cuda_stream);
+/* async != 0: ftran/btran return after enqueueing (device pointers only, timers not
+ * updated); the caller synchronises with p3dfft_b200_sync() or on its stream.            */
+void p3dfft_b200_set_async(int async);
+void p3dfft_b200_sync(void);
+/* number of kernels launched by the library since the last call with reset != 0          */
+long long p3dfft_b200_launch_count(int reset);
+
+/* ---- host-only planner queries (no GPU needed; used by the CPU test-suite) ------------- */
+typedef struct {
+  int32_t nx, ny, nz, nxc, nyc, nzc;
+  int32_t nxhp, nxhpc, nycph, nzcph;
+  int32_t iproc, jproc, ipid, jpid;
+  int32_t iistart, iiend, iisize, jistart, jiend, jisize;
+  int32_t jjstart, jjend, jjsize, kjstart, kjend, kjsize;
+  int32_t padi_work, padi;
+  int32_t memsize[3];
+  int64_t nm;
+  int64_t work_elems;
+} p3dfft_b200_decomp;
+
+/* flags: bit1 = STRIDE1, bit2 = DIMS_C.  Returns 0, or -1 and records the reference's
+ * error text (retrievable with p3dfft_b200_last_error).                                   */
+int p3dfft_b200_plan_decomp(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc,
+                            int flags, p3dfft_b200_decomp* out);
+
+/* Writes the step sequence of one transform into `steps` (array of P3dStep, see
+ * p3dfft_b200/csrc/stage.h: {int32 is_exchange; P3dStage st; P3dExchange ex;}) and returns
+ * the number of steps, or -1 on error.  elem_bytes = 8 (double) or 4 (single).            */
+int p3dfft_b200_plan_steps(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc,
+                           int flags, int backward, const char* op, int nv, int64_t dim_real, int64_t dim_cplx,
+                           int elem_bytes, void* steps, int max_steps);
+/* sizeof(P3dStep) as compiled, so bindings can check their struct mirror                  */
+int p3dfft_b200_sizeof_step(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -501,3 +501,50 @@ def rel_l2(a, b):
     num = np.linalg.norm((a.ravel() - b.ravel()).astype(
         np.complex128 if np.iscomplexobj(b) else np.float64))
     return float(num / den) if den > 0 else float(num)
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline: the reference's single-rank stage sequence on a bounded sample
+# --------------------------------------------------------------------------------------
+def cpu_pair_sampled(nx, ny, nz, frac_planes, dtype=np.float64, workers=None, seed=1):
+    """Times the reference's P=1 forward+backward stage sequence (ftran.F90:530,554,581-583,
+    756-757,660-683; btran.F90:437-466,618-623,663-671,655: FFT executes plus the seg_copy /
+    ar_copy passes) on 1/frac of the 1D lines of every stage at FULL line length, and
+    extrapolates linearly.  X and Y stages run on nz/frac z-planes; the Z stage runs on an
+    x-slab of nxhp/frac columns.  Returns (seconds_for_full_pair_extrapolated, seconds_measured,
+    description)."""
+    import time
+    w = workers or os.cpu_count()
+    rt = np.dtype(dtype)
+    ct = np.dtype(_ctype(dtype))
+    nxhp = nx // 2 + 1
+    nzs = max(1, nz // frac_planes)
+    nxs = max(1, nxhp // frac_planes)
+    rng = np.random.default_rng(seed)
+    A = np.asfortranarray(rng.random((nx, ny, nzs)).astype(rt))
+    Zin = np.asfortranarray((rng.random((nxs, ny, nz)) + 1j * rng.random((nxs, ny, nz))).astype(ct))
+    t = {}
+    t0 = time.perf_counter()
+    # forward
+    b2 = sfft.rfft(A, axis=0, workers=w)                       # exec_f_r2c
+    buf = np.array(b2[:nxhp], order="F", copy=True)            # seg_copy_x
+    buf = sfft.fft(buf, axis=1, workers=w, overwrite_x=True)   # Y, per z-plane
+    out = np.array(buf, order="F", copy=True)                  # seg_copy_y x2 into XYZg
+    t1 = time.perf_counter()
+    zf = sfft.fft(Zin, axis=2, workers=w)                      # exec_f_c2_same on the user array
+    t2 = time.perf_counter()
+    # backward
+    zb = sfft.ifft(zf, axis=2, norm="forward", workers=w)      # exec_b_c2_same
+    zc = np.array(zb, order="F", copy=True)                    # ar_copy into buf
+    t3 = time.perf_counter()
+    yb = sfft.ifft(out, axis=1, norm="forward", workers=w)     # Y inverse
+    xb = np.array(yb, order="F", copy=True)                    # seg_copy_x + seg_zero_x into buf1
+    R = sfft.irfft(xb, n=nx, axis=0, norm="forward", workers=w)   # exec_b_c2r
+    t4 = time.perf_counter()
+    meas_xy = (t1 - t0) + (t4 - t3)
+    meas_z = (t3 - t1)
+    full = meas_xy * (nz / nzs) + meas_z * (nxhp / nxs)
+    desc = (f"reference P=1 stage sequence restated with scipy/pocketfft ({w} threads): X,Y stages on {nzs}/{nz} "
+            f"z-planes, Z stage on {nxs}/{nxhp} x-columns, all 1D lines at full length; linearly extrapolated")
+    del R, zc
+    return full, meas_xy + meas_z, desc

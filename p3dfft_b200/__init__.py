@@ -1,0 +1,260 @@
+"""p3dfft_b200 -- host-side mirror of the P3DFFT interface over the B200 C-ABI library.
+
+The product is the shared library ``p3dfft_b200/lib/libp3dfft[_single].so`` (C++/CUDA,
+``p3dfft_b200/csrc``); its entry points are declared in ``include/p3dfft.h`` and
+``include/p3dfft_b200.h``.  This module is a thin ctypes binding with the reference's names and
+argument meaning (``build/module.F90:178-186`` public list), used by the tests, ``bench.py``
+and Python callers.  It contains no transform arithmetic and no CPU fallback: if the
+library is missing, importing :func:`load` raises.
+
+Arrays are passed as raw addresses: numpy arrays (host memory, staged over PCIe by the
+library) or torch CUDA tensors (device memory, used in place).  All arrays are Fortran
+ordered (x fastest) exactly as the reference expects.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+__all__ = ["load", "P3DFFT", "LibraryMissing", "Step", "Stage", "Exchange", "Seg", "Side", "DecompInfo"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MAXSEG, MAXFAC = 16, 24
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+# ---- ctypes mirrors of csrc/stage.h ------------------------------------------------------
+class Seg(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("buf", C.c_int32), ("peer", C.c_int32), ("off", C.c_int64),
+                ("start", C.c_int32), ("len", C.c_int32), ("ps", C.c_int64), ("sa", C.c_int64),
+                ("sb", C.c_int64), ("sc", C.c_int64)]
+
+
+class Side(C.Structure):
+    _fields_ = [("nseg", C.c_int32), ("cnt", C.c_int32), ("h1", C.c_int32), ("logical", C.c_int32),
+                ("seg", Seg * MAXSEG)]
+
+
+class Stage(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("nfft", C.c_int32), ("na", C.c_int32),
+                ("nb", C.c_int32), ("nc", C.c_int32), ("tile", C.c_int32), ("layx", C.c_int32),
+                ("need_zero", C.c_int32), ("nfac", C.c_int32), ("fac", C.c_int32 * MAXFAC),
+                ("timer", C.c_int32), ("tw", C.c_void_p), ("scale", C.c_double),
+                ("inp", Side), ("out", Side)]
+
+
+class Exchange(C.Structure):
+    _fields_ = [("comm", C.c_int32), ("npeer", C.c_int32), ("self", C.c_int32), ("sendbuf", C.c_int32),
+                ("recvbuf", C.c_int32), ("timer", C.c_int32),
+                ("sndoff", C.c_int64 * MAXSEG), ("sndcnt", C.c_int64 * MAXSEG),
+                ("rcvoff", C.c_int64 * MAXSEG), ("rcvcnt", C.c_int64 * MAXSEG)]
+
+
+class Step(C.Structure):
+    _fields_ = [("is_exchange", C.c_int32), ("pad_", C.c_int32), ("st", Stage), ("ex", Exchange)]
+
+
+class DecompInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "nx", "ny", "nz", "nxc", "nyc", "nzc", "nxhp", "nxhpc", "nycph", "nzcph", "iproc", "jproc", "ipid", "jpid",
+        "iistart", "iiend", "iisize", "jistart", "jiend", "jisize", "jjstart", "jjend", "jjsize",
+        "kjstart", "kjend", "kjsize", "padi_work", "padi")] + [
+        ("memsize", C.c_int32 * 3), ("nm", C.c_int64), ("work_elems", C.c_int64)]
+
+
+KIND_NAMES = {0: "c2c_fwd", 1: "c2c_bwd", 2: "r2c", 3: "c2r", 4: "dct1", 5: "dst1", 6: "noop"}
+BUF_USER_IN, BUF_USER_OUT, BUF_A, BUF_B, BUF_C = 0, 1, 2, 3, 4
+
+
+def lib_path(single: bool = False) -> str:
+    return os.path.join(_HERE, "lib", "libp3dfft_single.so" if single else "libp3dfft.so")
+
+
+def _addr(x) -> int:
+    """Raw address of a numpy array or torch tensor (no copies are ever made here)."""
+    if x is None:
+        return 0
+    if hasattr(x, "data_ptr"):
+        return int(x.data_ptr())
+    if hasattr(x, "ctypes"):
+        return int(x.ctypes.data)
+    if isinstance(x, int):
+        return x
+    raise TypeError(f"cannot take the address of {type(x)}")
+
+
+class P3DFFT:
+    """One loaded library = one P3DFFT "module" (one plan at a time, module.F90:103-176)."""
+
+    def __init__(self, single: bool = False, path: str | None = None):
+        path = path or lib_path(single)
+        if not os.path.exists(path):
+            raise LibraryMissing(f"{path} not built; run `python p3dfft_b200/build.py` (no CPU fallback exists)")
+        self.single = single
+        self.lib = lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        if bool(lib.p3dfft_b200_build_flags() & 1) != bool(single):
+            raise LibraryMissing(f"{path} has the wrong precision")
+        self.real = C.c_float if single else C.c_double
+        ip, vp = C.POINTER(C.c_int), C.c_void_p
+        lib.p3dfft_setup.argtypes = [ip] * 10
+        lib.p3dfft_setup.restype = None
+        lib.p3dfft_get_dims.argtypes = [ip] * 4
+        lib.p3dfft_ftran_r2c.argtypes = [vp, vp, C.c_char_p]
+        lib.p3dfft_btran_c2r.argtypes = [vp, vp, C.c_char_p]
+        lib.p3dfft_ftran_r2c_many.argtypes = [vp, ip, vp, ip, ip, C.c_char_p]
+        lib.p3dfft_btran_c2r_many.argtypes = [vp, ip, vp, ip, ip, C.c_char_p]
+        lib.p3dfft_cheby.argtypes = [vp, vp, C.POINTER(self.real)]
+        lib.p3dfft_cheby_many.argtypes = [vp, ip, vp, ip, ip, C.POINTER(self.real)]
+        lib.get_timers.argtypes = [C.POINTER(C.c_double)]
+        lib.p3dfft_b200_get_unique_id.argtypes = [vp]
+        lib.p3dfft_b200_comm_create.argtypes = [C.c_int, C.c_int, vp, C.c_int]
+        lib.p3dfft_b200_last_error.argtypes = [C.c_char_p, C.c_int]
+        lib.p3dfft_b200_set_stream.argtypes = [vp]
+        lib.p3dfft_b200_launch_count.restype = C.c_longlong
+        lib.p3dfft_b200_launch_count.argtypes = [C.c_int]
+        lib.p3dfft_b200_plan_decomp.argtypes = [ip] + [C.c_int] * 8 + [C.POINTER(DecompInfo)]
+        lib.p3dfft_b200_plan_steps.argtypes = [ip] + [C.c_int] * 9 + [C.c_char_p, C.c_int, C.c_int64, C.c_int64,
+                                                                     C.c_int, vp, C.c_int]
+        if lib.p3dfft_b200_sizeof_step() != C.sizeof(Step):
+            raise LibraryMissing("ctypes mirror of P3dStep is out of date")
+        lib.p3dfft_b200_set_error_mode(1)     # Python callers get exceptions instead of abort()
+
+    # ---- errors ------------------------------------------------------------------------
+    def _check(self):
+        buf = C.create_string_buffer(2048)
+        if self.lib.p3dfft_b200_last_error(buf, 2048) > 0:
+            raise RuntimeError(buf.value.decode(errors="replace"))
+
+    # ---- reference API -----------------------------------------------------------------
+    def p3dfft_setup(self, dims, nx, ny, nz, comm=0, nxcut=None, nycut=None, nzcut=None, overwrite=True):
+        """``p3dfft_setup`` (build/setup.F90:107); returns ``memsize``."""
+        d = (C.c_int * 2)(*dims)
+        mem = (C.c_int * 3)()
+        i = lambda v: C.byref(C.c_int(int(v)))
+        self.lib.p3dfft_setup(d, i(nx), i(ny), i(nz), i(comm), i(nx if nxcut is None else nxcut),
+                              i(ny if nycut is None else nycut), i(nz if nzcut is None else nzcut),
+                              i(1 if overwrite else 0), mem)
+        self._check()
+        return tuple(mem)
+
+    def p3dfft_get_dims(self, conf):
+        """``p3dfft_get_dims`` (build/module.F90:225): (istart, iend, isize), 1-based."""
+        a, b, c = (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 3)()
+        self.lib.p3dfft_get_dims(a, b, c, C.byref(C.c_int(conf)))
+        self._check()
+        return tuple(a), tuple(b), tuple(c)
+
+    def p3dfft_ftran_r2c(self, A, B, op="fft"):
+        self.lib.p3dfft_ftran_r2c(_addr(A), _addr(B), op.encode() + b"\0")
+        self._check()
+
+    def p3dfft_btran_c2r(self, A, B, op="tff"):
+        self.lib.p3dfft_btran_c2r(_addr(A), _addr(B), op.encode() + b"\0")
+        self._check()
+
+    def p3dfft_ftran_r2c_many(self, A, dim_in, B, dim_out, nv, op="fft"):
+        i = lambda v: C.byref(C.c_int(int(v)))
+        self.lib.p3dfft_ftran_r2c_many(_addr(A), i(dim_in), _addr(B), i(dim_out), i(nv), op.encode() + b"\0")
+        self._check()
+
+    def p3dfft_btran_c2r_many(self, A, dim_in, B, dim_out, nv, op="tff"):
+        i = lambda v: C.byref(C.c_int(int(v)))
+        self.lib.p3dfft_btran_c2r_many(_addr(A), i(dim_in), _addr(B), i(dim_out), i(nv), op.encode() + b"\0")
+        self._check()
+
+    def p3dfft_cheby(self, A, B, Lz):
+        self.lib.p3dfft_cheby(_addr(A), _addr(B), C.byref(self.real(Lz)))
+        self._check()
+
+    def p3dfft_cheby_many(self, A, dim_in, B, dim_out, nv, Lz):
+        i = lambda v: C.byref(C.c_int(int(v)))
+        self.lib.p3dfft_cheby_many(_addr(A), i(dim_in), _addr(B), i(dim_out), i(nv), C.byref(self.real(Lz)))
+        self._check()
+
+    def p3dfft_clean(self):
+        self.lib.p3dfft_clean()
+
+    def get_timers(self):
+        t = (C.c_double * 12)()
+        self.lib.get_timers(t)
+        return list(t)
+
+    def set_timers(self):
+        self.lib.set_timers()
+
+    # ---- extensions ----------------------------------------------------------------------
+    def set_layout(self, stride1=False, dims_c=False):
+        self.lib.p3dfft_b200_set_layout(int(stride1), int(dims_c))
+
+    def get_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        if self.lib.p3dfft_b200_get_unique_id(buf) != 0:
+            self._check()
+            raise RuntimeError("ncclGetUniqueId failed")
+        return buf.raw
+
+    def comm_create(self, rank, size, unique_id: bytes | None, device=-1) -> int:
+        buf = C.create_string_buffer(unique_id or b"\0" * 128, 128)
+        h = self.lib.p3dfft_b200_comm_create(rank, size, buf, device)
+        if h < 0:
+            self._check()
+            raise RuntimeError(f"p3dfft_b200_comm_create failed ({h})")
+        return h
+
+    def comm_destroy(self, handle):
+        self.lib.p3dfft_b200_comm_destroy(handle)
+
+    def set_stream(self, cuda_stream_ptr):
+        self.lib.p3dfft_b200_set_stream(cuda_stream_ptr)
+
+    def set_async(self, flag):
+        self.lib.p3dfft_b200_set_async(int(flag))
+
+    def sync(self):
+        self.lib.p3dfft_b200_sync()
+
+    def launch_count(self, reset=False) -> int:
+        return int(self.lib.p3dfft_b200_launch_count(int(reset)))
+
+    # ---- host-only planner ---------------------------------------------------------------
+    def plan_decomp(self, dims, nx, ny, nz, rank=0, nxc=None, nyc=None, nzc=None, stride1=False, dims_c=False):
+        info = DecompInfo()
+        d = (C.c_int * 2)(*dims)
+        flags = (2 if stride1 else 0) | (4 if dims_c else 0)
+        rc = self.lib.p3dfft_b200_plan_decomp(d, nx, ny, nz, rank, nxc or nx, nyc or ny, nzc or nz, flags,
+                                              C.byref(info))
+        if rc != 0:
+            self._check()
+            raise RuntimeError("plan_decomp failed")
+        return info
+
+    def plan_steps(self, dims, nx, ny, nz, rank, backward, op, nv=1, nxc=None, nyc=None, nzc=None, stride1=False,
+                   dims_c=False, dim_real=None, dim_cplx=None):
+        info = self.plan_decomp(dims, nx, ny, nz, rank, nxc, nyc, nzc, stride1, dims_c)
+        if dim_real is None:
+            dim_real = info.nx * info.jisize * info.kjsize
+        if dim_cplx is None:
+            dim_cplx = info.iisize * info.jjsize * info.nzc
+        arr = (Step * 16)()
+        d = (C.c_int * 2)(*dims)
+        flags = (2 if stride1 else 0) | (4 if dims_c else 0)
+        n = self.lib.p3dfft_b200_plan_steps(d, nx, ny, nz, rank, nxc or nx, nyc or ny, nzc or nz, flags,
+                                            1 if backward else 0, op.encode() + b"\0", nv, dim_real, dim_cplx,
+                                            4 if self.single else 8, arr, 16)
+        if n < 0:
+            self._check()
+            raise RuntimeError("plan_steps failed")
+        return [arr[i] for i in range(n)], info
+
+
+_cache: dict = {}
+
+
+def load(single: bool = False) -> P3DFFT:
+    """Load (once) the double or single precision library."""
+    if single not in _cache:
+        _cache[single] = P3DFFT(single)
+    return _cache[single]

@@ -1,0 +1,69 @@
+"""Builds the C-ABI shared libraries in-tree with nvcc for sm_100a.
+
+  p3dfft_b200/lib/libp3dfft.so          double precision (the reference's default build)
+  p3dfft_b200/lib/libp3dfft_single.so   -DSINGLE_PREC     (configure --enable-single)
+
+The STRIDE1 / DIMS_C switches of the reference's configure are run-time options of the same
+binaries (p3dfft_b200_set_layout); `--variants` additionally emits libraries with those
+defaults baked in (libp3dfft_stride1.so, ...), matching configure.ac:171-329.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+SOURCES = ["fft_kernels.cu", "api.cpp"]
+HEADERS = ["stage.h", "plan.h", "kernels.h"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_one(name: str, defines: list[str], verbose: bool = False, force: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj_" + name)
+    os.makedirs(objdir, exist_ok=True)
+    target = os.path.join(LIBDIR, f"lib{name}.so")
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [
+        os.path.join(HERE, "..", "include", "p3dfft_b200.h"), os.path.abspath(__file__)]
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, deps):
+            cmd = [NVCC, *ARCH, *COMMON, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
+            if src.endswith(".cu") and verbose:
+                cmd += ["-Xptxas", "-v"]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+    if force or _newer(target, objs):
+        cmd = [NVCC, *ARCH, "-shared", "-o", target, *objs, "-ldl"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return target
+
+
+def build_all(verbose: bool = False, variants: bool = False, force: bool = False) -> list[str]:
+    out = [build_one("p3dfft", [], verbose, force), build_one("p3dfft_single", ["-DSINGLE_PREC"], verbose, force)]
+    if variants:
+        out.append(build_one("p3dfft_stride1", ["-DSTRIDE1"], verbose, force))
+        out.append(build_one("p3dfft_single_stride1", ["-DSINGLE_PREC", "-DSTRIDE1"], verbose, force))
+    return out
+
+
+if __name__ == "__main__":
+    libs = build_all(verbose="-v" in sys.argv, variants="--variants" in sys.argv, force="-f" in sys.argv)
+    print("\n".join(libs))

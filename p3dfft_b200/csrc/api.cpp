@@ -1,0 +1,566 @@
+// C ABI of the B200 build: the eleven entry points of the reference's BIND(C) layer
+// (include/p3dfft.h cites the file:line each replaces) plus the p3dfft_b200_* extensions.
+//
+// State model follows the reference: ONE plan per process held in module-global variables
+// (build/module.F90:103-176), p3dfft_setup may be called again only after p3dfft_clean
+// (setup.F90:130-135), every rank calls every routine collectively.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/p3dfft_b200.h"
+#include "kernels.h"
+#include "plan.h"
+#include "stage.h"
+
+#ifdef SINGLE_PREC
+typedef float real_t;
+#else
+typedef double real_t;
+#endif
+static const size_t CSIZE = 2 * sizeof(real_t);
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------
+int g_error_mode = 0;
+std::string g_last_error;
+
+void report(bool fatal, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_last_error = buf;
+  fprintf(stderr, "%s\n", buf);
+  if (fatal && g_error_mode == 0) { fflush(stderr); abort(); }     // where the reference calls MPI_Abort
+}
+
+#define CUDA_OK(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      report(true, "P3DFFT(B200) CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, \
+             cudaGetErrorString(e__));                                                     \
+      return false;                                                                        \
+    }                                                                                      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------
+// NCCL, bound at run time so the library loads (and the planner works) without it
+// ------------------------------------------------------------------------------------
+struct Nccl {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i] && !h; i++) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { report(true, "P3DFFT(B200): cannot load libnccl.so.2: %s", dlerror()); return false; }
+#define SYM(f) *(void**)(&f) = dlsym(h, "nccl" #f); if (!f) { report(true, "P3DFFT(B200): nccl" #f " missing"); return false; }
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommSplit) SYM(CommDestroy) SYM(Send) SYM(Recv)
+    SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+    return true;
+  }
+} g_nccl;
+
+#define NCCL_OK(expr)                                                                      \
+  do {                                                                                     \
+    ncclResult_t r__ = (expr);                                                             \
+    if (r__ != ncclSuccess) {                                                              \
+      report(true, "P3DFFT(B200) NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(r__)); \
+      return false;                                                                        \
+    }                                                                                      \
+  } while (0)
+
+struct CommCtx {
+  int rank = 0, size = 1, device = -1;
+  ncclComm_t world = nullptr;
+};
+std::map<int, CommCtx*> g_comms;
+int g_next_handle = 1;
+
+// ------------------------------------------------------------------------------------
+// the plan (module-global state of the reference)
+// ------------------------------------------------------------------------------------
+struct PlanKey {
+  int backward, nv; char op; long long dim_real, dim_cplx;
+  bool operator<(const PlanKey& o) const {
+    return std::tie(backward, nv, op, dim_real, dim_cplx) < std::tie(o.backward, o.nv, o.op, o.dim_real, o.dim_cplx);
+  }
+};
+
+struct Lib {
+  bool set = false;
+  p3d::Decomp d;
+  bool overwrite = true;
+  CommCtx* comm = nullptr;
+  ncclComm_t row = nullptr, col = nullptr;
+  void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // indexed by P3dBuf (A,B,C used)
+  int nv_preset = 0;
+  void* stage_in = nullptr; size_t stage_in_bytes = 0;
+  void* stage_out = nullptr; size_t stage_out_bytes = 0;
+  cudaStream_t own_stream = nullptr, user_stream = nullptr;
+  bool async = false;
+  double timers[12] = {0};
+  std::map<int, void*> twiddles;
+  std::map<PlanKey, p3d::TransformPlan> plans;
+  std::vector<cudaEvent_t> events;
+  long long launches = 0;
+  int stride1 =
+#ifdef STRIDE1
+      1;
+#else
+      0;
+#endif
+  int dims_c =
+#ifdef DIMS_C
+      1;
+#else
+      0;
+#endif
+  cudaStream_t stream() { return user_stream ? user_stream : own_stream; }
+} L;
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+const void* twiddle_table(int nfft) {
+  auto it = L.twiddles.find(nfft);
+  if (it != L.twiddles.end()) return it->second;
+  std::vector<real_t> h(2 * (size_t)nfft);
+  const long double twopi = 6.283185307179586476925286766559L;
+  for (int k = 0; k < nfft; k++) {
+    // exact symmetries keep the table accurate to the last bit for the octant points
+    long double ang = -twopi * (long double)k / (long double)nfft;
+    h[2 * k] = (real_t)cosl(ang);
+    h[2 * k + 1] = (real_t)sinl(ang);
+  }
+  void* dptr = nullptr;
+  if (cudaMalloc(&dptr, h.size() * sizeof(real_t)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(dptr, h.data(), h.size() * sizeof(real_t), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  L.twiddles[nfft] = dptr;
+  return dptr;
+}
+
+bool alloc_work(int nv) {
+  if (nv <= L.nv_preset) return true;
+  // lazy growth like ftran.F90:133-157 (nv_preset)
+  cudaStreamSynchronize(L.stream());
+  size_t bytes = (size_t)L.d.work_elems(nv) * CSIZE;
+  int nbuf = (L.d.iproc * L.d.jproc > 1) ? 3 : 2;
+  for (int b = 0; b < nbuf; b++) {
+    int id = P3D_BUF_A + b;
+    if (L.buf[id]) { cudaFree(L.buf[id]); L.buf[id] = nullptr; }
+    CUDA_OK(cudaMalloc(&L.buf[id], bytes));
+  }
+  L.nv_preset = nv;
+  return true;
+}
+
+p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long dim_real, long long dim_cplx) {
+  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx};
+  auto it = L.plans.find(key);
+  if (it != L.plans.end()) return &it->second;
+  p3d::TransformPlan tp = p3d::build_plan(L.d, backward, op, nv, dim_real, dim_cplx);
+  if (!tp.error.empty()) {
+    // ftran.F90:640-643: print + MPI_Abort
+    report(true, "%s", tp.error.c_str());
+    return nullptr;
+  }
+  for (auto& s : tp.steps) {
+    if (s.is_exchange) continue;
+    s.st.tile = p3d::choose_tile<real_t>(s.st);
+    if (s.st.tile <= 0) { report(true, "P3DFFT(B200): transform length %d does not fit on chip", s.st.nfft); return nullptr; }
+    if (s.st.kind != P3D_NOOP) {
+      s.st.tw = twiddle_table(s.st.nfft);
+      if (!s.st.tw) { report(true, "P3DFFT(B200): cannot allocate twiddle table"); return nullptr; }
+    }
+  }
+  auto res = L.plans.emplace(key, std::move(tp));
+  return &res.first->second;
+}
+
+cudaEvent_t get_event(size_t i) {
+  while (L.events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); L.events.push_back(e); }
+  return L.events[i];
+}
+
+bool run_exchange(const P3dExchange& e, cudaStream_t st) {
+  ncclComm_t c = e.comm == 0 ? L.row : L.col;
+  char* sb = (char*)L.buf[e.sendbuf];
+  char* rb = (char*)L.buf[e.recvbuf];
+  NCCL_OK(g_nccl.GroupStart());
+  for (int p = 0; p < e.npeer; p++) {
+    if (p == e.self) continue;      // own block was written in place by the producing stage
+    if (e.sndcnt[p] > 0) NCCL_OK(g_nccl.Send(sb + e.sndoff[p] * CSIZE, (size_t)e.sndcnt[p] * CSIZE, ncclInt8, p, c, st));
+    if (e.rcvcnt[p] > 0) NCCL_OK(g_nccl.Recv(rb + e.rcvoff[p] * CSIZE, (size_t)e.rcvcnt[p] * CSIZE, ncclInt8, p, c, st));
+  }
+  NCCL_OK(g_nccl.GroupEnd());
+  return true;
+}
+
+// Runs one transform.  `in`/`out` may be host or device pointers.
+bool run_transform(bool backward, const void* in, void* out, const char* op, int nv, long long dim_real,
+                   long long dim_cplx, bool cheby, double Lz) {
+  if (!alloc_work(nv)) return false;
+  p3d::TransformPlan* tp = get_plan(backward, op, nv, dim_real, dim_cplx);
+  if (!tp) return false;
+  cudaStream_t st = L.stream();
+  const p3d::Decomp& d = L.d;
+  const size_t real_elems = (size_t)d.nx * d.jisize * d.kjsize, cplx_elems = (size_t)d.iisize * d.jjsize * d.nzc;
+  const size_t real_bytes = ((size_t)(nv - 1) * dim_real + real_elems) * sizeof(real_t);
+  const size_t cplx_bytes = ((size_t)(nv - 1) * dim_cplx + cplx_elems) * CSIZE;
+  const size_t in_bytes = backward ? cplx_bytes : real_bytes, out_bytes = backward ? real_bytes : cplx_bytes;
+  const bool in_dev = is_device_ptr(in), out_dev = is_device_ptr(out);
+  const void* din = in; void* dout = out;
+  if (!in_dev) {
+    if (L.stage_in_bytes < in_bytes) {
+      if (L.stage_in) cudaFree(L.stage_in);
+      CUDA_OK(cudaMalloc(&L.stage_in, in_bytes)); L.stage_in_bytes = in_bytes;
+    }
+    CUDA_OK(cudaMemcpyAsync(L.stage_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+    din = L.stage_in;
+  }
+  if (!out_dev) {
+    if (L.stage_out_bytes < out_bytes) {
+      if (L.stage_out) cudaFree(L.stage_out);
+      CUDA_OK(cudaMalloc(&L.stage_out, out_bytes)); L.stage_out_bytes = out_bytes;
+    }
+    dout = L.stage_out;
+  }
+  const bool timed = !L.async;
+  size_t nev = 0;
+  std::vector<int> slots;
+  for (auto& s : tp->steps) {
+    if (timed) { cudaEventRecord(get_event(nev++), st); }
+    if (s.is_exchange) {
+      if (!run_exchange(s.ex, st)) return false;
+      slots.push_back(s.ex.timer);
+    } else {
+      P3dStage stg = s.st;
+      for (int side = 0; side < 2; side++) {
+        P3dSide& sd = side ? stg.out : stg.in;
+        const size_t esz = (stg.kind == P3D_R2C && side == 0) || (stg.kind == P3D_C2R && side == 1) ? sizeof(real_t) : CSIZE;
+        for (int g = 0; g < sd.nseg; g++) {
+          P3dSeg& sg = sd.seg[g];
+          char* base = sg.buf == P3D_BUF_USER_IN ? (char*)din : sg.buf == P3D_BUF_USER_OUT ? (char*)dout : (char*)L.buf[sg.buf];
+          sg.base = base + sg.off * esz;
+        }
+      }
+      cudaError_t e = p3d::launch_stage<real_t>(stg, st);
+      if (e != cudaSuccess) { report(true, "P3DFFT(B200): stage launch failed: %s", cudaGetErrorString(e)); return false; }
+      L.launches++;
+      slots.push_back(stg.timer);
+    }
+  }
+  if (cheby) {
+    // p3dfft_cheby epilogue, ftran.F90:408-451
+    const double norm = 1.0 / ((double)d.nx * (double)d.ny * (double)(d.nzc - 1));
+    const double lfac = 4.0 / Lz;
+    if (timed) cudaEventRecord(get_event(nev++), st);
+    for (int v = 0; v < nv; v++) {
+      char* o = (char*)dout + (size_t)v * dim_cplx * CSIZE;
+      long long ncol = (long long)d.iisize * d.jjsize;
+      cudaError_t e = d.stride1 ? p3d::launch_cheby<real_t>(o, ncol, d.nzc, 1, d.nzc, norm, lfac, st)
+                                : p3d::launch_cheby<real_t>(o, ncol, d.nzc, ncol, 1, norm, lfac, st);
+      if (e != cudaSuccess) { report(true, "P3DFFT(B200): cheby launch failed: %s", cudaGetErrorString(e)); return false; }
+      L.launches++;
+    }
+    slots.push_back(8);
+  }
+  if (timed) cudaEventRecord(get_event(nev++), st);
+  if (!out_dev) CUDA_OK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+  if (!L.async || !in_dev || !out_dev) {
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (timed) {
+      for (size_t i = 0; i + 1 < nev; i++) {
+        float ms = 0; cudaEventElapsedTime(&ms, L.events[i], L.events[i + 1]);
+        int slot = slots[i];
+        if (slot >= 1 && slot <= 12) L.timers[slot - 1] += ms * 1e-3;
+      }
+    }
+  }
+  return true;
+}
+
+bool check_set() {
+  if (!L.set) {
+    // module.F90:231, ftran.F90:506-509: message and return
+    report(false, "P3DFFT error: call setup before other routines");
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+// ======================================================================================
+// reference entry points
+// ======================================================================================
+extern "C" {
+
+void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int* nyc, int* nzc, int* ow,
+                  int* memsize) {
+  if (L.set) {     // setup.F90:130-135
+    report(true, "P3DFFT Setup error: the problem is already initialized. \n"
+                 "Currently multiple setups not supported.\n"
+                 "Quit the library using p3dfft_clean before initializing another setup");
+    return;
+  }
+  CommCtx* cc = nullptr;
+  if (comm) { auto it = g_comms.find(*comm); if (it != g_comms.end()) cc = it->second; }
+  const int rank = cc ? cc->rank : 0, ntasks = cc ? cc->size : 1;
+  std::string err = L.d.init(*nx, *ny, *nz, dims[0], dims[1], rank, ntasks, nxc ? *nxc : *nx, nyc ? *nyc : *ny,
+                             nzc ? *nzc : *nz, L.dims_c != 0, L.stride1 != 0);
+  if (!err.empty()) { report(true, "%s", err.c_str()); return; }
+  L.overwrite = ow ? (*ow != 0) : true;
+  L.comm = cc;
+  if (cc && cc->device >= 0) cudaSetDevice(cc->device);
+  if (!L.own_stream && cudaStreamCreateWithFlags(&L.own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    report(true, "P3DFFT(B200): no usable CUDA device (%s)", cudaGetErrorString(cudaGetLastError()));
+    return;
+  }
+  L.row = L.col = nullptr;
+  if (ntasks > 1) {
+    if (!g_nccl.load()) return;
+    // mpi_comm_row: same jpid ordered by ipid; mpi_comm_col: same ipid ordered by jpid (setup.F90:245-261)
+    if (L.d.iproc > 1 && g_nccl.CommSplit(cc->world, L.d.jpid, L.d.ipid, &L.row, nullptr) != ncclSuccess) {
+      report(true, "P3DFFT(B200): ncclCommSplit(row) failed"); return;
+    }
+    if (L.d.jproc > 1 && g_nccl.CommSplit(cc->world, L.d.ipid, L.d.jpid, &L.col, nullptr) != ncclSuccess) {
+      report(true, "P3DFFT(B200): ncclCommSplit(col) failed"); return;
+    }
+  }
+  for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
+  L.nv_preset = 0;
+  L.set = true;
+  if (!alloc_work(1)) { L.set = false; return; }
+  if (memsize) { memsize[0] = L.d.memsize[0]; memsize[1] = L.d.memsize[1]; memsize[2] = L.d.memsize[2]; }
+  if (rank == 0 && getenv("P3DFFT_B200_VERBOSE"))
+    fprintf(stderr, "P3DFFT(B200): %d x %d x %d on a %d x %d grid%s\n", *nx, *ny, *nz, dims[0], dims[1],
+            L.stride1 ? ", stride-1 layout" : "");
+}
+
+void p3dfft_get_dims(int* istart, int* iend, int* isize, int* conf) {
+  if (!check_set()) return;
+  L.d.get_dims(istart, iend, isize, *conf);
+}
+
+void p3dfft_ftran_r2c(real_t* A, real_t* B, unsigned char* op) {
+  if (!check_set()) return;
+  const p3d::Decomp& d = L.d;
+  run_transform(false, A, B, (const char*)op, 1, (long long)d.nx * d.jisize * d.kjsize,
+                (long long)d.iisize * d.jjsize * d.nzc, false, 0.0);
+}
+
+void p3dfft_btran_c2r(real_t* A, real_t* B, unsigned char* op) {
+  if (!check_set()) return;
+  const p3d::Decomp& d = L.d;
+  run_transform(true, A, B, (const char*)op, 1, (long long)d.nx * d.jisize * d.kjsize,
+                (long long)d.iisize * d.jjsize * d.nzc, false, 0.0);
+}
+
+void p3dfft_ftran_r2c_many(real_t* A, int* dim_in, real_t* B, int* dim_out, int* nv, unsigned char* op) {
+  if (!check_set()) return;
+  const p3d::Decomp& d = L.d;
+  // ftran.F90:118-129: message only in the reference; here the call is also abandoned
+  if ((long long)*dim_in < (long long)d.nx * d.jisize * d.kjsize) {
+    report(false, "%d: ftran error: input array dimensions are too low: %d while expecting %lld", d.rank, *dim_in,
+           (long long)d.nx * d.jisize * d.kjsize);
+    return;
+  }
+  if ((long long)*dim_out < (long long)d.nzc * d.jjsize * d.iisize) {
+    report(false, "%d: ftran error: output array dimensions are too low: %d while expecting %lld", d.rank, *dim_out,
+           (long long)d.nzc * d.jjsize * d.iisize);
+    return;
+  }
+  if (*nv <= 0) return;
+  run_transform(false, A, B, (const char*)op, *nv, *dim_in, *dim_out, false, 0.0);
+}
+
+void p3dfft_btran_c2r_many(real_t* A, int* dim_in, real_t* B, int* dim_out, int* nv, unsigned char* op) {
+  if (!check_set()) return;
+  const p3d::Decomp& d = L.d;
+  if ((long long)*dim_in < (long long)d.nzc * d.jjsize * d.iisize) {      // btran.F90:118-129
+    report(false, "%d: btran error: input array dimensions are too low: %d while expecting %lld", d.rank, *dim_in,
+           (long long)d.nzc * d.jjsize * d.iisize);
+    return;
+  }
+  if ((long long)*dim_out < (long long)d.nx * d.jisize * d.kjsize) {
+    report(false, "%d: btran error: output array dimensions are too low: %d while expecting %lld", d.rank, *dim_out,
+           (long long)d.nx * d.jisize * d.kjsize);
+    return;
+  }
+  if (*nv <= 0) return;
+  run_transform(true, A, B, (const char*)op, *nv, *dim_out, *dim_in, false, 0.0);
+}
+
+void p3dfft_cheby(real_t* A, real_t* B, real_t* Lz) {
+  if (!check_set()) return;
+  const p3d::Decomp& d = L.d;
+  run_transform(false, A, B, "ffc", 1, (long long)d.nx * d.jisize * d.kjsize, (long long)d.iisize * d.jjsize * d.nzc,
+                true, (double)*Lz);
+}
+
+void p3dfft_cheby_many(real_t* A, int* dim_in, real_t* B, int* dim_out, int* nv, real_t* Lz) {
+  if (!check_set()) return;
+  if (*nv <= 0) return;
+  run_transform(false, A, B, "ffc", *nv, *dim_in, *dim_out, true, (double)*Lz);
+}
+
+void p3dfft_clean(void) {
+  // module.F90:309-420: destroy plans, free buffers, mpi_set = .false.
+  if (!L.set) return;
+  cudaStreamSynchronize(L.stream());
+  for (int b = P3D_BUF_A; b <= P3D_BUF_C; b++) if (L.buf[b]) { cudaFree(L.buf[b]); L.buf[b] = nullptr; }
+  if (L.stage_in) { cudaFree(L.stage_in); L.stage_in = nullptr; L.stage_in_bytes = 0; }
+  if (L.stage_out) { cudaFree(L.stage_out); L.stage_out = nullptr; L.stage_out_bytes = 0; }
+  for (auto& kv : L.twiddles) cudaFree(kv.second);
+  L.twiddles.clear();
+  L.plans.clear();
+  if (L.row) { g_nccl.CommDestroy(L.row); L.row = nullptr; }
+  if (L.col) { g_nccl.CommDestroy(L.col); L.col = nullptr; }
+  L.nv_preset = 0;
+  L.set = false;
+}
+
+void get_timers(double* timers) { for (int i = 0; i < 12; i++) timers[i] = L.timers[i]; }   // module.F90:726
+void set_timers(void) { for (int i = 0; i < 12; i++) L.timers[i] = 0.0; }                   // module.F90:742
+
+// ======================================================================================
+// extensions
+// ======================================================================================
+int p3dfft_b200_build_flags(void) {
+  int f = 0;
+#ifdef SINGLE_PREC
+  f |= 1;
+#endif
+#ifdef STRIDE1
+  f |= 2;
+#endif
+#ifdef DIMS_C
+  f |= 4;
+#endif
+  return f;
+}
+
+void p3dfft_b200_set_layout(int stride1, int dims_c) { L.stride1 = stride1 != 0; L.dims_c = dims_c != 0; }
+
+int p3dfft_b200_get_unique_id(void* id128) {
+  if (!g_nccl.load()) return -1;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return -2;
+  static_assert(sizeof(ncclUniqueId) == P3DFFT_B200_UNIQUE_ID_BYTES, "unique id size");
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+int p3dfft_b200_comm_create(int rank, int size, const void* id128, int device) {
+  if (size < 1 || rank < 0 || rank >= size) return -3;
+  CommCtx* c = new CommCtx;
+  c->rank = rank; c->size = size; c->device = device;
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { delete c; return -4; }
+  if (size > 1) {
+    if (!g_nccl.load()) { delete c; return -1; }
+    ncclUniqueId id; memcpy(&id, id128, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&c->world, size, id, rank);
+    if (r != ncclSuccess) { report(false, "P3DFFT(B200): ncclCommInitRank: %s", g_nccl.GetErrorString(r)); delete c; return -5; }
+  }
+  int h = g_next_handle++;
+  g_comms[h] = c;
+  return h;
+}
+
+void p3dfft_b200_comm_destroy(int handle) {
+  auto it = g_comms.find(handle);
+  if (it == g_comms.end()) return;
+  if (it->second->world) g_nccl.CommDestroy(it->second->world);
+  if (L.comm == it->second) L.comm = nullptr;
+  delete it->second;
+  g_comms.erase(it);
+}
+
+void p3dfft_b200_set_error_mode(int mode) { g_error_mode = mode; }
+
+int p3dfft_b200_last_error(char* buf, int buflen) {
+  int n = (int)g_last_error.size();
+  if (buf && buflen > 0) { snprintf(buf, buflen, "%s", g_last_error.c_str()); }
+  g_last_error.clear();
+  return n;
+}
+
+void p3dfft_b200_set_stream(void* s) { L.user_stream = (cudaStream_t)s; }
+void p3dfft_b200_set_async(int a) { L.async = a != 0; }
+void p3dfft_b200_sync(void) { cudaStreamSynchronize(L.stream()); }
+long long p3dfft_b200_launch_count(int reset) { long long n = L.launches; if (reset) L.launches = 0; return n; }
+
+int p3dfft_b200_plan_decomp(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc, int flags,
+                            p3dfft_b200_decomp* o) {
+  p3d::Decomp d;
+  std::string err = d.init(nx, ny, nz, dims[0], dims[1], rank, dims[0] * dims[1], nxc, nyc, nzc, (flags & 4) != 0,
+                           (flags & 2) != 0);
+  if (!err.empty()) { g_last_error = err; return -1; }
+  o->nx = d.nx; o->ny = d.ny; o->nz = d.nz; o->nxc = d.nxc; o->nyc = d.nyc; o->nzc = d.nzc;
+  o->nxhp = d.nxhp; o->nxhpc = d.nxhpc; o->nycph = d.nycph; o->nzcph = d.nzcph;
+  o->iproc = d.iproc; o->jproc = d.jproc; o->ipid = d.ipid; o->jpid = d.jpid;
+  o->iistart = d.iistart; o->iiend = d.iiend; o->iisize = d.iisize;
+  o->jistart = d.jistart; o->jiend = d.jiend; o->jisize = d.jisize;
+  o->jjstart = d.jjstart; o->jjend = d.jjend; o->jjsize = d.jjsize;
+  o->kjstart = d.kjstart; o->kjend = d.kjend; o->kjsize = d.kjsize;
+  o->padi_work = d.padi_work; o->padi = d.padi;
+  for (int i = 0; i < 3; i++) o->memsize[i] = d.memsize[i];
+  o->nm = d.nm; o->work_elems = d.work_elems(1);
+  return 0;
+}
+
+struct P3dStepC { int32_t is_exchange; int32_t pad_; P3dStage st; P3dExchange ex; };
+
+int p3dfft_b200_sizeof_step(void) { return (int)sizeof(P3dStepC); }
+
+int p3dfft_b200_plan_steps(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc, int flags,
+                           int backward, const char* op, int nv, int64_t dim_real, int64_t dim_cplx, int elem_bytes,
+                           void* steps, int max_steps) {
+  p3d::Decomp d;
+  std::string err = d.init(nx, ny, nz, dims[0], dims[1], rank, dims[0] * dims[1], nxc, nyc, nzc, (flags & 4) != 0,
+                           (flags & 2) != 0);
+  if (!err.empty()) { g_last_error = err; return -1; }
+  p3d::TransformPlan tp = p3d::build_plan(d, backward != 0, op, nv, dim_real, dim_cplx);
+  if (!tp.error.empty()) { g_last_error = tp.error; return -1; }
+  if ((int)tp.steps.size() > max_steps) { g_last_error = "step array too small"; return -1; }
+  P3dStepC* out = (P3dStepC*)steps;
+  for (size_t i = 0; i < tp.steps.size(); i++) {
+    memset(&out[i], 0, sizeof out[i]);
+    out[i].is_exchange = tp.steps[i].is_exchange ? 1 : 0;
+    out[i].st = tp.steps[i].st;
+    out[i].ex = tp.steps[i].ex;
+    if (!tp.steps[i].is_exchange)
+      out[i].st.tile = elem_bytes == 4 ? p3d::choose_tile<float>(out[i].st) : p3d::choose_tile<double>(out[i].st);
+  }
+  return (int)tp.steps.size();
+}
+
+}  // extern "C"

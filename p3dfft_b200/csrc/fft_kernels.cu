@@ -1,0 +1,347 @@
+// Batched 1D transform stage kernels for sm_100a.
+//
+// stage_kernel<T,KIND>: one CTA transforms `tile` lines.  Each input element is read once
+// from HBM (gathered through the segment list, so the unpack of the preceding all-to-all and
+// the zero-padding of pruned modes are free), the lines are transformed in shared memory by
+// an in-place decimation-in-frequency mixed-radix FFT, and each output element is written
+// once (scattered through the output segment list, so pruning and the pack for the next
+// all-to-all are free).  Replaces FFTW's execute calls in build/fft_exec.F90 together with
+// the pack/unpack loops of build/fcomm1.F90, fcomm2.F90, bcomm1.F90, bcomm2.F90 and the
+// seg_copy_*/seg_zero_* helpers of build/module.F90:427-706.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "stage.h"
+#include "kernels.h"
+
+namespace p3d {
+
+template <typename T> struct Cx;
+template <> struct Cx<double> { using type = double2; };
+template <> struct Cx<float>  { using type = float2; };
+
+template <typename T2> __device__ __forceinline__ T2 cadd(T2 a, T2 b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T2> __device__ __forceinline__ T2 csub(T2 a, T2 b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T2> __device__ __forceinline__ T2 cmul(T2 a, T2 b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+// multiply by -i
+template <typename T2> __device__ __forceinline__ T2 mul_mi(T2 a) { return {a.y, -a.x}; }
+
+// ---- forward DFT butterflies (sign -), natural order in and out --------------------
+template <typename T2> __device__ __forceinline__ void bfly2(T2& a, T2& b) {
+  T2 t = csub(a, b); a = cadd(a, b); b = t;
+}
+template <typename T2> __device__ __forceinline__ void bfly4(T2& v0, T2& v1, T2& v2, T2& v3) {
+  T2 a = cadd(v0, v2), b = csub(v0, v2), c = cadd(v1, v3), d = mul_mi(csub(v1, v3));
+  v0 = cadd(a, c); v2 = csub(a, c); v1 = cadd(b, d); v3 = csub(b, d);
+}
+template <typename T, typename T2> __device__ __forceinline__ void bfly8(T2* v) {
+  const T h = (T)0.70710678118654752440;
+  bfly4(v[0], v[2], v[4], v[6]);   // E0..E3 in v0,v2,v4,v6
+  bfly4(v[1], v[3], v[5], v[7]);   // O0..O3 in v1,v3,v5,v7
+  T2 o1 = {(v[3].x + v[3].y) * h, (v[3].y - v[3].x) * h};        // O1 * (1-i)/sqrt2
+  T2 o2 = mul_mi(v[5]);                                         // O2 * (-i)
+  T2 o3 = {(v[7].y - v[7].x) * h, -(v[7].x + v[7].y) * h};       // O3 * (-1-i)/sqrt2
+  T2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+template <typename T, typename T2> __device__ __forceinline__ void bfly3(T2& v0, T2& v1, T2& v2) {
+  const T s = (T)0.86602540378443864676;
+  T2 t1 = cadd(v1, v2);
+  T2 t2 = {v0.x - (T)0.5 * t1.x, v0.y - (T)0.5 * t1.y};
+  T2 d = csub(v1, v2);
+  T2 t3 = {d.y * s, -d.x * s};     // (-i) * s * (v1 - v2)
+  v0 = cadd(v0, t1); v1 = cadd(t2, t3); v2 = csub(t2, t3);
+}
+
+struct SmemMap {
+  int layx, tile, ldl;
+  __device__ __forceinline__ int operator()(int k, int t) const {
+    return layx ? t * ldl + k + (k >> 3) + (k >> 6) : k * tile + t;
+  }
+};
+
+// position of spectrum index k after the in-place DIF passes (mixed-radix digit reversal)
+__device__ __forceinline__ int digit_rev(int k, int nfft, int nfac, const int* fac) {
+  int pos = 0, ncur = nfft;
+  for (int i = 0; i < nfac; i++) {
+    int r = fac[i];
+    int q = k % r; k /= r; ncur /= r;
+    pos += q * ncur;
+  }
+  return pos;
+}
+
+template <typename T, int R>
+__device__ __forceinline__ void dif_pass(typename Cx<T>::type* s, const SmemMap& sm, int lines, int nfft,
+                                         int ncur, const typename Cx<T>::type* __restrict__ tw) {
+  using T2 = typename Cx<T>::type;
+  const int m = ncur / R, per_line = nfft / R, total = lines * per_line, twstep = nfft / ncur;
+  for (int w = threadIdx.x; w < total; w += blockDim.x) {
+    int t, u;
+    if (sm.layx) { t = w / per_line; u = w - t * per_line; } else { u = w / lines; t = w - u * lines; }
+    int blk = u / m, j = u - blk * m, base = blk * ncur + j;
+    T2 v[R];
+#pragma unroll
+    for (int p = 0; p < R; p++) v[p] = s[sm(base + p * m, t)];
+    if (R == 2) bfly2(v[0], v[1]);
+    else if (R == 3) bfly3<T>(v[0], v[1], v[2]);
+    else if (R == 4) bfly4(v[0], v[1], v[2], v[3]);
+    else if (R == 8) bfly8<T>(v);
+    if (m > 1) {
+#pragma unroll
+      for (int q = 1; q < R; q++) v[q] = cmul(v[q], tw[j * q * twstep]);
+    }
+#pragma unroll
+    for (int q = 0; q < R; q++) s[sm(base + q * m, t)] = v[q];
+  }
+}
+
+// any radix r <= 32 (odd primes): O(r^2) DFT with roots read from the twiddle table
+template <typename T>
+__device__ __noinline__ void dif_pass_generic(typename Cx<T>::type* s, const SmemMap& sm, int lines, int nfft,
+                                              int ncur, int r, const typename Cx<T>::type* __restrict__ tw) {
+  using T2 = typename Cx<T>::type;
+  const int m = ncur / r, per_line = nfft / r, total = lines * per_line, twstep = nfft / ncur, rstep = nfft / r;
+  for (int w = threadIdx.x; w < total; w += blockDim.x) {
+    int t, u;
+    if (sm.layx) { t = w / per_line; u = w - t * per_line; } else { u = w / lines; t = w - u * lines; }
+    int blk = u / m, j = u - blk * m, base = blk * ncur + j;
+    T2 v[32];
+    for (int p = 0; p < r; p++) v[p] = s[sm(base + p * m, t)];
+    for (int q = 0; q < r; q++) {
+      T2 acc = v[0];
+      int e = 0;
+      for (int p = 1; p < r; p++) {
+        e += q; if (e >= r) e -= r;
+        acc = cadd(acc, cmul(v[p], tw[e * rstep]));
+      }
+      if (m > 1 && q > 0) acc = cmul(acc, tw[j * q * twstep]);
+      s[sm(base + q * m, t)] = acc;
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void fft_inplace(typename Cx<T>::type* s, const SmemMap& sm, int lines,
+                                            const P3dStage& st, const typename Cx<T>::type* tw) {
+  int ncur = st.nfft;
+  for (int i = 0; i < st.nfac; i++) {
+    int r = st.fac[i];
+    switch (r) {
+      case 8: dif_pass<T, 8>(s, sm, lines, st.nfft, ncur, tw); break;
+      case 4: dif_pass<T, 4>(s, sm, lines, st.nfft, ncur, tw); break;
+      case 2: dif_pass<T, 2>(s, sm, lines, st.nfft, ncur, tw); break;
+      case 3: dif_pass<T, 3>(s, sm, lines, st.nfft, ncur, tw); break;
+      default: dif_pass_generic<T>(s, sm, lines, st.nfft, ncur, r, tw); break;
+    }
+    ncur /= r;
+    __syncthreads();
+  }
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ P3dStage st) {
+  using T2 = typename Cx<T>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T2* s = reinterpret_cast<T2*>(smem_raw);
+  const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
+
+  const int tiles_a = (st.na + st.tile - 1) / st.tile;
+  int bid = blockIdx.x;
+  const int ta = bid % tiles_a; bid /= tiles_a;
+  const int b = bid % st.nb;
+  const int c = bid / st.nb;
+  const int a0 = ta * st.tile;
+  const int lines = min(st.tile, st.na - a0);
+  const int nfft = st.nfft, n = st.n;
+  SmemMap sm{st.layx, lines, nfft + (nfft >> 3) + (nfft >> 6) + 1};
+  if (st.layx) sm.tile = st.tile;
+
+  // ---- clear (only when some logical inputs are not stored) -------------------------
+  if (st.need_zero) {
+    const int tot = st.layx ? st.tile * sm.ldl : nfft * lines;
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) s[i] = T2{0, 0};
+    __syncthreads();
+  }
+
+  // ---- load phase ------------------------------------------------------------------
+  {
+    const int shift = st.in.logical - st.in.cnt;
+    for (int g = 0; g < st.in.nseg; g++) {
+      const P3dSeg& sg = st.in.seg[g];
+      const int64_t lbase = (int64_t)b * sg.sb + (int64_t)c * sg.sc + (int64_t)a0 * sg.sa;
+      const int tot = sg.len * lines;
+      for (int w = threadIdx.x; w < tot; w += blockDim.x) {
+        int t, i;
+        if (sg.ps == 1) { t = w / sg.len; i = w - t * sg.len; } else { i = w / lines; t = w - i * lines; }
+        const int sidx = sg.start + i;
+        const int k = sidx < st.in.h1 ? sidx : sidx + shift;
+        const int64_t addr = lbase + (int64_t)i * sg.ps + (int64_t)t * sg.sa;
+        if (KIND == P3D_R2C) {
+          T v = reinterpret_cast<const T*>(sg.base)[addr];
+          s[sm(k, t)] = T2{v, 0};
+        } else {
+          T2 v = reinterpret_cast<const T2*>(sg.base)[addr];
+          if (KIND == P3D_C2C_FWD || KIND == P3D_NOOP) s[sm(k, t)] = v;
+          else if (KIND == P3D_C2C_BWD) s[sm(k, t)] = T2{v.x, -v.y};
+          else if (KIND == P3D_C2R) {
+            // Hermitian completion; x_j = Re FFT(conj X)_j.  imag of DC / Nyquist ignored like c2r.
+            if (k == 0 || 2 * k == n) s[sm(k, t)] = T2{v.x, 0};
+            else { s[sm(k, t)] = T2{v.x, -v.y}; s[sm(n - k, t)] = v; }
+          } else if (KIND == P3D_DCT1) {
+            s[sm(k, t)] = v;
+            if (k >= 1 && k <= n - 2) s[sm(nfft - k, t)] = v;
+          } else if (KIND == P3D_DST1) {
+            s[sm(k + 1, t)] = v;
+            s[sm(nfft - (k + 1), t)] = T2{-v.x, -v.y};
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- transform -------------------------------------------------------------------
+  if (KIND != P3D_NOOP) fft_inplace<T>(s, sm, lines, st, tw);
+
+  // ---- store phase -----------------------------------------------------------------
+  {
+    const int shift = st.out.logical - st.out.cnt;
+    const T scale = (T)st.scale;
+    for (int g = 0; g < st.out.nseg; g++) {
+      const P3dSeg& sg = st.out.seg[g];
+      const int64_t lbase = (int64_t)b * sg.sb + (int64_t)c * sg.sc + (int64_t)a0 * sg.sa;
+      const int tot = sg.len * lines;
+      for (int w = threadIdx.x; w < tot; w += blockDim.x) {
+        int t, i;
+        if (sg.ps == 1) { t = w / sg.len; i = w - t * sg.len; } else { i = w / lines; t = w - i * lines; }
+        const int sidx = sg.start + i;
+        int k = sidx < st.out.h1 ? sidx : sidx + shift;
+        if (KIND == P3D_DST1) k += 1;
+        const int pos = (KIND == P3D_NOOP) ? k : digit_rev(k, nfft, st.nfac, st.fac);
+        T2 v = s[sm(pos, t)];
+        const int64_t addr = lbase + (int64_t)i * sg.ps + (int64_t)t * sg.sa;
+        if (KIND == P3D_C2R) {
+          reinterpret_cast<T*>(sg.base)[addr] = v.x * scale;
+        } else {
+          if (KIND == P3D_C2C_BWD) v.y = -v.y;
+          if (KIND == P3D_DST1) v = T2{-v.y, v.x};     // Y_k = i * W_{k+1}
+          v.x *= scale; v.y *= scale;
+          reinterpret_cast<T2*>(sg.base)[addr] = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Chebyshev epilogue (ftran.F90:408-451): scale by 1/(nx ny (nzc-1)) then the derivative
+// recurrence along z, one thread per (x,y) column, coalesced across columns.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void cheby_kernel(typename Cx<T>::type* out, int64_t ncol, int nzc, int64_t zstride, int64_t colstride,
+                             T norm, T lfac) {
+  using T2 = typename Cx<T>::type;
+  int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  T2* p = out + col * colstride;
+  auto at = [&](int k) -> T2& { return p[(int64_t)(k - 1) * zstride]; };   // 1-based like the reference
+  if (nzc < 2) return;
+  T2 a_hi = at(nzc); a_hi.x *= norm; a_hi.y *= norm;          // a(nzc)
+  T2 old = at(nzc - 1); old.x *= norm; old.y *= norm;         // a(nzc-1)
+  T2 o_k2 = T2{0, 0};                                         // out(k+2), starts as out(nzc) = 0
+  T2 o_k1 = T2{lfac * (T)(nzc - 1) * a_hi.x * (T)0.5, lfac * (T)(nzc - 1) * a_hi.y * (T)0.5};  // out(nzc-1)
+  at(nzc) = o_k2;
+  at(nzc - 1) = o_k1;
+  for (int k = nzc - 2; k >= 1; k--) {
+    T2 nw = at(k); nw.x *= norm; nw.y *= norm;                // a(k)
+    T2 o = T2{lfac * (T)k * old.x + o_k2.x, lfac * (T)k * old.y + o_k2.y};
+    if (k == 1) { o.x *= (T)0.5; o.y *= (T)0.5; }
+    at(k) = o;
+    o_k2 = o_k1; o_k1 = o; old = nw;
+  }
+  if (nzc == 2) { T2 o = at(1); o.x *= (T)0.5; o.y *= (T)0.5; at(1) = o; }
+}
+
+// ------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------
+template <typename T>
+size_t stage_smem_bytes(const P3dStage& st) {
+  using T2 = typename Cx<T>::type;
+  size_t per_line = st.layx ? (size_t)(st.nfft + (st.nfft >> 3) + (st.nfft >> 6) + 1) : (size_t)st.nfft;
+  return per_line * st.tile * sizeof(T2);
+}
+
+template <typename T>
+int choose_tile(const P3dStage& st) {
+  using T2 = typename Cx<T>::type;
+  const size_t budget = 64 * 1024, hard = 200 * 1024;
+  size_t per_line = (st.layx ? (size_t)(st.nfft + (st.nfft >> 3) + (st.nfft >> 6) + 1) : (size_t)st.nfft) * sizeof(T2);
+  int want = st.layx ? 8 : (int)(128 / sizeof(T2));   // interleaved layout: one 128 B row of lines
+  int tile = (int)(budget / per_line);
+  if (tile > want) tile = want;
+  if (tile < 4 && !st.layx) { tile = (int)(hard / per_line); if (tile > 4) tile = 4; }
+  if (tile < 1) tile = (per_line <= hard) ? 1 : 0;
+  if (tile > st.na) tile = st.na;
+  return tile;
+}
+
+template <typename T, int KIND>
+static cudaError_t launch_kind(const P3dStage& st, cudaStream_t stream) {
+  size_t smem = stage_smem_bytes<T>(st);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(stage_kernel<T, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  long long tiles_a = (st.na + st.tile - 1) / st.tile;
+  long long grid = tiles_a * st.nb * st.nc;
+  if (grid <= 0) return cudaSuccess;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  stage_kernel<T, KIND><<<(unsigned)grid, 256, smem, stream>>>(st);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_stage(const P3dStage& st, cudaStream_t stream) {
+  if (st.tile <= 0) return cudaErrorInvalidValue;
+  switch (st.kind) {
+    case P3D_C2C_FWD: return launch_kind<T, P3D_C2C_FWD>(st, stream);
+    case P3D_C2C_BWD: return launch_kind<T, P3D_C2C_BWD>(st, stream);
+    case P3D_R2C: return launch_kind<T, P3D_R2C>(st, stream);
+    case P3D_C2R: return launch_kind<T, P3D_C2R>(st, stream);
+    case P3D_DCT1: return launch_kind<T, P3D_DCT1>(st, stream);
+    case P3D_DST1: return launch_kind<T, P3D_DST1>(st, stream);
+    case P3D_NOOP: return launch_kind<T, P3D_NOOP>(st, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <typename T>
+cudaError_t launch_cheby(void* out, long long ncol, int nzc, long long zstride, long long colstride,
+                         double norm, double lfac, cudaStream_t stream) {
+  if (ncol <= 0) return cudaSuccess;
+  unsigned grid = (unsigned)((ncol + 127) / 128);
+  cheby_kernel<T><<<grid, 128, 0, stream>>>(reinterpret_cast<typename Cx<T>::type*>(out), ncol, nzc, zstride,
+                                            colstride, (T)norm, (T)lfac);
+  return cudaGetLastError();
+}
+
+template cudaError_t launch_stage<double>(const P3dStage&, cudaStream_t);
+template cudaError_t launch_stage<float>(const P3dStage&, cudaStream_t);
+template int choose_tile<double>(const P3dStage&);
+template int choose_tile<float>(const P3dStage&);
+template size_t stage_smem_bytes<double>(const P3dStage&);
+template size_t stage_smem_bytes<float>(const P3dStage&);
+template cudaError_t launch_cheby<double>(void*, long long, int, long long, long long, double, double, cudaStream_t);
+template cudaError_t launch_cheby<float>(void*, long long, int, long long, long long, double, double, cudaStream_t);
+
+}  // namespace p3d

@@ -1,0 +1,333 @@
+// Host-side planner: decomposition arithmetic and the stage/exchange sequence of one
+// forward or backward transform.  Pure integer code, no CUDA -- it is exercised on CPU by
+// tests/ through the p3dfft_b200_plan_* entry points.
+//
+// Restates build/setup.F90:148-176 (derived extents), :192-219 (rank -> (ipid,jpid)),
+// :279-312 (block maps), :382-398 (padi,nm), :481-518 (alltoallv tables), :580-603
+// (memsize), :608-635 (MapDataToProc); build/module.F90:225-273 (get_dims); stage order of
+// build/ftran.F90:489-780 and build/btran.F90:396-679.
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "stage.h"
+
+namespace p3d {
+
+struct BlockMap {
+  std::vector<int> st, en, sz;   // 1-based starts/ends like the reference
+};
+
+// MapDataToProc (setup.F90:608-635): the LAST (data mod proc) ranks get one extra element.
+inline BlockMap map_data_to_proc(int data, int proc) {
+  BlockMap m;
+  m.st.assign(proc, 0); m.en.assign(proc, 0); m.sz.assign(proc, 0);
+  int size = data / proc, nu = data - size * proc, nl = proc - nu;
+  m.st[0] = 1; m.sz[0] = size; m.en[0] = size;
+  for (int i = 1; i < nl; i++) { m.st[i] = m.st[i-1] + size; m.sz[i] = size; m.en[i] = m.en[i-1] + size; }
+  for (int i = std::max(nl, 1); i < proc; i++) {
+    m.st[i] = m.en[i-1] + 1; m.sz[i] = size + 1; m.en[i] = m.en[i-1] + size + 1;
+  }
+  m.en[proc-1] = data;
+  m.sz[proc-1] = data - m.st[proc-1] + 1;
+  return m;
+}
+
+struct Decomp {
+  int nx = 0, ny = 0, nz = 0, nxc = 0, nyc = 0, nzc = 0;
+  int nxh, nxhp, nxhc, nxhpc, nyh, nzh, nyhc, nzhc, nycph, nzcph;
+  int iproc = 1, jproc = 1, ipid = 0, jpid = 0, rank = 0, numtasks = 1;
+  bool dims_c = false, stride1 = false;
+  BlockMap ii, ji, jj, kj;   // x(nxhpc)/iproc, y(ny)/iproc, y(nyc)/jproc, z(nz)/jproc
+  int iistart, iiend, iisize, jistart, jiend, jisize, jjstart, jjend, jjsize, kjstart, kjend, kjsize;
+  int padi_work = 0, padi = 0;
+  long long nm = 0;
+  int memsize[3] = {0, 0, 0};
+
+  // returns empty string on success, else the reference's error text
+  std::string init(int nx_, int ny_, int nz_, int d0, int d1, int rank_, int ntasks,
+                   int nxc_, int nyc_, int nzc_, bool dims_c_, bool stride1_) {
+    char msg[256];
+    if (nx_ <= 0 || ny_ <= 0 || nz_ <= 0) {                       // setup.F90:125-128
+      snprintf(msg, sizeof msg, "Invalid dimensions : %d %d %d", nx_, ny_, nz_);
+      return msg;
+    }
+    if (d0 <= 0 || d1 <= 0 || d0 * d1 != ntasks) {                // setup.F90:181-184
+      snprintf(msg, sizeof msg, "Invalid processor geometry: %d %d for %d tasks", d0, d1, ntasks);
+      return msg;
+    }
+    nx = nx_; ny = ny_; nz = nz_; nxc = nxc_; nyc = nyc_; nzc = nzc_;
+    if (nxc <= 0 || nxc > nx || nyc <= 0 || nyc > ny || nzc <= 0 || nzc > nz) {
+      snprintf(msg, sizeof msg, "Invalid pruned dimensions : %d %d %d", nxc, nyc, nzc);
+      return msg;
+    }
+    dims_c = dims_c_; stride1 = stride1_;
+    iproc = d0; jproc = d1; rank = rank_; numtasks = ntasks;
+    nxh = nx / 2; nxhp = nxh + 1; nxhc = nxc / 2; nxhpc = nxhc + 1;
+    nyh = ny / 2; nzh = nz / 2; nyhc = nyc / 2; nzhc = nzc / 2;
+    nycph = (nyc + 1) / 2; nzcph = (nzc + 1) / 2;
+    if (dims_c) { ipid = rank / jproc; jpid = rank % jproc; }     // setup.F90:195-219
+    else        { ipid = rank % iproc; jpid = rank / iproc; }
+    ii = map_data_to_proc(nxhpc, iproc);
+    ji = map_data_to_proc(ny, iproc);
+    jj = map_data_to_proc(nyc, jproc);
+    kj = map_data_to_proc(nz, jproc);
+    iistart = ii.st[ipid]; iiend = ii.en[ipid]; iisize = ii.sz[ipid];
+    jistart = ji.st[ipid]; jiend = ji.en[ipid]; jisize = ji.sz[ipid];
+    jjstart = jj.st[jpid]; jjend = jj.en[jpid]; jjsize = jj.sz[jpid];
+    kjstart = kj.st[jpid]; kjend = kj.en[jpid]; kjsize = kj.sz[jpid];
+    // setup.F90:382-398
+    long long padd = std::max((long long)iisize * jjsize * nz, (long long)iisize * ny * kjsize)
+                     - (long long)nxhp * jisize * kjsize;
+    long long d = (long long)nxhp * jisize;
+    if (padd <= 0 || d == 0) padi_work = 0;
+    else padi_work = (int)(padd / d + (padd % d ? 1 : 0));
+    nm = (long long)nxhp * jisize * (kjsize + padi_work);
+    // setup.F90:580-603
+    long long pad1 = 2 * std::max((long long)nz * jjsize * iisize, (long long)ny * kjsize * iisize)
+                     - (long long)nx * jisize * kjsize;
+    if (pad1 < 0) pad1 = 0;
+    long long dm = (long long)nx * jisize;
+    padi = dm > 0 ? (int)(pad1 / dm + (pad1 % dm ? 1 : 0)) : 0;
+    memsize[0] = nx; memsize[1] = jisize; memsize[2] = kjsize + padi;
+    return "";
+  }
+
+  int rank_of(int ip, int jp) const { return dims_c ? ip * jproc + jp : jp * iproc + ip; }
+
+  // p3dfft_get_dims (module.F90:225-273)
+  bool get_dims(int* st, int* en, int* sz, int conf) const {
+    if (conf == 1) {
+      st[0] = 1; en[0] = nx; sz[0] = nx;
+      st[1] = jistart; en[1] = jiend; sz[1] = jisize;
+      st[2] = kjstart; en[2] = kjend; sz[2] = kjsize;
+    } else if (conf == 2) {
+      if (stride1) {
+        st[0] = 1; en[0] = nzc; sz[0] = nzc;
+        st[1] = jjstart; en[1] = jjend; sz[1] = jjsize;
+        st[2] = iistart; en[2] = iiend; sz[2] = iisize;
+      } else {
+        st[0] = iistart; en[0] = iiend; sz[0] = iisize;
+        st[1] = jjstart; en[1] = jjend; sz[1] = jjsize;
+        st[2] = 1; en[2] = nzc; sz[2] = nzc;
+      }
+    } else if (conf == 3) {
+      for (int i = 0; i < 3; i++) { st[i] = 0; en[i] = memsize[i]; sz[i] = memsize[i]; }
+    } else return false;
+    return true;
+  }
+
+  // complex elements each work buffer must hold for nv variables
+  long long work_elems(int nv) const {
+    long long m = (long long)nxhpc * jisize * kjsize;
+    m = std::max(m, (long long)iisize * ny * kjsize);
+    m = std::max(m, (long long)iisize * nyc * kjsize);
+    m = std::max(m, (long long)iisize * jjsize * nz);
+    return std::max<long long>(m, 1) * nv;
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// FFT length factorisation for the on-chip engine
+// ------------------------------------------------------------------------------------
+inline bool factorize(int n, int* fac, int* nfac, int maxprime = 32) {
+  int k = 0;
+  while (n % 8 == 0) { fac[k++] = 8; n /= 8; }
+  while (n % 4 == 0) { fac[k++] = 4; n /= 4; }
+  while (n % 2 == 0) { fac[k++] = 2; n /= 2; }
+  for (int p = 3; p <= maxprime && n > 1; p += 2)
+    while (n % p == 0) { if (k >= P3D_MAXFAC) return false; fac[k++] = p; n /= p; }
+  *nfac = k;
+  return n == 1;
+}
+
+struct Step {
+  bool is_exchange = false;
+  P3dStage st;
+  P3dExchange ex;
+};
+
+struct TransformPlan {
+  std::vector<Step> steps;
+  std::string error;
+};
+
+inline int kind_of_letter(char ch, bool backward) {
+  switch (ch) {
+    case 't': case 'f': return backward ? P3D_C2C_BWD : P3D_C2C_FWD;
+    case 'c': return P3D_DCT1;
+    case 's': return P3D_DST1;
+    case 'n': case '0': return P3D_NOOP;
+    default: return -1;      // "Unknown transform type" (ftran.F90:640-643)
+  }
+}
+
+inline int fft_len(int kind, int n) {
+  switch (kind) {
+    case P3D_DCT1: return n > 1 ? 2 * (n - 1) : 1;
+    case P3D_DST1: return 2 * (n + 1);
+    default: return n;
+  }
+}
+
+inline void stage_init(P3dStage& s, int kind, int n, int na, int nb, int nc, int timer) {
+  memset(&s, 0, sizeof s);
+  s.kind = kind; s.n = n; s.nfft = fft_len(kind, n);
+  s.na = na; s.nb = nb; s.nc = nc; s.timer = timer; s.scale = 1.0;
+}
+
+inline void side_init(P3dSide& sd, int logical, int cnt, int h1) {
+  sd.nseg = 0; sd.logical = logical; sd.cnt = cnt; sd.h1 = h1;
+}
+
+inline void add_seg(P3dSide& sd, int buf, int peer, long long off, int start, int len,
+                    long long ps, long long sa, long long sb, long long sc) {
+  if (len <= 0) return;
+  P3dSeg& g = sd.seg[sd.nseg++];
+  g.base = nullptr; g.buf = buf; g.peer = peer; g.off = off; g.start = start; g.len = len;
+  g.ps = ps; g.sa = sa; g.sb = sb; g.sc = sc;
+}
+
+// Forward: X r2c -> T1(row) -> Y c2c -> T2(col) -> Z.   ftran.F90:489-780.
+// Backward: Z -> T3(col) -> Y c2c -> T4(row) -> X c2r.   btran.F90:396-679.
+// dim_real / dim_cplx: per-variable element strides of the user arrays (reals for the
+// real-space array, complex elements for the wavenumber array), as in the *_many API.
+//
+// Work buffers rotate among A, B, C (the reference also owns three: buf, buf1, buf2,
+// setup.F90:401-423): a stage never writes a buffer it reads, every non-self block of an
+// exchange is written into the send buffer `snd`, and the rank's own block is written
+// straight to its landing place in the receive buffer `rcv`.
+inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, int nv,
+                                long long dim_real, long long dim_cplx) {
+  TransformPlan tp;
+  const int M1 = d.iproc, M2 = d.jproc;
+  if (M1 > P3D_MAXSEG || M2 > P3D_MAXSEG) { tp.error = "processor grid dimension exceeds P3D_MAXSEG"; return tp; }
+  const long long ii = d.iisize, ji = d.jisize, jj = d.jjsize, kj = d.kjsize;
+  const long long nx = d.nx, ny = d.ny, nz = d.nz, nxhpc = d.nxhpc, nyc = d.nyc, nzc = d.nzc;
+  const int zkind = kind_of_letter(backward ? op[0] : op[2], backward);
+  if (zkind < 0) { tp.error = std::string("Unknown transform type: ") + (backward ? op[0] : op[2]); return tp; }
+  int cur = -1, snd = P3D_BUF_A, rcv = P3D_BUF_B;
+  auto rotate = [&]() {   // choose snd/rcv different from the buffer holding the data (cur)
+    int f[2], k = 0;
+    for (int b = P3D_BUF_A; b <= P3D_BUF_C; b++) if (b != cur && k < 2) f[k++] = b;
+    snd = f[0]; rcv = f[1];
+  };
+
+  auto push_stage = [&](P3dStage& s) {
+    if ((long long)s.na * s.nb * s.nc <= 0) return;
+    if (s.kind == P3D_NOOP) s.nfac = 0;
+    else if (!factorize(s.nfft, s.fac, &s.nfac)) {
+      char m[128]; snprintf(m, sizeof m, "transform length %d needs a prime factor > 32 (unsupported)", s.nfft);
+      tp.error = m; return;
+    }
+    s.need_zero = (s.in.cnt < s.in.logical) || s.kind == P3D_DST1;
+    Step st; st.is_exchange = false; st.st = s; tp.steps.push_back(st);
+  };
+  auto push_exchange = [&](int comm, int npeer, int self, int timer, const BlockMap& sm, long long sunit,
+                           const BlockMap& rm, long long runit) {
+    Step st; st.is_exchange = true; P3dExchange& e = st.ex; memset(&e, 0, sizeof e);
+    e.comm = comm; e.npeer = npeer; e.self = self; e.sendbuf = snd; e.recvbuf = rcv; e.timer = timer;
+    for (int p = 0; p < npeer; p++) {
+      e.sndoff[p] = nv * (long long)(sm.st[p] - 1) * sunit; e.sndcnt[p] = nv * (long long)sm.sz[p] * sunit;
+      e.rcvoff[p] = nv * (long long)(rm.st[p] - 1) * runit; e.rcvcnt[p] = nv * (long long)rm.sz[p] * runit;
+    }
+    tp.steps.push_back(st);
+  };
+  // Piecewise side over the blocks of `bm` (one per peer of an exchange).  Block p holds
+  // nv variables of extent unit*bm.sz[p]; `strides(p)` gives (ps,sa,sb) and sc = unit*sz.
+  // send=true : stage OUTPUT feeding an exchange (self block redirected into rcv at selfoff)
+  // send=false: stage INPUT reading what an exchange delivered into `cur`.
+  auto piecewise = [&](P3dSide& sd, const BlockMap& bm, int npeer, int self, long long unit, bool send,
+                       long long selfoff, long long ps_mul, int mode) {
+    for (int p = 0; p < npeer; p++) {
+      long long sz = bm.sz[p];
+      long long ps, sa, sb;
+      if (mode == 0)      { ps = 1;      sa = sz;  sb = sz * ji; }        // x-blocks   (sz, ji, kj)
+      else if (mode == 1) { ps = ii;     sa = 1;   sb = ii * sz; }        // y-blocks   (ii, sz, kj)
+      else                { ps = ii*jj;  sa = 1;   sb = d.stride1 ? ii : 0; }   // z-slabs (ii, jj, sz)
+      (void)ps_mul;
+      long long sc = unit * sz;
+      long long off = nv * (long long)(bm.st[p] - 1) * unit;
+      if (send && p == self) add_seg(sd, rcv, -1, selfoff, bm.st[p] - 1, (int)sz, ps, sa, sb, sc);
+      else add_seg(sd, send ? snd : cur, send ? p : -1, off, bm.st[p] - 1, (int)sz, ps, sa, sb, sc);
+    }
+  };
+
+  P3dStage s;
+  if (!backward) {
+    // ---- K1: X r2c (+ X-prune, + pack for T1).
+    // exec_f_r2c ftran.F90:530; fcomm1.F90:239-253; seg_copy_x ftran.F90:554
+    stage_init(s, P3D_R2C, d.nx, (int)ji, (int)kj, nv, 5); s.layx = 1;
+    side_init(s.in, d.nx, d.nx, d.nx);
+    add_seg(s.in, P3D_BUF_USER_IN, -1, 0, 0, d.nx, 1, nx, nx * ji, dim_real);
+    side_init(s.out, d.nxhp, d.nxhpc, d.nxhpc);
+    rotate();
+    if (M1 == 1) { add_seg(s.out, snd, -1, 0, 0, d.nxhpc, 1, nxhpc, nxhpc * ji, nxhpc * ji * kj); cur = snd; }
+    else piecewise(s.out, d.ii, M1, d.ipid, ji * kj, true, nv * (long long)(d.ji.st[d.ipid] - 1) * ii * kj, 0, 0);
+    push_stage(s);
+    if (M1 > 1) { push_exchange(0, M1, d.ipid, 1, d.ii, ji * kj, d.ji, ii * kj); cur = rcv; }   // T1 fcomm1.F90:271
+    // ---- K2: Y c2c (+ unpack of T1, + Y-prune and pack for T2).
+    // fcomm1.F90:284-320; ftran.F90:581-583; pack_fcomm2 fcomm2.F90:321-386; seg_copy_y ftran.F90:756-757
+    stage_init(s, P3D_C2C_FWD, d.ny, (int)ii, (int)kj, nv, 7);
+    side_init(s.in, d.ny, d.ny, d.ny);
+    if (M1 == 1) add_seg(s.in, cur, -1, 0, 0, d.ny, ii, 1, ii * ny, ii * ny * kj);
+    else piecewise(s.in, d.ji, M1, d.ipid, ii * kj, false, 0, 0, 1);
+    side_init(s.out, d.ny, d.nyc, d.nycph);
+    rotate();
+    if (M2 == 1) add_seg(s.out, snd, -1, 0, 0, d.nyc, ii, 1, ii * nyc, ii * nyc * kj);
+    else piecewise(s.out, d.jj, M2, d.jpid, ii * kj, true, nv * (long long)(d.kj.st[d.jpid] - 1) * ii * jj, 0, 1);
+    push_stage(s);
+    if (M2 == 1) cur = snd;
+    else { push_exchange(1, M2, d.jpid, 2, d.jj, ii * kj, d.kj, ii * jj); cur = rcv; }          // T2 fcomm2.F90:313
+    // ---- K3: Z transform (+ Z-prune, + STRIDE1 output reorder).  ftran.F90:605-683; seg_copy_z :645-646
+    if (d.stride1) stage_init(s, zkind, d.nz, (int)ii, (int)jj, nv, 8);
+    else           stage_init(s, zkind, d.nz, (int)(ii * jj), 1, nv, 8);
+    side_init(s.in, d.nz, d.nz, d.nz);
+    if (M2 == 1) add_seg(s.in, cur, -1, 0, 0, d.nz, ii * jj, 1, d.stride1 ? ii : 0, ii * jj * nz);
+    else piecewise(s.in, d.kj, M2, d.jpid, ii * jj, false, 0, 0, 2);
+    side_init(s.out, d.nz, d.nzc, d.nzcph);
+    if (d.stride1) add_seg(s.out, P3D_BUF_USER_OUT, -1, 0, 0, d.nzc, 1, nzc * jj, nzc, dim_cplx);
+    else           add_seg(s.out, P3D_BUF_USER_OUT, -1, 0, 0, d.nzc, ii * jj, 1, 0, dim_cplx);
+    push_stage(s);
+  } else {
+    // ---- K4: Z inverse (+ zero-pad of pruned Z, + pack for T3).  btran.F90:437-509
+    if (d.stride1) stage_init(s, zkind, d.nz, (int)ii, (int)jj, nv, 9);
+    else           stage_init(s, zkind, d.nz, (int)(ii * jj), 1, nv, 9);
+    side_init(s.in, d.nz, d.nzc, d.nzcph);
+    if (d.stride1) add_seg(s.in, P3D_BUF_USER_IN, -1, 0, 0, d.nzc, 1, nzc * jj, nzc, dim_cplx);
+    else           add_seg(s.in, P3D_BUF_USER_IN, -1, 0, 0, d.nzc, ii * jj, 1, 0, dim_cplx);
+    side_init(s.out, d.nz, d.nz, d.nz);
+    rotate();
+    if (M2 == 1) { add_seg(s.out, snd, -1, 0, 0, d.nz, ii * jj, 1, d.stride1 ? ii : 0, ii * jj * nz); cur = snd; }
+    else piecewise(s.out, d.kj, M2, d.jpid, ii * jj, true, nv * (long long)(d.jj.st[d.jpid] - 1) * ii * kj, 0, 2);
+    push_stage(s);
+    if (M2 > 1) { push_exchange(1, M2, d.jpid, 3, d.kj, ii * jj, d.jj, ii * kj); cur = rcv; }   // T3 bcomm1.F90:295
+    // ---- K5: Y inverse (+ unpack of T3 with zero-fill of the pruned Y band, + pack for T4)
+    // unpack_bcomm1 bcomm1.F90:309-380; btran.F90:618-623; bcomm2.F90:233-273
+    stage_init(s, P3D_C2C_BWD, d.ny, (int)ii, (int)kj, nv, 10);
+    side_init(s.in, d.ny, d.nyc, d.nycph);
+    if (M2 == 1) add_seg(s.in, cur, -1, 0, 0, d.nyc, ii, 1, ii * nyc, ii * nyc * kj);
+    else piecewise(s.in, d.jj, M2, d.jpid, ii * kj, false, 0, 0, 1);
+    side_init(s.out, d.ny, d.ny, d.ny);
+    rotate();
+    if (M1 == 1) add_seg(s.out, snd, -1, 0, 0, d.ny, ii, 1, ii * ny, ii * ny * kj);
+    else piecewise(s.out, d.ji, M1, d.ipid, ii * kj, true, nv * (long long)(d.ii.st[d.ipid] - 1) * ji * kj, 0, 1);
+    push_stage(s);
+    if (M1 == 1) cur = snd;
+    else { push_exchange(0, M1, d.ipid, 4, d.ji, ii * kj, d.ii, ji * kj); cur = rcv; }          // T4 bcomm2.F90:281
+    // ---- K6: X c2r (+ unpack of T4 with zero-fill of x > nxhpc).  bcomm2.F90:290-313; btran.F90:655
+    stage_init(s, P3D_C2R, d.nx, (int)ji, (int)kj, nv, 12); s.layx = 1;
+    side_init(s.in, d.nxhp, d.nxhpc, d.nxhpc);
+    if (M1 == 1) add_seg(s.in, cur, -1, 0, 0, d.nxhpc, 1, nxhpc, nxhpc * ji, nxhpc * ji * kj);
+    else piecewise(s.in, d.ii, M1, d.ipid, ji * kj, false, 0, 0, 0);
+    side_init(s.out, d.nx, d.nx, d.nx);
+    add_seg(s.out, P3D_BUF_USER_OUT, -1, 0, 0, d.nx, 1, nx, nx * ji, dim_real);
+    push_stage(s);
+  }
+  return tp;
+}
+
+}  // namespace p3d
