@@ -253,6 +253,7 @@ def main():
         del hA, hF, hB
 
     L.p3dfft_clean()
+    L.reset_stream()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -43,12 +43,18 @@ int p3dfft_b200_last_error(char* buf, int buflen);
 /* ---- execution control ---------------------------------------------------------------- */
 /* transforms are issued on this CUDA stream (cudaStream_t passed as void*; NULL = own)    */
 void p3dfft_b200_set_stream(void* cuda_stream);
+/* back to the library's own stream                                                         */
+void p3dfft_b200_reset_stream(void);
 /* async != 0: ftran/btran return after enqueueing (device pointers only, timers not
  * updated); the caller synchronises with p3dfft_b200_sync() or on its stream.            */
 void p3dfft_b200_set_async(int async);
 void p3dfft_b200_sync(void);
 /* number of kernels launched by the library since the last call with reset != 0          */
 long long p3dfft_b200_launch_count(int reset);
+/* ... of which launches of the specialised power-of-two kernels (fft_fast.cuh)              */
+long long p3dfft_b200_fast_launch_count(int reset);
+/* on != 0: use only the any-length kernel (A/B checks; also env P3DFFT_B200_GENERIC)        */
+void p3dfft_b200_force_generic(int on);
 
 /* ---- host-only planner queries (no GPU needed; used by the CPU test-suite) ------------- */
 typedef struct {

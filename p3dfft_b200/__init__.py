@@ -115,6 +115,8 @@ class P3DFFT:
         lib.p3dfft_b200_set_stream.argtypes = [vp]
         lib.p3dfft_b200_launch_count.restype = C.c_longlong
         lib.p3dfft_b200_launch_count.argtypes = [C.c_int]
+        lib.p3dfft_b200_fast_launch_count.restype = C.c_longlong
+        lib.p3dfft_b200_fast_launch_count.argtypes = [C.c_int]
         lib.p3dfft_b200_plan_decomp.argtypes = [ip] + [C.c_int] * 8 + [C.POINTER(DecompInfo)]
         lib.p3dfft_b200_plan_steps.argtypes = [ip] + [C.c_int] * 9 + [C.c_char_p, C.c_int, C.c_int64, C.c_int64,
                                                                      C.c_int, vp, C.c_int]
@@ -209,6 +211,15 @@ class P3DFFT:
 
     def set_stream(self, cuda_stream_ptr):
         self.lib.p3dfft_b200_set_stream(cuda_stream_ptr)
+
+    def reset_stream(self):
+        self.lib.p3dfft_b200_reset_stream()
+
+    def force_generic(self, on=True):
+        self.lib.p3dfft_b200_force_generic(int(on))
+
+    def fast_launch_count(self, reset=False) -> int:
+        return int(self.lib.p3dfft_b200_fast_launch_count(int(reset)))
 
     def set_async(self, flag):
         self.lib.p3dfft_b200_set_async(int(flag))

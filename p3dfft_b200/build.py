@@ -12,6 +12,7 @@ from __future__ import annotations
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -19,8 +20,8 @@ LIBDIR = os.path.join(HERE, "lib")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-SOURCES = ["fft_kernels.cu", "api.cpp"]
-HEADERS = ["stage.h", "plan.h", "kernels.h"]
+SOURCES = ["fft_kernels.cu", "fft_fast.cu", "api.cpp"]
+HEADERS = ["stage.h", "plan.h", "kernels.h", "fast.h", "fft_fast.cuh"]
 
 
 def _newer(target, deps):
@@ -37,7 +38,7 @@ def build_one(name: str, defines: list[str], verbose: bool = False, force: bool 
     target = os.path.join(LIBDIR, f"lib{name}.so")
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [
         os.path.join(HERE, "..", "include", "p3dfft_b200.h"), os.path.abspath(__file__)]
-    objs = []
+    objs, cmds = [], []
     for src in SOURCES:
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
@@ -45,9 +46,14 @@ def build_one(name: str, defines: list[str], verbose: bool = False, force: bool 
             cmd = [NVCC, *ARCH, *COMMON, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
             if src.endswith(".cu") and verbose:
                 cmd += ["-Xptxas", "-v"]
+            cmds.append(cmd)
+    if cmds:
+        def run(cmd):
             if verbose:
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
+        with ThreadPoolExecutor(max_workers=len(cmds)) as ex:
+            list(ex.map(run, cmds))
     if force or _newer(target, objs):
         cmd = [NVCC, *ARCH, "-shared", "-o", target, *objs, "-ldl"]
         if verbose:
@@ -57,11 +63,11 @@ def build_one(name: str, defines: list[str], verbose: bool = False, force: bool 
 
 
 def build_all(verbose: bool = False, variants: bool = False, force: bool = False) -> list[str]:
-    out = [build_one("p3dfft", [], verbose, force), build_one("p3dfft_single", ["-DSINGLE_PREC"], verbose, force)]
+    jobs = [("p3dfft", []), ("p3dfft_single", ["-DSINGLE_PREC"])]
     if variants:
-        out.append(build_one("p3dfft_stride1", ["-DSTRIDE1"], verbose, force))
-        out.append(build_one("p3dfft_single_stride1", ["-DSINGLE_PREC", "-DSTRIDE1"], verbose, force))
-    return out
+        jobs += [("p3dfft_stride1", ["-DSTRIDE1"]), ("p3dfft_single_stride1", ["-DSINGLE_PREC", "-DSTRIDE1"])]
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        return list(ex.map(lambda j: build_one(j[0], j[1], verbose, force), jobs))
 
 
 if __name__ == "__main__":

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/p3dfft_b200.h"
+#include "fast.h"
 #include "kernels.h"
 #include "plan.h"
 #include "stage.h"
@@ -120,7 +121,11 @@ struct Lib {
   void* stage_in = nullptr; size_t stage_in_bytes = 0;
   void* stage_out = nullptr; size_t stage_out_bytes = 0;
   cudaStream_t own_stream = nullptr, user_stream = nullptr;
+  bool has_user_stream = false;
   bool async = false;
+  bool force_generic = false;
+  long long fast_launches = 0;
+  std::map<std::pair<int, int>, void*> fast_twiddles;   // (x-stage?, nfft) -> device block
   double timers[12] = {0};
   std::map<int, void*> twiddles;
   std::map<PlanKey, p3d::TransformPlan> plans;
@@ -138,7 +143,7 @@ struct Lib {
 #else
       0;
 #endif
-  cudaStream_t stream() { return user_stream ? user_stream : own_stream; }
+  cudaStream_t stream() { return has_user_stream ? user_stream : own_stream; }
 } L;
 
 bool is_device_ptr(const void* p) {
@@ -163,6 +168,22 @@ const void* twiddle_table(int nfft) {
   if (cudaMalloc(&dptr, h.size() * sizeof(real_t)) != cudaSuccess) return nullptr;
   if (cudaMemcpy(dptr, h.data(), h.size() * sizeof(real_t), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
   L.twiddles[nfft] = dptr;
+  return dptr;
+}
+
+// twiddle block of the specialised kernels (fft_fast.cu), one per (stage class, length)
+const void* fast_twiddle_block(int kind, int nfft) {
+  const bool xs = kind == P3D_R2C || kind == P3D_C2R;
+  auto key = std::make_pair(xs ? 1 : 0, nfft);
+  auto it = L.fast_twiddles.find(key);
+  if (it != L.fast_twiddles.end()) return it->second;
+  const size_t n = p3d::fast_twiddle_elems<real_t>(kind, nfft);
+  std::vector<real_t> h(2 * n + 2);
+  p3d::fast_twiddle_fill<real_t>(kind, nfft, h.data());
+  void* dptr = nullptr;
+  if (cudaMalloc(&dptr, h.size() * sizeof(real_t)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(dptr, h.data(), h.size() * sizeof(real_t), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  L.fast_twiddles[key] = dptr;
   return dptr;
 }
 
@@ -271,7 +292,16 @@ bool run_transform(bool backward, const void* in, void* out, const char* op, int
           sg.base = base + sg.off * esz;
         }
       }
-      cudaError_t e = p3d::launch_stage<real_t>(stg, st);
+      cudaError_t e = cudaErrorMisalignedAddress;
+      if (!L.force_generic && p3d::fast_supported<real_t>(stg)) {
+        p3d::FastStage fs;
+        p3d::to_fast(stg, fs, sizeof(real_t));
+        fs.tw = fast_twiddle_block(stg.kind, stg.nfft);
+        if (!fs.tw) { report(true, "P3DFFT(B200): cannot allocate twiddle table"); return false; }
+        e = p3d::launch_fast<real_t>(stg, fs, st);
+        if (e == cudaSuccess) L.fast_launches++;
+      }
+      if (e == cudaErrorMisalignedAddress) e = p3d::launch_stage<real_t>(stg, st);   // any length / alignment
       if (e != cudaSuccess) { report(true, "P3DFFT(B200): stage launch failed: %s", cudaGetErrorString(e)); return false; }
       L.launches++;
       slots.push_back(stg.timer);
@@ -340,7 +370,8 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   L.overwrite = ow ? (*ow != 0) : true;
   L.comm = cc;
   if (cc && cc->device >= 0) cudaSetDevice(cc->device);
-  if (!L.own_stream && cudaStreamCreateWithFlags(&L.own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // a blocking stream: ordered after work the caller queued on the legacy default stream
+  if (!L.own_stream && cudaStreamCreate(&L.own_stream) != cudaSuccess) {
     report(true, "P3DFFT(B200): no usable CUDA device (%s)", cudaGetErrorString(cudaGetLastError()));
     return;
   }
@@ -355,6 +386,7 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
       report(true, "P3DFFT(B200): ncclCommSplit(col) failed"); return;
     }
   }
+  L.force_generic = getenv("P3DFFT_B200_GENERIC") != nullptr;
   for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
   L.nv_preset = 0;
   L.set = true;
@@ -441,6 +473,8 @@ void p3dfft_clean(void) {
   if (L.stage_out) { cudaFree(L.stage_out); L.stage_out = nullptr; L.stage_out_bytes = 0; }
   for (auto& kv : L.twiddles) cudaFree(kv.second);
   L.twiddles.clear();
+  for (auto& kv : L.fast_twiddles) cudaFree(kv.second);
+  L.fast_twiddles.clear();
   L.plans.clear();
   if (L.row) { g_nccl.CommDestroy(L.row); L.row = nullptr; }
   if (L.col) { g_nccl.CommDestroy(L.col); L.col = nullptr; }
@@ -513,7 +547,10 @@ int p3dfft_b200_last_error(char* buf, int buflen) {
   return n;
 }
 
-void p3dfft_b200_set_stream(void* s) { L.user_stream = (cudaStream_t)s; }
+void p3dfft_b200_set_stream(void* s) { L.user_stream = (cudaStream_t)s; L.has_user_stream = true; }
+void p3dfft_b200_reset_stream(void) { L.user_stream = nullptr; L.has_user_stream = false; }
+void p3dfft_b200_force_generic(int on) { L.force_generic = on != 0; }
+long long p3dfft_b200_fast_launch_count(int reset) { long long n = L.fast_launches; if (reset) L.fast_launches = 0; return n; }
 void p3dfft_b200_set_async(int a) { L.async = a != 0; }
 void p3dfft_b200_sync(void) { cudaStreamSynchronize(L.stream()); }
 long long p3dfft_b200_launch_count(int reset) { long long n = L.launches; if (reset) L.launches = 0; return n; }

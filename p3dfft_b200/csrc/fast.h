@@ -1,0 +1,51 @@
+// Descriptor and launcher of the specialised power-of-two stage kernels (fft_fast.cuh).
+//
+// The generic stage_kernel (fft_kernels.cu) accepts any length; the kernels behind
+// launch_fast() cover the lengths the headline configurations use (64 ... 2048) with
+// compile-time radix schedules, register butterflies and one shared-memory exchange
+// between passes.  Both read the same planner output (P3dStage); to_fast() turns its
+// segment lists into "runs" of consecutive LOGICAL rows so that the kernels can map a row
+// of the transform axis to an address with one table lookup.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "stage.h"
+
+#define P3D_MAXRUN (P3D_MAXSEG + 1)
+
+namespace p3d {
+
+// element address of logical row k of line (a,b,c):
+//     base + ((k - kstart)*ps + a*sa + b*sb + c*sc) * sizeof(element)
+struct FastRun {
+  const void* base;
+  int32_t kstart, len;
+  int64_t ps, sa, sb, sc;
+};
+
+struct FastSide {
+  int32_t nrun, pad_;
+  FastRun run[P3D_MAXRUN];
+};
+
+struct FastStage {
+  int32_t na, nb, nc;    // batch extents; CTAs tile a
+  int32_t n;             // logical length of the transform axis (nx, ny, nz)
+  int32_t mirror;        // 1: DCT-I -- FFT row r >= n reads logical row nfft - r
+  int32_t pad_;
+  const void* tw;        // device twiddle block of this (kind, nfft), see fast_twiddle_*
+  FastSide in, out;
+};
+
+// true when a specialised kernel exists for this stage (kind, length, strides, alignment)
+template <typename T> bool fast_supported(const P3dStage& st);
+// number of T2 elements of the twiddle block and its host-side fill
+template <typename T> size_t fast_twiddle_elems(int kind, int nfft);
+template <typename T> void fast_twiddle_fill(int kind, int nfft, void* host);
+// converts resolved segments (seg.base set) into runs; real_bytes = sizeof(real)
+void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes);
+template <typename T> cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t stream);
+
+}  // namespace p3d

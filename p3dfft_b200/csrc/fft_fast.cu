@@ -1,0 +1,225 @@
+// Host side of the specialised stage kernels: eligibility, twiddle blocks, plan-segment ->
+// run conversion and the length dispatch.  Instantiated for the library's precision only
+// (SINGLE_PREC selects float, as configure --enable-single does for the reference).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+
+#include "fast.h"
+#include "fft_fast.cuh"
+
+namespace p3d {
+
+using namespace fast;
+
+namespace {
+
+bool c2c_len_ok(int n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048; }
+bool x_half_ok(int h) { return h == 32 || h == 64 || h == 128 || h == 256 || h == 512 || h == 1024; }
+
+template <class S>
+void fill_pass_tables(long double n_total, std::vector<long double>& re, std::vector<long double>& im) {
+  const long double twopi = 6.283185307179586476925286766559L;
+  (void)n_total;
+  for (int i = 0; i < S::L - 1; i++) {
+    const int R = S::r(i), M = S::m(i), NC = S::ncur(i);
+    for (int q = 1; q < R; q++)
+      for (int j = 0; j < M; j++) {
+        long double ang = -twopi * (long double)((long long)q * j % NC) / (long double)NC;
+        re.push_back(cosl(ang)); im.push_back(sinl(ang));
+      }
+  }
+}
+
+template <typename T, class S>
+void fill_block(bool xstage, void* host) {
+  std::vector<long double> re, im;
+  fill_pass_tables<S>(S::N, re, im);
+  if (xstage) {
+    const long double twopi = 6.283185307179586476925286766559L;
+    const int H = S::N, N = 2 * H;
+    for (int k = 0; k < H; k++) {
+      long double ang = -twopi * (long double)k / (long double)N;
+      re.push_back(cosl(ang)); im.push_back(sinl(ang));
+    }
+  }
+  T* o = reinterpret_cast<T*>(host);
+  for (size_t i = 0; i < re.size(); i++) { o[2 * i] = (T)re[i]; o[2 * i + 1] = (T)im[i]; }
+}
+
+template <class S> size_t block_elems(bool xstage) { return (size_t)S::twtotal() + (xstage ? S::N : 0); }
+
+bool is_x(int kind) { return kind == P3D_R2C || kind == P3D_C2R; }
+
+}  // namespace
+
+template <typename T>
+bool fast_supported(const P3dStage& st) {
+  if (st.scale != 1.0) return false;
+  if (st.in.nseg + 1 > P3D_MAXRUN || st.out.nseg + 1 > P3D_MAXRUN) return false;
+  if (st.nc > 65535) return false;
+  switch (st.kind) {
+    case P3D_C2C_FWD: case P3D_C2C_BWD: case P3D_DCT1:
+      return c2c_len_ok(st.nfft);
+    case P3D_R2C: case P3D_C2R: {
+      if (st.n % 2 || !x_half_ok(st.n / 2)) return false;
+      const P3dSide& rs = st.kind == P3D_R2C ? st.in : st.out;
+      if (rs.nseg != 1 || rs.cnt != rs.logical) return false;
+      const P3dSeg& g = rs.seg[0];
+      if (g.ps != 1 || g.start != 0 || g.len != st.n) return false;
+      if ((g.sa & 1) || (st.nb > 1 && (g.sb & 1)) || (st.nc > 1 && (g.sc & 1)) || (g.off & 1)) return false;
+      return true;
+    }
+    default: return false;
+  }
+}
+
+template <class F>
+bool dispatch_c(int n, F&& f) {
+  switch (n) {
+    case 64:   f(std::integral_constant<int, 64>{});   return true;
+    case 128:  f(std::integral_constant<int, 128>{});  return true;
+    case 256:  f(std::integral_constant<int, 256>{});  return true;
+    case 512:  f(std::integral_constant<int, 512>{});  return true;
+    case 1024: f(std::integral_constant<int, 1024>{}); return true;
+    case 2048: f(std::integral_constant<int, 2048>{}); return true;
+    default: return false;
+  }
+}
+template <class F>
+bool dispatch_x(int h, F&& f) {
+  switch (h) {
+    case 32:   f(std::integral_constant<int, 32>{});   return true;
+    case 64:   f(std::integral_constant<int, 64>{});   return true;
+    case 128:  f(std::integral_constant<int, 128>{});  return true;
+    case 256:  f(std::integral_constant<int, 256>{});  return true;
+    case 512:  f(std::integral_constant<int, 512>{});  return true;
+    case 1024: f(std::integral_constant<int, 1024>{}); return true;
+    default: return false;
+  }
+}
+
+template <typename T>
+size_t fast_twiddle_elems(int kind, int nfft) {
+  size_t n = 0;
+  if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { n = block_elems<typename XCfg<T, decltype(h)::value>::S>(true); });
+  else dispatch_c(nfft, [&](auto nn) { n = block_elems<typename CCfg<T, decltype(nn)::value>::S>(false); });
+  return n;
+}
+
+template <typename T>
+void fast_twiddle_fill(int kind, int nfft, void* host) {
+  if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { fill_block<T, typename XCfg<T, decltype(h)::value>::S>(true, host); });
+  else dispatch_c(nfft, [&](auto nn) { fill_block<T, typename CCfg<T, decltype(nn)::value>::S>(false, host); });
+}
+
+// stored index s -> logical k:  k = s (s < h1),  k = s + (logical - cnt) (s >= h1); a segment that
+// straddles h1 becomes two runs.
+static void side_to_runs(const P3dSide& sd, FastSide& f, size_t esz) {
+  f.nrun = 0;
+  const int shift = sd.logical - sd.cnt;
+  for (int g = 0; g < sd.nseg; g++) {
+    const P3dSeg& sg = sd.seg[g];
+    const int s0 = sg.start, s1 = sg.start + sg.len;
+    const int cut = shift > 0 ? sd.h1 : s1;
+    const int parts[2][2] = {{s0, s1 < cut ? s1 : cut}, {s0 > cut ? s0 : cut, s1}};
+    for (int p = 0; p < 2; p++) {
+      const int a = parts[p][0], b = parts[p][1];
+      if (b <= a) continue;
+      FastRun& r = f.run[f.nrun++];
+      r.base = (const char*)sg.base + (long long)(a - s0) * sg.ps * (long long)esz;
+      r.kstart = (shift > 0 && a >= sd.h1) ? a + shift : a;
+      r.len = b - a;
+      r.ps = sg.ps; r.sa = sg.sa; r.sb = sg.sb; r.sc = sg.sc;
+    }
+  }
+}
+
+void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes) {
+  memset(&f, 0, sizeof f);
+  f.na = st.na; f.nb = st.nb; f.nc = st.nc; f.n = st.n;
+  f.mirror = st.kind == P3D_DCT1;
+  f.tw = nullptr;
+  side_to_runs(st.in, f.in, st.kind == P3D_R2C ? real_bytes : 2 * real_bytes);
+  side_to_runs(st.out, f.out, st.kind == P3D_C2R ? real_bytes : 2 * real_bytes);
+}
+
+template <typename K>
+static cudaError_t launch_cfg(K kernel, size_t smem, bool& configured) {
+  if (configured) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) configured = true;
+  return e;
+}
+
+template <typename T, int HH>
+static cudaError_t launch_x(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  constexpr int TX = XCfg<T, HH>::TX, NT = XCfg<T, HH>::NT;
+  constexpr size_t smem = xstage_smem<T, HH>();
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb;
+  if (tiles <= 0 || st.nc <= 0) return cudaSuccess;
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  dim3 grid((unsigned)tiles, (unsigned)st.nc);
+  cudaError_t e;
+  if (st.kind == P3D_R2C) {
+    static bool cfg = false;
+    if ((e = launch_cfg(xr2c_kernel<T, HH>, smem, cfg)) != cudaSuccess) return e;
+    xr2c_kernel<T, HH><<<grid, NT, smem, stream>>>(f);
+  } else {
+    static bool cfg = false;
+    if ((e = launch_cfg(xc2r_kernel<T, HH>, smem, cfg)) != cudaSuccess) return e;
+    xc2r_kernel<T, HH><<<grid, NT, smem, stream>>>(f);
+  }
+  return cudaGetLastError();
+}
+
+template <typename T, int NN>
+static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  constexpr int TX = CCfg<T, NN>::TX, NT = CCfg<T, NN>::NT;
+  constexpr size_t smem = cstage_smem<T, NN>();
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb;
+  if (tiles <= 0 || st.nc <= 0) return cudaSuccess;
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  dim3 grid((unsigned)tiles, (unsigned)st.nc);
+  cudaError_t e;
+  if (st.kind == P3D_C2C_BWD) {
+    static bool cfg = false;
+    if ((e = launch_cfg(cstage_kernel<T, NN, true>, smem, cfg)) != cudaSuccess) return e;
+    cstage_kernel<T, NN, true><<<grid, NT, smem, stream>>>(f);
+  } else {
+    static bool cfg = false;
+    if ((e = launch_cfg(cstage_kernel<T, NN, false>, smem, cfg)) != cudaSuccess) return e;
+    cstage_kernel<T, NN, false><<<grid, NT, smem, stream>>>(f);
+  }
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  using T2 = typename Cx<T>::type;
+  // alignment of every block base: the kernels move whole complex elements
+  for (int side = 0; side < 2; side++) {
+    const FastSide& sd = side ? f.out : f.in;
+    for (int g = 0; g < sd.nrun; g++)
+      if (reinterpret_cast<uintptr_t>(sd.run[g].base) % sizeof(T2)) return cudaErrorMisalignedAddress;
+  }
+  cudaError_t err = cudaErrorInvalidValue;
+  if (is_x(st.kind)) dispatch_x(st.n / 2, [&](auto h) { err = launch_x<T, decltype(h)::value>(st, f, stream); });
+  else dispatch_c(st.nfft, [&](auto nn) { err = launch_c<T, decltype(nn)::value>(st, f, stream); });
+  return err;
+}
+
+#ifdef SINGLE_PREC
+typedef float fast_real_t;
+#else
+typedef double fast_real_t;
+#endif
+template bool fast_supported<fast_real_t>(const P3dStage&);
+template size_t fast_twiddle_elems<fast_real_t>(int, int);
+template void fast_twiddle_fill<fast_real_t>(int, int, void*);
+template cudaError_t launch_fast<fast_real_t>(const P3dStage&, const FastStage&, cudaStream_t);
+
+}  // namespace p3d

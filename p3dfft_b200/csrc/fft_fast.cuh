@@ -1,0 +1,594 @@
+// Specialised sm_100a stage kernels for power-of-two transform lengths.
+//
+// One CTA transforms a tile of TX lines that are adjacent along the CONTIGUOUS direction of
+// the pencil (x for the Y and Z stages, so every row of the tile is one 64- or 128-byte
+// chunk of HBM; for the X stage the lines themselves are contiguous and a warp covers
+// 128 bytes of each of four lines).  The transform is an in-place decimation-in-frequency
+// FFT with a compile-time radix schedule:
+//
+//   pass 1      global -> registers (R1 independent 16-byte loads in flight per thread),
+//               radix-R1 butterfly, twiddle, registers -> shared memory
+//   pass 2..L-1 shared -> registers -> shared
+//   pass L      shared -> registers, butterfly, registers -> global
+//
+// so a line makes ONE trip through HBM in each direction and L-1 trips through shared
+// memory.  The unpack of the preceding all-to-all, the pack for the next one, pruning and
+// zero padding are row -> address lookups (FastSide runs) on the two global sides.
+//
+// Shared-memory layout: element (row k, line t) of the tile lives at [k'][t] with TX
+// elements (64 or 128 bytes) per row.  With 64-byte rows two rows share one 128-byte bank
+// window, so k' = k ^ parity(k >> 1): any two rows whose indices differ in exactly one bit
+// (all the pairs adjacent threads touch in a power-of-two DIF pass) land in different
+// halves of the window and every pass is bank-conflict free.  Because the rows of one
+// butterfly differ only in a bit-field disjoint from the rest of the index, the swizzle of
+// row base|p*m is swizzle(base) ^ const(p): one POPC per butterfly, one XOR per access.
+//
+// X stage (r2c / c2r): the real line of length N is transformed as a complex FFT of length
+// H = N/2 on the packed pairs (x[2j], x[2j+1]); the Hermitian post-/pre-processing needs the
+// pair (k, H-k), which is produced by two butterflies of the last (r2c) or consumed by two
+// butterflies of the first (c2r) pass.  One thread owns both, so the combination happens in
+// registers and costs no extra pass (replaces exec_f_r2c / exec_b_c2r, fft_exec.F90:495,298).
+//
+// Backward transforms use FFT^-1(z) = swap(FFT(swap(z))) (swap = exchange re and im): the
+// same forward butterflies and tables, the swap is free at the load and the store.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fast.h"
+#include "stage.h"
+
+namespace p3d {
+namespace fast {
+
+template <typename T> struct Cx;
+template <> struct Cx<double> { using type = double2; };
+template <> struct Cx<float>  { using type = float2; };
+
+// ---------------------------------------------------------------------------------------
+// radix schedules
+// ---------------------------------------------------------------------------------------
+template <int A, int B = 1, int C = 1, int D = 1>
+struct RS {
+  static constexpr int L = 1 + (B > 1) + (C > 1) + (D > 1);
+  static constexpr int N = A * B * C * D;
+  __host__ __device__ static constexpr int r(int i) { return i == 0 ? A : i == 1 ? B : i == 2 ? C : D; }
+  // length of the sub-transforms entering pass i
+  __host__ __device__ static constexpr int ncur(int i) { int n = N; for (int k = 0; k < i; k++) n /= r(k); return n; }
+  __host__ __device__ static constexpr int m(int i) { return ncur(i) / r(i); }
+  // offset (elements) of pass i's twiddle table inside the block: sum_{k<i} (r_k-1)*m_k
+  __host__ __device__ static constexpr int twoff(int i) { int o = 0; for (int k = 0; k < i; k++) o += (r(k) - 1) * m(k); return o; }
+  __host__ __device__ static constexpr int twtotal() { return twoff(L - 1); }   // last pass has m = 1: no table
+};
+
+// c2c configuration per (type, length): schedule, lines per tile, threads per CTA, CTAs/SM hint
+template <typename T, int N> struct CCfg;
+template <> struct CCfg<double, 64>   { using S = RS<8, 8>;       static constexpr int TX = 8, NT = 64,  MINB = 8; };
+template <> struct CCfg<double, 128>  { using S = RS<16, 8>;      static constexpr int TX = 8, NT = 128, MINB = 4; };
+template <> struct CCfg<double, 256>  { using S = RS<16, 16>;     static constexpr int TX = 8, NT = 128, MINB = 3; };
+template <> struct CCfg<double, 512>  { using S = RS<8, 8, 8>;    static constexpr int TX = 4, NT = 256, MINB = 3; };
+template <> struct CCfg<double, 1024> { using S = RS<16, 8, 8>;   static constexpr int TX = 4, NT = 256, MINB = 2; };
+template <> struct CCfg<double, 2048> { using S = RS<16, 16, 8>;  static constexpr int TX = 4, NT = 512, MINB = 1; };
+template <> struct CCfg<float, 64>    { using S = RS<8, 8>;       static constexpr int TX = 16, NT = 128, MINB = 8; };
+template <> struct CCfg<float, 128>   { using S = RS<16, 8>;      static constexpr int TX = 16, NT = 256, MINB = 4; };
+template <> struct CCfg<float, 256>   { using S = RS<16, 16>;     static constexpr int TX = 16, NT = 256, MINB = 3; };
+template <> struct CCfg<float, 512>   { using S = RS<8, 8, 8>;    static constexpr int TX = 8, NT = 256, MINB = 3; };
+template <> struct CCfg<float, 1024>  { using S = RS<16, 8, 8>;   static constexpr int TX = 8, NT = 512, MINB = 2; };
+template <> struct CCfg<float, 2048>  { using S = RS<16, 16, 8>;  static constexpr int TX = 8, NT = 512, MINB = 1; };
+
+// X-stage configuration per (type, H = nx/2).  The first (c2r) / last (r2c) pass works on
+// butterfly PAIRS, i.e. 2R complex values per thread, so those radices stay <= 8.
+template <typename T, int H> struct XCfg;
+template <> struct XCfg<double, 32>   { using S = RS<4, 8>;       static constexpr int TX = 4, NT = 32,  MINB = 8; };
+template <> struct XCfg<double, 64>   { using S = RS<8, 8>;       static constexpr int TX = 4, NT = 32,  MINB = 8; };
+template <> struct XCfg<double, 128>  { using S = RS<4, 4, 8>;    static constexpr int TX = 4, NT = 64,  MINB = 8; };
+template <> struct XCfg<double, 256>  { using S = RS<8, 4, 8>;    static constexpr int TX = 4, NT = 128, MINB = 4; };
+template <> struct XCfg<double, 512>  { using S = RS<8, 8, 8>;    static constexpr int TX = 4, NT = 256, MINB = 2; };
+template <> struct XCfg<double, 1024> { using S = RS<8, 16, 8>;   static constexpr int TX = 4, NT = 256, MINB = 2; };
+template <> struct XCfg<float, 32>    { using S = RS<4, 8>;       static constexpr int TX = 8, NT = 64,  MINB = 8; };
+template <> struct XCfg<float, 64>    { using S = RS<8, 8>;       static constexpr int TX = 8, NT = 64,  MINB = 8; };
+template <> struct XCfg<float, 128>   { using S = RS<4, 4, 8>;    static constexpr int TX = 8, NT = 128, MINB = 6; };
+template <> struct XCfg<float, 256>   { using S = RS<8, 4, 8>;    static constexpr int TX = 8, NT = 256, MINB = 3; };
+template <> struct XCfg<float, 512>   { using S = RS<8, 8, 8>;    static constexpr int TX = 8, NT = 256, MINB = 3; };
+template <> struct XCfg<float, 1024>  { using S = RS<8, 16, 8>;   static constexpr int TX = 8, NT = 512, MINB = 2; };
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------
+// complex helpers and natural-order forward butterflies
+// ---------------------------------------------------------------------------------------
+template <typename T2> __device__ __forceinline__ T2 cadd(T2 a, T2 b) { return T2{a.x + b.x, a.y + b.y}; }
+template <typename T2> __device__ __forceinline__ T2 csub(T2 a, T2 b) { return T2{a.x - b.x, a.y - b.y}; }
+template <typename T2> __device__ __forceinline__ T2 cmul(T2 a, T2 b) {
+  return T2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T2> __device__ __forceinline__ T2 cconj(T2 a) { return T2{a.x, -a.y}; }
+template <typename T2> __device__ __forceinline__ T2 mul_mi(T2 a) { return T2{a.y, -a.x}; }   // * (-i)
+template <typename T2> __device__ __forceinline__ T2 mul_pi(T2 a) { return T2{-a.y, a.x}; }   // * (+i)
+template <typename T2> __device__ __forceinline__ T2 cswap(T2 a) { return T2{a.y, a.x}; }
+
+template <typename T2> __device__ __forceinline__ void bf2(T2& a, T2& b) { T2 t = csub(a, b); a = cadd(a, b); b = t; }
+template <typename T2> __device__ __forceinline__ void bf4(T2& v0, T2& v1, T2& v2, T2& v3) {
+  T2 a = cadd(v0, v2), b = csub(v0, v2), c = cadd(v1, v3), d = mul_mi(csub(v1, v3));
+  v0 = cadd(a, c); v2 = csub(a, c); v1 = cadd(b, d); v3 = csub(b, d);
+}
+
+template <typename T, int R> struct Bfly;
+template <typename T> struct Bfly<T, 2> {
+  using T2 = typename Cx<T>::type;
+  __device__ __forceinline__ static void run(T2* v) { bf2(v[0], v[1]); }
+};
+template <typename T> struct Bfly<T, 4> {
+  using T2 = typename Cx<T>::type;
+  __device__ __forceinline__ static void run(T2* v) { bf4(v[0], v[1], v[2], v[3]); }
+};
+template <typename T> struct Bfly<T, 8> {
+  using T2 = typename Cx<T>::type;
+  __device__ __forceinline__ static void run(T2* v) {
+    const T h = (T)0.70710678118654752440;
+    bf4(v[0], v[2], v[4], v[6]);
+    bf4(v[1], v[3], v[5], v[7]);
+    T2 o1 = T2{(v[3].x + v[3].y) * h, (v[3].y - v[3].x) * h};        // O1 * W8^1
+    T2 o2 = mul_mi(v[5]);                                            // O2 * W8^2
+    T2 o3 = T2{(v[7].y - v[7].x) * h, -(v[7].x + v[7].y) * h};       // O3 * W8^3
+    T2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+  }
+};
+template <typename T> struct Bfly<T, 16> {
+  using T2 = typename Cx<T>::type;
+  // p = 4a + b, q = c + 4d:  W16^(pq) = W4^(ac) * W16^(bc) * W4^(bd)
+  __device__ __forceinline__ static void run(T2* v) {
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, h = (T)0.70710678118654752440;
+#pragma unroll
+    for (int b = 0; b < 4; b++) bf4(v[b], v[4 + b], v[8 + b], v[12 + b]);    // v[4c+b] = A_b[c]
+    v[5]  = cmul(v[5],  T2{c1, -s1});     // (b,c) = (1,1): W^1
+    v[9]  = cmul(v[9],  T2{h, -h});       // (1,2): W^2
+    v[13] = cmul(v[13], T2{s1, -c1});     // (1,3): W^3
+    v[6]  = cmul(v[6],  T2{h, -h});       // (2,1): W^2
+    v[10] = mul_mi(v[10]);                // (2,2): W^4
+    v[14] = cmul(v[14], T2{-h, -h});      // (2,3): W^6
+    v[7]  = cmul(v[7],  T2{s1, -c1});     // (3,1): W^3
+    v[11] = cmul(v[11], T2{-h, -h});      // (3,2): W^6
+    v[15] = cmul(v[15], T2{-c1, s1});     // (3,3): W^9
+#pragma unroll
+    for (int c = 0; c < 4; c++) bf4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);   // v[4c+d] = y[c+4d]
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int d = c + 1; d < 4; d++) { T2 t = v[4 * c + d]; v[4 * c + d] = v[4 * d + c]; v[4 * d + c] = t; }
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// memory access
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ldg_stream(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_stream(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(double2* p, double2 v) {
+  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream(float2* p, float2 v) {
+  asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+constexpr int cpar(int x) { int p = 0; while (x) { p ^= x & 1; x >>= 1; } return p; }
+// swizzle of a row offset that occupies a bit-field disjoint from the rest of the index
+template <bool SWZ> __host__ __device__ constexpr int swz_const(int off) { return SWZ ? (off ^ cpar(off >> 1)) : off; }
+template <bool SWZ> __device__ __forceinline__ int swz_base(int row) { return SWZ ? (row ^ (__popc(row >> 1) & 1)) : row; }
+
+// ---------------------------------------------------------------------------------------
+// row -> address tables of one global side, built once per CTA in shared memory
+// ---------------------------------------------------------------------------------------
+template <int TX>
+struct SideTab {
+  char* tb[P3D_MAXRUN][TX];     // address of logical row 0 of line t for run g (may point before the block)
+  long long psb[P3D_MAXRUN];    // row pitch in bytes
+};
+
+template <int TX, int NT, int ESZ>
+__device__ __forceinline__ void build_side(const FastSide& sd, SideTab<TX>& tab, unsigned char* rowseg, int nrows,
+                                           int nlogical, int mirror_nfft, int a0, int b, int c) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < sd.nrun * TX; i += NT) {
+    const int g = i / TX, t = i - g * TX;
+    const FastRun& r = sd.run[g];
+    const long long off = (long long)(a0 + t) * r.sa + (long long)b * r.sb + (long long)c * r.sc - (long long)r.kstart * r.ps;
+    tab.tb[g][t] = (char*)r.base + off * ESZ;
+    if (t == 0) tab.psb[g] = r.ps * ESZ;
+  }
+  for (int row = tid; row < nrows; row += NT) {
+    int k = row;
+    if (mirror_nfft && row >= nlogical) k = mirror_nfft - row;
+    int g = 0xFF;
+    for (int i = 0; i < sd.nrun; i++) {
+      const int ks = sd.run[i].kstart;
+      if (k >= ks && k < ks + sd.run[i].len) g = i;
+    }
+    rowseg[row] = (unsigned char)g;
+  }
+}
+
+template <typename T2, int TX>
+__device__ __forceinline__ T2 load_row(const SideTab<TX>& tab, const unsigned char* rowseg, int row, int k, int t, bool live) {
+  const int g = rowseg[row];
+  T2 v = T2{0, 0};
+  if (live && g != 0xFF) v = ldg_stream(reinterpret_cast<const T2*>(tab.tb[g][t] + (long long)k * tab.psb[g]));
+  return v;
+}
+template <typename T2, int TX>
+__device__ __forceinline__ void store_row(const SideTab<TX>& tab, const unsigned char* rowseg, int k, int t, bool live, T2 v) {
+  const int g = rowseg[k];
+  if (live && g != 0xFF) stg_stream(reinterpret_cast<T2*>(tab.tb[g][t] + (long long)k * tab.psb[g]), v);
+}
+
+// ---------------------------------------------------------------------------------------
+// passes over the shared-memory tile
+// ---------------------------------------------------------------------------------------
+// digit reversal: kappa = q1 + R1*q2 + ... (digits of passes 1..L-1)  ->  block index of the last pass
+template <class S> __device__ __forceinline__ int blk_of_kappa(int kappa) {
+  int blk = 0;
+#pragma unroll
+  for (int i = 0; i < S::L - 1; i++) {
+    const int R = S::r(i);
+    const int q = kappa % R; kappa /= R;
+    blk = (i == 0) ? q : blk * R + q;
+  }
+  return blk;
+}
+
+template <typename T, class S, int PI, int TX, bool SWZ>
+__device__ __forceinline__ void twiddle_store(typename Cx<T>::type* v, typename Cx<T>::type* s, const typename Cx<T>::type* __restrict__ tw,
+                                              int base_row, int j, int t) {
+  using T2 = typename Cx<T>::type;
+  constexpr int R = S::r(PI), M = S::m(PI);
+  const T2* twp = tw + S::twoff(PI) + j;
+#pragma unroll
+  for (int q = 1; q < R; q++) v[q] = cmul(v[q], __ldg(twp + (q - 1) * M));
+  const int bi = swz_base<SWZ>(base_row) * TX + t;
+#pragma unroll
+  for (int q = 0; q < R; q++) s[bi ^ (swz_const<SWZ>(q * M) * TX)] = v[q];
+}
+
+// middle pass PI (0 < PI < L-1): shared -> shared, in place
+template <typename T, class S, int PI, int TX, int NT, bool SWZ>
+__device__ __forceinline__ void mid_pass(typename Cx<T>::type* s, const typename Cx<T>::type* __restrict__ tw) {
+  using T2 = typename Cx<T>::type;
+  constexpr int R = S::r(PI), NCUR = S::ncur(PI), M = S::m(PI), ITEMS = (S::N / R) * TX;
+#pragma unroll 1
+  for (int w = threadIdx.x; w < ITEMS; w += NT) {
+    const int t = w % TX, u = w / TX;
+    const int blk = u / M, j = u % M, base = blk * NCUR + j;
+    const int bi = swz_base<SWZ>(base) * TX + t;
+    T2 v[R];
+#pragma unroll
+    for (int p = 0; p < R; p++) v[p] = s[bi ^ (swz_const<SWZ>(p * M) * TX)];
+    Bfly<T, R>::run(v);
+    twiddle_store<T, S, PI, TX, SWZ>(v, s, tw, base, j, t);
+  }
+}
+
+template <typename T, class S, int PI, int TX, int NT, bool SWZ>
+__device__ __forceinline__ void mid_passes(typename Cx<T>::type* s, const typename Cx<T>::type* __restrict__ tw) {
+  if constexpr (PI < S::L - 1) {
+    mid_pass<T, S, PI, TX, NT, SWZ>(s, tw);
+    __syncthreads();
+    mid_passes<T, S, PI + 1, TX, NT, SWZ>(s, tw);
+  }
+}
+
+// reads the R_L rows of last-pass butterfly kappa (natural output order) and transforms them:
+// v[q] = Z[kappa + q*ML]
+template <typename T, class S, int TX, bool SWZ>
+__device__ __forceinline__ void last_bfly(const typename Cx<T>::type* s, int kappa, int t, typename Cx<T>::type* v) {
+  constexpr int RL = S::r(S::L - 1);
+  const int base = blk_of_kappa<S>(kappa) * RL;
+  const int bi = swz_base<SWZ>(base) * TX + t;
+#pragma unroll
+  for (int p = 0; p < RL; p++) v[p] = s[bi ^ (swz_const<SWZ>(p) * TX)];
+  Bfly<T, RL>::run(v);
+}
+
+// ---------------------------------------------------------------------------------------
+// c2c stage kernel (Y and Z stages, forward/backward, DCT-I by even extension)
+// ---------------------------------------------------------------------------------------
+template <int TX> struct CShared {
+  SideTab<TX> in, out;
+};
+
+template <typename T, int N, bool SWAP>
+__global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
+  using T2 = typename Cx<T>::type;
+  using C = CCfg<T, N>;
+  using S = typename C::S;
+  constexpr int TX = C::TX, NT = C::NT, L = S::L;
+  constexpr bool SWZ = (TX * sizeof(T2) == 64);
+  static_assert(TX * sizeof(T2) == 64 || TX * sizeof(T2) == 128, "row must be 64 or 128 bytes");
+  static_assert(NT % TX == 0, "t must be constant per thread");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T2* s = reinterpret_cast<T2*>(smem_raw);
+  CShared<TX>* sh = reinterpret_cast<CShared<TX>*>(smem_raw + sizeof(T2) * N * TX);
+  unsigned char* rs_in = reinterpret_cast<unsigned char*>(sh + 1);
+  unsigned char* rs_out = rs_in + N;
+  const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
+
+  const int tiles_a = (st.na + TX - 1) / TX;
+  const int ta = blockIdx.x % tiles_a, b = blockIdx.x / tiles_a, c = blockIdx.y;
+  const int a0 = ta * TX;
+  const int t = threadIdx.x % TX;
+  const bool live = a0 + t < st.na;
+
+  build_side<TX, NT, sizeof(T2)>(st.in, sh->in, rs_in, N, st.n, st.mirror ? N : 0, a0, b, c);
+  build_side<TX, NT, sizeof(T2)>(st.out, sh->out, rs_out, N, N, 0, a0, b, c);
+  __syncthreads();
+
+  // ---- pass 1: global -> registers -> shared -------------------------------------------
+  {
+    constexpr int R = S::r(0), M = S::m(0), ITEMS = M * TX;
+#pragma unroll
+    for (int w0 = 0; w0 < ITEMS; w0 += NT) {
+      const int w = w0 + threadIdx.x;
+      if (ITEMS % NT == 0 || w < ITEMS) {
+        const int u = w / TX;
+        T2 v[R];
+#pragma unroll
+        for (int p = 0; p < R; p++) {
+          const int row = u + p * M;
+          const int k = (st.mirror && row >= st.n) ? N - row : row;
+          v[p] = load_row<T2, TX>(sh->in, rs_in, row, k, t, live);
+          if (SWAP) v[p] = cswap(v[p]);
+        }
+        Bfly<T, R>::run(v);
+        twiddle_store<T, S, 0, TX, SWZ>(v, s, tw, u, u, t);
+      }
+    }
+  }
+  __syncthreads();
+  mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
+  // ---- pass L: shared -> registers -> global -------------------------------------------
+  {
+    constexpr int RL = S::r(L - 1), ML = N / RL, ITEMS = ML * TX;
+#pragma unroll 1
+    for (int w = threadIdx.x; w < ITEMS; w += NT) {
+      const int kappa = w / TX;
+      T2 v[RL];
+      last_bfly<T, S, TX, SWZ>(s, kappa, t, v);
+#pragma unroll
+      for (int q = 0; q < RL; q++) {
+        T2 o = SWAP ? cswap(v[q]) : v[q];
+        store_row<T2, TX>(sh->out, rs_out, kappa + q * ML, t, live, o);
+      }
+    }
+  }
+}
+
+template <typename T, int N> constexpr size_t cstage_smem() {
+  using T2 = typename Cx<T>::type;
+  return sizeof(T2) * N * CCfg<T, N>::TX + sizeof(CShared<CCfg<T, N>::TX>) + 2 * N;
+}
+
+// ---------------------------------------------------------------------------------------
+// X stage, forward: real line (N = 2H) -> H+1 complex, exec_f_r2c (fft_exec.F90:495)
+// twiddle block: pass tables of the H-point schedule, then wx[k] = exp(-2 pi i k / N), k < H
+// ---------------------------------------------------------------------------------------
+// E = (Zk + conj Zm)/2, O = -(i/2)(Zk - conj Zm);  X[k] = E + w O,  X[H-k] = conj(E - w O)
+template <typename T, typename T2>
+__device__ __forceinline__ void r2c_combine(T2 zk, T2 zm, T2 w, T2& xk, T2& xm) {
+  const T hf = (T)0.5;
+  T2 e = T2{(zk.x + zm.x) * hf, (zk.y - zm.y) * hf};
+  T2 o = T2{(zk.y + zm.y) * hf, (zm.x - zk.x) * hf};
+  T2 wo = cmul(w, o);
+  xk = cadd(e, wo);
+  xm = cconj(csub(e, wo));
+}
+
+template <typename T, int H>
+__global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(const __grid_constant__ FastStage st) {
+  using T2 = typename Cx<T>::type;
+  using C = XCfg<T, H>;
+  using S = typename C::S;
+  constexpr int TX = C::TX, NT = C::NT, L = S::L;
+  constexpr bool SWZ = (TX * sizeof(T2) == 64);
+  static_assert(NT % TX == 0, "t must be constant per thread");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T2* s = reinterpret_cast<T2*>(smem_raw);
+  SideTab<TX>* tab = reinterpret_cast<SideTab<TX>*>(smem_raw + sizeof(T2) * H * TX);
+  unsigned char* rs_out = reinterpret_cast<unsigned char*>(tab + 1);
+  const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
+  const T2* __restrict__ wx = tw + S::twtotal();
+
+  const int tiles_a = (st.na + TX - 1) / TX;
+  const int ta = blockIdx.x % tiles_a, b = blockIdx.x / tiles_a, c = blockIdx.y;
+  const int a0 = ta * TX;
+  const int t = threadIdx.x % TX;
+  const bool live = a0 + t < st.na;
+
+  build_side<TX, NT, sizeof(T2)>(st.out, *tab, rs_out, H + 1, H + 1, 0, a0, b, c);
+  const FastRun& rin = st.in.run[0];
+  const T2* line = reinterpret_cast<const T2*>(reinterpret_cast<const T*>(rin.base) + (long long)(a0 + t) * rin.sa +
+                                               (long long)b * rin.sb + (long long)c * rin.sc);
+  // ---- pass 1: packed real pairs -> registers -> shared -----------------------------------
+  {
+    constexpr int R = S::r(0), M = S::m(0), ITEMS = M * TX;
+#pragma unroll
+    for (int w0 = 0; w0 < ITEMS; w0 += NT) {
+      const int w = w0 + threadIdx.x;
+      if (ITEMS % NT == 0 || w < ITEMS) {
+        const int u = w / TX;
+        T2 v[R];
+#pragma unroll
+        for (int p = 0; p < R; p++) v[p] = live ? ldg_stream(line + u + p * M) : T2{0, 0};
+        Bfly<T, R>::run(v);
+        twiddle_store<T, S, 0, TX, SWZ>(v, s, tw, u, u, t);
+      }
+    }
+  }
+  __syncthreads();
+  mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
+  // ---- pass L on butterfly pairs (kappa, ML-kappa) + Hermitian post-processing -----------
+  {
+    constexpr int RL = S::r(L - 1), ML = H / RL, ITEMS = (ML / 2) * TX;
+    static_assert(ML >= 2, "last pass needs at least two butterflies per line");
+#pragma unroll 1
+    for (int w = threadIdx.x; w < ITEMS; w += NT) {
+      const int i = w / TX;
+      T2 za[RL], zb[RL];
+      last_bfly<T, S, TX, SWZ>(s, i == 0 ? 0 : i, t, za);
+      last_bfly<T, S, TX, SWZ>(s, i == 0 ? ML / 2 : ML - i, t, zb);
+      if (i != 0) {
+#pragma unroll
+        for (int q = 0; q < RL; q++) {
+          const int k = i + q * ML;
+          T2 xk, xm;
+          r2c_combine<T>(za[q], zb[RL - 1 - q], __ldg(wx + k), xk, xm);
+          store_row<T2, TX>(*tab, rs_out, k, t, live, xk);
+          store_row<T2, TX>(*tab, rs_out, H - k, t, live, xm);
+        }
+      } else {
+        store_row<T2, TX>(*tab, rs_out, 0, t, live, T2{za[0].x + za[0].y, 0});
+        store_row<T2, TX>(*tab, rs_out, H, t, live, T2{za[0].x - za[0].y, 0});
+#pragma unroll
+        for (int q = 1; q <= RL / 2; q++) {          // kappa = 0: k = q*ML pairs with (RL-q)*ML
+          const int k = q * ML;
+          T2 xk, xm;
+          r2c_combine<T>(za[q], za[RL - q], __ldg(wx + k), xk, xm);
+          store_row<T2, TX>(*tab, rs_out, k, t, live, xk);
+          if (q != RL / 2) store_row<T2, TX>(*tab, rs_out, H - k, t, live, xm);
+        }
+#pragma unroll
+        for (int q = 0; q < RL / 2; q++) {           // kappa = ML/2: k pairs inside the butterfly
+          const int k = ML / 2 + q * ML;
+          T2 xk, xm;
+          r2c_combine<T>(zb[q], zb[RL - 1 - q], __ldg(wx + k), xk, xm);
+          store_row<T2, TX>(*tab, rs_out, k, t, live, xk);
+          store_row<T2, TX>(*tab, rs_out, H - k, t, live, xm);
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int H> constexpr size_t xstage_smem() {
+  using T2 = typename Cx<T>::type;
+  return sizeof(T2) * H * XCfg<T, H>::TX + sizeof(SideTab<XCfg<T, H>::TX>) + (H + 1 + 15) / 16 * 16;
+}
+
+// ---------------------------------------------------------------------------------------
+// X stage, backward: H+1 complex -> real line (N = 2H), exec_b_c2r (fft_exec.F90:298)
+// E = Xk + conj Xm, O = conj(w)(Xk - conj Xm);  Z[k] = E + i O,  Z[H-k] = conj(E - i O)
+// (unnormalised: the line comes out multiplied by N like FFTW's c2r)
+// ---------------------------------------------------------------------------------------
+template <typename T, typename T2>
+__device__ __forceinline__ void c2r_combine(T2 xk, T2 xm, T2 w, T2& zk, T2& zm) {
+  T2 e = T2{xk.x + xm.x, xk.y - xm.y};
+  T2 d = T2{xk.x - xm.x, xk.y + xm.y};
+  T2 o = cmul(cconj(w), d);
+  // stored swapped (re <-> im) for the swap-trick inverse FFT
+  T2 a = T2{e.x - o.y, e.y + o.x};          // E + iO
+  T2 bb = T2{e.x + o.y, -(e.y - o.x)};      // conj(E - iO)
+  zk = cswap(a);
+  zm = cswap(bb);
+}
+
+template <typename T, int H>
+__global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(const __grid_constant__ FastStage st) {
+  using T2 = typename Cx<T>::type;
+  using C = XCfg<T, H>;
+  using S = typename C::S;
+  constexpr int TX = C::TX, NT = C::NT, L = S::L;
+  constexpr bool SWZ = (TX * sizeof(T2) == 64);
+  static_assert(NT % TX == 0, "t must be constant per thread");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T2* s = reinterpret_cast<T2*>(smem_raw);
+  SideTab<TX>* tab = reinterpret_cast<SideTab<TX>*>(smem_raw + sizeof(T2) * H * TX);
+  unsigned char* rs_in = reinterpret_cast<unsigned char*>(tab + 1);
+  const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
+  const T2* __restrict__ wx = tw + S::twtotal();
+
+  const int tiles_a = (st.na + TX - 1) / TX;
+  const int ta = blockIdx.x % tiles_a, b = blockIdx.x / tiles_a, c = blockIdx.y;
+  const int a0 = ta * TX;
+  const int t = threadIdx.x % TX;
+  const bool live = a0 + t < st.na;
+
+  build_side<TX, NT, sizeof(T2)>(st.in, *tab, rs_in, H + 1, H + 1, 0, a0, b, c);
+  __syncthreads();
+  // ---- pass 1 on butterfly pairs (u, M-u) with the Hermitian pre-processing --------------
+  {
+    constexpr int R = S::r(0), M = S::m(0), ITEMS = (M / 2) * TX;
+    static_assert(M >= 2, "first pass needs at least two butterflies per line");
+#pragma unroll 1
+    for (int w = threadIdx.x; w < ITEMS; w += NT) {
+      const int i = w / TX;
+      T2 za[R], zb[R];
+      if (i != 0) {
+#pragma unroll
+        for (int p = 0; p < R; p++) {
+          const int k = i + p * M;
+          T2 xk = load_row<T2, TX>(*tab, rs_in, k, k, t, live);
+          T2 xm = load_row<T2, TX>(*tab, rs_in, H - k, H - k, t, live);
+          c2r_combine<T>(xk, xm, __ldg(wx + k), za[p], zb[R - 1 - p]);
+        }
+      } else {
+        T2 x0 = load_row<T2, TX>(*tab, rs_in, 0, 0, t, live);
+        T2 xh = load_row<T2, TX>(*tab, rs_in, H, H, t, live);
+        za[0] = cswap(T2{x0.x + xh.x, x0.x - xh.x});
+#pragma unroll
+        for (int p = 1; p <= R / 2; p++) {
+          const int k = p * M;
+          T2 xk = load_row<T2, TX>(*tab, rs_in, k, k, t, live);
+          T2 xm = load_row<T2, TX>(*tab, rs_in, H - k, H - k, t, live);
+          T2 zk, zm;
+          c2r_combine<T>(xk, xm, __ldg(wx + k), zk, zm);
+          za[p] = zk;
+          if (p != R / 2) za[R - p] = zm;
+        }
+#pragma unroll
+        for (int p = 0; p < R / 2; p++) {
+          const int k = M / 2 + p * M;
+          T2 xk = load_row<T2, TX>(*tab, rs_in, k, k, t, live);
+          T2 xm = load_row<T2, TX>(*tab, rs_in, H - k, H - k, t, live);
+          c2r_combine<T>(xk, xm, __ldg(wx + k), zb[p], zb[R - 1 - p]);
+        }
+      }
+      const int ua = i, ub = (i == 0) ? M / 2 : M - i;
+      Bfly<T, R>::run(za);
+      twiddle_store<T, S, 0, TX, SWZ>(za, s, tw, ua, ua, t);
+      Bfly<T, R>::run(zb);
+      twiddle_store<T, S, 0, TX, SWZ>(zb, s, tw, ub, ub, t);
+    }
+  }
+  __syncthreads();
+  mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
+  // ---- pass L: shared -> registers -> packed real pairs -------------------------------------
+  {
+    const FastRun& ro = st.out.run[0];
+    T2* line = reinterpret_cast<T2*>(const_cast<T*>(reinterpret_cast<const T*>(ro.base)) + (long long)(a0 + t) * ro.sa +
+                                     (long long)b * ro.sb + (long long)c * ro.sc);
+    constexpr int RL = S::r(L - 1), ML = H / RL, ITEMS = ML * TX;
+#pragma unroll 1
+    for (int w = threadIdx.x; w < ITEMS; w += NT) {
+      const int kappa = w / TX;
+      T2 v[RL];
+      last_bfly<T, S, TX, SWZ>(s, kappa, t, v);
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < RL; q++) stg_stream(line + kappa + q * ML, cswap(v[q]));
+      }
+    }
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace fast
+}  // namespace p3d

@@ -127,6 +127,34 @@ __device__ __noinline__ void dif_pass_generic(typename Cx<T>::type* s, const Sme
   }
 }
 
+// radix r > 32 (large prime factors, e.g. the even extension 2*(nz-1) of an odd-length DCT-I):
+// O(r^2) DFT computed out of place into the second half of the tile, then copied back.
+template <typename T>
+__device__ __noinline__ void dif_pass_big(typename Cx<T>::type* s, typename Cx<T>::type* s2, const SmemMap& sm, int lines,
+                                          int nfft, int ncur, int r, const typename Cx<T>::type* __restrict__ tw) {
+  using T2 = typename Cx<T>::type;
+  const int m = ncur / r, twstep = nfft / ncur, rstep = nfft / r, total = lines * nfft;
+  for (int w = threadIdx.x; w < total; w += blockDim.x) {
+    int t, k;
+    if (sm.layx) { t = w / nfft; k = w - t * nfft; } else { k = w / lines; t = w - k * lines; }
+    const int blk = k / ncur, rem = k - blk * ncur, q = rem / m, j = rem - q * m, base = blk * ncur + j;
+    T2 acc = s[sm(base, t)];
+    int e = 0;
+    for (int p = 1; p < r; p++) {
+      e += q; if (e >= r) e -= r;
+      acc = cadd(acc, cmul(s[sm(base + p * m, t)], tw[e * rstep]));
+    }
+    if (m > 1 && q > 0) acc = cmul(acc, tw[(int)(((long long)j * q * twstep) % nfft)]);
+    s2[sm(k, t)] = acc;
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < total; w += blockDim.x) {
+    int t, k;
+    if (sm.layx) { t = w / nfft; k = w - t * nfft; } else { k = w / lines; t = w - k * lines; }
+    s[sm(k, t)] = s2[sm(k, t)];
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void fft_inplace(typename Cx<T>::type* s, const SmemMap& sm, int lines,
                                             const P3dStage& st, const typename Cx<T>::type* tw) {
@@ -138,7 +166,10 @@ __device__ __forceinline__ void fft_inplace(typename Cx<T>::type* s, const SmemM
       case 4: dif_pass<T, 4>(s, sm, lines, st.nfft, ncur, tw); break;
       case 2: dif_pass<T, 2>(s, sm, lines, st.nfft, ncur, tw); break;
       case 3: dif_pass<T, 3>(s, sm, lines, st.nfft, ncur, tw); break;
-      default: dif_pass_generic<T>(s, sm, lines, st.nfft, ncur, r, tw); break;
+      default:
+        if (r <= 32) dif_pass_generic<T>(s, sm, lines, st.nfft, ncur, r, tw);
+        else dif_pass_big<T>(s, s + st.tile * (st.layx ? sm.ldl : st.nfft), sm, lines, st.nfft, ncur, r, tw);
+        break;
     }
     ncur /= r;
     __syncthreads();
@@ -272,18 +303,23 @@ __global__ void cheby_kernel(typename Cx<T>::type* out, int64_t ncol, int nzc, i
 // ------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------
+static int big_factor(const P3dStage& st) {
+  for (int i = 0; i < st.nfac; i++) if (st.fac[i] > 32) return 2;    // out-of-place pass needs a second tile
+  return 1;
+}
+
 template <typename T>
 size_t stage_smem_bytes(const P3dStage& st) {
   using T2 = typename Cx<T>::type;
   size_t per_line = st.layx ? (size_t)(st.nfft + (st.nfft >> 3) + (st.nfft >> 6) + 1) : (size_t)st.nfft;
-  return per_line * st.tile * sizeof(T2);
+  return per_line * st.tile * sizeof(T2) * big_factor(st);
 }
 
 template <typename T>
 int choose_tile(const P3dStage& st) {
   using T2 = typename Cx<T>::type;
   const size_t budget = 64 * 1024, hard = 200 * 1024;
-  size_t per_line = (st.layx ? (size_t)(st.nfft + (st.nfft >> 3) + (st.nfft >> 6) + 1) : (size_t)st.nfft) * sizeof(T2);
+  size_t per_line = (st.layx ? (size_t)(st.nfft + (st.nfft >> 3) + (st.nfft >> 6) + 1) : (size_t)st.nfft) * sizeof(T2) * big_factor(st);
   int want = st.layx ? 8 : (int)(128 / sizeof(T2));   // interleaved layout: one 128 B row of lines
   int tile = (int)(budget / per_line);
   if (tile > want) tile = want;

@@ -133,7 +133,7 @@ struct Decomp {
 // ------------------------------------------------------------------------------------
 // FFT length factorisation for the on-chip engine
 // ------------------------------------------------------------------------------------
-inline bool factorize(int n, int* fac, int* nfac, int maxprime = 32) {
+inline bool factorize(int n, int* fac, int* nfac, int maxprime = 4096) {
   int k = 0;
   while (n % 8 == 0) { fac[k++] = 8; n /= 8; }
   while (n % 4 == 0) { fac[k++] = 4; n /= 4; }
@@ -220,7 +220,7 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
     if ((long long)s.na * s.nb * s.nc <= 0) return;
     if (s.kind == P3D_NOOP) s.nfac = 0;
     else if (!factorize(s.nfft, s.fac, &s.nfac)) {
-      char m[128]; snprintf(m, sizeof m, "transform length %d needs a prime factor > 32 (unsupported)", s.nfft);
+      char m[128]; snprintf(m, sizeof m, "transform length %d needs a prime factor > 4096 (unsupported)", s.nfft);
       tp.error = m; return;
     }
     s.need_zero = (s.in.cnt < s.in.logical) || s.kind == P3D_DST1;

@@ -106,6 +106,51 @@ def test_single_precision(libf, n, cut):
     _fwd_bwd(libf, n, cut, single=True, device=True)
 
 
+FAST_CASES = [((64, 64, 64), None), ((128, 256, 64), None), ((256, 64, 128), None), ((512, 128, 64), None),
+              ((1024, 64, 256), None), ((2048, 64, 64), None), ((64, 1024, 64), None), ((64, 64, 2048), None),
+              ((64, 512, 512), None), ((128, 128, 128), (64, 64, 64)), ((256, 256, 64), (170, 170, 42)),
+              ((512, 64, 64), (340, 42, 42))]
+
+
+@pytest.mark.parametrize("n,cut", FAST_CASES)
+def test_fast_kernels_double(lib, n, cut):
+    """Power-of-two lengths run on the specialised kernels (fft_fast.cuh): all six stages."""
+    lib.fast_launch_count(True)
+    _fwd_bwd(lib, n, cut, device=True)
+    assert lib.fast_launch_count() == 6
+    lib.force_generic(True)           # A/B: the any-length kernel on the same input
+    try:
+        lib.fast_launch_count(True)
+        _fwd_bwd(lib, n, cut, device=True)
+        assert lib.fast_launch_count() == 0
+    finally:
+        lib.force_generic(False)
+
+
+@pytest.mark.parametrize("n,cut", FAST_CASES[:9] + FAST_CASES[10:11])
+def test_fast_kernels_single(libf, n, cut):
+    libf.fast_launch_count(True)
+    _fwd_bwd(libf, n, cut, single=True, device=True)
+    assert libf.fast_launch_count() == 6
+
+
+@pytest.mark.parametrize("stride1", [False, True])
+@pytest.mark.parametrize("n,cut", [((64, 64, 33), None), ((128, 64, 65), None), ((64, 128, 129), None),
+                                   ((64, 64, 513), None), ((128, 128, 65), (64, 64, 33))])
+def test_fast_kernels_dct(lib, n, cut, stride1):
+    """Chebyshev third dimension: DCT-I of odd nz as an even-extended FFT of length 2(nz-1)."""
+    lib.fast_launch_count(True)
+    _fwd_bwd(lib, n, cut, "ffc", "cff", stride1=stride1, device=True)
+    assert lib.fast_launch_count() == 6
+
+
+@pytest.mark.parametrize("n", [(64, 64, 64), (128, 64, 256)])
+def test_fast_kernels_stride1(lib, n):
+    lib.fast_launch_count(True)
+    _fwd_bwd(lib, n, None, stride1=True, device=True)
+    assert lib.fast_launch_count() == 6
+
+
 def test_driver_sine_known_answer_and_roundtrip(lib):
     """driver_sine.c: spikes of modulus N/8 at 1-based (2,{2,ny},{2,nz}); round trip <= 1e-14*N/4."""
     nx = ny = nz = 64

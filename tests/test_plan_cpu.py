@@ -64,7 +64,9 @@ def test_decomp_errors(lib):
     with pytest.raises(RuntimeError, match="Invalid dimensions"):
         lib.plan_decomp((1, 1), 0, 4, 4)
     with pytest.raises(RuntimeError, match="transform length|prime"):
-        lib.plan_steps((1, 1), 8, 8, 74, 0, False, "fft")       # 74 = 2*37
+        lib.plan_steps((1, 1), 8, 8, 2 * 4099, 0, False, "fft")     # prime factor 4099 > 4096
+    steps, _ = lib.plan_steps((1, 1), 8, 8, 74, 0, False, "fft")    # 74 = 2*37: the O(r^2) pass covers it
+    assert list(steps[-1].st.fac)[: steps[-1].st.nfac] == [2, 37]
     with pytest.raises(RuntimeError, match="Unknown transform type"):
         lib.plan_steps((1, 1), 8, 8, 8, 0, False, "ffx")
 
