@@ -386,7 +386,7 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
       report(true, "P3DFFT(B200): ncclCommSplit(col) failed"); return;
     }
   }
-  L.force_generic = getenv("P3DFFT_B200_GENERIC") != nullptr;
+  if (getenv("P3DFFT_B200_GENERIC")) L.force_generic = true;
   for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
   L.nv_preset = 0;
   L.set = true;

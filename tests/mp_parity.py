@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Multi-GPU parity driver (one process per GPU, launched by torchrun; NCCL transposes).
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+      --master-port 29511 tests/mp_parity.py [--grids 2x2,1x4,4x1]
+
+Every rank transforms its pencil of ONE global Philox field through the C ABI and compares
+with the oracle's slice of the global transform (relative L2 <= 1e-12 double / 1e-5 single).
+Covers the reference's own matrix (extra/makejob.py:122-152): even 32^3 and 128^3, uneven
+14x26x38, pruned 64^3 -> 32^3, Chebyshev 32x32x33, the *_many calls and the STRIDE1 layout.
+Exit code 0 iff every case passes on every rank.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+import p3dfft_b200 as pb
+from oracle import p3dfft_oracle as po
+
+CASES = [
+    # (n, cut, opf, opb, stride1, nv, single)
+    ((128, 128, 128), None, "fft", "tff", False, 1, False),        # BASELINE config 1 (driver_inverse/driver_sine size)
+    ((32, 32, 32), None, "fft", "tff", False, 1, False),
+    ((14, 26, 38), None, "fft", "tff", False, 1, False),
+    ((64, 64, 64), (32, 32, 32), "fft", "tff", False, 1, False),
+    ((32, 32, 33), None, "ffc", "cff", False, 1, False),
+    ((32, 32, 32), None, "ffn", "nff", False, 1, False),
+    ((32, 32, 32), None, "fft", "tff", False, 2, False),
+    ((64, 32, 48), None, "fft", "tff", True, 1, False),
+    ((256, 128, 64), None, "fft", "tff", False, 1, False),
+    ((128, 128, 128), None, "fft", "tff", False, 1, True),
+    ((64, 64, 64), (42, 42, 42), "fft", "tff", False, 1, True),
+]
+
+
+def run_case(L, comm, dims, rank, case):
+    n, cut, opf, opb, stride1, nv, single = case
+    nx, ny, nz = n
+    c = cut or (None, None, None)
+    rt, ct = (np.float32, np.complex64) if single else (np.float64, np.complex128)
+    tt = torch.float32 if single else torch.float64
+    L.set_layout(stride1, False)
+    L.p3dfft_setup(dims, nx, ny, nz, comm, *c)
+    d = po.Decomp(nx, ny, nz, dims, rank, *c, stride1=stride1, elem=4 if single else 8)
+    _, _, isz = L.p3dfft_get_dims(1)
+    _, _, fsz = L.p3dfft_get_dims(2)
+    assert list(isz) == d.get_dims(1)[2] and list(fsz) == d.get_dims(2)[2]
+    nreal, ncplx = int(np.prod(isz)), int(np.prod(fsz))
+    fields = [po.philox_field(nx, ny, nz, seed=20240229 + v) for v in range(nv)]
+    loc = [np.asfortranarray(f[po.local_in_slice(d)]).astype(rt) for f in fields]
+    tA = torch.from_numpy(np.concatenate([a.ravel(order="F") for a in loc])).cuda()
+    tF = torch.zeros(2 * ncplx * nv, dtype=tt, device="cuda")
+    if nv == 1:
+        L.p3dfft_ftran_r2c(tA, tF, opf)
+    else:
+        L.p3dfft_ftran_r2c_many(tA, nreal, tF, ncplx, nv, opf)
+    F = tF.cpu().numpy().view(ct).reshape(nv, ncplx)
+    errs = []
+    for v in range(nv):
+        exp = po.local_forward(fields[v].astype(rt).astype(np.float64), d, opf)
+        errs.append(po.rel_l2(F[v], np.asfortranarray(exp).ravel(order="F")))
+    # backward from the oracle's global spectrum
+    Fg = [po.global_forward(f.astype(rt).astype(np.float64), d, opf) for f in fields]
+    parts = []
+    for f in Fg:
+        l = f[po.local_out_slice(d)]
+        if stride1:
+            l = l.transpose(2, 1, 0)
+        parts.append(np.asfortranarray(l).astype(ct).ravel(order="F"))
+    tFi = torch.from_numpy(np.concatenate(parts).view(rt)).cuda()
+    tB = torch.zeros(nreal * nv, dtype=tt, device="cuda")
+    if nv == 1:
+        L.p3dfft_btran_c2r(tFi, tB, opb)
+    else:
+        L.p3dfft_btran_c2r_many(tFi, ncplx, tB, nreal, nv, opb)
+    B = tB.cpu().numpy().reshape(nv, nreal)
+    for v in range(nv):
+        exp = po.local_backward(Fg[v], d, opb)
+        errs.append(po.rel_l2(B[v], np.asfortranarray(exp).ravel(order="F")))
+    L.p3dfft_clean()
+    return max(errs)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grids", default="")
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    grids = [tuple(int(x) for x in g.split("x")) for g in a.grids.split(",") if g] or \
+        [(m1, world // m1) for m1 in range(1, world + 1) if world % m1 == 0]
+    ok = True
+    comms = {}
+    for single in (False, True):
+        L = pb.load(single)
+        L.p3dfft_clean()
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(L.get_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        comms[single] = L.comm_create(rank, world, bytes(uid.cpu().numpy().tobytes()), local)
+    for dims in grids:
+        for case in CASES:
+            single = case[6]
+            L = pb.load(single)
+            tol = 1e-5 if single else 1e-12
+            try:
+                err = run_case(L, comms[single], dims, rank, case)
+                good = err <= tol
+            except Exception as e:     # noqa: BLE001 - report and fail
+                err, good = float("nan"), False
+                print(f"rank {rank} grid {dims} case {case}: EXCEPTION {e!r}", flush=True)
+                L.p3dfft_clean()
+            flag = torch.tensor([0 if good else 1], device="cuda")
+            worst = torch.tensor([err if err == err else 1e9], dtype=torch.float64, device="cuda")
+            dist.all_reduce(flag)
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(f"grid {dims[0]}x{dims[1]} n={case[0]} cut={case[1]} op={case[2]}/{case[3]} stride1={case[4]} "
+                      f"nv={case[5]} {'sp' if single else 'dp'}: max rel-L2 {float(worst):.2e} "
+                      f"{'ok' if int(flag) == 0 else 'FAIL'}", flush=True)
+            ok = ok and int(flag) == 0
+    for single, h in comms.items():
+        pb.load(single).comm_destroy(h)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MP PARITY", "PASS" if ok else "FAIL", flush=True)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Minimal driver for profilers: N forward+backward pairs on device-resident arrays, 1x1 grid.
+
+  ncu --set full ... python tools/prof_pair.py --size 1024 --pairs 2 [--single] [--op fft]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import p3dfft_b200 as pb
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--size", type=int, nargs="+", default=[1024])
+ap.add_argument("--pairs", type=int, default=2)
+ap.add_argument("--single", action="store_true")
+ap.add_argument("--opf", default="fft")
+ap.add_argument("--opb", default="tff")
+ap.add_argument("--cut", type=int, nargs=3, default=None)
+a = ap.parse_args()
+n = a.size * 3 if len(a.size) == 1 else a.size
+nx, ny, nz = n
+L = pb.load(a.single)
+L.p3dfft_clean()
+c = a.cut or (None, None, None)
+L.p3dfft_setup((1, 1), nx, ny, nz, 0, *c)
+_, _, isz = L.p3dfft_get_dims(1)
+_, _, fsz = L.p3dfft_get_dims(2)
+dt = torch.float32 if a.single else torch.float64
+A = torch.rand(isz[0] * isz[1] * isz[2], dtype=dt, device="cuda")
+F = torch.empty(2 * fsz[0] * fsz[1] * fsz[2], dtype=dt, device="cuda")
+B = torch.empty_like(A)
+torch.cuda.synchronize()
+for _ in range(a.pairs):
+    L.p3dfft_ftran_r2c(A, F, a.opf)
+    L.p3dfft_btran_c2r(F, B, a.opb)
+torch.cuda.synchronize()
+N = float(nx) * ny * nz
+print("roundtrip max err", float((B / N - A).abs().max()), "timers(ms)", [round(t * 1e3, 3) for t in L.get_timers()])
+L.p3dfft_clean()
