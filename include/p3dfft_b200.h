@@ -55,6 +55,11 @@ long long p3dfft_b200_launch_count(int reset);
 long long p3dfft_b200_fast_launch_count(int reset);
 /* on != 0: use only the any-length kernel (A/B checks; also env P3DFFT_B200_GENERIC)        */
 void p3dfft_b200_force_generic(int on);
+/* on != 0: keep the reference's pack-buffer layouts and exact alltoallv counts in the
+ * library's own work buffers instead of the tile-blocked B200 layouts (plan.h); results are
+ * identical, only the order of elements inside the internal buffers changes
+ * (also env P3DFFT_B200_PLAIN)                                                              */
+void p3dfft_b200_plain_layout(int on);
 
 /* ---- host-only planner queries (no GPU needed; used by the CPU test-suite) ------------- */
 typedef struct {
@@ -69,7 +74,8 @@ typedef struct {
   int64_t work_elems;
 } p3dfft_b200_decomp;
 
-/* flags: bit1 = STRIDE1, bit2 = DIMS_C.  Returns 0, or -1 and records the reference's
+/* flags: bit0 = single precision (sizes the blocked layouts), bit1 = STRIDE1, bit2 = DIMS_C,
+ * bit3 = plain (reference) internal layouts.  Returns 0, or -1 and records the reference's
  * error text (retrievable with p3dfft_b200_last_error).                                   */
 int p3dfft_b200_plan_decomp(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc,
                             int flags, p3dfft_b200_decomp* out);

@@ -30,7 +30,8 @@ class LibraryMissing(RuntimeError):
 class Seg(C.Structure):
     _fields_ = [("base", C.c_void_p), ("buf", C.c_int32), ("peer", C.c_int32), ("off", C.c_int64),
                 ("start", C.c_int32), ("len", C.c_int32), ("ps", C.c_int64), ("sa", C.c_int64),
-                ("sb", C.c_int64), ("sc", C.c_int64)]
+                ("sb", C.c_int64), ("sc", C.c_int64), ("kw", C.c_int32), ("aw", C.c_int32),
+                ("psh", C.c_int64), ("sah", C.c_int64)]
 
 
 class Side(C.Structure):
@@ -231,10 +232,14 @@ class P3DFFT:
         return int(self.lib.p3dfft_b200_launch_count(int(reset)))
 
     # ---- host-only planner ---------------------------------------------------------------
-    def plan_decomp(self, dims, nx, ny, nz, rank=0, nxc=None, nyc=None, nzc=None, stride1=False, dims_c=False):
+    def plain_layout(self, on=True):
+        self.lib.p3dfft_b200_plain_layout(int(on))
+
+    def plan_decomp(self, dims, nx, ny, nz, rank=0, nxc=None, nyc=None, nzc=None, stride1=False, dims_c=False,
+                    plain=False):
         info = DecompInfo()
         d = (C.c_int * 2)(*dims)
-        flags = (2 if stride1 else 0) | (4 if dims_c else 0)
+        flags = (1 if self.single else 0) | (2 if stride1 else 0) | (4 if dims_c else 0) | (8 if plain else 0)
         rc = self.lib.p3dfft_b200_plan_decomp(d, nx, ny, nz, rank, nxc or nx, nyc or ny, nzc or nz, flags,
                                               C.byref(info))
         if rc != 0:
@@ -243,15 +248,15 @@ class P3DFFT:
         return info
 
     def plan_steps(self, dims, nx, ny, nz, rank, backward, op, nv=1, nxc=None, nyc=None, nzc=None, stride1=False,
-                   dims_c=False, dim_real=None, dim_cplx=None):
-        info = self.plan_decomp(dims, nx, ny, nz, rank, nxc, nyc, nzc, stride1, dims_c)
+                   dims_c=False, dim_real=None, dim_cplx=None, plain=False):
+        info = self.plan_decomp(dims, nx, ny, nz, rank, nxc, nyc, nzc, stride1, dims_c, plain)
         if dim_real is None:
             dim_real = info.nx * info.jisize * info.kjsize
         if dim_cplx is None:
             dim_cplx = info.iisize * info.jjsize * info.nzc
         arr = (Step * 16)()
         d = (C.c_int * 2)(*dims)
-        flags = (2 if stride1 else 0) | (4 if dims_c else 0)
+        flags = (2 if stride1 else 0) | (4 if dims_c else 0) | (8 if plain else 0)
         n = self.lib.p3dfft_b200_plan_steps(d, nx, ny, nz, rank, nxc or nx, nyc or ny, nzc or nz, flags,
                                             1 if backward else 0, op.encode() + b"\0", nv, dim_real, dim_cplx,
                                             4 if self.single else 8, arr, 16)

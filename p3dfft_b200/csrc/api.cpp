@@ -104,9 +104,9 @@ int g_next_handle = 1;
 // the plan (module-global state of the reference)
 // ------------------------------------------------------------------------------------
 struct PlanKey {
-  int backward, nv; char op; long long dim_real, dim_cplx;
+  int backward, nv; char op; long long dim_real, dim_cplx; int w;
   bool operator<(const PlanKey& o) const {
-    return std::tie(backward, nv, op, dim_real, dim_cplx) < std::tie(o.backward, o.nv, o.op, o.dim_real, o.dim_cplx);
+    return std::tie(backward, nv, op, dim_real, dim_cplx, w) < std::tie(o.backward, o.nv, o.op, o.dim_real, o.dim_cplx, o.w);
   }
 };
 
@@ -124,6 +124,8 @@ struct Lib {
   bool has_user_stream = false;
   bool async = false;
   bool force_generic = false;
+  bool plain_layout = false;     // true: the reference's pack-buffer layouts instead of the tile-blocked ones
+  int W() const { return plain_layout ? 0 : (int)(64 / CSIZE); }
   long long fast_launches = 0;
   std::map<std::pair<int, int>, void*> fast_twiddles;   // (x-stage?, nfft) -> device block
   double timers[12] = {0};
@@ -191,7 +193,7 @@ bool alloc_work(int nv) {
   if (nv <= L.nv_preset) return true;
   // lazy growth like ftran.F90:133-157 (nv_preset)
   cudaStreamSynchronize(L.stream());
-  size_t bytes = (size_t)L.d.work_elems(nv) * CSIZE;
+  size_t bytes = (size_t)L.d.work_elems(nv, L.W()) * CSIZE;
   int nbuf = (L.d.iproc * L.d.jproc > 1) ? 3 : 2;
   for (int b = 0; b < nbuf; b++) {
     int id = P3D_BUF_A + b;
@@ -203,10 +205,10 @@ bool alloc_work(int nv) {
 }
 
 p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long dim_real, long long dim_cplx) {
-  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx};
+  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx, L.W()};
   auto it = L.plans.find(key);
   if (it != L.plans.end()) return &it->second;
-  p3d::TransformPlan tp = p3d::build_plan(L.d, backward, op, nv, dim_real, dim_cplx);
+  p3d::TransformPlan tp = p3d::build_plan(L.d, backward, op, nv, dim_real, dim_cplx, L.W());
   if (!tp.error.empty()) {
     // ftran.F90:640-643: print + MPI_Abort
     report(true, "%s", tp.error.c_str());
@@ -387,6 +389,7 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
     }
   }
   if (getenv("P3DFFT_B200_GENERIC")) L.force_generic = true;
+  if (getenv("P3DFFT_B200_PLAIN")) L.plain_layout = true;
   for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
   L.nv_preset = 0;
   L.set = true;
@@ -550,6 +553,10 @@ int p3dfft_b200_last_error(char* buf, int buflen) {
 void p3dfft_b200_set_stream(void* s) { L.user_stream = (cudaStream_t)s; L.has_user_stream = true; }
 void p3dfft_b200_reset_stream(void) { L.user_stream = nullptr; L.has_user_stream = false; }
 void p3dfft_b200_force_generic(int on) { L.force_generic = on != 0; }
+void p3dfft_b200_plain_layout(int on) {
+  if (L.set && (on != 0) != L.plain_layout) { cudaStreamSynchronize(L.stream()); L.plans.clear(); L.nv_preset = 0; }
+  L.plain_layout = on != 0;
+}
 long long p3dfft_b200_fast_launch_count(int reset) { long long n = L.fast_launches; if (reset) L.fast_launches = 0; return n; }
 void p3dfft_b200_set_async(int a) { L.async = a != 0; }
 void p3dfft_b200_sync(void) { cudaStreamSynchronize(L.stream()); }
@@ -570,7 +577,7 @@ int p3dfft_b200_plan_decomp(const int* dims, int nx, int ny, int nz, int rank, i
   o->kjstart = d.kjstart; o->kjend = d.kjend; o->kjsize = d.kjsize;
   o->padi_work = d.padi_work; o->padi = d.padi;
   for (int i = 0; i < 3; i++) o->memsize[i] = d.memsize[i];
-  o->nm = d.nm; o->work_elems = d.work_elems(1);
+  o->nm = d.nm; o->work_elems = d.work_elems(1, (flags & 8) ? 0 : ((flags & 1) ? 8 : 4));
   return 0;
 }
 
@@ -585,7 +592,8 @@ int p3dfft_b200_plan_steps(const int* dims, int nx, int ny, int nz, int rank, in
   std::string err = d.init(nx, ny, nz, dims[0], dims[1], rank, dims[0] * dims[1], nxc, nyc, nzc, (flags & 4) != 0,
                            (flags & 2) != 0);
   if (!err.empty()) { g_last_error = err; return -1; }
-  p3d::TransformPlan tp = p3d::build_plan(d, backward != 0, op, nv, dim_real, dim_cplx);
+  p3d::TransformPlan tp = p3d::build_plan(d, backward != 0, op, nv, dim_real, dim_cplx,
+                                          (flags & 8) ? 0 : 64 / (2 * elem_bytes));
   if (!tp.error.empty()) { g_last_error = tp.error; return -1; }
   if ((int)tp.steps.size() > max_steps) { g_last_error = "step array too small"; return -1; }
   P3dStepC* out = (P3dStepC*)steps;

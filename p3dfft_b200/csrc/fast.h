@@ -17,12 +17,15 @@
 
 namespace p3d {
 
-// element address of logical row k of line (a,b,c):
-//     base + ((k - kstart)*ps + a*sa + b*sb + c*sc) * sizeof(element)
+// element address of logical row k of line (a,b,c), a = ta*TX + t (TX = lines per tile):
+//     base + (R(k - kstart) + ta*sat + t*sa + b*sb + c*sc) * sizeof(element)
+//     R(i) = i*ps  (kw <= 1)   or   (i / kw)*psh + (i % kw)*ps  (rows blocked by kw, stage.h)
+// (sat = TX*sa for a plain strided layout; the tile-blocked internal buffers give it directly)
 struct FastRun {
   const void* base;
   int32_t kstart, len;
-  int64_t ps, sa, sb, sc;
+  int32_t kw, pad_;
+  int64_t ps, psh, sa, sat, sb, sc;
 };
 
 struct FastSide {

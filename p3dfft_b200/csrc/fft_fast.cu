@@ -56,27 +56,6 @@ bool is_x(int kind) { return kind == P3D_R2C || kind == P3D_C2R; }
 
 }  // namespace
 
-template <typename T>
-bool fast_supported(const P3dStage& st) {
-  if (st.scale != 1.0) return false;
-  if (st.in.nseg + 1 > P3D_MAXRUN || st.out.nseg + 1 > P3D_MAXRUN) return false;
-  if (st.nc > 65535) return false;
-  switch (st.kind) {
-    case P3D_C2C_FWD: case P3D_C2C_BWD: case P3D_DCT1:
-      return c2c_len_ok(st.nfft);
-    case P3D_R2C: case P3D_C2R: {
-      if (st.n % 2 || !x_half_ok(st.n / 2)) return false;
-      const P3dSide& rs = st.kind == P3D_R2C ? st.in : st.out;
-      if (rs.nseg != 1 || rs.cnt != rs.logical) return false;
-      const P3dSeg& g = rs.seg[0];
-      if (g.ps != 1 || g.start != 0 || g.len != st.n) return false;
-      if ((g.sa & 1) || (st.nb > 1 && (g.sb & 1)) || (st.nc > 1 && (g.sc & 1)) || (g.off & 1)) return false;
-      return true;
-    }
-    default: return false;
-  }
-}
-
 template <class F>
 bool dispatch_c(int n, F&& f) {
   switch (n) {
@@ -103,6 +82,47 @@ bool dispatch_x(int h, F&& f) {
 }
 
 template <typename T>
+static int tile_lines(const P3dStage& st) {
+  int tx = 1;
+  if (is_x(st.kind)) dispatch_x(st.n / 2, [&](auto h) { tx = XCfg<T, decltype(h)::value>::TX; });
+  else dispatch_c(st.nfft, [&](auto nn) { tx = CCfg<T, decltype(nn)::value>::TX; });
+  return tx;
+}
+
+template <typename T>
+bool fast_supported(const P3dStage& st) {
+  if (st.scale != 1.0) return false;
+  if (st.in.nseg + 1 > P3D_MAXRUN || st.out.nseg + 1 > P3D_MAXRUN) return false;
+  switch (st.kind) {
+    case P3D_C2C_FWD: case P3D_C2C_BWD: case P3D_DCT1: {
+      if (!c2c_len_ok(st.nfft)) return false;
+      const int tx = tile_lines<T>(st);
+      for (int side = 0; side < 2; side++) {          // one line pitch per side (the kernels keep it in a register)
+        const P3dSide& sd = side ? st.out : st.in;
+        for (int g = 0; g < sd.nseg; g++) {
+          const P3dSeg& sg = sd.seg[g];
+          if (sg.sa != sd.seg[0].sa || sg.kw > 1 || (sg.aw > 1 && sg.aw != tx)) return false;
+        }
+      }
+      return true;
+    }
+    case P3D_R2C: case P3D_C2R: {
+      if (st.n % 2 || !x_half_ok(st.n / 2)) return false;
+      const P3dSide& rs = st.kind == P3D_R2C ? st.in : st.out;
+      if (rs.nseg != 1 || rs.cnt != rs.logical) return false;
+      const P3dSeg& g = rs.seg[0];
+      if (g.ps != 1 || g.start != 0 || g.len != st.n) return false;
+      if ((g.sa & 1) || (st.nb > 1 && (g.sb & 1)) || (st.nc > 1 && (g.sc & 1)) || (g.off & 1)) return false;
+      const P3dSide& cs = st.kind == P3D_R2C ? st.out : st.in;      // complex side: plain lines, one pitch
+      for (int i = 0; i < cs.nseg; i++)
+        if (cs.seg[i].sa != cs.seg[0].sa || cs.seg[i].aw > 1) return false;
+      return true;
+    }
+    default: return false;
+  }
+}
+
+template <typename T>
 size_t fast_twiddle_elems(int kind, int nfft) {
   size_t n = 0;
   if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { n = block_elems<typename XCfg<T, decltype(h)::value>::S>(true); });
@@ -118,7 +138,7 @@ void fast_twiddle_fill(int kind, int nfft, void* host) {
 
 // stored index s -> logical k:  k = s (s < h1),  k = s + (logical - cnt) (s >= h1); a segment that
 // straddles h1 becomes two runs.
-static void side_to_runs(const P3dSide& sd, FastSide& f, size_t esz) {
+static void side_to_runs(const P3dSide& sd, FastSide& f, size_t esz, int tx) {
   f.nrun = 0;
   const int shift = sd.logical - sd.cnt;
   for (int g = 0; g < sd.nseg; g++) {
@@ -134,17 +154,20 @@ static void side_to_runs(const P3dSide& sd, FastSide& f, size_t esz) {
       r.kstart = (shift > 0 && a >= sd.h1) ? a + shift : a;
       r.len = b - a;
       r.ps = sg.ps; r.sa = sg.sa; r.sb = sg.sb; r.sc = sg.sc;
+      r.kw = sg.kw; r.psh = sg.psh;
+      r.sat = sg.aw > 1 ? sg.sah : sg.sa * tx;         // fast_supported() guarantees aw == tx when blocked
     }
   }
 }
 
 void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes) {
   memset(&f, 0, sizeof f);
+  const int tx = real_bytes == 4 ? tile_lines<float>(st) : tile_lines<double>(st);
   f.na = st.na; f.nb = st.nb; f.nc = st.nc; f.n = st.n;
   f.mirror = st.kind == P3D_DCT1;
   f.tw = nullptr;
-  side_to_runs(st.in, f.in, st.kind == P3D_R2C ? real_bytes : 2 * real_bytes);
-  side_to_runs(st.out, f.out, st.kind == P3D_C2R ? real_bytes : 2 * real_bytes);
+  side_to_runs(st.in, f.in, st.kind == P3D_R2C ? real_bytes : 2 * real_bytes, tx);
+  side_to_runs(st.out, f.out, st.kind == P3D_C2R ? real_bytes : 2 * real_bytes, tx);
 }
 
 template <typename K>
@@ -155,23 +178,43 @@ static cudaError_t launch_cfg(K kernel, size_t smem, bool& configured) {
   return e;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// persistent grid: as many CTAs as stay resident (occupancy query, cached), never more than tiles
+template <typename K>
+static unsigned persistent_grid(K kernel, int nt, size_t smem, long long tiles, int& per_sm) {
+  if (per_sm <= 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem) != cudaSuccess || per_sm <= 0) per_sm = 1;
+  }
+  const long long g = (long long)per_sm * sm_count();
+  return (unsigned)(tiles < g ? tiles : g);
+}
+
 template <typename T, int HH>
 static cudaError_t launch_x(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
   constexpr int TX = XCfg<T, HH>::TX, NT = XCfg<T, HH>::NT;
   constexpr size_t smem = xstage_smem<T, HH>();
-  const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb;
-  if (tiles <= 0 || st.nc <= 0) return cudaSuccess;
-  if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  dim3 grid((unsigned)tiles, (unsigned)st.nc);
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb * st.nc;
+  if (tiles <= 0) return cudaSuccess;
   cudaError_t e;
   if (st.kind == P3D_R2C) {
     static bool cfg = false;
+    static int per_sm = 0;
     if ((e = launch_cfg(xr2c_kernel<T, HH>, smem, cfg)) != cudaSuccess) return e;
-    xr2c_kernel<T, HH><<<grid, NT, smem, stream>>>(f);
+    xr2c_kernel<T, HH><<<persistent_grid(xr2c_kernel<T, HH>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
   } else {
     static bool cfg = false;
+    static int per_sm = 0;
     if ((e = launch_cfg(xc2r_kernel<T, HH>, smem, cfg)) != cudaSuccess) return e;
-    xc2r_kernel<T, HH><<<grid, NT, smem, stream>>>(f);
+    xc2r_kernel<T, HH><<<persistent_grid(xc2r_kernel<T, HH>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
   }
   return cudaGetLastError();
 }
@@ -180,19 +223,19 @@ template <typename T, int NN>
 static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
   constexpr int TX = CCfg<T, NN>::TX, NT = CCfg<T, NN>::NT;
   constexpr size_t smem = cstage_smem<T, NN>();
-  const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb;
-  if (tiles <= 0 || st.nc <= 0) return cudaSuccess;
-  if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  dim3 grid((unsigned)tiles, (unsigned)st.nc);
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb * st.nc;
+  if (tiles <= 0) return cudaSuccess;
   cudaError_t e;
   if (st.kind == P3D_C2C_BWD) {
     static bool cfg = false;
+    static int per_sm = 0;
     if ((e = launch_cfg(cstage_kernel<T, NN, true>, smem, cfg)) != cudaSuccess) return e;
-    cstage_kernel<T, NN, true><<<grid, NT, smem, stream>>>(f);
+    cstage_kernel<T, NN, true><<<persistent_grid(cstage_kernel<T, NN, true>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
   } else {
     static bool cfg = false;
+    static int per_sm = 0;
     if ((e = launch_cfg(cstage_kernel<T, NN, false>, smem, cfg)) != cudaSuccess) return e;
-    cstage_kernel<T, NN, false><<<grid, NT, smem, stream>>>(f);
+    cstage_kernel<T, NN, false><<<persistent_grid(cstage_kernel<T, NN, false>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
   }
   return cudaGetLastError();
 }

@@ -188,51 +188,6 @@ template <bool SWZ> __host__ __device__ constexpr int swz_const(int off) { retur
 template <bool SWZ> __device__ __forceinline__ int swz_base(int row) { return SWZ ? (row ^ (__popc(row >> 1) & 1)) : row; }
 
 // ---------------------------------------------------------------------------------------
-// row -> address tables of one global side, built once per CTA in shared memory
-// ---------------------------------------------------------------------------------------
-template <int TX>
-struct SideTab {
-  char* tb[P3D_MAXRUN][TX];     // address of logical row 0 of line t for run g (may point before the block)
-  long long psb[P3D_MAXRUN];    // row pitch in bytes
-};
-
-template <int TX, int NT, int ESZ>
-__device__ __forceinline__ void build_side(const FastSide& sd, SideTab<TX>& tab, unsigned char* rowseg, int nrows,
-                                           int nlogical, int mirror_nfft, int a0, int b, int c) {
-  const int tid = threadIdx.x;
-  for (int i = tid; i < sd.nrun * TX; i += NT) {
-    const int g = i / TX, t = i - g * TX;
-    const FastRun& r = sd.run[g];
-    const long long off = (long long)(a0 + t) * r.sa + (long long)b * r.sb + (long long)c * r.sc - (long long)r.kstart * r.ps;
-    tab.tb[g][t] = (char*)r.base + off * ESZ;
-    if (t == 0) tab.psb[g] = r.ps * ESZ;
-  }
-  for (int row = tid; row < nrows; row += NT) {
-    int k = row;
-    if (mirror_nfft && row >= nlogical) k = mirror_nfft - row;
-    int g = 0xFF;
-    for (int i = 0; i < sd.nrun; i++) {
-      const int ks = sd.run[i].kstart;
-      if (k >= ks && k < ks + sd.run[i].len) g = i;
-    }
-    rowseg[row] = (unsigned char)g;
-  }
-}
-
-template <typename T2, int TX>
-__device__ __forceinline__ T2 load_row(const SideTab<TX>& tab, const unsigned char* rowseg, int row, int k, int t, bool live) {
-  const int g = rowseg[row];
-  T2 v = T2{0, 0};
-  if (live && g != 0xFF) v = ldg_stream(reinterpret_cast<const T2*>(tab.tb[g][t] + (long long)k * tab.psb[g]));
-  return v;
-}
-template <typename T2, int TX>
-__device__ __forceinline__ void store_row(const SideTab<TX>& tab, const unsigned char* rowseg, int k, int t, bool live, T2 v) {
-  const int g = rowseg[k];
-  if (live && g != 0xFF) stg_stream(reinterpret_cast<T2*>(tab.tb[g][t] + (long long)k * tab.psb[g]), v);
-}
-
-// ---------------------------------------------------------------------------------------
 // passes over the shared-memory tile
 // ---------------------------------------------------------------------------------------
 // digit reversal: kappa = q1 + R1*q2 + ... (digits of passes 1..L-1)  ->  block index of the last pass
@@ -301,10 +256,47 @@ __device__ __forceinline__ void last_bfly(const typename Cx<T>::type* s, int kap
 
 // ---------------------------------------------------------------------------------------
 // c2c stage kernel (Y and Z stages, forward/backward, DCT-I by even extension)
+//
+// Persistent CTAs: each walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  While the row
+// table of the current tile is built, the rows of the NEXT tile of this CTA are prefetched
+// into L2, so that tile's pass-1 loads find their data on chip and HBM stays busy while the
+// SM computes.
 // ---------------------------------------------------------------------------------------
-template <int TX> struct CShared {
-  SideTab<TX> in, out;
-};
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// run index of every FFT row on one side (0xFF: row not stored -> zero / dropped); tile independent
+template <int NT>
+__device__ __forceinline__ void build_rowrun(const FastSide& sd, unsigned char* rowrun, int nrows, int nlogical,
+                                             int mirror_nfft) {
+  for (int row = threadIdx.x; row < nrows; row += NT) {
+    int k = row;
+    if (mirror_nfft && row >= nlogical) k = mirror_nfft - row;
+    int g = 0xFF;
+    for (int i = 0; i < sd.nrun; i++) {
+      const int ks = sd.run[i].kstart;
+      if (k >= ks && k < ks + sd.run[i].len) g = i;
+    }
+    rowrun[row] = (unsigned char)g;
+  }
+}
+
+// byte offset of (logical row k, first line of a-tile ta, b, c) inside run r
+template <int ESZ>
+__device__ __forceinline__ long long run_offset(const FastRun& r, int k, int ta, int b, int c) {
+  const int i = k - r.kstart;
+  const long long ro = r.kw > 1 ? (long long)(i / r.kw) * r.psh + (long long)(i % r.kw) * r.ps : (long long)i * r.ps;
+  return (ro + (long long)ta * r.sat + (long long)b * r.sb + (long long)c * r.sc) * ESZ;
+}
+
+struct TileIdx { int ta, b, c; };
+__device__ __forceinline__ TileIdx tile_decode(long long tile, int tiles_a, int nb) {
+  TileIdx x;
+  x.ta = (int)(tile % tiles_a);
+  const long long r = tile / tiles_a;
+  x.b = (int)(r % nb);
+  x.c = (int)(r / nb);
+  return x;
+}
 
 template <typename T, int N, bool SWAP>
 __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
@@ -317,64 +309,92 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
   static_assert(NT % TX == 0, "t must be constant per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T2* s = reinterpret_cast<T2*>(smem_raw);
-  CShared<TX>* sh = reinterpret_cast<CShared<TX>*>(smem_raw + sizeof(T2) * N * TX);
-  unsigned char* rs_in = reinterpret_cast<unsigned char*>(sh + 1);
-  unsigned char* rs_out = rs_in + N;
+  char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * N * TX);     // [N], in side then out side
+  unsigned char* rr_in = reinterpret_cast<unsigned char*>(rowptr + N);
+  unsigned char* rr_out = rr_in + N;
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
 
   const int tiles_a = (st.na + TX - 1) / TX;
-  const int ta = blockIdx.x % tiles_a, b = blockIdx.x / tiles_a, c = blockIdx.y;
-  const int a0 = ta * TX;
+  const long long ntiles = (long long)tiles_a * st.nb * st.nc;
   const int t = threadIdx.x % TX;
-  const bool live = a0 + t < st.na;
+  const long long lin = (long long)t * st.in.run[0].sa * (long long)sizeof(T2);     // line offsets inside a tile
+  const long long lout = (long long)t * st.out.run[0].sa * (long long)sizeof(T2);
 
-  build_side<TX, NT, sizeof(T2)>(st.in, sh->in, rs_in, N, st.n, st.mirror ? N : 0, a0, b, c);
-  build_side<TX, NT, sizeof(T2)>(st.out, sh->out, rs_out, N, N, 0, a0, b, c);
+  build_rowrun<NT>(st.in, rr_in, N, st.n, st.mirror ? N : 0);
+  build_rowrun<NT>(st.out, rr_out, N, N, 0);
   __syncthreads();
 
-  // ---- pass 1: global -> registers -> shared -------------------------------------------
-  {
-    constexpr int R = S::r(0), M = S::m(0), ITEMS = M * TX;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const TileIdx ti = tile_decode(tile, tiles_a, st.nb);
+    const bool live = ti.ta * TX + t < st.na;
+    const long long nxt = tile + gridDim.x;
+    const bool has_next = nxt < ntiles;
+    const TileIdx tn = tile_decode(has_next ? nxt : tile, tiles_a, st.nb);
+    // ---- input row table of this tile; L2 prefetch of the next one -------------------------
+    for (int row = threadIdx.x; row < N; row += NT) {
+      const int g = rr_in[row];
+      char* p = nullptr;
+      if (g != 0xFF) {
+        const FastRun& r = st.in.run[g];
+        const int k = (st.mirror && row >= st.n) ? N - row : row;
+        p = (char*)r.base + run_offset<sizeof(T2)>(r, k, ti.ta, ti.b, ti.c);
+        if (has_next && k == row) prefetch_l2((char*)r.base + run_offset<sizeof(T2)>(r, k, tn.ta, tn.b, tn.c));
+      }
+      rowptr[row] = p;
+    }
+    __syncthreads();
+    // ---- pass 1: global -> registers -> shared ---------------------------------------------
+    {
+      constexpr int R = S::r(0), M = S::m(0), ITEMS = M * TX;
 #pragma unroll
-    for (int w0 = 0; w0 < ITEMS; w0 += NT) {
-      const int w = w0 + threadIdx.x;
-      if (ITEMS % NT == 0 || w < ITEMS) {
-        const int u = w / TX;
-        T2 v[R];
+      for (int w0 = 0; w0 < ITEMS; w0 += NT) {
+        const int w = w0 + threadIdx.x;
+        if (ITEMS % NT == 0 || w < ITEMS) {
+          const int u = w / TX;
+          T2 v[R];
 #pragma unroll
-        for (int p = 0; p < R; p++) {
-          const int row = u + p * M;
-          const int k = (st.mirror && row >= st.n) ? N - row : row;
-          v[p] = load_row<T2, TX>(sh->in, rs_in, row, k, t, live);
-          if (SWAP) v[p] = cswap(v[p]);
+          for (int p = 0; p < R; p++) {
+            const char* rp = rowptr[u + p * M];
+            v[p] = (live && rp) ? ldg_stream(reinterpret_cast<const T2*>(rp + lin)) : T2{0, 0};
+            if (SWAP) v[p] = cswap(v[p]);
+          }
+          Bfly<T, R>::run(v);
+          twiddle_store<T, S, 0, TX, SWZ>(v, s, tw, u, u, t);
         }
-        Bfly<T, R>::run(v);
-        twiddle_store<T, S, 0, TX, SWZ>(v, s, tw, u, u, t);
       }
     }
-  }
-  __syncthreads();
-  mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
-  // ---- pass L: shared -> registers -> global -------------------------------------------
-  {
-    constexpr int RL = S::r(L - 1), ML = N / RL, ITEMS = ML * TX;
+    __syncthreads();
+    // ---- output row table (the input one is dead now) ---------------------------------------
+    for (int row = threadIdx.x; row < N; row += NT) {
+      const int g = rr_out[row];
+      char* p = nullptr;
+      if (g != 0xFF) p = (char*)st.out.run[g].base + run_offset<sizeof(T2)>(st.out.run[g], row, ti.ta, ti.b, ti.c);
+      rowptr[row] = p;
+    }
+    if constexpr (L == 2) __syncthreads();
+    mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
+    // ---- pass L: shared -> registers -> global ----------------------------------------------
+    {
+      constexpr int RL = S::r(L - 1), ML = N / RL, ITEMS = ML * TX;
 #pragma unroll 1
-    for (int w = threadIdx.x; w < ITEMS; w += NT) {
-      const int kappa = w / TX;
-      T2 v[RL];
-      last_bfly<T, S, TX, SWZ>(s, kappa, t, v);
+      for (int w = threadIdx.x; w < ITEMS; w += NT) {
+        const int kappa = w / TX;
+        T2 v[RL];
+        last_bfly<T, S, TX, SWZ>(s, kappa, t, v);
 #pragma unroll
-      for (int q = 0; q < RL; q++) {
-        T2 o = SWAP ? cswap(v[q]) : v[q];
-        store_row<T2, TX>(sh->out, rs_out, kappa + q * ML, t, live, o);
+        for (int q = 0; q < RL; q++) {
+          char* rp = rowptr[kappa + q * ML];
+          if (live && rp) stg_stream(reinterpret_cast<T2*>(rp + lout), SWAP ? cswap(v[q]) : v[q]);
+        }
       }
     }
+    __syncthreads();      // tile buffer and row table are reused by the next tile
   }
 }
 
 template <typename T, int N> constexpr size_t cstage_smem() {
   using T2 = typename Cx<T>::type;
-  return sizeof(T2) * N * CCfg<T, N>::TX + sizeof(CShared<CCfg<T, N>::TX>) + 2 * N;
+  return sizeof(T2) * N * CCfg<T, N>::TX + sizeof(char*) * N + 2 * N;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -402,85 +422,112 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
   static_assert(NT % TX == 0, "t must be constant per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T2* s = reinterpret_cast<T2*>(smem_raw);
-  SideTab<TX>* tab = reinterpret_cast<SideTab<TX>*>(smem_raw + sizeof(T2) * H * TX);
-  unsigned char* rs_out = reinterpret_cast<unsigned char*>(tab + 1);
+  char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * H * TX);      // [H+1] output rows
+  unsigned char* rr_out = reinterpret_cast<unsigned char*>(rowptr + H + 1);
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
   const T2* __restrict__ wx = tw + S::twtotal();
 
   const int tiles_a = (st.na + TX - 1) / TX;
-  const int ta = blockIdx.x % tiles_a, b = blockIdx.x / tiles_a, c = blockIdx.y;
-  const int a0 = ta * TX;
+  const long long ntiles = (long long)tiles_a * st.nb * st.nc;
   const int t = threadIdx.x % TX;
-  const bool live = a0 + t < st.na;
-
-  build_side<TX, NT, sizeof(T2)>(st.out, *tab, rs_out, H + 1, H + 1, 0, a0, b, c);
   const FastRun& rin = st.in.run[0];
-  const T2* line = reinterpret_cast<const T2*>(reinterpret_cast<const T*>(rin.base) + (long long)(a0 + t) * rin.sa +
-                                               (long long)b * rin.sb + (long long)c * rin.sc);
-  // ---- pass 1: packed real pairs -> registers -> shared -----------------------------------
-  {
-    constexpr int R = S::r(0), M = S::m(0), ITEMS = M * TX;
-#pragma unroll
-    for (int w0 = 0; w0 < ITEMS; w0 += NT) {
-      const int w = w0 + threadIdx.x;
-      if (ITEMS % NT == 0 || w < ITEMS) {
-        const int u = w / TX;
-        T2 v[R];
-#pragma unroll
-        for (int p = 0; p < R; p++) v[p] = live ? ldg_stream(line + u + p * M) : T2{0, 0};
-        Bfly<T, R>::run(v);
-        twiddle_store<T, S, 0, TX, SWZ>(v, s, tw, u, u, t);
-      }
-    }
-  }
+  const long long lout = (long long)t * st.out.run[0].sa * (long long)sizeof(T2);
+
+  build_rowrun<NT>(st.out, rr_out, H + 1, H + 1, 0);
   __syncthreads();
-  mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
-  // ---- pass L on butterfly pairs (kappa, ML-kappa) + Hermitian post-processing -----------
-  {
-    constexpr int RL = S::r(L - 1), ML = H / RL, ITEMS = (ML / 2) * TX;
-    static_assert(ML >= 2, "last pass needs at least two butterflies per line");
-#pragma unroll 1
-    for (int w = threadIdx.x; w < ITEMS; w += NT) {
-      const int i = w / TX;
-      T2 za[RL], zb[RL];
-      last_bfly<T, S, TX, SWZ>(s, i == 0 ? 0 : i, t, za);
-      last_bfly<T, S, TX, SWZ>(s, i == 0 ? ML / 2 : ML - i, t, zb);
-      if (i != 0) {
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const TileIdx ti = tile_decode(tile, tiles_a, st.nb);
+    const bool live = ti.ta * TX + t < st.na;
+    const T2* line = reinterpret_cast<const T2*>(reinterpret_cast<const T*>(rin.base) + (long long)(ti.ta * TX + t) * rin.sa +
+                                                 (long long)ti.b * rin.sb + (long long)ti.c * rin.sc);
+    // ---- output row table; L2 prefetch of the real lines of this CTA's next tile ------------
+    for (int row = threadIdx.x; row <= H; row += NT) {
+      const int g = rr_out[row];
+      char* p = nullptr;
+      if (g != 0xFF) p = (char*)st.out.run[g].base + run_offset<sizeof(T2)>(st.out.run[g], row, ti.ta, ti.b, ti.c);
+      rowptr[row] = p;
+    }
+    if (tile + gridDim.x < ntiles) {
+      const TileIdx tn = tile_decode(tile + gridDim.x, tiles_a, st.nb);
+      constexpr int PER_LINE = (int)(H * sizeof(T2) / 128);          // 128-byte lines per real line
+      for (int i = threadIdx.x; i < PER_LINE * TX; i += NT) {
+        const int l = i / PER_LINE, j = i - l * PER_LINE;
+        if (tn.ta * TX + l < st.na)
+          prefetch_l2(reinterpret_cast<const char*>(reinterpret_cast<const T*>(rin.base) + (long long)(tn.ta * TX + l) * rin.sa +
+                                                    (long long)tn.b * rin.sb + (long long)tn.c * rin.sc) + j * 128);
+      }
+    }
+    // ---- pass 1: packed real pairs -> registers -> shared ------------------------------------
+    {
+      constexpr int R = S::r(0), M = S::m(0), ITEMS = M * TX;
 #pragma unroll
-        for (int q = 0; q < RL; q++) {
-          const int k = i + q * ML;
-          T2 xk, xm;
-          r2c_combine<T>(za[q], zb[RL - 1 - q], __ldg(wx + k), xk, xm);
-          store_row<T2, TX>(*tab, rs_out, k, t, live, xk);
-          store_row<T2, TX>(*tab, rs_out, H - k, t, live, xm);
-        }
-      } else {
-        store_row<T2, TX>(*tab, rs_out, 0, t, live, T2{za[0].x + za[0].y, 0});
-        store_row<T2, TX>(*tab, rs_out, H, t, live, T2{za[0].x - za[0].y, 0});
+      for (int w0 = 0; w0 < ITEMS; w0 += NT) {
+        const int w = w0 + threadIdx.x;
+        if (ITEMS % NT == 0 || w < ITEMS) {
+          const int u = w / TX;
+          T2 v[R];
 #pragma unroll
-        for (int q = 1; q <= RL / 2; q++) {          // kappa = 0: k = q*ML pairs with (RL-q)*ML
-          const int k = q * ML;
-          T2 xk, xm;
-          r2c_combine<T>(za[q], za[RL - q], __ldg(wx + k), xk, xm);
-          store_row<T2, TX>(*tab, rs_out, k, t, live, xk);
-          if (q != RL / 2) store_row<T2, TX>(*tab, rs_out, H - k, t, live, xm);
-        }
-#pragma unroll
-        for (int q = 0; q < RL / 2; q++) {           // kappa = ML/2: k pairs inside the butterfly
-          const int k = ML / 2 + q * ML;
-          T2 xk, xm;
-          r2c_combine<T>(zb[q], zb[RL - 1 - q], __ldg(wx + k), xk, xm);
-          store_row<T2, TX>(*tab, rs_out, k, t, live, xk);
-          store_row<T2, TX>(*tab, rs_out, H - k, t, live, xm);
+          for (int p = 0; p < R; p++) v[p] = live ? ldg_stream(line + u + p * M) : T2{0, 0};
+          Bfly<T, R>::run(v);
+          twiddle_store<T, S, 0, TX, SWZ>(v, s, tw, u, u, t);
         }
       }
     }
+    __syncthreads();
+    mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
+    // ---- pass L on butterfly pairs (kappa, ML-kappa) + Hermitian post-processing -------------
+    {
+      constexpr int RL = S::r(L - 1), ML = H / RL, ITEMS = (ML / 2) * TX;
+      static_assert(ML >= 2, "last pass needs at least two butterflies per line");
+      auto put = [&](int k, T2 v) {
+        char* rp = rowptr[k];
+        if (live && rp) stg_stream(reinterpret_cast<T2*>(rp + lout), v);
+      };
+#pragma unroll 1
+      for (int w = threadIdx.x; w < ITEMS; w += NT) {
+        const int i = w / TX;
+        T2 za[RL], zb[RL];
+        last_bfly<T, S, TX, SWZ>(s, i == 0 ? 0 : i, t, za);
+        last_bfly<T, S, TX, SWZ>(s, i == 0 ? ML / 2 : ML - i, t, zb);
+        if (i != 0) {
+#pragma unroll
+          for (int q = 0; q < RL; q++) {
+            const int k = i + q * ML;
+            T2 xk, xm;
+            r2c_combine<T>(za[q], zb[RL - 1 - q], __ldg(wx + k), xk, xm);
+            put(k, xk);
+            put(H - k, xm);
+          }
+        } else {
+          put(0, T2{za[0].x + za[0].y, 0});
+          put(H, T2{za[0].x - za[0].y, 0});
+#pragma unroll
+          for (int q = 1; q <= RL / 2; q++) {          // kappa = 0: k = q*ML pairs with (RL-q)*ML
+            const int k = q * ML;
+            T2 xk, xm;
+            r2c_combine<T>(za[q], za[RL - q], __ldg(wx + k), xk, xm);
+            put(k, xk);
+            if (q != RL / 2) put(H - k, xm);
+          }
+#pragma unroll
+          for (int q = 0; q < RL / 2; q++) {           // kappa = ML/2: k pairs inside the butterfly
+            const int k = ML / 2 + q * ML;
+            T2 xk, xm;
+            r2c_combine<T>(zb[q], zb[RL - 1 - q], __ldg(wx + k), xk, xm);
+            put(k, xk);
+            put(H - k, xm);
+          }
+        }
+      }
+    }
+    __syncthreads();      // tile buffer and row table are reused by the next tile
   }
 }
 
 template <typename T, int H> constexpr size_t xstage_smem() {
   using T2 = typename Cx<T>::type;
-  return sizeof(T2) * H * XCfg<T, H>::TX + sizeof(SideTab<XCfg<T, H>::TX>) + (H + 1 + 15) / 16 * 16;
+  return sizeof(T2) * H * XCfg<T, H>::TX + sizeof(char*) * (H + 1) + (H + 1 + 15) / 16 * 16;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -510,82 +557,101 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
   static_assert(NT % TX == 0, "t must be constant per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T2* s = reinterpret_cast<T2*>(smem_raw);
-  SideTab<TX>* tab = reinterpret_cast<SideTab<TX>*>(smem_raw + sizeof(T2) * H * TX);
-  unsigned char* rs_in = reinterpret_cast<unsigned char*>(tab + 1);
+  char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * H * TX);      // [H+1] input rows
+  unsigned char* rr_in = reinterpret_cast<unsigned char*>(rowptr + H + 1);
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
   const T2* __restrict__ wx = tw + S::twtotal();
 
   const int tiles_a = (st.na + TX - 1) / TX;
-  const int ta = blockIdx.x % tiles_a, b = blockIdx.x / tiles_a, c = blockIdx.y;
-  const int a0 = ta * TX;
+  const long long ntiles = (long long)tiles_a * st.nb * st.nc;
   const int t = threadIdx.x % TX;
-  const bool live = a0 + t < st.na;
+  const long long sab = st.in.run[0].sa * (long long)sizeof(T2);
+  const long long lin = (long long)t * sab;
+  const FastRun& ro = st.out.run[0];
 
-  build_side<TX, NT, sizeof(T2)>(st.in, *tab, rs_in, H + 1, H + 1, 0, a0, b, c);
+  build_rowrun<NT>(st.in, rr_in, H + 1, H + 1, 0);
   __syncthreads();
-  // ---- pass 1 on butterfly pairs (u, M-u) with the Hermitian pre-processing --------------
-  {
-    constexpr int R = S::r(0), M = S::m(0), ITEMS = (M / 2) * TX;
-    static_assert(M >= 2, "first pass needs at least two butterflies per line");
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const TileIdx ti = tile_decode(tile, tiles_a, st.nb);
+    const bool live = ti.ta * TX + t < st.na;
+    const long long nxt = tile + gridDim.x;
+    const bool has_next = nxt < ntiles;
+    const TileIdx tn = tile_decode(has_next ? nxt : tile, tiles_a, st.nb);
+    // ---- input row table; L2 prefetch of the next tile (row k on line k % TX: every 64 bytes) --
+    for (int row = threadIdx.x; row <= H; row += NT) {
+      const int g = rr_in[row];
+      char* p = nullptr;
+      if (g != 0xFF) {
+        const FastRun& r = st.in.run[g];
+        p = (char*)r.base + run_offset<sizeof(T2)>(r, row, ti.ta, ti.b, ti.c);
+        if (has_next && tn.ta * TX + (row % TX) < st.na)
+          prefetch_l2((char*)r.base + run_offset<sizeof(T2)>(r, row, tn.ta, tn.b, tn.c) + (row % TX) * sab);
+      }
+      rowptr[row] = p;
+    }
+    __syncthreads();
+    auto get = [&](int k) -> T2 {
+      const char* rp = rowptr[k];
+      return (live && rp) ? ldg_stream(reinterpret_cast<const T2*>(rp + lin)) : T2{0, 0};
+    };
+    // ---- pass 1 on butterfly pairs (u, M-u) with the Hermitian pre-processing ----------------
+    {
+      constexpr int R = S::r(0), M = S::m(0), ITEMS = (M / 2) * TX;
+      static_assert(M >= 2, "first pass needs at least two butterflies per line");
 #pragma unroll 1
-    for (int w = threadIdx.x; w < ITEMS; w += NT) {
-      const int i = w / TX;
-      T2 za[R], zb[R];
-      if (i != 0) {
+      for (int w = threadIdx.x; w < ITEMS; w += NT) {
+        const int i = w / TX;
+        T2 za[R], zb[R];
+        if (i != 0) {
+          T2 xk[R], xm[R];
 #pragma unroll
-        for (int p = 0; p < R; p++) {
-          const int k = i + p * M;
-          T2 xk = load_row<T2, TX>(*tab, rs_in, k, k, t, live);
-          T2 xm = load_row<T2, TX>(*tab, rs_in, H - k, H - k, t, live);
-          c2r_combine<T>(xk, xm, __ldg(wx + k), za[p], zb[R - 1 - p]);
+          for (int p = 0; p < R; p++) { xk[p] = get(i + p * M); xm[p] = get(H - i - p * M); }
+#pragma unroll
+          for (int p = 0; p < R; p++) c2r_combine<T>(xk[p], xm[p], __ldg(wx + i + p * M), za[p], zb[R - 1 - p]);
+        } else {
+          T2 x0 = get(0), xh = get(H);
+          za[0] = cswap(T2{x0.x + xh.x, x0.x - xh.x});
+#pragma unroll
+          for (int p = 1; p <= R / 2; p++) {
+            const int k = p * M;
+            T2 zk, zm;
+            c2r_combine<T>(get(k), get(H - k), __ldg(wx + k), zk, zm);
+            za[p] = zk;
+            if (p != R / 2) za[R - p] = zm;
+          }
+#pragma unroll
+          for (int p = 0; p < R / 2; p++) {
+            const int k = M / 2 + p * M;
+            c2r_combine<T>(get(k), get(H - k), __ldg(wx + k), zb[p], zb[R - 1 - p]);
+          }
         }
-      } else {
-        T2 x0 = load_row<T2, TX>(*tab, rs_in, 0, 0, t, live);
-        T2 xh = load_row<T2, TX>(*tab, rs_in, H, H, t, live);
-        za[0] = cswap(T2{x0.x + xh.x, x0.x - xh.x});
+        const int ua = i, ub = (i == 0) ? M / 2 : M - i;
+        Bfly<T, R>::run(za);
+        twiddle_store<T, S, 0, TX, SWZ>(za, s, tw, ua, ua, t);
+        Bfly<T, R>::run(zb);
+        twiddle_store<T, S, 0, TX, SWZ>(zb, s, tw, ub, ub, t);
+      }
+    }
+    __syncthreads();
+    mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
+    // ---- pass L: shared -> registers -> packed real pairs ---------------------------------------
+    {
+      T2* line = reinterpret_cast<T2*>(const_cast<T*>(reinterpret_cast<const T*>(ro.base)) + (long long)(ti.ta * TX + t) * ro.sa +
+                                       (long long)ti.b * ro.sb + (long long)ti.c * ro.sc);
+      constexpr int RL = S::r(L - 1), ML = H / RL, ITEMS = ML * TX;
+#pragma unroll 1
+      for (int w = threadIdx.x; w < ITEMS; w += NT) {
+        const int kappa = w / TX;
+        T2 v[RL];
+        last_bfly<T, S, TX, SWZ>(s, kappa, t, v);
+        if (live) {
 #pragma unroll
-        for (int p = 1; p <= R / 2; p++) {
-          const int k = p * M;
-          T2 xk = load_row<T2, TX>(*tab, rs_in, k, k, t, live);
-          T2 xm = load_row<T2, TX>(*tab, rs_in, H - k, H - k, t, live);
-          T2 zk, zm;
-          c2r_combine<T>(xk, xm, __ldg(wx + k), zk, zm);
-          za[p] = zk;
-          if (p != R / 2) za[R - p] = zm;
-        }
-#pragma unroll
-        for (int p = 0; p < R / 2; p++) {
-          const int k = M / 2 + p * M;
-          T2 xk = load_row<T2, TX>(*tab, rs_in, k, k, t, live);
-          T2 xm = load_row<T2, TX>(*tab, rs_in, H - k, H - k, t, live);
-          c2r_combine<T>(xk, xm, __ldg(wx + k), zb[p], zb[R - 1 - p]);
+          for (int q = 0; q < RL; q++) stg_stream(line + kappa + q * ML, cswap(v[q]));
         }
       }
-      const int ua = i, ub = (i == 0) ? M / 2 : M - i;
-      Bfly<T, R>::run(za);
-      twiddle_store<T, S, 0, TX, SWZ>(za, s, tw, ua, ua, t);
-      Bfly<T, R>::run(zb);
-      twiddle_store<T, S, 0, TX, SWZ>(zb, s, tw, ub, ub, t);
     }
-  }
-  __syncthreads();
-  mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
-  // ---- pass L: shared -> registers -> packed real pairs -------------------------------------
-  {
-    const FastRun& ro = st.out.run[0];
-    T2* line = reinterpret_cast<T2*>(const_cast<T*>(reinterpret_cast<const T*>(ro.base)) + (long long)(a0 + t) * ro.sa +
-                                     (long long)b * ro.sb + (long long)c * ro.sc);
-    constexpr int RL = S::r(L - 1), ML = H / RL, ITEMS = ML * TX;
-#pragma unroll 1
-    for (int w = threadIdx.x; w < ITEMS; w += NT) {
-      const int kappa = w / TX;
-      T2 v[RL];
-      last_bfly<T, S, TX, SWZ>(s, kappa, t, v);
-      if (live) {
-#pragma unroll
-        for (int q = 0; q < RL; q++) stg_stream(line + kappa + q * ML, cswap(v[q]));
-      }
-    }
+    __syncthreads();      // tile buffer and row table are reused by the next tile
   }
 }
 #endif  // __CUDACC__

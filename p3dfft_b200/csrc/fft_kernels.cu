@@ -59,6 +59,14 @@ template <typename T, typename T2> __device__ __forceinline__ void bfly3(T2& v0,
   v0 = cadd(v0, t1); v1 = cadd(t2, t3); v2 = csub(t2, t3);
 }
 
+// two-level strides of the tile-blocked buffers (stage.h)
+__device__ __forceinline__ int64_t seg_row_off(const P3dSeg& sg, int i) {
+  return sg.kw > 1 ? (int64_t)(i / sg.kw) * sg.psh + (int64_t)(i % sg.kw) * sg.ps : (int64_t)i * sg.ps;
+}
+__device__ __forceinline__ int64_t seg_line_off(const P3dSeg& sg, int a) {
+  return sg.aw > 1 ? (int64_t)(a / sg.aw) * sg.sah + (int64_t)(a % sg.aw) * sg.sa : (int64_t)a * sg.sa;
+}
+
 struct SmemMap {
   int layx, tile, ldl;
   __device__ __forceinline__ int operator()(int k, int t) const {
@@ -206,14 +214,14 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ P3dS
     const int shift = st.in.logical - st.in.cnt;
     for (int g = 0; g < st.in.nseg; g++) {
       const P3dSeg& sg = st.in.seg[g];
-      const int64_t lbase = (int64_t)b * sg.sb + (int64_t)c * sg.sc + (int64_t)a0 * sg.sa;
+      const int64_t lbase = (int64_t)b * sg.sb + (int64_t)c * sg.sc;
       const int tot = sg.len * lines;
       for (int w = threadIdx.x; w < tot; w += blockDim.x) {
         int t, i;
         if (sg.ps == 1) { t = w / sg.len; i = w - t * sg.len; } else { i = w / lines; t = w - i * lines; }
         const int sidx = sg.start + i;
         const int k = sidx < st.in.h1 ? sidx : sidx + shift;
-        const int64_t addr = lbase + (int64_t)i * sg.ps + (int64_t)t * sg.sa;
+        const int64_t addr = lbase + seg_row_off(sg, i) + seg_line_off(sg, a0 + t);
         if (KIND == P3D_R2C) {
           T v = reinterpret_cast<const T*>(sg.base)[addr];
           s[sm(k, t)] = T2{v, 0};
@@ -247,7 +255,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ P3dS
     const T scale = (T)st.scale;
     for (int g = 0; g < st.out.nseg; g++) {
       const P3dSeg& sg = st.out.seg[g];
-      const int64_t lbase = (int64_t)b * sg.sb + (int64_t)c * sg.sc + (int64_t)a0 * sg.sa;
+      const int64_t lbase = (int64_t)b * sg.sb + (int64_t)c * sg.sc;
       const int tot = sg.len * lines;
       for (int w = threadIdx.x; w < tot; w += blockDim.x) {
         int t, i;
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ P3dS
         if (KIND == P3D_DST1) k += 1;
         const int pos = (KIND == P3D_NOOP) ? k : digit_rev(k, nfft, st.nfac, st.fac);
         T2 v = s[sm(pos, t)];
-        const int64_t addr = lbase + (int64_t)i * sg.ps + (int64_t)t * sg.sa;
+        const int64_t addr = lbase + seg_row_off(sg, i) + seg_line_off(sg, a0 + t);
         if (KIND == P3D_C2R) {
           reinterpret_cast<T*>(sg.base)[addr] = v.x * scale;
         } else {

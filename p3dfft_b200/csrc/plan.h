@@ -120,12 +120,24 @@ struct Decomp {
     return true;
   }
 
-  // complex elements each work buffer must hold for nv variables
-  long long work_elems(int nv) const {
-    long long m = (long long)nxhpc * jisize * kjsize;
-    m = std::max(m, (long long)iisize * ny * kjsize);
-    m = std::max(m, (long long)iisize * nyc * kjsize);
-    m = std::max(m, (long long)iisize * jjsize * nz);
+  // complex elements each work buffer must hold for nv variables.  W = lines per 64-byte tile
+  // row of the blocked internal layouts (0: the reference's plain layouts)
+  long long work_elems(int nv, int W = 0) const {
+    long long m;
+    if (W <= 0) {
+      m = (long long)nxhpc * jisize * kjsize;
+      m = std::max(m, (long long)iisize * ny * kjsize);
+      m = std::max(m, (long long)iisize * nyc * kjsize);
+      m = std::max(m, (long long)iisize * jjsize * nz);
+    } else {
+      long long nxb_all = 0;
+      for (int p = 0; p < iproc; p++) nxb_all += (ii.sz[p] + W - 1) / W;
+      const long long nxb = (iisize + W - 1) / W;
+      m = nxb_all * W * jisize * kjsize;                         // X side of the X<->Y buffer
+      m = std::max(m, nxb * W * (long long)ny * kjsize);         // Y side of it
+      m = std::max(m, nxb * W * (long long)nyc * kjsize);        // Y side of the Y<->Z buffer
+      m = std::max(m, nxb * W * (long long)jjsize * nz);         // Z side of it
+    }
     return std::max<long long>(m, 1) * nv;
   }
 };
@@ -189,6 +201,16 @@ inline void add_seg(P3dSide& sd, int buf, int peer, long long off, int start, in
   P3dSeg& g = sd.seg[sd.nseg++];
   g.base = nullptr; g.buf = buf; g.peer = peer; g.off = off; g.start = start; g.len = len;
   g.ps = ps; g.sa = sa; g.sb = sb; g.sc = sc;
+  g.kw = 0; g.aw = 0; g.psh = 0; g.sah = 0;
+}
+
+// segment of a tile-blocked buffer: rows blocked by kw (stride psh) and/or lines blocked by aw (stride sah)
+inline void add_seg_blk(P3dSide& sd, int buf, int peer, long long off, int start, int len, long long ps, int kw,
+                        long long psh, long long sa, int aw, long long sah, long long sb, long long sc) {
+  if (len <= 0) return;
+  add_seg(sd, buf, peer, off, start, len, ps, sa, sb, sc);
+  P3dSeg& g = sd.seg[sd.nseg - 1];
+  g.kw = kw; g.psh = psh; g.aw = aw; g.sah = sah;
 }
 
 // Forward: X r2c -> T1(row) -> Y c2c -> T2(col) -> Z.   ftran.F90:489-780.
@@ -200,8 +222,19 @@ inline void add_seg(P3dSide& sd, int buf, int peer, long long off, int start, in
 // setup.F90:401-423): a stage never writes a buffer it reads, every non-self block of an
 // exchange is written into the send buffer `snd`, and the rank's own block is written
 // straight to its landing place in the receive buffer `rcv`.
+//
+// W > 0 selects the B200 layouts of the internal buffers: W = 64 bytes / sizeof(complex) lines
+// that are adjacent in x form one row of a kernel tile, and every buffer is ordered so that
+// the tile of the stage that READS it is contiguous in memory --
+//   X<->Y buffer (both directions)   [z][x/W][y][x%W]   Y-stage tile = (z, x/W), rows y
+//   Y->Z buffer (forward)            [x/W][y][z][x%W]   Z-stage tile = (x/W, y), rows z
+//   Z->Y buffer (backward)           [z][x/W][y][x%W]   Y-stage tile = (z, x/W), rows y
+// per peer block (blocks padded in x to a multiple of W).  The exchange still moves one
+// contiguous block per peer; only the order of the elements inside a block differs from the
+// reference's pack buffers, which no caller can observe.  W = 0 keeps the reference's plain
+// layouts and its exact alltoallv tables (setup.F90:481-518).
 inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, int nv,
-                                long long dim_real, long long dim_cplx) {
+                                long long dim_real, long long dim_cplx, int W = 0) {
   TransformPlan tp;
   const int M1 = d.iproc, M2 = d.jproc;
   if (M1 > P3D_MAXSEG || M2 > P3D_MAXSEG) { tp.error = "processor grid dimension exceeds P3D_MAXSEG"; return tp; }
@@ -257,6 +290,126 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
   };
 
   P3dStage s;
+  if (W > 0) {
+    // ================= tile-blocked internal buffers =====================================
+    auto cdiv = [&](long long a) { return (a + W - 1) / W; };
+    const long long nxb = cdiv(ii);
+    // exchange whose per-peer element counts are given explicitly
+    auto push_exchange_cnt = [&](int comm, int npeer, int self, int timer, const std::vector<long long>& sc_,
+                                 const std::vector<long long>& rc_) {
+      Step st; st.is_exchange = true; P3dExchange& e = st.ex; memset(&e, 0, sizeof e);
+      e.comm = comm; e.npeer = npeer; e.self = self; e.sendbuf = snd; e.recvbuf = rcv; e.timer = timer;
+      long long so = 0, ro = 0;
+      for (int p = 0; p < npeer; p++) {
+        e.sndoff[p] = so; e.sndcnt[p] = nv * sc_[p]; so += e.sndcnt[p];
+        e.rcvoff[p] = ro; e.rcvcnt[p] = nv * rc_[p]; ro += e.rcvcnt[p];
+      }
+      tp.steps.push_back(st);
+    };
+    // ---- per-peer block sizes (elements per variable) --------------------------------------
+    std::vector<long long> xy_x(M1), xy_y(M1), yz_y(M2), yz_z(M2);
+    for (int p = 0; p < M1; p++) { xy_x[p] = kj * cdiv(d.ii.sz[p]) * ji * W; xy_y[p] = kj * nxb * d.ji.sz[p] * W; }
+    for (int p = 0; p < M2; p++) { yz_y[p] = nxb * d.jj.sz[p] * kj * W; yz_z[p] = nxb * jj * d.kj.sz[p] * W; }
+    auto offs = [&](const std::vector<long long>& v, int p) { long long o = 0; for (int q = 0; q < p; q++) o += nv * v[q]; return o; };
+    // X side of the X<->Y buffer: rows = x (blocked by W), lines = y, b = z.   [z][xb][y][xi] per peer block
+    auto xy_xside = [&](P3dSide& sd, bool send) {
+      for (int p = 0; p < M1; p++) {
+        const long long nxbp = cdiv(d.ii.sz[p]);
+        const bool self_redirect = send && M1 > 1 && p == d.ipid;
+        const int buf = send ? (self_redirect ? rcv : snd) : cur;
+        const long long off = self_redirect ? offs(xy_y, d.ipid) : offs(xy_x, p);
+        add_seg_blk(sd, buf, (send && !self_redirect && M1 > 1) ? p : -1, off, d.ii.st[p] - 1, d.ii.sz[p],
+                    1, W, ji * W, W, 0, 0, nxbp * ji * W, xy_x[p]);
+      }
+    };
+    // Y side of the X<->Y buffer: rows = y, lines = x (blocked by W), b = z
+    auto xy_yside = [&](P3dSide& sd, bool send) {
+      for (int q = 0; q < M1; q++) {
+        const long long nyq = d.ji.sz[q];
+        const bool self_redirect = send && M1 > 1 && q == d.ipid;
+        const int buf = send ? (self_redirect ? rcv : snd) : cur;
+        const long long off = self_redirect ? offs(xy_x, d.ipid) : offs(xy_y, q);
+        add_seg_blk(sd, buf, (send && !self_redirect && M1 > 1) ? q : -1, off, d.ji.st[q] - 1, (int)nyq,
+                    W, 0, 0, 1, W, nyq * W, nxb * nyq * W, xy_y[q]);
+      }
+    };
+    // Y side of the Y<->Z buffer.  fwd (Y writes): [xb][y][z][xi]; bwd (Y reads): [z][xb][y][xi]
+    auto yz_yside = [&](P3dSide& sd, bool send) {
+      for (int p = 0; p < M2; p++) {
+        const long long nyp = d.jj.sz[p];
+        const bool self_redirect = send && M2 > 1 && p == d.jpid;
+        const int buf = send ? (self_redirect ? rcv : snd) : cur;
+        const long long off = self_redirect ? offs(yz_z, d.jpid) : offs(yz_y, p);
+        if (send) add_seg_blk(sd, buf, (!self_redirect && M2 > 1) ? p : -1, off, d.jj.st[p] - 1, (int)nyp,
+                              kj * W, 0, 0, 1, W, nyp * kj * W, W, yz_y[p]);
+        else      add_seg_blk(sd, buf, -1, off, d.jj.st[p] - 1, (int)nyp,
+                              W, 0, 0, 1, W, nyp * W, nxb * nyp * W, yz_y[p]);
+      }
+    };
+    // Z side of the Y<->Z buffer.  fwd (Z reads): [xb][y][z][xi]; bwd (Z writes): [z][xb][y][xi]
+    auto yz_zside = [&](P3dSide& sd, bool send) {
+      for (int q = 0; q < M2; q++) {
+        const long long nzq = d.kj.sz[q];
+        const bool self_redirect = send && M2 > 1 && q == d.jpid;
+        const int buf = send ? (self_redirect ? rcv : snd) : cur;
+        const long long off = self_redirect ? offs(yz_y, d.jpid) : offs(yz_z, q);
+        if (send) add_seg_blk(sd, buf, (!self_redirect && M2 > 1) ? q : -1, off, d.kj.st[q] - 1, (int)nzq,
+                              nxb * jj * W, 0, 0, 1, W, jj * W, W, yz_z[q]);
+        else      add_seg_blk(sd, buf, -1, off, d.kj.st[q] - 1, (int)nzq,
+                              W, 0, 0, 1, W, jj * nzq * W, nzq * W, yz_z[q]);
+      }
+    };
+    if (!backward) {
+      stage_init(s, P3D_R2C, d.nx, (int)ji, (int)kj, nv, 5); s.layx = 1;
+      side_init(s.in, d.nx, d.nx, d.nx);
+      add_seg(s.in, P3D_BUF_USER_IN, -1, 0, 0, d.nx, 1, nx, nx * ji, dim_real);
+      side_init(s.out, d.nxhp, d.nxhpc, d.nxhpc);
+      rotate();
+      xy_xside(s.out, true);
+      push_stage(s);
+      if (M1 > 1) { push_exchange_cnt(0, M1, d.ipid, 1, xy_x, xy_y); cur = rcv; } else cur = snd;
+      stage_init(s, P3D_C2C_FWD, d.ny, (int)ii, (int)kj, nv, 7);
+      side_init(s.in, d.ny, d.ny, d.ny);
+      xy_yside(s.in, false);
+      side_init(s.out, d.ny, d.nyc, d.nycph);
+      rotate();
+      yz_yside(s.out, true);
+      push_stage(s);
+      if (M2 > 1) { push_exchange_cnt(1, M2, d.jpid, 2, yz_y, yz_z); cur = rcv; } else cur = snd;
+      stage_init(s, zkind, d.nz, (int)ii, (int)jj, nv, 8);
+      side_init(s.in, d.nz, d.nz, d.nz);
+      yz_zside(s.in, false);
+      side_init(s.out, d.nz, d.nzc, d.nzcph);
+      if (d.stride1) add_seg(s.out, P3D_BUF_USER_OUT, -1, 0, 0, d.nzc, 1, nzc * jj, nzc, dim_cplx);
+      else           add_seg(s.out, P3D_BUF_USER_OUT, -1, 0, 0, d.nzc, ii * jj, 1, ii, dim_cplx);
+      push_stage(s);
+    } else {
+      stage_init(s, zkind, d.nz, (int)ii, (int)jj, nv, 9);
+      side_init(s.in, d.nz, d.nzc, d.nzcph);
+      if (d.stride1) add_seg(s.in, P3D_BUF_USER_IN, -1, 0, 0, d.nzc, 1, nzc * jj, nzc, dim_cplx);
+      else           add_seg(s.in, P3D_BUF_USER_IN, -1, 0, 0, d.nzc, ii * jj, 1, ii, dim_cplx);
+      side_init(s.out, d.nz, d.nz, d.nz);
+      rotate();
+      yz_zside(s.out, true);
+      push_stage(s);
+      if (M2 > 1) { push_exchange_cnt(1, M2, d.jpid, 3, yz_z, yz_y); cur = rcv; } else cur = snd;
+      stage_init(s, P3D_C2C_BWD, d.ny, (int)ii, (int)kj, nv, 10);
+      side_init(s.in, d.ny, d.nyc, d.nycph);
+      yz_yside(s.in, false);
+      side_init(s.out, d.ny, d.ny, d.ny);
+      rotate();
+      xy_yside(s.out, true);
+      push_stage(s);
+      if (M1 > 1) { push_exchange_cnt(0, M1, d.ipid, 4, xy_y, xy_x); cur = rcv; } else cur = snd;
+      stage_init(s, P3D_C2R, d.nx, (int)ji, (int)kj, nv, 12); s.layx = 1;
+      side_init(s.in, d.nxhp, d.nxhpc, d.nxhpc);
+      xy_xside(s.in, false);
+      side_init(s.out, d.nx, d.nx, d.nx);
+      add_seg(s.out, P3D_BUF_USER_OUT, -1, 0, 0, d.nx, 1, nx, nx * ji, dim_real);
+      push_stage(s);
+    }
+    return tp;
+  }
   if (!backward) {
     // ---- K1: X r2c (+ X-prune, + pack for T1).
     // exec_f_r2c ftran.F90:530; fcomm1.F90:239-253; seg_copy_x ftran.F90:554

@@ -72,6 +72,11 @@ def test_decomp_errors(lib):
 
 
 def _run(lib, n, dims, cut, opf, opb, stride1=False, nv=1, dims_c=False):
+    for plain in (False, True):
+        _run_layout(lib, n, dims, cut, opf, opb, stride1, nv, dims_c, plain)
+
+
+def _run_layout(lib, n, dims, cut, opf, opb, stride1, nv, dims_c, plain):
     nx, ny, nz = n
     c = cut or (None, None, None)
     P = dims[0] * dims[1]
@@ -80,11 +85,11 @@ def _run(lib, n, dims, cut, opf, opb, stride1=False, nv=1, dims_c=False):
     ds = [po.Decomp(nx, ny, nz, dims, r, *c, stride1=stride1, dims_c=dims_c) for r in range(P)]
     plans, infos = [], []
     for r in range(P):
-        s, inf = lib.plan_steps(dims, nx, ny, nz, r, False, opf, nv, *c, stride1=stride1, dims_c=dims_c)
+        s, inf = lib.plan_steps(dims, nx, ny, nz, r, False, opf, nv, *c, stride1=stride1, dims_c=dims_c, plain=plain)
         plans.append(s)
         infos.append(inf)
     ins = [np.concatenate([a[po.local_in_slice(d)].ravel(order="F") for a in A]) for d in ds]
-    outs = pi.run_world(plans, infos, ins, False, nv)
+    outs = pi.run_world(plans, infos, ins, False, nv, allow_padding=not plain)
     Fg = [po.global_forward(a, ds[0], opf) for a in A]
     for d, o in zip(ds, outs):
         exp = np.concatenate([po.local_forward(a, d, opf).ravel(order="F") for a in A])
@@ -92,7 +97,7 @@ def _run(lib, n, dims, cut, opf, opb, stride1=False, nv=1, dims_c=False):
     # backward from the oracle's spectrum
     plans, infos = [], []
     for r in range(P):
-        s, inf = lib.plan_steps(dims, nx, ny, nz, r, True, opb, nv, *c, stride1=stride1, dims_c=dims_c)
+        s, inf = lib.plan_steps(dims, nx, ny, nz, r, True, opb, nv, *c, stride1=stride1, dims_c=dims_c, plain=plain)
         plans.append(s)
         infos.append(inf)
     ins = []
@@ -104,7 +109,7 @@ def _run(lib, n, dims, cut, opf, opb, stride1=False, nv=1, dims_c=False):
                 loc = loc.transpose(2, 1, 0)
             parts.append(np.asfortranarray(loc).ravel(order="F"))
         ins.append(np.concatenate(parts))
-    outs = pi.run_world(plans, infos, ins, True, nv)
+    outs = pi.run_world(plans, infos, ins, True, nv, allow_padding=not plain)
     for d, o in zip(ds, outs):
         exp = np.concatenate([po.local_backward(f, d, opb).ravel(order="F") for f in Fg])
         assert po.rel_l2(o, exp) < 1e-13
@@ -136,7 +141,7 @@ def test_exchange_tables_equal_reference_byte_counts(lib):
     n, dims = (128, 128, 128), (2, 2)
     for r in range(4):
         d = po.Decomp(*n, dims, r)
-        steps, _ = lib.plan_steps(dims, *n, r, False, "fft")
+        steps, _ = lib.plan_steps(dims, *n, r, False, "fft", plain=True)
         ex = [s.ex for s in steps if s.is_exchange]
         assert [e.comm for e in ex] == [0, 1]
         assert list(ex[0].sndcnt[:2]) == [c // 16 for c in d.IfSndCnts]
@@ -145,7 +150,7 @@ def test_exchange_tables_equal_reference_byte_counts(lib):
         assert list(ex[0].rcvoff[:2]) == [c // 16 for c in d.IfRcvStrt]
         assert list(ex[1].sndcnt[:2]) == [c // 16 for c in d.KfSndCnts]
         assert list(ex[1].rcvoff[:2]) == [c // 16 for c in d.KfRcvStrt]
-        steps, _ = lib.plan_steps(dims, *n, r, True, "tff")
+        steps, _ = lib.plan_steps(dims, *n, r, True, "tff", plain=True)
         ex = [s.ex for s in steps if s.is_exchange]
         assert [e.comm for e in ex] == [1, 0]
         assert list(ex[0].sndcnt[:2]) == [c // 16 for c in d.JrSndCnts]
