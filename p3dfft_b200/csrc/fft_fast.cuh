@@ -61,17 +61,18 @@ struct RS {
   __host__ __device__ static constexpr int twtotal() { return twoff(L - 1); }   // last pass has m = 1: no table
 };
 
-// c2c configuration per (type, length): schedule, lines per tile, threads per CTA, CTAs/SM hint
+// c2c configuration per (type, length): schedule, lines per tile (TX * sizeof(complex) = 64 bytes =
+// the block width W of the planner's internal layouts), threads per CTA, CTAs/SM hint
 template <typename T, int N> struct CCfg;
-template <> struct CCfg<double, 64>   { using S = RS<8, 8>;       static constexpr int TX = 8, NT = 64,  MINB = 8; };
-template <> struct CCfg<double, 128>  { using S = RS<16, 8>;      static constexpr int TX = 8, NT = 128, MINB = 4; };
-template <> struct CCfg<double, 256>  { using S = RS<16, 16>;     static constexpr int TX = 8, NT = 128, MINB = 3; };
+template <> struct CCfg<double, 64>   { using S = RS<8, 8>;       static constexpr int TX = 4, NT = 32,  MINB = 16; };
+template <> struct CCfg<double, 128>  { using S = RS<16, 8>;      static constexpr int TX = 4, NT = 64,  MINB = 8; };
+template <> struct CCfg<double, 256>  { using S = RS<16, 16>;     static constexpr int TX = 4, NT = 64,  MINB = 6; };
 template <> struct CCfg<double, 512>  { using S = RS<8, 8, 8>;    static constexpr int TX = 4, NT = 256, MINB = 3; };
 template <> struct CCfg<double, 1024> { using S = RS<16, 8, 8>;   static constexpr int TX = 4, NT = 256, MINB = 2; };
 template <> struct CCfg<double, 2048> { using S = RS<16, 16, 8>;  static constexpr int TX = 4, NT = 512, MINB = 1; };
-template <> struct CCfg<float, 64>    { using S = RS<8, 8>;       static constexpr int TX = 16, NT = 128, MINB = 8; };
-template <> struct CCfg<float, 128>   { using S = RS<16, 8>;      static constexpr int TX = 16, NT = 256, MINB = 4; };
-template <> struct CCfg<float, 256>   { using S = RS<16, 16>;     static constexpr int TX = 16, NT = 256, MINB = 3; };
+template <> struct CCfg<float, 64>    { using S = RS<8, 8>;       static constexpr int TX = 8, NT = 64,  MINB = 16; };
+template <> struct CCfg<float, 128>   { using S = RS<16, 8>;      static constexpr int TX = 8, NT = 128, MINB = 8; };
+template <> struct CCfg<float, 256>   { using S = RS<16, 16>;     static constexpr int TX = 8, NT = 128, MINB = 6; };
 template <> struct CCfg<float, 512>   { using S = RS<8, 8, 8>;    static constexpr int TX = 8, NT = 256, MINB = 3; };
 template <> struct CCfg<float, 1024>  { using S = RS<16, 8, 8>;   static constexpr int TX = 8, NT = 512, MINB = 2; };
 template <> struct CCfg<float, 2048>  { using S = RS<16, 16, 8>;  static constexpr int TX = 8, NT = 512, MINB = 1; };
@@ -83,7 +84,7 @@ template <> struct XCfg<double, 32>   { using S = RS<4, 8>;       static constex
 template <> struct XCfg<double, 64>   { using S = RS<8, 8>;       static constexpr int TX = 4, NT = 32,  MINB = 8; };
 template <> struct XCfg<double, 128>  { using S = RS<4, 4, 8>;    static constexpr int TX = 4, NT = 64,  MINB = 8; };
 template <> struct XCfg<double, 256>  { using S = RS<8, 4, 8>;    static constexpr int TX = 4, NT = 128, MINB = 4; };
-template <> struct XCfg<double, 512>  { using S = RS<8, 8, 8>;    static constexpr int TX = 4, NT = 256, MINB = 2; };
+template <> struct XCfg<double, 512>  { using S = RS<8, 8, 8>;    static constexpr int TX = 4, NT = 128, MINB = 4; };
 template <> struct XCfg<double, 1024> { using S = RS<8, 16, 8>;   static constexpr int TX = 4, NT = 256, MINB = 2; };
 template <> struct XCfg<float, 32>    { using S = RS<4, 8>;       static constexpr int TX = 8, NT = 64,  MINB = 8; };
 template <> struct XCfg<float, 64>    { using S = RS<8, 8>;       static constexpr int TX = 8, NT = 64,  MINB = 8; };
@@ -298,6 +299,24 @@ __device__ __forceinline__ TileIdx tile_decode(long long tile, int tiles_a, int 
   return x;
 }
 
+// per-run tile bases: the run-dependent 64-bit arithmetic is done once per run and tile, a row
+// then costs one multiply-add
+struct RunTab {
+  char* tb[2][2][P3D_MAXRUN];      // [tile parity][side][run]: address of logical row 0, line 0 of the tile
+  long long psb[2][P3D_MAXRUN];    // [side][run]: row pitch in bytes
+};
+
+template <int NT, int ESZ>
+__device__ __forceinline__ void fill_tilebase(const FastStage& st, RunTab& rt, int slot, TileIdx ti) {
+  const int nin = st.in.nrun, ntot = nin + st.out.nrun;
+  for (int i = threadIdx.x; i < ntot; i += NT) {
+    const int side = i >= nin, g = side ? i - nin : i;
+    const FastRun& r = side ? st.out.run[g] : st.in.run[g];
+    rt.tb[slot][side][g] = (char*)r.base + ((long long)ti.ta * r.sat + (long long)ti.b * r.sb + (long long)ti.c * r.sc -
+                                            (long long)r.kstart * r.ps) * ESZ;
+  }
+}
+
 template <typename T, int N, bool SWAP>
 __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
@@ -310,7 +329,8 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T2* s = reinterpret_cast<T2*>(smem_raw);
   char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * N * TX);     // [N], in side then out side
-  unsigned char* rr_in = reinterpret_cast<unsigned char*>(rowptr + N);
+  RunTab* rt = reinterpret_cast<RunTab*>(rowptr + N);
+  unsigned char* rr_in = reinterpret_cast<unsigned char*>(rt + 1);
   unsigned char* rr_out = rr_in + N;
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
 
@@ -322,25 +342,22 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
 
   build_rowrun<NT>(st.in, rr_in, N, st.n, st.mirror ? N : 0);
   build_rowrun<NT>(st.out, rr_out, N, N, 0);
+  for (int i = threadIdx.x; i < st.in.nrun; i += NT) rt->psb[0][i] = st.in.run[i].ps * (long long)sizeof(T2);
+  for (int i = threadIdx.x; i < st.out.nrun; i += NT) rt->psb[1][i] = st.out.run[i].ps * (long long)sizeof(T2);
+  if ((long long)blockIdx.x < ntiles) fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb));
   __syncthreads();
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  int slot = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, slot ^= 1) {
     const TileIdx ti = tile_decode(tile, tiles_a, st.nb);
     const bool live = ti.ta * TX + t < st.na;
-    const long long nxt = tile + gridDim.x;
-    const bool has_next = nxt < ntiles;
-    const TileIdx tn = tile_decode(has_next ? nxt : tile, tiles_a, st.nb);
-    // ---- input row table of this tile; L2 prefetch of the next one -------------------------
+    const bool has_next = tile + gridDim.x < ntiles;
+    if (has_next) fill_tilebase<NT, sizeof(T2)>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb));
+    // ---- input row table of this tile ---------------------------------------------------------
     for (int row = threadIdx.x; row < N; row += NT) {
       const int g = rr_in[row];
-      char* p = nullptr;
-      if (g != 0xFF) {
-        const FastRun& r = st.in.run[g];
-        const int k = (st.mirror && row >= st.n) ? N - row : row;
-        p = (char*)r.base + run_offset<sizeof(T2)>(r, k, ti.ta, ti.b, ti.c);
-        if (has_next && k == row) prefetch_l2((char*)r.base + run_offset<sizeof(T2)>(r, k, tn.ta, tn.b, tn.c));
-      }
-      rowptr[row] = p;
+      const int k = (st.mirror && row >= st.n) ? N - row : row;
+      rowptr[row] = g != 0xFF ? rt->tb[slot][0][g] + k * rt->psb[0][g] : nullptr;
     }
     __syncthreads();
     // ---- pass 1: global -> registers -> shared ---------------------------------------------
@@ -364,12 +381,17 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
       }
     }
     __syncthreads();
-    // ---- output row table (the input one is dead now) ---------------------------------------
+    // ---- output row table (the input one is dead now); L2 prefetch of the next tile's rows ----
     for (int row = threadIdx.x; row < N; row += NT) {
       const int g = rr_out[row];
-      char* p = nullptr;
-      if (g != 0xFF) p = (char*)st.out.run[g].base + run_offset<sizeof(T2)>(st.out.run[g], row, ti.ta, ti.b, ti.c);
-      rowptr[row] = p;
+      rowptr[row] = g != 0xFF ? rt->tb[slot][1][g] + row * rt->psb[1][g] : nullptr;
+      if (has_next && st.prefetch) {
+        const int gi = rr_in[row];
+        // one request per 128-byte line: contiguous tiles need every other row only
+        if (gi != 0xFF && !(st.mirror && row >= st.n) && (st.prefetch == 2 || rt->psb[0][gi] == (long long)(TX * sizeof(T2))) &&
+            (rt->psb[0][gi] != 64 || !(row & 1)))
+          prefetch_l2(rt->tb[slot ^ 1][0][gi] + row * rt->psb[0][gi]);
+      }
     }
     if constexpr (L == 2) __syncthreads();
     mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
@@ -394,7 +416,7 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
 
 template <typename T, int N> constexpr size_t cstage_smem() {
   using T2 = typename Cx<T>::type;
-  return sizeof(T2) * N * CCfg<T, N>::TX + sizeof(char*) * N + 2 * N;
+  return sizeof(T2) * N * CCfg<T, N>::TX + sizeof(char*) * N + sizeof(RunTab) + 2 * N;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -448,7 +470,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
       if (g != 0xFF) p = (char*)st.out.run[g].base + run_offset<sizeof(T2)>(st.out.run[g], row, ti.ta, ti.b, ti.c);
       rowptr[row] = p;
     }
-    if (tile + gridDim.x < ntiles) {
+    if (st.prefetch && tile + gridDim.x < ntiles) {
       const TileIdx tn = tile_decode(tile + gridDim.x, tiles_a, st.nb);
       constexpr int PER_LINE = (int)(H * sizeof(T2) / 128);          // 128-byte lines per real line
       for (int i = threadIdx.x; i < PER_LINE * TX; i += NT) {
@@ -585,7 +607,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
       if (g != 0xFF) {
         const FastRun& r = st.in.run[g];
         p = (char*)r.base + run_offset<sizeof(T2)>(r, row, ti.ta, ti.b, ti.c);
-        if (has_next && tn.ta * TX + (row % TX) < st.na)
+        if (has_next && st.prefetch && tn.ta * TX + (row % TX) < st.na)
           prefetch_l2((char*)r.base + run_offset<sizeof(T2)>(r, row, tn.ta, tn.b, tn.c) + (row % TX) * sab);
       }
       rowptr[row] = p;
