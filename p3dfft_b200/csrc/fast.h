@@ -37,7 +37,7 @@ struct FastStage {
   int32_t na, nb, nc;    // batch extents; CTAs tile a
   int32_t n;             // logical length of the transform axis (nx, ny, nz)
   int32_t mirror;        // 1: DCT-I -- FFT row r >= n reads logical row nfft - r
-  int32_t prefetch;      // L2 prefetch of a CTA's next tile: 0 off, 1 tile-contiguous inputs only, 2 always
+  int32_t prefetch;      // L2 prefetch of a CTA's next tile for inputs whose row pitch is <= this many bytes (0: off)
   const void* tw;        // device twiddle block of this (kind, nfft), see fast_twiddle_*
   FastSide in, out;
 };

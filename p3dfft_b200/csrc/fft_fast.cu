@@ -166,7 +166,7 @@ void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes) {
   const int tx = real_bytes == 4 ? tile_lines<float>(st) : tile_lines<double>(st);
   f.na = st.na; f.nb = st.nb; f.nc = st.nc; f.n = st.n;
   f.mirror = st.kind == P3D_DCT1;
-  static const int pf = getenv("P3DFFT_B200_PREFETCH") ? atoi(getenv("P3DFFT_B200_PREFETCH")) : 1;
+  static const int pf = getenv("P3DFFT_B200_PREFETCH") ? atoi(getenv("P3DFFT_B200_PREFETCH")) : 64;
   f.prefetch = pf;
   f.tw = nullptr;
   side_to_runs(st.in, f.in, st.kind == P3D_R2C ? real_bytes : 2 * real_bytes, tx);

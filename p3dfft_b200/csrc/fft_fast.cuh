@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
       if (has_next && st.prefetch) {
         const int gi = rr_in[row];
         // one request per 128-byte line: contiguous tiles need every other row only
-        if (gi != 0xFF && !(st.mirror && row >= st.n) && (st.prefetch == 2 || rt->psb[0][gi] == (long long)(TX * sizeof(T2))) &&
+        if (gi != 0xFF && !(st.mirror && row >= st.n) && rt->psb[0][gi] <= (long long)st.prefetch &&
             (rt->psb[0][gi] != 64 || !(row & 1)))
           prefetch_l2(rt->tb[slot ^ 1][0][gi] + row * rt->psb[0][gi]);
       }

@@ -226,9 +226,8 @@ inline void add_seg_blk(P3dSide& sd, int buf, int peer, long long off, int start
 // W > 0 selects the B200 layouts of the internal buffers: W = 64 bytes / sizeof(complex) lines
 // that are adjacent in x form one row of a kernel tile, and every buffer is ordered so that
 // the tile of the stage that READS it is contiguous in memory --
-//   X<->Y buffer (both directions)   [z][x/W][y][x%W]   Y-stage tile = (z, x/W), rows y
-//   Y->Z buffer (forward)            [x/W][y][z][x%W]   Z-stage tile = (x/W, y), rows z
-//   Z->Y buffer (backward)           [z][x/W][y][x%W]   Y-stage tile = (z, x/W), rows y
+//   X<->Y buffer   [z][x/W][y][x%W]   Y-stage tile = (z, x/W), rows y: contiguous
+//   Y<->Z buffer   [x/W][y][z][x%W]   Z-stage tile = (x/W, y), rows z: contiguous
 // per peer block (blocks padded in x to a multiple of W).  The exchange still moves one
 // contiguous block per peer; only the order of the elements inside a block differs from the
 // reference's pack buffers, which no caller can observe.  W = 0 keeps the reference's plain
@@ -333,30 +332,27 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
                     W, 0, 0, 1, W, nyq * W, nxb * nyq * W, xy_y[q]);
       }
     };
-    // Y side of the Y<->Z buffer.  fwd (Y writes): [xb][y][z][xi]; bwd (Y reads): [z][xb][y][xi]
+    // Y side of the Y<->Z buffer, [xb][y][z][xi] per peer block in both directions: the Z-stage tile
+    // (x/W, y) is contiguous, the Y stage touches 64-byte rows kjsize*64 bytes apart
     auto yz_yside = [&](P3dSide& sd, bool send) {
       for (int p = 0; p < M2; p++) {
         const long long nyp = d.jj.sz[p];
         const bool self_redirect = send && M2 > 1 && p == d.jpid;
         const int buf = send ? (self_redirect ? rcv : snd) : cur;
         const long long off = self_redirect ? offs(yz_z, d.jpid) : offs(yz_y, p);
-        if (send) add_seg_blk(sd, buf, (!self_redirect && M2 > 1) ? p : -1, off, d.jj.st[p] - 1, (int)nyp,
-                              kj * W, 0, 0, 1, W, nyp * kj * W, W, yz_y[p]);
-        else      add_seg_blk(sd, buf, -1, off, d.jj.st[p] - 1, (int)nyp,
-                              W, 0, 0, 1, W, nyp * W, nxb * nyp * W, yz_y[p]);
+        add_seg_blk(sd, buf, (send && !self_redirect && M2 > 1) ? p : -1, off, d.jj.st[p] - 1, (int)nyp,
+                    kj * W, 0, 0, 1, W, nyp * kj * W, W, yz_y[p]);
       }
     };
-    // Z side of the Y<->Z buffer.  fwd (Z reads): [xb][y][z][xi]; bwd (Z writes): [z][xb][y][xi]
+    // Z side of the Y<->Z buffer
     auto yz_zside = [&](P3dSide& sd, bool send) {
       for (int q = 0; q < M2; q++) {
         const long long nzq = d.kj.sz[q];
         const bool self_redirect = send && M2 > 1 && q == d.jpid;
         const int buf = send ? (self_redirect ? rcv : snd) : cur;
         const long long off = self_redirect ? offs(yz_y, d.jpid) : offs(yz_z, q);
-        if (send) add_seg_blk(sd, buf, (!self_redirect && M2 > 1) ? q : -1, off, d.kj.st[q] - 1, (int)nzq,
-                              nxb * jj * W, 0, 0, 1, W, jj * W, W, yz_z[q]);
-        else      add_seg_blk(sd, buf, -1, off, d.kj.st[q] - 1, (int)nzq,
-                              W, 0, 0, 1, W, jj * nzq * W, nzq * W, yz_z[q]);
+        add_seg_blk(sd, buf, (send && !self_redirect && M2 > 1) ? q : -1, off, d.kj.st[q] - 1, (int)nzq,
+                    W, 0, 0, 1, W, jj * nzq * W, nzq * W, yz_z[q]);
       }
     };
     if (!backward) {
