@@ -250,6 +250,7 @@ def main():
                "note": "host pinned buffers through p3dfft_ftran_r2c/p3dfft_btran_c2r; wall clock, max over ranks"}
         del hA, hF, hB
 
+    p2p_on = L.p2p_active()
     L.p3dfft_clean()
     L.reset_stream()
     if rank != 0:
@@ -287,6 +288,8 @@ def main():
                      "stages_ms": {k: v[0] * 1e3 for k, v in stage_t.items()},
                      "exchange_ms": {"T1": tm[0] * 1e3, "T2": tm[1] * 1e3, "T3": tm[2] * 1e3, "T4": tm[3] * 1e3}},
         "gpu_launches": int(launches[0]), "gpu_launches_specialised_kernels": int(launches[1]),
+        "transpose": ("none" if world == 1 else ("nvlink peer stores from the stage kernels + barrier" if p2p_on
+                      else "grouped ncclSend/ncclRecv")),
         "clocks": clocks, "roundtrip_max_err": err,
     }
     if e2e:

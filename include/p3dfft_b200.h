@@ -55,6 +55,12 @@ long long p3dfft_b200_launch_count(int reset);
 long long p3dfft_b200_fast_launch_count(int reset);
 /* on != 0: use only the any-length kernel (A/B checks; also env P3DFFT_B200_GENERIC)        */
 void p3dfft_b200_force_generic(int on);
+/* Peer-to-peer transposes (default on when every rank of a row/column can map its peers' work
+ * buffers with CUDA IPC): the stage kernels store each block straight into the destination rank's
+ * receive buffer over NVLink and the exchange step is only a barrier.  on = 0 keeps grouped
+ * ncclSend/ncclRecv.  Must precede p3dfft_setup (also env P3DFFT_B200_P2P=0/1).               */
+void p3dfft_b200_set_p2p(int on);
+int p3dfft_b200_p2p_active(void);
 /* on != 0: keep the reference's pack-buffer layouts and exact alltoallv counts in the
  * library's own work buffers instead of the tile-blocked B200 layouts (plan.h); results are
  * identical, only the order of elements inside the internal buffers changes
@@ -75,7 +81,7 @@ typedef struct {
 } p3dfft_b200_decomp;
 
 /* flags: bit0 = single precision (sizes the blocked layouts), bit1 = STRIDE1, bit2 = DIMS_C,
- * bit3 = plain (reference) internal layouts.  Returns 0, or -1 and records the reference's
+ * bit3 = plain (reference) internal layouts, bit4 = peer-to-peer plan.  Returns 0, or -1 and records the reference's
  * error text (retrievable with p3dfft_b200_last_error).                                   */
 int p3dfft_b200_plan_decomp(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc,
                             int flags, p3dfft_b200_decomp* out);

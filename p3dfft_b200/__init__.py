@@ -49,7 +49,7 @@ class Stage(C.Structure):
 
 class Exchange(C.Structure):
     _fields_ = [("comm", C.c_int32), ("npeer", C.c_int32), ("self", C.c_int32), ("sendbuf", C.c_int32),
-                ("recvbuf", C.c_int32), ("timer", C.c_int32),
+                ("recvbuf", C.c_int32), ("timer", C.c_int32), ("p2p", C.c_int32), ("pad_", C.c_int32),
                 ("sndoff", C.c_int64 * MAXSEG), ("sndcnt", C.c_int64 * MAXSEG),
                 ("rcvoff", C.c_int64 * MAXSEG), ("rcvcnt", C.c_int64 * MAXSEG)]
 
@@ -232,6 +232,12 @@ class P3DFFT:
         return int(self.lib.p3dfft_b200_launch_count(int(reset)))
 
     # ---- host-only planner ---------------------------------------------------------------
+    def set_p2p(self, on=True):
+        self.lib.p3dfft_b200_set_p2p(int(on))
+
+    def p2p_active(self) -> bool:
+        return bool(self.lib.p3dfft_b200_p2p_active())
+
     def plain_layout(self, on=True):
         self.lib.p3dfft_b200_plain_layout(int(on))
 
@@ -248,7 +254,7 @@ class P3DFFT:
         return info
 
     def plan_steps(self, dims, nx, ny, nz, rank, backward, op, nv=1, nxc=None, nyc=None, nzc=None, stride1=False,
-                   dims_c=False, dim_real=None, dim_cplx=None, plain=False):
+                   dims_c=False, dim_real=None, dim_cplx=None, plain=False, p2p=False):
         info = self.plan_decomp(dims, nx, ny, nz, rank, nxc, nyc, nzc, stride1, dims_c, plain)
         if dim_real is None:
             dim_real = info.nx * info.jisize * info.kjsize
@@ -256,7 +262,7 @@ class P3DFFT:
             dim_cplx = info.iisize * info.jjsize * info.nzc
         arr = (Step * 16)()
         d = (C.c_int * 2)(*dims)
-        flags = (2 if stride1 else 0) | (4 if dims_c else 0) | (8 if plain else 0)
+        flags = (2 if stride1 else 0) | (4 if dims_c else 0) | (8 if plain else 0) | (16 if p2p else 0)
         n = self.lib.p3dfft_b200_plan_steps(d, nx, ny, nz, rank, nxc or nx, nyc or ny, nzc or nz, flags,
                                             1 if backward else 0, op.encode() + b"\0", nv, dim_real, dim_cplx,
                                             4 if self.single else 8, arr, 16)

@@ -68,6 +68,8 @@ struct Nccl {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -78,7 +80,7 @@ struct Nccl {
     if (!h) { report(true, "P3DFFT(B200): cannot load libnccl.so.2: %s", dlerror()); return false; }
 #define SYM(f) *(void**)(&f) = dlsym(h, "nccl" #f); if (!f) { report(true, "P3DFFT(B200): nccl" #f " missing"); return false; }
     SYM(GetUniqueId) SYM(CommInitRank) SYM(CommSplit) SYM(CommDestroy) SYM(Send) SYM(Recv)
-    SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+    SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString) SYM(AllGather) SYM(AllReduce)
 #undef SYM
     return true;
   }
@@ -104,9 +106,10 @@ int g_next_handle = 1;
 // the plan (module-global state of the reference)
 // ------------------------------------------------------------------------------------
 struct PlanKey {
-  int backward, nv; char op; long long dim_real, dim_cplx; int w;
+  int backward, nv; char op; long long dim_real, dim_cplx; int w, p2p;
   bool operator<(const PlanKey& o) const {
-    return std::tie(backward, nv, op, dim_real, dim_cplx, w) < std::tie(o.backward, o.nv, o.op, o.dim_real, o.dim_cplx, o.w);
+    return std::tie(backward, nv, op, dim_real, dim_cplx, w, p2p) <
+           std::tie(o.backward, o.nv, o.op, o.dim_real, o.dim_cplx, o.w, o.p2p);
   }
 };
 
@@ -124,6 +127,11 @@ struct Lib {
   bool has_user_stream = false;
   bool async = false;
   bool force_generic = false;
+  // peer-to-peer transposes: stage kernels store each block straight into the destination rank's
+  // receive buffer over NVLink (CUDA IPC mappings of the peers' work buffers); exchange = barrier
+  bool want_p2p = true, p2p = false;
+  std::vector<void*> peer_buf;   // [world rank * 3 + (buffer id - P3D_BUF_A)], own entries = own buffers
+  float* bar_scratch = nullptr;
   bool plain_layout = false;     // true: the reference's pack-buffer layouts instead of the tile-blocked ones
   int W() const { return plain_layout ? 0 : (int)(64 / CSIZE); }
   long long fast_launches = 0;
@@ -189,10 +197,73 @@ const void* fast_twiddle_block(int kind, int nfft) {
   return dptr;
 }
 
+void close_peer_maps() {
+  const int me = L.comm ? L.comm->rank : 0;
+  for (size_t i = 0; i < L.peer_buf.size(); i++)
+    if (L.peer_buf[i] && (int)(i / 3) != me) cudaIpcCloseMemHandle(L.peer_buf[i]);
+  L.peer_buf.clear();
+  L.p2p = false;
+}
+
+bool world_barrier(cudaStream_t st) {
+  if (!L.comm || !L.comm->world) return true;
+  if (!L.bar_scratch) { CUDA_OK(cudaMalloc(&L.bar_scratch, 256)); CUDA_OK(cudaMemset(L.bar_scratch, 0, 256)); }
+  NCCL_OK(g_nccl.AllReduce(L.bar_scratch, L.bar_scratch + 32, 1, ncclFloat, ncclSum, L.comm->world, st));
+  return true;
+}
+
+// maps the work buffers of every rank in this rank's row and column (collective over the world)
+bool open_peer_maps() {
+  close_peer_maps();
+  const int P = L.comm->size, me = L.comm->rank;
+  struct Rec { cudaIpcMemHandle_t h[3]; };
+  Rec mine;
+  memset(&mine, 0, sizeof mine);
+  for (int b = 0; b < 3; b++)
+    if (cudaIpcGetMemHandle(&mine.h[b], L.buf[P3D_BUF_A + b]) != cudaSuccess) { cudaGetLastError(); return false; }
+  Rec* dev = nullptr;
+  CUDA_OK(cudaMalloc(&dev, sizeof(Rec) * (P + 1)));
+  CUDA_OK(cudaMemcpy(dev + P, &mine, sizeof mine, cudaMemcpyHostToDevice));
+  cudaStream_t st = L.stream();
+  NCCL_OK(g_nccl.AllGather(dev + P, dev, sizeof(Rec), ncclInt8, L.comm->world, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<Rec> all(P);
+  CUDA_OK(cudaMemcpy(all.data(), dev, sizeof(Rec) * P, cudaMemcpyDeviceToHost));
+  cudaFree(dev);
+  L.peer_buf.assign((size_t)P * 3, nullptr);
+  bool ok = true;
+  for (int r = 0; r < P; r++) {
+    const int ip = L.d.dims_c ? r / L.d.jproc : r % L.d.iproc, jp = L.d.dims_c ? r % L.d.jproc : r / L.d.iproc;
+    if (r == me) { for (int b = 0; b < 3; b++) L.peer_buf[(size_t)r * 3 + b] = L.buf[P3D_BUF_A + b]; continue; }
+    if (ip != L.d.ipid && jp != L.d.jpid) continue;      // neither in my row nor in my column
+    for (int b = 0; b < 3 && ok; b++) {
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[r].h[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
+      L.peer_buf[(size_t)r * 3 + b] = ptr;
+    }
+  }
+  // all ranks must agree: one failure anywhere disables the path everywhere
+  float flag = ok ? 0.f : 1.f, sum = 0.f;
+  if (!L.bar_scratch) { CUDA_OK(cudaMalloc(&L.bar_scratch, 256)); CUDA_OK(cudaMemset(L.bar_scratch, 0, 256)); }
+  CUDA_OK(cudaMemcpy(L.bar_scratch + 1, &flag, sizeof flag, cudaMemcpyHostToDevice));
+  NCCL_OK(g_nccl.AllReduce(L.bar_scratch + 1, L.bar_scratch + 2, 1, ncclFloat, ncclSum, L.comm->world, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaMemcpy(&sum, L.bar_scratch + 2, sizeof sum, cudaMemcpyDeviceToHost));
+  if (sum != 0.f) { close_peer_maps(); return false; }
+  L.p2p = true;
+  return true;
+}
+
 bool alloc_work(int nv) {
   if (nv <= L.nv_preset) return true;
   // lazy growth like ftran.F90:133-157 (nv_preset)
   cudaStreamSynchronize(L.stream());
+  const bool multi = L.comm && L.comm->size > 1;
+  if (multi && !L.peer_buf.empty()) {       // peers may still be storing into the old buffers
+    if (!world_barrier(L.stream())) return false;
+    cudaStreamSynchronize(L.stream());
+    close_peer_maps();
+  }
   size_t bytes = (size_t)L.d.work_elems(nv, L.W()) * CSIZE;
   int nbuf = (L.d.iproc * L.d.jproc > 1) ? 3 : 2;
   for (int b = 0; b < nbuf; b++) {
@@ -201,14 +272,19 @@ bool alloc_work(int nv) {
     CUDA_OK(cudaMalloc(&L.buf[id], bytes));
   }
   L.nv_preset = nv;
+  L.plans.clear();
+  if (multi && L.want_p2p && L.W() > 0 && nbuf == 3) {
+    if (!open_peer_maps() && L.comm->rank == 0 && getenv("P3DFFT_B200_VERBOSE"))
+      fprintf(stderr, "P3DFFT(B200): peer mapping unavailable, transposes use ncclSend/ncclRecv\n");
+  }
   return true;
 }
 
 p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long dim_real, long long dim_cplx) {
-  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx, L.W()};
+  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx, L.W(), L.p2p ? 1 : 0};
   auto it = L.plans.find(key);
   if (it != L.plans.end()) return &it->second;
-  p3d::TransformPlan tp = p3d::build_plan(L.d, backward, op, nv, dim_real, dim_cplx, L.W());
+  p3d::TransformPlan tp = p3d::build_plan(L.d, backward, op, nv, dim_real, dim_cplx, L.W(), L.p2p);
   if (!tp.error.empty()) {
     // ftran.F90:640-643: print + MPI_Abort
     report(true, "%s", tp.error.c_str());
@@ -233,6 +309,7 @@ cudaEvent_t get_event(size_t i) {
 }
 
 bool run_exchange(const P3dExchange& e, cudaStream_t st) {
+  if (e.p2p) return world_barrier(st);     // data already landed: order it against the consumers
   ncclComm_t c = e.comm == 0 ? L.row : L.col;
   char* sb = (char*)L.buf[e.sendbuf];
   char* rb = (char*)L.buf[e.recvbuf];
@@ -291,6 +368,7 @@ bool run_transform(bool backward, const void* in, void* out, const char* op, int
         for (int g = 0; g < sd.nseg; g++) {
           P3dSeg& sg = sd.seg[g];
           char* base = sg.buf == P3D_BUF_USER_IN ? (char*)din : sg.buf == P3D_BUF_USER_OUT ? (char*)dout : (char*)L.buf[sg.buf];
+          if (sg.peer >= 0) base = (char*)L.peer_buf[(size_t)sg.peer * 3 + (sg.buf - P3D_BUF_A)];     // NVLink peer mapping
           sg.base = base + sg.off * esz;
         }
       }
@@ -390,6 +468,7 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   }
   if (getenv("P3DFFT_B200_GENERIC")) L.force_generic = true;
   if (getenv("P3DFFT_B200_PLAIN")) L.plain_layout = true;
+  if (getenv("P3DFFT_B200_P2P")) L.want_p2p = atoi(getenv("P3DFFT_B200_P2P")) != 0;
   for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
   L.nv_preset = 0;
   L.set = true;
@@ -471,6 +550,12 @@ void p3dfft_clean(void) {
   // module.F90:309-420: destroy plans, free buffers, mpi_set = .false.
   if (!L.set) return;
   cudaStreamSynchronize(L.stream());
+  if (!L.peer_buf.empty()) {       // nobody frees while a peer may still store into its buffers
+    world_barrier(L.stream());
+    cudaStreamSynchronize(L.stream());
+    close_peer_maps();
+  }
+  if (L.bar_scratch) { cudaFree(L.bar_scratch); L.bar_scratch = nullptr; }
   for (int b = P3D_BUF_A; b <= P3D_BUF_C; b++) if (L.buf[b]) { cudaFree(L.buf[b]); L.buf[b] = nullptr; }
   if (L.stage_in) { cudaFree(L.stage_in); L.stage_in = nullptr; L.stage_in_bytes = 0; }
   if (L.stage_out) { cudaFree(L.stage_out); L.stage_out = nullptr; L.stage_out_bytes = 0; }
@@ -553,6 +638,8 @@ int p3dfft_b200_last_error(char* buf, int buflen) {
 void p3dfft_b200_set_stream(void* s) { L.user_stream = (cudaStream_t)s; L.has_user_stream = true; }
 void p3dfft_b200_reset_stream(void) { L.user_stream = nullptr; L.has_user_stream = false; }
 void p3dfft_b200_force_generic(int on) { L.force_generic = on != 0; }
+void p3dfft_b200_set_p2p(int on) { L.want_p2p = on != 0; }
+int p3dfft_b200_p2p_active(void) { return L.p2p ? 1 : 0; }
 void p3dfft_b200_plain_layout(int on) {
   if (L.set && (on != 0) != L.plain_layout) { cudaStreamSynchronize(L.stream()); L.plans.clear(); L.nv_preset = 0; }
   L.plain_layout = on != 0;
@@ -593,7 +680,7 @@ int p3dfft_b200_plan_steps(const int* dims, int nx, int ny, int nz, int rank, in
                            (flags & 2) != 0);
   if (!err.empty()) { g_last_error = err; return -1; }
   p3d::TransformPlan tp = p3d::build_plan(d, backward != 0, op, nv, dim_real, dim_cplx,
-                                          (flags & 8) ? 0 : 64 / (2 * elem_bytes));
+                                          (flags & 8) ? 0 : 64 / (2 * elem_bytes), (flags & 16) != 0 && !(flags & 8));
   if (!tp.error.empty()) { g_last_error = tp.error; return -1; }
   if ((int)tp.steps.size() > max_steps) { g_last_error = "step array too small"; return -1; }
   P3dStepC* out = (P3dStepC*)steps;

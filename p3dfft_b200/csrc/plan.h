@@ -232,8 +232,15 @@ inline void add_seg_blk(P3dSide& sd, int buf, int peer, long long off, int start
 // contiguous block per peer; only the order of the elements inside a block differs from the
 // reference's pack buffers, which no caller can observe.  W = 0 keeps the reference's plain
 // layouts and its exact alltoallv tables (setup.F90:481-518).
+//
+// p2p (needs W > 0): a stage writes the block destined to peer p straight into p's RECEIVE buffer
+// through a peer-mapped pointer (NVLink stores issued by the FFT kernel itself), at the offset where
+// p expects the block from this rank; the exchange step degenerates to a barrier.  seg.peer then
+// holds the WORLD rank owning the memory.  Every rank runs the same step sequence, so buffer ids
+// rotate identically everywhere and a world barrier after each producing stage orders both the
+// read-after-write and the write-after-read hazards (api.cpp, run_exchange).
 inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, int nv,
-                                long long dim_real, long long dim_cplx, int W = 0) {
+                                long long dim_real, long long dim_cplx, int W = 0, bool p2p = false) {
   TransformPlan tp;
   const int M1 = d.iproc, M2 = d.jproc;
   if (M1 > P3D_MAXSEG || M2 > P3D_MAXSEG) { tp.error = "processor grid dimension exceeds P3D_MAXSEG"; return tp; }
@@ -284,7 +291,7 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
       long long sc = unit * sz;
       long long off = nv * (long long)(bm.st[p] - 1) * unit;
       if (send && p == self) add_seg(sd, rcv, -1, selfoff, bm.st[p] - 1, (int)sz, ps, sa, sb, sc);
-      else add_seg(sd, send ? snd : cur, send ? p : -1, off, bm.st[p] - 1, (int)sz, ps, sa, sb, sc);
+      else add_seg(sd, send ? snd : cur, -1, off, bm.st[p] - 1, (int)sz, ps, sa, sb, sc);
     }
   };
 
@@ -298,6 +305,7 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
                                  const std::vector<long long>& rc_) {
       Step st; st.is_exchange = true; P3dExchange& e = st.ex; memset(&e, 0, sizeof e);
       e.comm = comm; e.npeer = npeer; e.self = self; e.sendbuf = snd; e.recvbuf = rcv; e.timer = timer;
+      e.p2p = p2p ? 1 : 0;
       long long so = 0, ro = 0;
       for (int p = 0; p < npeer; p++) {
         e.sndoff[p] = so; e.sndcnt[p] = nv * sc_[p]; so += e.sndcnt[p];
@@ -315,9 +323,14 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
       for (int p = 0; p < M1; p++) {
         const long long nxbp = cdiv(d.ii.sz[p]);
         const bool self_redirect = send && M1 > 1 && p == d.ipid;
-        const int buf = send ? (self_redirect ? rcv : snd) : cur;
-        const long long off = self_redirect ? offs(xy_y, d.ipid) : offs(xy_x, p);
-        add_seg_blk(sd, buf, (send && !self_redirect && M1 > 1) ? p : -1, off, d.ii.st[p] - 1, d.ii.sz[p],
+        const bool remote = send && !self_redirect && M1 > 1 && p2p;
+        const int buf = send ? ((self_redirect || remote) ? rcv : snd) : cur;
+        long long off = self_redirect ? offs(xy_y, d.ipid) : offs(xy_x, p);
+        if (remote) {     // where peer p expects the block from this rank (its Y side of the buffer)
+          off = 0;
+          for (int q = 0; q < d.ipid; q++) off += nv * kj * nxbp * d.ji.sz[q] * W;
+        }
+        add_seg_blk(sd, buf, remote ? d.rank_of(p, d.jpid) : -1, off, d.ii.st[p] - 1, d.ii.sz[p],
                     1, W, ji * W, W, 0, 0, nxbp * ji * W, xy_x[p]);
       }
     };
@@ -326,9 +339,14 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
       for (int q = 0; q < M1; q++) {
         const long long nyq = d.ji.sz[q];
         const bool self_redirect = send && M1 > 1 && q == d.ipid;
-        const int buf = send ? (self_redirect ? rcv : snd) : cur;
-        const long long off = self_redirect ? offs(xy_x, d.ipid) : offs(xy_y, q);
-        add_seg_blk(sd, buf, (send && !self_redirect && M1 > 1) ? q : -1, off, d.ji.st[q] - 1, (int)nyq,
+        const bool remote = send && !self_redirect && M1 > 1 && p2p;
+        const int buf = send ? ((self_redirect || remote) ? rcv : snd) : cur;
+        long long off = self_redirect ? offs(xy_x, d.ipid) : offs(xy_y, q);
+        if (remote) {     // peer q's X side: blocks ordered by sender, sender p' holds x in ii(p'), y in ji(q)
+          off = 0;
+          for (int pp = 0; pp < d.ipid; pp++) off += nv * kj * cdiv(d.ii.sz[pp]) * nyq * W;
+        }
+        add_seg_blk(sd, buf, remote ? d.rank_of(q, d.jpid) : -1, off, d.ji.st[q] - 1, (int)nyq,
                     W, 0, 0, 1, W, nyq * W, nxb * nyq * W, xy_y[q]);
       }
     };
@@ -338,9 +356,14 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
       for (int p = 0; p < M2; p++) {
         const long long nyp = d.jj.sz[p];
         const bool self_redirect = send && M2 > 1 && p == d.jpid;
-        const int buf = send ? (self_redirect ? rcv : snd) : cur;
-        const long long off = self_redirect ? offs(yz_z, d.jpid) : offs(yz_y, p);
-        add_seg_blk(sd, buf, (send && !self_redirect && M2 > 1) ? p : -1, off, d.jj.st[p] - 1, (int)nyp,
+        const bool remote = send && !self_redirect && M2 > 1 && p2p;
+        const int buf = send ? ((self_redirect || remote) ? rcv : snd) : cur;
+        long long off = self_redirect ? offs(yz_z, d.jpid) : offs(yz_y, p);
+        if (remote) {     // peer p's Z side: block from sender q' holds y in jj(p), z in kj(q')
+          off = 0;
+          for (int q = 0; q < d.jpid; q++) off += nv * nxb * nyp * d.kj.sz[q] * W;
+        }
+        add_seg_blk(sd, buf, remote ? d.rank_of(d.ipid, p) : -1, off, d.jj.st[p] - 1, (int)nyp,
                     kj * W, 0, 0, 1, W, nyp * kj * W, W, yz_y[p]);
       }
     };
@@ -349,9 +372,14 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
       for (int q = 0; q < M2; q++) {
         const long long nzq = d.kj.sz[q];
         const bool self_redirect = send && M2 > 1 && q == d.jpid;
-        const int buf = send ? (self_redirect ? rcv : snd) : cur;
-        const long long off = self_redirect ? offs(yz_y, d.jpid) : offs(yz_z, q);
-        add_seg_blk(sd, buf, (send && !self_redirect && M2 > 1) ? q : -1, off, d.kj.st[q] - 1, (int)nzq,
+        const bool remote = send && !self_redirect && M2 > 1 && p2p;
+        const int buf = send ? ((self_redirect || remote) ? rcv : snd) : cur;
+        long long off = self_redirect ? offs(yz_y, d.jpid) : offs(yz_z, q);
+        if (remote) {     // peer q's Y side: block from sender p' holds y in jj(p'), z in kj(q)
+          off = 0;
+          for (int pp = 0; pp < d.jpid; pp++) off += nv * nxb * d.jj.sz[pp] * nzq * W;
+        }
+        add_seg_blk(sd, buf, remote ? d.rank_of(d.ipid, q) : -1, off, d.kj.st[q] - 1, (int)nzq,
                     W, 0, 0, 1, W, jj * nzq * W, nzq * W, yz_z[q]);
       }
     };

@@ -37,7 +37,7 @@ enum P3dBuf { P3D_BUF_USER_IN = 0, P3D_BUF_USER_OUT = 1, P3D_BUF_A = 2, P3D_BUF_
 struct P3dSeg {
   void* base;        // resolved block base (device pointer; may be a peer-mapped pointer)
   int32_t buf;       // P3dBuf the planner refers to
-  int32_t peer;      // index in the row/column communicator whose memory holds it (-1: local)
+  int32_t peer;      // -1: this rank's memory; >= 0 (peer-to-peer plans): world rank whose buffer `buf` holds it
   int64_t off;       // element offset inside buf
   int32_t start, len;
   int64_t ps, sa, sb, sc;
@@ -75,5 +75,7 @@ struct P3dExchange {
   int32_t comm, npeer, self;
   int32_t sendbuf, recvbuf;
   int32_t timer;
+  int32_t p2p;       // 1: the producing stage already stored every block at its destination; barrier only
+  int32_t pad_;
   int64_t sndoff[P3D_MAXSEG], sndcnt[P3D_MAXSEG], rcvoff[P3D_MAXSEG], rcvcnt[P3D_MAXSEG];
 };

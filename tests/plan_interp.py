@@ -51,21 +51,23 @@ def _side_indices(side, na, nb, nc):
         addr = sg.off + ro[:, None, None, None] + ao + b * sg.sb + c * sg.sc
         ks.append(k)
         addrs.append(addr)
-        bufs.append((sg.buf, sg.len))
+        bufs.append((sg.buf, sg.peer))
     assert np.all(covered == 1), "segments must cover every stored point exactly once"
     return ks, addrs, bufs
 
 
-def run_stage(st, bufs):
+def run_stage(st, bufs, world=None):
+    """bufs = this rank's buffers; world[r] = rank r's buffers (peer-to-peer plans store into them)."""
     na, nb, nc = st.na, st.nb, st.nc
     ks, addrs, binfo = _side_indices(st.inp, na, nb, nc)
     X = np.zeros((st.inp.logical, na, nb, nc), dtype=np.complex128)
-    for k, addr, (bid, _) in zip(ks, addrs, binfo):
+    for k, addr, (bid, peer) in zip(ks, addrs, binfo):
+        assert peer < 0, "stages read local memory only"
         X[k] = bufs[bid][addr]
     Y = _line_transform(X, st.kind, st.n) * st.scale
     ks, addrs, binfo = _side_indices(st.out, na, nb, nc)
-    for k, addr, (bid, _) in zip(ks, addrs, binfo):
-        tgt = bufs[bid]
+    for k, addr, (bid, peer) in zip(ks, addrs, binfo):
+        tgt = bufs[bid] if peer < 0 else world[peer][bid]
         flat = addr.ravel()
         assert len(np.unique(flat)) == flat.size, "output scatter writes an address twice"
         tgt[addr] = Y[k].real if st.kind == 3 else Y[k]
@@ -93,6 +95,8 @@ def run_world(plans, infos, inputs, backward, nv=1, check_hazards=True, allow_pa
             for r in range(P):
                 ex = plans[r][i].ex
                 me = infos[r]
+                if ex.p2p:          # blocks were stored at their destination by the producing stage
+                    continue
                 for p in range(ex.npeer):
                     if p == ex.self:
                         continue
@@ -117,7 +121,7 @@ def run_world(plans, infos, inputs, backward, nv=1, check_hazards=True, allow_pa
                     ins = {st.inp.seg[g].buf for g in range(st.inp.nseg)}
                     outs = {st.out.seg[g].buf for g in range(st.out.nseg)}
                     assert not (ins & outs), "a stage must not write a buffer it reads"
-                run_stage(st, bufs[r])
+                run_stage(st, bufs[r], bufs)
     for r in range(P):
         o = bufs[r][BUF_USER_OUT]
         assert not np.any(np.isnan(o)), "user output not fully written"
