@@ -31,7 +31,7 @@ class Seg(C.Structure):
     _fields_ = [("base", C.c_void_p), ("buf", C.c_int32), ("peer", C.c_int32), ("off", C.c_int64),
                 ("start", C.c_int32), ("len", C.c_int32), ("ps", C.c_int64), ("sa", C.c_int64),
                 ("sb", C.c_int64), ("sc", C.c_int64), ("kw", C.c_int32), ("aw", C.c_int32),
-                ("psh", C.c_int64), ("sah", C.c_int64)]
+                ("psh", C.c_int64), ("sah", C.c_int64), ("bw", C.c_int32), ("pad_", C.c_int32), ("sbh", C.c_int64)]
 
 
 class Side(C.Structure):

@@ -18,14 +18,17 @@
 namespace p3d {
 
 // element address of logical row k of line (a,b,c), a = ta*TX + t (TX = lines per tile):
-//     base + (R(k - kstart) + ta*sat + t*sa + b*sb + c*sc) * sizeof(element)
+//     base + (R(k - korg) + ta*sat + t*sa + B(b) + c*sc) * sizeof(element)     for kstart <= k < kstart+len
 //     R(i) = i*ps  (kw <= 1)   or   (i / kw)*psh + (i % kw)*ps  (rows blocked by kw, stage.h)
+//     B(b) = b*sb  (bw <= 1)   or   (b / bw)*sbh + (b % bw)*sb
 // (sat = TX*sa for a plain strided layout; the tile-blocked internal buffers give it directly)
 struct FastRun {
   const void* base;
   int32_t kstart, len;
-  int32_t kw, pad_;
-  int64_t ps, psh, sa, sat, sb, sc;
+  int32_t korg, pad_;    // logical index that maps to the block's first stored row (== kstart unless a
+                         // pruned segment was split: the upper part keeps the block's origin)
+  int32_t kw, bw;
+  int64_t ps, psh, sa, sat, sb, sbh, sc;
 };
 
 struct FastSide {

@@ -102,7 +102,7 @@ bool fast_supported(const P3dStage& st) {
         const P3dSide& sd = side ? st.out : st.in;
         for (int g = 0; g < sd.nseg; g++) {
           const P3dSeg& sg = sd.seg[g];
-          if (sg.sa != sd.seg[0].sa || sg.kw > 1 || (sg.aw > 1 && sg.aw != tx)) return false;
+          if (sg.sa != sd.seg[0].sa || (sg.aw > 1 && sg.aw != tx)) return false;
         }
       }
       return true;
@@ -151,11 +151,13 @@ static void side_to_runs(const P3dSide& sd, FastSide& f, size_t esz, int tx) {
       const int a = parts[p][0], b = parts[p][1];
       if (b <= a) continue;
       FastRun& r = f.run[f.nrun++];
-      r.base = (const char*)sg.base + (long long)(a - s0) * sg.ps * (long long)esz;
-      r.kstart = (shift > 0 && a >= sd.h1) ? a + shift : a;
+      const int sh = (shift > 0 && a >= sd.h1) ? shift : 0;
+      r.base = sg.base;
+      r.kstart = a + sh;
+      r.korg = s0 + sh;
       r.len = b - a;
       r.ps = sg.ps; r.sa = sg.sa; r.sb = sg.sb; r.sc = sg.sc;
-      r.kw = sg.kw; r.psh = sg.psh;
+      r.kw = sg.kw; r.psh = sg.psh; r.bw = sg.bw; r.sbh = sg.sbh;
       r.sat = sg.aw > 1 ? sg.sah : sg.sa * tx;         // fast_supported() guarantees aw == tx when blocked
     }
   }

@@ -284,9 +284,10 @@ __device__ __forceinline__ void build_rowrun(const FastSide& sd, unsigned char* 
 // byte offset of (logical row k, first line of a-tile ta, b, c) inside run r
 template <int ESZ>
 __device__ __forceinline__ long long run_offset(const FastRun& r, int k, int ta, int b, int c) {
-  const int i = k - r.kstart;
+  const int i = k - r.korg;
   const long long ro = r.kw > 1 ? (long long)(i / r.kw) * r.psh + (long long)(i % r.kw) * r.ps : (long long)i * r.ps;
-  return (ro + (long long)ta * r.sat + (long long)b * r.sb + (long long)c * r.sc) * ESZ;
+  const long long bo = r.bw > 1 ? (long long)(b / r.bw) * r.sbh + (long long)(b % r.bw) * r.sb : (long long)b * r.sb;
+  return (ro + (long long)ta * r.sat + bo + (long long)c * r.sc) * ESZ;
 }
 
 struct TileIdx { int ta, b, c; };
@@ -302,9 +303,16 @@ __device__ __forceinline__ TileIdx tile_decode(long long tile, int tiles_a, int 
 // per-run tile bases: the run-dependent 64-bit arithmetic is done once per run and tile, a row
 // then costs one multiply-add
 struct RunTab {
-  char* tb[2][2][P3D_MAXRUN];      // [tile parity][side][run]: address of logical row 0, line 0 of the tile
+  char* tb[2][2][P3D_MAXRUN];      // [tile parity][side][run]: address of the run's first row, line 0 of the tile
   long long psb[2][P3D_MAXRUN];    // [side][run]: row pitch in bytes
+  long long phb[2][P3D_MAXRUN];    //              pitch of a block of kw rows (rows blocked by kw)
+  int kw[2][P3D_MAXRUN], ks[2][P3D_MAXRUN];
 };
+// byte offset of logical row k inside run g relative to tb
+__device__ __forceinline__ long long row_off(const RunTab& rt, int side, int g, int k) {
+  const int i = k - rt.ks[side][g], kw = rt.kw[side][g];
+  return kw > 1 ? (long long)(i / kw) * rt.phb[side][g] + (long long)(i % kw) * rt.psb[side][g] : (long long)i * rt.psb[side][g];
+}
 
 template <int NT, int ESZ>
 __device__ __forceinline__ void fill_tilebase(const FastStage& st, RunTab& rt, int slot, TileIdx ti) {
@@ -312,8 +320,8 @@ __device__ __forceinline__ void fill_tilebase(const FastStage& st, RunTab& rt, i
   for (int i = threadIdx.x; i < ntot; i += NT) {
     const int side = i >= nin, g = side ? i - nin : i;
     const FastRun& r = side ? st.out.run[g] : st.in.run[g];
-    rt.tb[slot][side][g] = (char*)r.base + ((long long)ti.ta * r.sat + (long long)ti.b * r.sb + (long long)ti.c * r.sc -
-                                            (long long)r.kstart * r.ps) * ESZ;
+    const long long bo = r.bw > 1 ? (long long)(ti.b / r.bw) * r.sbh + (long long)(ti.b % r.bw) * r.sb : (long long)ti.b * r.sb;
+    rt.tb[slot][side][g] = (char*)r.base + ((long long)ti.ta * r.sat + bo + (long long)ti.c * r.sc) * ESZ;
   }
 }
 
@@ -342,8 +350,14 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
 
   build_rowrun<NT>(st.in, rr_in, N, st.n, st.mirror ? N : 0);
   build_rowrun<NT>(st.out, rr_out, N, N, 0);
-  for (int i = threadIdx.x; i < st.in.nrun; i += NT) rt->psb[0][i] = st.in.run[i].ps * (long long)sizeof(T2);
-  for (int i = threadIdx.x; i < st.out.nrun; i += NT) rt->psb[1][i] = st.out.run[i].ps * (long long)sizeof(T2);
+  for (int i = threadIdx.x; i < st.in.nrun + st.out.nrun; i += NT) {
+    const int side = i >= st.in.nrun, g = side ? i - st.in.nrun : i;
+    const FastRun& r = side ? st.out.run[g] : st.in.run[g];
+    rt->psb[side][g] = r.ps * (long long)sizeof(T2);
+    rt->phb[side][g] = r.psh * (long long)sizeof(T2);
+    rt->kw[side][g] = r.kw;
+    rt->ks[side][g] = r.korg;
+  }
   if ((long long)blockIdx.x < ntiles) fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb));
   __syncthreads();
 
@@ -357,7 +371,7 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
     for (int row = threadIdx.x; row < N; row += NT) {
       const int g = rr_in[row];
       const int k = (st.mirror && row >= st.n) ? N - row : row;
-      rowptr[row] = g != 0xFF ? rt->tb[slot][0][g] + k * rt->psb[0][g] : nullptr;
+      rowptr[row] = g != 0xFF ? rt->tb[slot][0][g] + row_off(*rt, 0, g, k) : nullptr;
     }
     __syncthreads();
     // ---- pass 1: global -> registers -> shared ---------------------------------------------
@@ -384,13 +398,13 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
     // ---- output row table (the input one is dead now); L2 prefetch of the next tile's rows ----
     for (int row = threadIdx.x; row < N; row += NT) {
       const int g = rr_out[row];
-      rowptr[row] = g != 0xFF ? rt->tb[slot][1][g] + row * rt->psb[1][g] : nullptr;
+      rowptr[row] = g != 0xFF ? rt->tb[slot][1][g] + row_off(*rt, 1, g, row) : nullptr;
       if (has_next && st.prefetch) {
         const int gi = rr_in[row];
         // one request per 128-byte line: contiguous tiles need every other row only
         if (gi != 0xFF && !(st.mirror && row >= st.n) && rt->psb[0][gi] <= (long long)st.prefetch &&
             (rt->psb[0][gi] != 64 || !(row & 1)))
-          prefetch_l2(rt->tb[slot ^ 1][0][gi] + row * rt->psb[0][gi]);
+          prefetch_l2(rt->tb[slot ^ 1][0][gi] + row_off(*rt, 0, gi, row));
       }
     }
     if constexpr (L == 2) __syncthreads();

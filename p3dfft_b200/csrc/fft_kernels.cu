@@ -67,6 +67,10 @@ __device__ __forceinline__ int64_t seg_line_off(const P3dSeg& sg, int a) {
   return sg.aw > 1 ? (int64_t)(a / sg.aw) * sg.sah + (int64_t)(a % sg.aw) * sg.sa : (int64_t)a * sg.sa;
 }
 
+__device__ __forceinline__ int64_t seg_b_off(const P3dSeg& sg, int b) {
+  return sg.bw > 1 ? (int64_t)(b / sg.bw) * sg.sbh + (int64_t)(b % sg.bw) * sg.sb : (int64_t)b * sg.sb;
+}
+
 struct SmemMap {
   int layx, tile, ldl;
   __device__ __forceinline__ int operator()(int k, int t) const {
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ P3dS
     const int shift = st.in.logical - st.in.cnt;
     for (int g = 0; g < st.in.nseg; g++) {
       const P3dSeg& sg = st.in.seg[g];
-      const int64_t lbase = (int64_t)b * sg.sb + (int64_t)c * sg.sc;
+      const int64_t lbase = seg_b_off(sg, b) + (int64_t)c * sg.sc;
       const int tot = sg.len * lines;
       for (int w = threadIdx.x; w < tot; w += blockDim.x) {
         int t, i;
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ P3dS
     const T scale = (T)st.scale;
     for (int g = 0; g < st.out.nseg; g++) {
       const P3dSeg& sg = st.out.seg[g];
-      const int64_t lbase = (int64_t)b * sg.sb + (int64_t)c * sg.sc;
+      const int64_t lbase = seg_b_off(sg, b) + (int64_t)c * sg.sc;
       const int tot = sg.len * lines;
       for (int w = threadIdx.x; w < tot; w += blockDim.x) {
         int t, i;

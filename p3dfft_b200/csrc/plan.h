@@ -135,8 +135,10 @@ struct Decomp {
       const long long nxb = (iisize + W - 1) / W;
       m = nxb_all * W * jisize * kjsize;                         // X side of the X<->Y buffer
       m = std::max(m, nxb * W * (long long)ny * kjsize);         // Y side of it
-      m = std::max(m, nxb * W * (long long)nyc * kjsize);        // Y side of the Y<->Z buffer
-      m = std::max(m, nxb * W * (long long)jjsize * nz);         // Z side of it
+      long long nyb_all = 0;                                     // forward Y->Z blocks pad y to multiples of 8
+      for (int p = 0; p < jproc; p++) nyb_all += (jj.sz[p] + 7) / 8;
+      m = std::max(m, nxb * W * nyb_all * 8 * kjsize);           // Y side of the Y<->Z buffer
+      m = std::max(m, nxb * W * ((jjsize + 7) / 8) * 8 * (long long)nz);   // Z side of it
     }
     return std::max<long long>(m, 1) * nv;
   }
@@ -201,7 +203,7 @@ inline void add_seg(P3dSide& sd, int buf, int peer, long long off, int start, in
   P3dSeg& g = sd.seg[sd.nseg++];
   g.base = nullptr; g.buf = buf; g.peer = peer; g.off = off; g.start = start; g.len = len;
   g.ps = ps; g.sa = sa; g.sb = sb; g.sc = sc;
-  g.kw = 0; g.aw = 0; g.psh = 0; g.sah = 0;
+  g.kw = 0; g.aw = 0; g.psh = 0; g.sah = 0; g.bw = 0; g.pad_ = 0; g.sbh = 0;
 }
 
 // segment of a tile-blocked buffer: rows blocked by kw (stride psh) and/or lines blocked by aw (stride sah)
@@ -227,7 +229,8 @@ inline void add_seg_blk(P3dSide& sd, int buf, int peer, long long off, int start
 // that are adjacent in x form one row of a kernel tile, and every buffer is ordered so that
 // the tile of the stage that READS it is contiguous in memory --
 //   X<->Y buffer   [z][x/W][y][x%W]   Y-stage tile = (z, x/W), rows y: contiguous
-//   Y<->Z buffer   [x/W][y][z][x%W]   Z-stage tile = (x/W, y), rows z: contiguous
+//   Z->Y buffer    [x/W][y][z][x%W]   Z-stage tile = (x/W, y), rows z: contiguous (backward)
+//   Y->Z buffer    [x/W][y/8][z][y%8][x%W]   Y stage stores 512-byte pieces, 8 Z tiles share a panel (forward)
 // per peer block (blocks padded in x to a multiple of W).  The exchange still moves one
 // contiguous block per peer; only the order of the elements inside a block differs from the
 // reference's pack buffers, which no caller can observe.  W = 0 keeps the reference's plain
@@ -350,37 +353,55 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
                     W, 0, 0, 1, W, nyq * W, nxb * nyq * W, xy_y[q]);
       }
     };
-    // Y side of the Y<->Z buffer, [xb][y][z][xi] per peer block in both directions: the Z-stage tile
-    // (x/W, y) is contiguous, the Y stage touches 64-byte rows kjsize*64 bytes apart
+    // Y<->Z buffer.  Backward (Z stage writes, Y stage reads): [xb][y][z][xi] -- the Z-stage tile
+    // (x/W, y) is one contiguous run per peer.  Forward (Y stage writes, Z stage reads):
+    // [xb][y/YB][z][y%YB][xi] -- the Y stage (tile (z, x/W), rows y) stores YB*64-byte pieces, which is
+    // what NVLink peer stores and HBM writes want, and the YB Z-stage tiles that share one
+    // [z][y%YB][xi] panel run on neighbouring CTAs, so the panel is read from HBM once.
+    const int YB = 8;
+    auto nyb = [&](long long n) { return (n + YB - 1) / YB; };
+    std::vector<long long> fz_y(M2), fz_z(M2);       // forward block sizes (y padded to YB)
+    for (int p = 0; p < M2; p++) { fz_y[p] = nxb * nyb(d.jj.sz[p]) * YB * kj * W; fz_z[p] = nxb * nyb(jj) * YB * d.kj.sz[p] * W; }
     auto yz_yside = [&](P3dSide& sd, bool send) {
       for (int p = 0; p < M2; p++) {
         const long long nyp = d.jj.sz[p];
         const bool self_redirect = send && M2 > 1 && p == d.jpid;
         const bool remote = send && !self_redirect && M2 > 1 && p2p;
         const int buf = send ? ((self_redirect || remote) ? rcv : snd) : cur;
-        long long off = self_redirect ? offs(yz_z, d.jpid) : offs(yz_y, p);
-        if (remote) {     // peer p's Z side: block from sender q' holds y in jj(p), z in kj(q')
-          off = 0;
-          for (int q = 0; q < d.jpid; q++) off += nv * nxb * nyp * d.kj.sz[q] * W;
+        if (send) {     // forward: this rank's Y stage writes
+          long long off = self_redirect ? offs(fz_z, d.jpid) : offs(fz_y, p);
+          if (remote) {     // peer p's Z side: block from sender q' holds y in jj(p), z in kj(q')
+            off = 0;
+            for (int q = 0; q < d.jpid; q++) off += nv * nxb * nyb(nyp) * YB * d.kj.sz[q] * W;
+          }
+          add_seg_blk(sd, buf, remote ? d.rank_of(d.ipid, p) : -1, off, d.jj.st[p] - 1, (int)nyp,
+                      W, YB, kj * YB * W, 1, W, nyb(nyp) * kj * YB * W, YB * W, fz_y[p]);
+        } else {        // backward: this rank's Y stage reads what the Z stages stored
+          add_seg_blk(sd, buf, -1, offs(yz_y, p), d.jj.st[p] - 1, (int)nyp,
+                      kj * W, 0, 0, 1, W, nyp * kj * W, W, yz_y[p]);
         }
-        add_seg_blk(sd, buf, remote ? d.rank_of(d.ipid, p) : -1, off, d.jj.st[p] - 1, (int)nyp,
-                    kj * W, 0, 0, 1, W, nyp * kj * W, W, yz_y[p]);
       }
     };
-    // Z side of the Y<->Z buffer
     auto yz_zside = [&](P3dSide& sd, bool send) {
       for (int q = 0; q < M2; q++) {
         const long long nzq = d.kj.sz[q];
         const bool self_redirect = send && M2 > 1 && q == d.jpid;
         const bool remote = send && !self_redirect && M2 > 1 && p2p;
         const int buf = send ? ((self_redirect || remote) ? rcv : snd) : cur;
-        long long off = self_redirect ? offs(yz_y, d.jpid) : offs(yz_z, q);
-        if (remote) {     // peer q's Y side: block from sender p' holds y in jj(p'), z in kj(q)
-          off = 0;
-          for (int pp = 0; pp < d.jpid; pp++) off += nv * nxb * d.jj.sz[pp] * nzq * W;
+        if (send) {     // backward: this rank's Z stage writes
+          long long off = self_redirect ? offs(yz_y, d.jpid) : offs(yz_z, q);
+          if (remote) {     // peer q's Y side: block from sender p' holds y in jj(p'), z in kj(q)
+            off = 0;
+            for (int pp = 0; pp < d.jpid; pp++) off += nv * nxb * d.jj.sz[pp] * nzq * W;
+          }
+          add_seg_blk(sd, buf, remote ? d.rank_of(d.ipid, q) : -1, off, d.kj.st[q] - 1, (int)nzq,
+                      W, 0, 0, 1, W, jj * nzq * W, nzq * W, yz_z[q]);
+        } else {        // forward: this rank's Z stage reads; b = y is blocked by YB
+          add_seg_blk(sd, buf, -1, offs(fz_z, q), d.kj.st[q] - 1, (int)nzq,
+                      YB * W, 0, 0, 1, W, nyb(jj) * nzq * YB * W, W, fz_z[q]);
+          P3dSeg& g = sd.seg[sd.nseg - 1];
+          g.bw = YB; g.sbh = nzq * YB * W;
         }
-        add_seg_blk(sd, buf, remote ? d.rank_of(d.ipid, q) : -1, off, d.kj.st[q] - 1, (int)nzq,
-                    W, 0, 0, 1, W, jj * nzq * W, nzq * W, yz_z[q]);
       }
     };
     if (!backward) {
@@ -399,7 +420,7 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
       rotate();
       yz_yside(s.out, true);
       push_stage(s);
-      if (M2 > 1) { push_exchange_cnt(1, M2, d.jpid, 2, yz_y, yz_z); cur = rcv; } else cur = snd;
+      if (M2 > 1) { push_exchange_cnt(1, M2, d.jpid, 2, fz_y, fz_z); cur = rcv; } else cur = snd;
       stage_init(s, zkind, d.nz, (int)ii, (int)jj, nv, 8);
       side_init(s.in, d.nz, d.nz, d.nz);
       yz_zside(s.in, false);

@@ -28,9 +28,10 @@ enum P3dBuf { P3D_BUF_USER_IN = 0, P3D_BUF_USER_OUT = 1, P3D_BUF_A = 2, P3D_BUF_
 
 // One run of consecutive stored points along the transform axis living in one block.
 // Address (in elements of the side's type) of stored point s of line (a,b,c), i = s - start:
-//     off + R(i) + A(a) + b*sb + c*sc
+//     off + R(i) + A(a) + B(b) + c*sc
 //     R(i) = i*ps                       (kw <= 1)     (i / kw)*psh + (i % kw)*ps   (kw > 1)
 //     A(a) = a*sa                       (aw <= 1)     (a / aw)*sah + (a % aw)*sa   (aw > 1)
+//     B(b) = b*sb                       (bw <= 1)     (b / bw)*sbh + (b % bw)*sb   (bw > 1)
 // The two-level forms describe the tile-blocked layouts of the library's own pencil buffers
 // (plan.h): aw lines that are adjacent along the contiguous direction form one 64-byte row
 // of a kernel tile, and a tile's rows are consecutive in memory.
@@ -43,6 +44,8 @@ struct P3dSeg {
   int64_t ps, sa, sb, sc;
   int32_t kw, aw;    // block widths along the transform axis / along a (0 or 1: plain strides)
   int64_t psh, sah;  // strides of whole blocks
+  int32_t bw, pad_;  // block width along b
+  int64_t sbh;
 };
 
 // Stored points s in [0,cnt) map to logical indices k in [0,L):

@@ -48,7 +48,8 @@ def _side_indices(side, na, nb, nc):
         k = np.where(s < side.h1, s, s + shift)
         ro = (i // sg.kw) * sg.psh + (i % sg.kw) * sg.ps if sg.kw > 1 else i * sg.ps
         ao = (a // sg.aw) * sg.sah + (a % sg.aw) * sg.sa if sg.aw > 1 else a * sg.sa
-        addr = sg.off + ro[:, None, None, None] + ao + b * sg.sb + c * sg.sc
+        bo = (b // sg.bw) * sg.sbh + (b % sg.bw) * sg.sb if sg.bw > 1 else b * sg.sb
+        addr = sg.off + ro[:, None, None, None] + ao + bo + c * sg.sc
         ks.append(k)
         addrs.append(addr)
         bufs.append((sg.buf, sg.peer))
