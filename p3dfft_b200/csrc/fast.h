@@ -41,6 +41,7 @@ struct FastStage {
   int32_t n;             // logical length of the transform axis (nx, ny, nz)
   int32_t mirror;        // 1: DCT-I -- FFT row r >= n reads logical row nfft - r
   int32_t prefetch;      // L2 prefetch of a CTA's next tile for inputs whose row pitch is <= this many bytes (0: off)
+  int32_t bord, pad_;    // tile order: this many consecutive b are innermost (input blocked along b), else 1
   const void* tw;        // device twiddle block of this (kind, nfft), see fast_twiddle_*
   FastSide in, out;
 };

@@ -168,8 +168,11 @@ void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes) {
   const int tx = real_bytes == 4 ? tile_lines<float>(st) : tile_lines<double>(st);
   f.na = st.na; f.nb = st.nb; f.nc = st.nc; f.n = st.n;
   f.mirror = st.kind == P3D_DCT1;
-  static const int pf = getenv("P3DFFT_B200_PREFETCH") ? atoi(getenv("P3DFFT_B200_PREFETCH")) : 64;
+  static const int pf = getenv("P3DFFT_B200_PREFETCH") ? atoi(getenv("P3DFFT_B200_PREFETCH")) : 131072;
   f.prefetch = pf;
+  static const int bo = getenv("P3DFFT_B200_BORD") ? atoi(getenv("P3DFFT_B200_BORD")) : 1;
+  f.bord = 1;
+  if (bo && !is_x(st.kind) && st.in.nseg > 0 && st.in.seg[0].bw > 1) f.bord = st.in.seg[0].bw;
   f.tw = nullptr;
   side_to_runs(st.in, f.in, st.kind == P3D_R2C ? real_bytes : 2 * real_bytes, tx);
   side_to_runs(st.out, f.out, st.kind == P3D_C2R ? real_bytes : 2 * real_bytes, tx);
@@ -228,7 +231,8 @@ template <typename T, int NN>
 static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
   constexpr int TX = CCfg<T, NN>::TX, NT = CCfg<T, NN>::NT;
   constexpr size_t smem = cstage_smem<T, NN>();
-  const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb * st.nc;
+  const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
   if (tiles <= 0) return cudaSuccess;
   cudaError_t e;
   if (st.kind == P3D_C2C_BWD) {

@@ -290,14 +290,31 @@ __device__ __forceinline__ long long run_offset(const FastRun& r, int k, int ta,
   return (ro + (long long)ta * r.sat + bo + (long long)c * r.sc) * ESZ;
 }
 
+// Tile order: a-tiles fastest, then b, then c -- except that bord consecutive b's are innermost when the
+// input is blocked along b (bord Z-stage tiles share one [z][y%bord][xi] panel and must run together).
+// b >= nb marks a padding slot of the last b-block (no work).
 struct TileIdx { int ta, b, c; };
-__device__ __forceinline__ TileIdx tile_decode(long long tile, int tiles_a, int nb) {
+__device__ __forceinline__ TileIdx tile_decode(long long tile, int tiles_a, int nb, int bord) {
   TileIdx x;
-  x.ta = (int)(tile % tiles_a);
-  const long long r = tile / tiles_a;
-  x.b = (int)(r % nb);
-  x.c = (int)(r / nb);
+  if (bord <= 1) {
+    x.ta = (int)(tile % tiles_a);
+    const long long r = tile / tiles_a;
+    x.b = (int)(r % nb);
+    x.c = (int)(r / nb);
+  } else {
+    const int nbb = (nb + bord - 1) / bord;
+    const int bl = (int)(tile % bord);
+    long long r = tile / bord;
+    x.ta = (int)(r % tiles_a);
+    r /= tiles_a;
+    x.b = (int)(r % nbb) * bord + bl;
+    x.c = (int)(r / nbb);
+  }
   return x;
+}
+__device__ __forceinline__ long long tile_count(int tiles_a, int nb, int nc, int bord) {
+  const long long nbp = bord <= 1 ? nb : (long long)((nb + bord - 1) / bord) * bord;
+  return (long long)tiles_a * nbp * nc;
 }
 
 // per-run tile bases: the run-dependent 64-bit arithmetic is done once per run and tile, a row
@@ -343,7 +360,7 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
 
   const int tiles_a = (st.na + TX - 1) / TX;
-  const long long ntiles = (long long)tiles_a * st.nb * st.nc;
+  const long long ntiles = tile_count(tiles_a, st.nb, st.nc, st.bord);
   const int t = threadIdx.x % TX;
   const long long lin = (long long)t * st.in.run[0].sa * (long long)sizeof(T2);     // line offsets inside a tile
   const long long lout = (long long)t * st.out.run[0].sa * (long long)sizeof(T2);
@@ -358,15 +375,15 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
     rt->kw[side][g] = r.kw;
     rt->ks[side][g] = r.korg;
   }
-  if ((long long)blockIdx.x < ntiles) fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb));
+  if ((long long)blockIdx.x < ntiles) fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
   __syncthreads();
 
   int slot = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, slot ^= 1) {
-    const TileIdx ti = tile_decode(tile, tiles_a, st.nb);
-    const bool live = ti.ta * TX + t < st.na;
+    const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
+    const bool live = ti.ta * TX + t < st.na && ti.b < st.nb;       // b >= nb: padding slot, nothing loaded or stored
     const bool has_next = tile + gridDim.x < ntiles;
-    if (has_next) fill_tilebase<NT, sizeof(T2)>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb));
+    if (has_next) fill_tilebase<NT, sizeof(T2)>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord));
     // ---- input row table of this tile ---------------------------------------------------------
     for (int row = threadIdx.x; row < N; row += NT) {
       const int g = rr_in[row];
@@ -464,7 +481,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
   const T2* __restrict__ wx = tw + S::twtotal();
 
   const int tiles_a = (st.na + TX - 1) / TX;
-  const long long ntiles = (long long)tiles_a * st.nb * st.nc;
+  const long long ntiles = tile_count(tiles_a, st.nb, st.nc, st.bord);
   const int t = threadIdx.x % TX;
   const FastRun& rin = st.in.run[0];
   const long long lout = (long long)t * st.out.run[0].sa * (long long)sizeof(T2);
@@ -473,7 +490,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
   __syncthreads();
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const TileIdx ti = tile_decode(tile, tiles_a, st.nb);
+    const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
     const bool live = ti.ta * TX + t < st.na;
     const T2* line = reinterpret_cast<const T2*>(reinterpret_cast<const T*>(rin.base) + (long long)(ti.ta * TX + t) * rin.sa +
                                                  (long long)ti.b * rin.sb + (long long)ti.c * rin.sc);
@@ -485,7 +502,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
       rowptr[row] = p;
     }
     if (st.prefetch && tile + gridDim.x < ntiles) {
-      const TileIdx tn = tile_decode(tile + gridDim.x, tiles_a, st.nb);
+      const TileIdx tn = tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord);
       constexpr int PER_LINE = (int)(H * sizeof(T2) / 128);          // 128-byte lines per real line
       for (int i = threadIdx.x; i < PER_LINE * TX; i += NT) {
         const int l = i / PER_LINE, j = i - l * PER_LINE;
@@ -599,7 +616,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
   const T2* __restrict__ wx = tw + S::twtotal();
 
   const int tiles_a = (st.na + TX - 1) / TX;
-  const long long ntiles = (long long)tiles_a * st.nb * st.nc;
+  const long long ntiles = tile_count(tiles_a, st.nb, st.nc, st.bord);
   const int t = threadIdx.x % TX;
   const long long sab = st.in.run[0].sa * (long long)sizeof(T2);
   const long long lin = (long long)t * sab;
@@ -609,11 +626,11 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
   __syncthreads();
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const TileIdx ti = tile_decode(tile, tiles_a, st.nb);
+    const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
     const bool live = ti.ta * TX + t < st.na;
     const long long nxt = tile + gridDim.x;
     const bool has_next = nxt < ntiles;
-    const TileIdx tn = tile_decode(has_next ? nxt : tile, tiles_a, st.nb);
+    const TileIdx tn = tile_decode(has_next ? nxt : tile, tiles_a, st.nb, st.bord);
     // ---- input row table; L2 prefetch of the next tile (row k on line k % TX: every 64 bytes) --
     for (int row = threadIdx.x; row <= H; row += NT) {
       const int g = rr_in[row];

@@ -135,10 +135,11 @@ struct Decomp {
       const long long nxb = (iisize + W - 1) / W;
       m = nxb_all * W * jisize * kjsize;                         // X side of the X<->Y buffer
       m = std::max(m, nxb * W * (long long)ny * kjsize);         // Y side of it
-      long long nyb_all = 0;                                     // forward Y->Z blocks pad y to multiples of 8
-      for (int p = 0; p < jproc; p++) nyb_all += (jj.sz[p] + 7) / 8;
-      m = std::max(m, nxb * W * nyb_all * 8 * kjsize);           // Y side of the Y<->Z buffer
-      m = std::max(m, nxb * W * ((jjsize + 7) / 8) * 8 * (long long)nz);   // Z side of it
+      const int yb = jproc > 1 ? 8 : 1;                          // forward Y->Z blocks pad y to multiples of 8
+      long long nyb_all = 0;
+      for (int p = 0; p < jproc; p++) nyb_all += (jj.sz[p] + yb - 1) / yb;
+      m = std::max(m, nxb * W * nyb_all * yb * kjsize);          // Y side of the Y<->Z buffer
+      m = std::max(m, nxb * W * ((jjsize + yb - 1) / yb) * yb * (long long)nz);   // Z side of it
     }
     return std::max<long long>(m, 1) * nv;
   }
@@ -358,7 +359,8 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
     // [xb][y/YB][z][y%YB][xi] -- the Y stage (tile (z, x/W), rows y) stores YB*64-byte pieces, which is
     // what NVLink peer stores and HBM writes want, and the YB Z-stage tiles that share one
     // [z][y%YB][xi] panel run on neighbouring CTAs, so the panel is read from HBM once.
-    const int YB = 8;
+    // (single column: nothing crosses NVLink and the Z-contiguous order measured faster -> YB = 1)
+    const int YB = M2 > 1 ? 8 : 1;
     auto nyb = [&](long long n) { return (n + YB - 1) / YB; };
     std::vector<long long> fz_y(M2), fz_z(M2);       // forward block sizes (y padded to YB)
     for (int p = 0; p < M2; p++) { fz_y[p] = nxb * nyb(d.jj.sz[p]) * YB * kj * W; fz_z[p] = nxb * nyb(jj) * YB * d.kj.sz[p] * W; }
@@ -375,7 +377,7 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
             for (int q = 0; q < d.jpid; q++) off += nv * nxb * nyb(nyp) * YB * d.kj.sz[q] * W;
           }
           add_seg_blk(sd, buf, remote ? d.rank_of(d.ipid, p) : -1, off, d.jj.st[p] - 1, (int)nyp,
-                      W, YB, kj * YB * W, 1, W, nyb(nyp) * kj * YB * W, YB * W, fz_y[p]);
+                      YB > 1 ? W : kj * W, YB > 1 ? YB : 0, kj * YB * W, 1, W, nyb(nyp) * kj * YB * W, YB * W, fz_y[p]);
         } else {        // backward: this rank's Y stage reads what the Z stages stored
           add_seg_blk(sd, buf, -1, offs(yz_y, p), d.jj.st[p] - 1, (int)nyp,
                       kj * W, 0, 0, 1, W, nyp * kj * W, W, yz_y[p]);
@@ -398,9 +400,9 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
                       W, 0, 0, 1, W, jj * nzq * W, nzq * W, yz_z[q]);
         } else {        // forward: this rank's Z stage reads; b = y is blocked by YB
           add_seg_blk(sd, buf, -1, offs(fz_z, q), d.kj.st[q] - 1, (int)nzq,
-                      YB * W, 0, 0, 1, W, nyb(jj) * nzq * YB * W, W, fz_z[q]);
+                      YB * W, 0, 0, 1, W, nyb(jj) * nzq * YB * W, YB > 1 ? W : nzq * W, fz_z[q]);
           P3dSeg& g = sd.seg[sd.nseg - 1];
-          g.bw = YB; g.sbh = nzq * YB * W;
+          if (YB > 1) { g.bw = YB; g.sbh = nzq * YB * W; }
         }
       }
     };
