@@ -267,6 +267,14 @@ def main():
     dom = max(stage_t, key=lambda k: stage_t[k][0])
     dt, db = stage_t[dom]
     kname = {"x_r2c": "xr2c_kernel", "x_c2r": "xc2r_kernel"}.get(dom, "cstage_kernel") + f" ({dom})"
+    traffic = None      # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload only)
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if world == 1 and n == 1024:
+            traffic = tj["per_launch"][dom]["dram_bytes"]
+    except Exception:
+        traffic = None
     ach = db / dt / 1e9 if dt > 0 else 0.0
     hbm_pair = 2 * (sb["x"] + sb["y"] + sb["z"])
     M1, M2 = dims
@@ -283,7 +291,7 @@ def main():
         "gflops_5NlogN": 2 * 5 * ntot * math.log2(ntot) / (ms * 1e-3) / 1e9,
         "roofline_pair_ms": roof_ms, "roofline_pair_frac": roof_ms / ms,
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": db, "avg_launch_ms": dt * 1e3,
                      "stages_ms": {k: v[0] * 1e3 for k, v in stage_t.items()},
                      "exchange_ms": {"T1": tm[0] * 1e3, "T2": tm[1] * 1e3, "T3": tm[2] * 1e3, "T4": tm[3] * 1e3}},
