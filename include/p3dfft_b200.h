@@ -66,6 +66,9 @@ int p3dfft_b200_p2p_active(void);
  * identical, only the order of elements inside the internal buffers changes
  * (also env P3DFFT_B200_PLAIN)                                                              */
 void p3dfft_b200_plain_layout(int on);
+/* Width of one tile row of the internal layouts: 0 = planner's rule (128 bytes unless a Y/Z length exceeds
+ * 1024), 64 or 128 = forced.  Takes effect at the next p3dfft_setup (also env P3DFFT_B200_ROWB)      */
+void p3dfft_b200_row_bytes(int rb);
 
 /* ---- host-only planner queries (no GPU needed; used by the CPU test-suite) ------------- */
 typedef struct {
@@ -81,7 +84,8 @@ typedef struct {
 } p3dfft_b200_decomp;
 
 /* flags: bit0 = single precision (sizes the blocked layouts), bit1 = STRIDE1, bit2 = DIMS_C,
- * bit3 = plain (reference) internal layouts, bit4 = peer-to-peer plan.  Returns 0, or -1 and records the reference's
+ * bit3 = plain (reference) internal layouts, bit4 = peer-to-peer plan, bit5 / bit6 = force 64- / 128-byte
+ * tile rows (default: the planner's rule).  Returns 0, or -1 and records the reference's
  * error text (retrievable with p3dfft_b200_last_error).                                   */
 int p3dfft_b200_plan_decomp(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc,
                             int flags, p3dfft_b200_decomp* out);

@@ -43,7 +43,7 @@ class Stage(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("nfft", C.c_int32), ("na", C.c_int32),
                 ("nb", C.c_int32), ("nc", C.c_int32), ("tile", C.c_int32), ("layx", C.c_int32),
                 ("need_zero", C.c_int32), ("nfac", C.c_int32), ("fac", C.c_int32 * MAXFAC),
-                ("timer", C.c_int32), ("tw", C.c_void_p), ("scale", C.c_double),
+                ("timer", C.c_int32), ("bord", C.c_int32), ("tw", C.c_void_p), ("scale", C.c_double),
                 ("inp", Side), ("out", Side)]
 
 
@@ -241,11 +241,16 @@ class P3DFFT:
     def plain_layout(self, on=True):
         self.lib.p3dfft_b200_plain_layout(int(on))
 
+    def row_bytes(self, rb=0):
+        """Tile row width of the internal layouts: 0 = planner's rule, 64 or 128 forced (next setup)."""
+        self.lib.p3dfft_b200_row_bytes(int(rb))
+
     def plan_decomp(self, dims, nx, ny, nz, rank=0, nxc=None, nyc=None, nzc=None, stride1=False, dims_c=False,
-                    plain=False):
+                    plain=False, row_bytes=0):
         info = DecompInfo()
         d = (C.c_int * 2)(*dims)
         flags = (1 if self.single else 0) | (2 if stride1 else 0) | (4 if dims_c else 0) | (8 if plain else 0)
+        flags |= 32 if row_bytes == 64 else 64 if row_bytes == 128 else 0
         rc = self.lib.p3dfft_b200_plan_decomp(d, nx, ny, nz, rank, nxc or nx, nyc or ny, nzc or nz, flags,
                                               C.byref(info))
         if rc != 0:
@@ -254,8 +259,8 @@ class P3DFFT:
         return info
 
     def plan_steps(self, dims, nx, ny, nz, rank, backward, op, nv=1, nxc=None, nyc=None, nzc=None, stride1=False,
-                   dims_c=False, dim_real=None, dim_cplx=None, plain=False, p2p=False):
-        info = self.plan_decomp(dims, nx, ny, nz, rank, nxc, nyc, nzc, stride1, dims_c, plain)
+                   dims_c=False, dim_real=None, dim_cplx=None, plain=False, p2p=False, row_bytes=0):
+        info = self.plan_decomp(dims, nx, ny, nz, rank, nxc, nyc, nzc, stride1, dims_c, plain, row_bytes)
         if dim_real is None:
             dim_real = info.nx * info.jisize * info.kjsize
         if dim_cplx is None:
@@ -263,6 +268,7 @@ class P3DFFT:
         arr = (Step * 16)()
         d = (C.c_int * 2)(*dims)
         flags = (2 if stride1 else 0) | (4 if dims_c else 0) | (8 if plain else 0) | (16 if p2p else 0)
+        flags |= 32 if row_bytes == 64 else 64 if row_bytes == 128 else 0
         n = self.lib.p3dfft_b200_plan_steps(d, nx, ny, nz, rank, nxc or nx, nyc or ny, nzc or nz, flags,
                                             1 if backward else 0, op.encode() + b"\0", nv, dim_real, dim_cplx,
                                             4 if self.single else 8, arr, 16)

@@ -133,7 +133,8 @@ struct Lib {
   std::vector<void*> peer_buf;   // [world rank * 3 + (buffer id - P3D_BUF_A)], own entries = own buffers
   float* bar_scratch = nullptr;
   bool plain_layout = false;     // true: the reference's pack-buffer layouts instead of the tile-blocked ones
-  int W() const { return plain_layout ? 0 : (int)(64 / CSIZE); }
+  int force_row_bytes = 0;       // 64 / 128: override the planner's choice of the tile row width
+  int W() const { return plain_layout ? 0 : p3d::pick_W(d.ny, d.nz, (int)CSIZE, force_row_bytes); }
   long long fast_launches = 0;
   std::map<std::pair<int, int>, void*> fast_twiddles;   // (x-stage?, nfft) -> device block
   double timers[12] = {0};
@@ -469,6 +470,7 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   if (getenv("P3DFFT_B200_GENERIC")) L.force_generic = true;
   if (getenv("P3DFFT_B200_PLAIN")) L.plain_layout = true;
   if (getenv("P3DFFT_B200_P2P")) L.want_p2p = atoi(getenv("P3DFFT_B200_P2P")) != 0;
+  if (getenv("P3DFFT_B200_ROWB")) L.force_row_bytes = atoi(getenv("P3DFFT_B200_ROWB"));
   for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
   L.nv_preset = 0;
   L.set = true;
@@ -640,6 +642,9 @@ void p3dfft_b200_reset_stream(void) { L.user_stream = nullptr; L.has_user_stream
 void p3dfft_b200_force_generic(int on) { L.force_generic = on != 0; }
 void p3dfft_b200_set_p2p(int on) { L.want_p2p = on != 0; }
 int p3dfft_b200_p2p_active(void) { return L.p2p ? 1 : 0; }
+void p3dfft_b200_row_bytes(int rb) {      // 0: planner's rule; 64 / 128: forced.  Takes effect at the next p3dfft_setup
+  L.force_row_bytes = (rb == 64 || rb == 128) ? rb : 0;
+}
 void p3dfft_b200_plain_layout(int on) {
   if (L.set && (on != 0) != L.plain_layout) { cudaStreamSynchronize(L.stream()); L.plans.clear(); L.nv_preset = 0; }
   L.plain_layout = on != 0;
@@ -664,7 +669,8 @@ int p3dfft_b200_plan_decomp(const int* dims, int nx, int ny, int nz, int rank, i
   o->kjstart = d.kjstart; o->kjend = d.kjend; o->kjsize = d.kjsize;
   o->padi_work = d.padi_work; o->padi = d.padi;
   for (int i = 0; i < 3; i++) o->memsize[i] = d.memsize[i];
-  o->nm = d.nm; o->work_elems = d.work_elems(1, (flags & 8) ? 0 : ((flags & 1) ? 8 : 4));
+  o->nm = d.nm;
+  o->work_elems = d.work_elems(1, (flags & 8) ? 0 : p3d::pick_W(ny, nz, (flags & 1) ? 8 : 16, (flags & 32) ? 64 : (flags & 64) ? 128 : 0));
   return 0;
 }
 
@@ -680,7 +686,8 @@ int p3dfft_b200_plan_steps(const int* dims, int nx, int ny, int nz, int rank, in
                            (flags & 2) != 0);
   if (!err.empty()) { g_last_error = err; return -1; }
   p3d::TransformPlan tp = p3d::build_plan(d, backward != 0, op, nv, dim_real, dim_cplx,
-                                          (flags & 8) ? 0 : 64 / (2 * elem_bytes), (flags & 16) != 0 && !(flags & 8));
+                                          (flags & 8) ? 0 : p3d::pick_W(ny, nz, 2 * elem_bytes, (flags & 32) ? 64 : (flags & 64) ? 128 : 0),
+                                          (flags & 16) != 0 && !(flags & 8));
   if (!tp.error.empty()) { g_last_error = tp.error; return -1; }
   if ((int)tp.steps.size() > max_steps) { g_last_error = "step array too small"; return -1; }
   P3dStepC* out = (P3dStepC*)steps;

@@ -41,7 +41,9 @@ struct FastStage {
   int32_t n;             // logical length of the transform axis (nx, ny, nz)
   int32_t mirror;        // 1: DCT-I -- FFT row r >= n reads logical row nfft - r
   int32_t prefetch;      // L2 prefetch of a CTA's next tile for inputs whose row pitch is <= this many bytes (0: off)
-  int32_t bord, pad_;    // tile order: this many consecutive b are innermost (input blocked along b), else 1
+  int32_t bord;          // tile order: this many consecutive b are innermost (the tiles that share memory lines of a
+                         // gathered input run on neighbouring CTAs at the same time), else 1
+  int32_t rowb;          // bytes per tile row (64 or 128) = block width of the internal layouts
   const void* tw;        // device twiddle block of this (kind, nfft), see fast_twiddle_*
   FastSide in, out;
 };

@@ -82,11 +82,28 @@ bool dispatch_x(int h, F&& f) {
   }
 }
 
+// bytes per tile row of a c2c stage: fixed by the block width of its tile-blocked segments (plan.h, W);
+// plain strided layouts take 128-byte rows whenever that tile fits on chip.  0: inconsistent widths
+template <typename T>
+static int row_bytes(const P3dStage& st) {
+  int aw = 0;
+  for (int side = 0; side < 2; side++) {
+    const P3dSide& sd = side ? st.out : st.in;
+    for (int g = 0; g < sd.nseg; g++) {
+      if (sd.seg[g].aw <= 1) continue;
+      if (aw && sd.seg[g].aw != aw) return 0;
+      aw = sd.seg[g].aw;
+    }
+  }
+  if (!aw) return st.nfft <= 1024 ? 128 : 64;
+  return aw * 2 * (int)sizeof(T);
+}
+
 template <typename T>
 static int tile_lines(const P3dStage& st) {
   int tx = 1;
   if (is_x(st.kind)) dispatch_x(st.n / 2, [&](auto h) { tx = XCfg<T, decltype(h)::value>::TX; });
-  else dispatch_c(st.nfft, [&](auto nn) { tx = CCfg<T, decltype(nn)::value>::TX; });
+  else tx = row_bytes<T>(st) / (2 * (int)sizeof(T));
   return tx;
 }
 
@@ -97,6 +114,8 @@ bool fast_supported(const P3dStage& st) {
   switch (st.kind) {
     case P3D_C2C_FWD: case P3D_C2C_BWD: case P3D_DCT1: {
       if (!c2c_len_ok(st.nfft)) return false;
+      const int rb = row_bytes<T>(st);
+      if ((rb != 64 && rb != 128) || !ccfg_exists(st.nfft, rb)) return false;
       const int tx = tile_lines<T>(st);
       for (int side = 0; side < 2; side++) {          // one line pitch per side (the kernels keep it in a register)
         const P3dSide& sd = side ? st.out : st.in;
@@ -127,14 +146,14 @@ template <typename T>
 size_t fast_twiddle_elems(int kind, int nfft) {
   size_t n = 0;
   if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { n = block_elems<typename XCfg<T, decltype(h)::value>::S>(true); });
-  else dispatch_c(nfft, [&](auto nn) { n = block_elems<typename CCfg<T, decltype(nn)::value>::S>(false); });
+  else dispatch_c(nfft, [&](auto nn) { n = block_elems<typename CCfg<T, decltype(nn)::value, 64>::S>(false); });
   return n;
 }
 
 template <typename T>
 void fast_twiddle_fill(int kind, int nfft, void* host) {
   if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { fill_block<T, typename XCfg<T, decltype(h)::value>::S>(true, host); });
-  else dispatch_c(nfft, [&](auto nn) { fill_block<T, typename CCfg<T, decltype(nn)::value>::S>(false, host); });
+  else dispatch_c(nfft, [&](auto nn) { fill_block<T, typename CCfg<T, decltype(nn)::value, 64>::S>(false, host); });
 }
 
 // stored index s -> logical k:  k = s (s < h1),  k = s + (logical - cnt) (s >= h1); a segment that
@@ -170,9 +189,10 @@ void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes) {
   f.mirror = st.kind == P3D_DCT1;
   static const int pf = getenv("P3DFFT_B200_PREFETCH") ? atoi(getenv("P3DFFT_B200_PREFETCH")) : 131072;
   f.prefetch = pf;
-  static const int bo = getenv("P3DFFT_B200_BORD") ? atoi(getenv("P3DFFT_B200_BORD")) : 1;
+  static const int bo = getenv("P3DFFT_B200_BORD") ? atoi(getenv("P3DFFT_B200_BORD")) : -1;
   f.bord = 1;
-  if (bo && !is_x(st.kind) && st.in.nseg > 0 && st.in.seg[0].bw > 1) f.bord = st.in.seg[0].bw;
+  if (!is_x(st.kind) && st.bord > 1) f.bord = bo >= 0 ? (bo > 1 ? bo : 1) : st.bord;
+  f.rowb = is_x(st.kind) ? 0 : (real_bytes == 4 ? row_bytes<float>(st) : row_bytes<double>(st));
   f.tw = nullptr;
   side_to_runs(st.in, f.in, st.kind == P3D_R2C ? real_bytes : 2 * real_bytes, tx);
   side_to_runs(st.out, f.out, st.kind == P3D_C2R ? real_bytes : 2 * real_bytes, tx);
@@ -227,10 +247,10 @@ static cudaError_t launch_x(const P3dStage& st, const FastStage& f, cudaStream_t
   return cudaGetLastError();
 }
 
-template <typename T, int NN>
+template <typename T, int NN, int RB>
 static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
-  constexpr int TX = CCfg<T, NN>::TX, NT = CCfg<T, NN>::NT;
-  constexpr size_t smem = cstage_smem<T, NN>();
+  constexpr int TX = CCfg<T, NN, RB>::TX, NT = CCfg<T, NN, RB>::NT;
+  constexpr size_t smem = cstage_smem<T, NN, RB>();
   const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
   const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
   if (tiles <= 0) return cudaSuccess;
@@ -238,13 +258,13 @@ static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t
   if (st.kind == P3D_C2C_BWD) {
     static bool cfg = false;
     static int per_sm = 0;
-    if ((e = launch_cfg(cstage_kernel<T, NN, true>, smem, cfg)) != cudaSuccess) return e;
-    cstage_kernel<T, NN, true><<<persistent_grid(cstage_kernel<T, NN, true>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
+    if ((e = launch_cfg(cstage_kernel<T, NN, RB, true>, smem, cfg)) != cudaSuccess) return e;
+    cstage_kernel<T, NN, RB, true><<<persistent_grid(cstage_kernel<T, NN, RB, true>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
   } else {
     static bool cfg = false;
     static int per_sm = 0;
-    if ((e = launch_cfg(cstage_kernel<T, NN, false>, smem, cfg)) != cudaSuccess) return e;
-    cstage_kernel<T, NN, false><<<persistent_grid(cstage_kernel<T, NN, false>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
+    if ((e = launch_cfg(cstage_kernel<T, NN, RB, false>, smem, cfg)) != cudaSuccess) return e;
+    cstage_kernel<T, NN, RB, false><<<persistent_grid(cstage_kernel<T, NN, RB, false>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
   }
   return cudaGetLastError();
 }
@@ -260,7 +280,11 @@ cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t str
   }
   cudaError_t err = cudaErrorInvalidValue;
   if (is_x(st.kind)) dispatch_x(st.n / 2, [&](auto h) { err = launch_x<T, decltype(h)::value>(st, f, stream); });
-  else dispatch_c(st.nfft, [&](auto nn) { err = launch_c<T, decltype(nn)::value>(st, f, stream); });
+  else dispatch_c(st.nfft, [&](auto nn) {
+    constexpr int NN = decltype(nn)::value;
+    if (f.rowb == 64) err = launch_c<T, NN, 64>(st, f, stream);
+    else if constexpr (ccfg_exists(NN, 128)) { if (f.rowb == 128) err = launch_c<T, NN, 128>(st, f, stream); }
+  });
   return err;
 }
 

@@ -61,37 +61,70 @@ struct RS {
   __host__ __device__ static constexpr int twtotal() { return twoff(L - 1); }   // last pass has m = 1: no table
 };
 
-// c2c configuration per (type, length): schedule, lines per tile (TX * sizeof(complex) = 64 bytes =
-// the block width W of the planner's internal layouts), threads per CTA, CTAs/SM hint
-template <typename T, int N> struct CCfg;
-template <> struct CCfg<double, 64>   { using S = RS<8, 8>;       static constexpr int TX = 4, NT = 32,  MINB = 16; };
-template <> struct CCfg<double, 128>  { using S = RS<16, 8>;      static constexpr int TX = 4, NT = 64,  MINB = 8; };
-template <> struct CCfg<double, 256>  { using S = RS<16, 16>;     static constexpr int TX = 4, NT = 64,  MINB = 6; };
-template <> struct CCfg<double, 512>  { using S = RS<8, 8, 8>;    static constexpr int TX = 4, NT = 256, MINB = 3; };
-template <> struct CCfg<double, 1024> { using S = RS<16, 8, 8>;   static constexpr int TX = 4, NT = 256, MINB = 2; };
-template <> struct CCfg<double, 2048> { using S = RS<16, 16, 8>;  static constexpr int TX = 4, NT = 512, MINB = 1; };
-template <> struct CCfg<float, 64>    { using S = RS<8, 8>;       static constexpr int TX = 8, NT = 64,  MINB = 16; };
-template <> struct CCfg<float, 128>   { using S = RS<16, 8>;      static constexpr int TX = 8, NT = 128, MINB = 8; };
-template <> struct CCfg<float, 256>   { using S = RS<16, 16>;     static constexpr int TX = 8, NT = 128, MINB = 6; };
-template <> struct CCfg<float, 512>   { using S = RS<8, 8, 8>;    static constexpr int TX = 8, NT = 256, MINB = 3; };
-template <> struct CCfg<float, 1024>  { using S = RS<16, 8, 8>;   static constexpr int TX = 8, NT = 512, MINB = 2; };
-template <> struct CCfg<float, 2048>  { using S = RS<16, 16, 8>;  static constexpr int TX = 8, NT = 512, MINB = 1; };
+// c2c configuration per (type, length, row bytes): schedule, threads per CTA, CTAs/SM hint.  A tile row is
+// RB = 64 or 128 bytes of lines adjacent in x (TX = RB / sizeof(complex) lines = the block width W of the
+// planner's internal layouts).  128-byte rows are one full L1 wavefront / DRAM burst pair per row and are
+// the default; 64-byte rows halve the tile and exist for lengths whose 128-byte tile exceeds shared memory.
+template <typename T, int N, int RB> struct CCfg;
+#define P3D_CCFG(T, N, RB, SCHED, NTV, MINBV)                                                    \
+  template <> struct CCfg<T, N, RB> {                                                            \
+    using S = SCHED;                                                                             \
+    static constexpr int TX = RB / (2 * (int)sizeof(T)), NT = NTV, MINB = MINBV;                 \
+  };
+#define P3D_RS(...) RS<__VA_ARGS__>
+P3D_CCFG(double, 64, 64, P3D_RS(8, 8), 32, 16)
+P3D_CCFG(double, 128, 64, P3D_RS(16, 8), 64, 8)
+P3D_CCFG(double, 256, 64, P3D_RS(16, 16), 64, 6)
+P3D_CCFG(double, 512, 64, P3D_RS(8, 8, 8), 256, 3)
+P3D_CCFG(double, 1024, 64, P3D_RS(16, 8, 8), 256, 2)
+P3D_CCFG(double, 2048, 64, P3D_RS(16, 16, 8), 512, 1)
+P3D_CCFG(double, 64, 128, P3D_RS(8, 8), 64, 8)
+P3D_CCFG(double, 128, 128, P3D_RS(16, 8), 64, 8)
+P3D_CCFG(double, 256, 128, P3D_RS(16, 16), 128, 4)
+P3D_CCFG(double, 512, 128, P3D_RS(8, 8, 8), 256, 2)
+P3D_CCFG(double, 1024, 128, P3D_RS(16, 8, 8), 512, 1)
+P3D_CCFG(float, 64, 64, P3D_RS(8, 8), 64, 16)
+P3D_CCFG(float, 128, 64, P3D_RS(16, 8), 128, 8)
+P3D_CCFG(float, 256, 64, P3D_RS(16, 16), 128, 6)
+P3D_CCFG(float, 512, 64, P3D_RS(8, 8, 8), 256, 3)
+P3D_CCFG(float, 1024, 64, P3D_RS(16, 8, 8), 512, 2)
+P3D_CCFG(float, 2048, 64, P3D_RS(16, 16, 8), 512, 1)
+P3D_CCFG(float, 64, 128, P3D_RS(8, 8), 128, 8)
+P3D_CCFG(float, 128, 128, P3D_RS(16, 8), 128, 8)
+P3D_CCFG(float, 256, 128, P3D_RS(16, 16), 256, 4)
+P3D_CCFG(float, 512, 128, P3D_RS(8, 8, 8), 256, 2)
+P3D_CCFG(float, 1024, 128, P3D_RS(16, 8, 8), 512, 1)
+#undef P3D_CCFG
+// the 128-byte tile of a 2048-point transform (256 KB) does not fit in shared memory
+constexpr bool ccfg_exists(int n, int rb) { return rb == 64 || (rb == 128 && n <= 1024); }
 
 // X-stage configuration per (type, H = nx/2).  The first (c2r) / last (r2c) pass works on
 // butterfly PAIRS, i.e. 2R complex values per thread, so those radices stay <= 8.
-template <typename T, int H> struct XCfg;
-template <> struct XCfg<double, 32>   { using S = RS<4, 8>;       static constexpr int TX = 4, NT = 32,  MINB = 8; };
-template <> struct XCfg<double, 64>   { using S = RS<8, 8>;       static constexpr int TX = 4, NT = 32,  MINB = 8; };
-template <> struct XCfg<double, 128>  { using S = RS<4, 4, 8>;    static constexpr int TX = 4, NT = 64,  MINB = 8; };
-template <> struct XCfg<double, 256>  { using S = RS<8, 4, 8>;    static constexpr int TX = 4, NT = 128, MINB = 4; };
-template <> struct XCfg<double, 512>  { using S = RS<8, 8, 8>;    static constexpr int TX = 4, NT = 128, MINB = 4; };
-template <> struct XCfg<double, 1024> { using S = RS<8, 16, 8>;   static constexpr int TX = 4, NT = 256, MINB = 2; };
-template <> struct XCfg<float, 32>    { using S = RS<4, 8>;       static constexpr int TX = 8, NT = 64,  MINB = 8; };
-template <> struct XCfg<float, 64>    { using S = RS<8, 8>;       static constexpr int TX = 8, NT = 64,  MINB = 8; };
-template <> struct XCfg<float, 128>   { using S = RS<4, 4, 8>;    static constexpr int TX = 8, NT = 128, MINB = 6; };
-template <> struct XCfg<float, 256>   { using S = RS<8, 4, 8>;    static constexpr int TX = 8, NT = 256, MINB = 3; };
-template <> struct XCfg<float, 512>   { using S = RS<8, 8, 8>;    static constexpr int TX = 8, NT = 256, MINB = 3; };
-template <> struct XCfg<float, 1024>  { using S = RS<8, 16, 8>;   static constexpr int TX = 8, NT = 512, MINB = 2; };
+// The X tile is kept LINE-major in shared memory ([line][k], pitch H + 4 elements) because the
+// lines are contiguous in HBM: a warp then loads / stores 512 contiguous bytes of one line.
+// Element k of a line sits at k ^ (((k >> SA) ^ (k >> SB)) & 7) (SB = 0: one term): with these
+// shifts every pass of the schedule -- including the digit-reversed last pass and the
+// (k, H-k) pair pass -- is free of bank conflicts (H = 128: 12 % replays).
+template <typename T, int HH> struct XCfg;
+#define P3D_XCFG(T, HV, SCHED, TXV, NTV, MINBV, SAV, SBV)                                          \
+  template <> struct XCfg<T, HV> {                                                                 \
+    using S = SCHED;                                                                               \
+    static constexpr int H = HV, TX = TXV, NT = NTV, MINB = MINBV, SA = SAV, SB = SBV, LP = HV + 4; \
+  };
+P3D_XCFG(double, 32, P3D_RS(4, 8), 4, 32, 8, 3, 0)
+P3D_XCFG(double, 64, P3D_RS(8, 8), 4, 32, 8, 3, 0)
+P3D_XCFG(double, 128, P3D_RS(4, 4, 8), 4, 64, 8, 3, 5)
+P3D_XCFG(double, 256, P3D_RS(8, 4, 8), 4, 128, 4, 5, 0)
+P3D_XCFG(double, 512, P3D_RS(8, 8, 8), 4, 128, 4, 6, 0)
+P3D_XCFG(double, 1024, P3D_RS(8, 16, 8), 4, 256, 2, 7, 0)
+P3D_XCFG(float, 32, P3D_RS(4, 8), 8, 64, 8, 3, 0)
+P3D_XCFG(float, 64, P3D_RS(8, 8), 8, 64, 8, 3, 0)
+P3D_XCFG(float, 128, P3D_RS(4, 4, 8), 8, 128, 6, 3, 5)
+P3D_XCFG(float, 256, P3D_RS(8, 4, 8), 8, 256, 3, 5, 0)
+P3D_XCFG(float, 512, P3D_RS(8, 8, 8), 8, 256, 3, 6, 0)
+P3D_XCFG(float, 1024, P3D_RS(8, 16, 8), 8, 512, 2, 7, 0)
+#undef P3D_XCFG
+#undef P3D_RS
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------
@@ -342,10 +375,10 @@ __device__ __forceinline__ void fill_tilebase(const FastStage& st, RunTab& rt, i
   }
 }
 
-template <typename T, int N, bool SWAP>
-__global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
+template <typename T, int N, int RB, bool SWAP>
+__global__ void __launch_bounds__(CCfg<T, N, RB>::NT, CCfg<T, N, RB>::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
-  using C = CCfg<T, N>;
+  using C = CCfg<T, N, RB>;
   using S = typename C::S;
   constexpr int TX = C::TX, NT = C::NT, L = S::L;
   constexpr bool SWZ = (TX * sizeof(T2) == 64);
@@ -445,9 +478,78 @@ __global__ void __launch_bounds__(CCfg<T, N>::NT, CCfg<T, N>::MINB) cstage_kerne
   }
 }
 
-template <typename T, int N> constexpr size_t cstage_smem() {
+template <typename T, int N, int RB> constexpr size_t cstage_smem() {
   using T2 = typename Cx<T>::type;
-  return sizeof(T2) * N * CCfg<T, N>::TX + sizeof(char*) * N + sizeof(RunTab) + 2 * N;
+  return sizeof(T2) * N * CCfg<T, N, RB>::TX + sizeof(char*) * N + sizeof(RunTab) + 2 * N;
+}
+
+// ---------------------------------------------------------------------------------------
+// X stage: line-major shared-memory tile
+// ---------------------------------------------------------------------------------------
+template <class C> __device__ __forceinline__ int xs_idx(int t, int e) {
+  int x = e >> C::SA;
+  if constexpr (C::SB > 0) x ^= e >> C::SB;
+  return t * C::LP + (e ^ (x & 7));
+}
+
+template <typename T, class C, int PI>
+__device__ __forceinline__ void xtwiddle_store(typename Cx<T>::type* v, typename Cx<T>::type* s,
+                                               const typename Cx<T>::type* __restrict__ tw, int t, int base, int j) {
+  using T2 = typename Cx<T>::type;
+  using S = typename C::S;
+  constexpr int R = S::r(PI), M = S::m(PI);
+  const T2* twp = tw + S::twoff(PI) + j;
+#pragma unroll
+  for (int q = 1; q < R; q++) v[q] = cmul(v[q], __ldg(twp + (q - 1) * M));
+#pragma unroll
+  for (int q = 0; q < R; q++) s[xs_idx<C>(t, base + q * M)] = v[q];
+}
+
+template <typename T, class C, int PI>
+__device__ __forceinline__ void xmid_pass(typename Cx<T>::type* s, const typename Cx<T>::type* __restrict__ tw) {
+  using T2 = typename Cx<T>::type;
+  using S = typename C::S;
+  constexpr int R = S::r(PI), NCUR = S::ncur(PI), M = S::m(PI), PER = C::H / R, ITEMS = PER * C::TX;
+#pragma unroll 1
+  for (int w = threadIdx.x; w < ITEMS; w += C::NT) {
+    const int t = w / PER, rest = w % PER;
+    const int blk = rest / M, j = rest % M, base = blk * NCUR + j;
+    T2 v[R];
+#pragma unroll
+    for (int p = 0; p < R; p++) v[p] = s[xs_idx<C>(t, base + p * M)];
+    Bfly<T, R>::run(v);
+    xtwiddle_store<T, C, PI>(v, s, tw, t, base, j);
+  }
+}
+
+template <typename T, class C, int PI>
+__device__ __forceinline__ void xmid_passes(typename Cx<T>::type* s, const typename Cx<T>::type* __restrict__ tw) {
+  if constexpr (PI < C::S::L - 1) {
+    xmid_pass<T, C, PI>(s, tw);
+    __syncthreads();
+    xmid_passes<T, C, PI + 1>(s, tw);
+  }
+}
+
+// v[q] = Z[kappa + q*ML] of line t
+template <typename T, class C>
+__device__ __forceinline__ void xlast_bfly(const typename Cx<T>::type* s, int t, int kappa, typename Cx<T>::type* v) {
+  using S = typename C::S;
+  constexpr int RL = S::r(S::L - 1);
+  const int base = blk_of_kappa<S>(kappa) * RL;
+#pragma unroll
+  for (int p = 0; p < RL; p++) v[p] = s[xs_idx<C>(t, base + p)];
+  Bfly<T, RL>::run(v);
+}
+
+// Lanes of the (k, H-k) pair pass: `il` consecutive k (one piece of the blocked X<->Y layout, or a whole
+// warp when the complex side is plain), then the TX lines, then the remaining k -- so that a warp touches
+// il * TX * sizeof(complex) contiguous bytes of the [xb][y][xi] buffer.
+// returns log2(il)
+__device__ __forceinline__ int pair_lanes_log(const FastRun& r, int half) {
+  int il = r.kw > 1 ? r.kw : 32;
+  while (il > half) il >>= 1;
+  return 31 - __clz(il);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -471,29 +573,26 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
   using C = XCfg<T, H>;
   using S = typename C::S;
   constexpr int TX = C::TX, NT = C::NT, L = S::L;
-  constexpr bool SWZ = (TX * sizeof(T2) == 64);
-  static_assert(NT % TX == 0, "t must be constant per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T2* s = reinterpret_cast<T2*>(smem_raw);
-  char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * H * TX);      // [H+1] output rows
+  char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * C::LP * TX);      // [H+1] output rows
   unsigned char* rr_out = reinterpret_cast<unsigned char*>(rowptr + H + 1);
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
   const T2* __restrict__ wx = tw + S::twtotal();
 
   const int tiles_a = (st.na + TX - 1) / TX;
   const long long ntiles = tile_count(tiles_a, st.nb, st.nc, st.bord);
-  const int t = threadIdx.x % TX;
   const FastRun& rin = st.in.run[0];
-  const long long lout = (long long)t * st.out.run[0].sa * (long long)sizeof(T2);
+  const long long sao = st.out.run[0].sa * (long long)sizeof(T2);
+  constexpr int RL = S::r(L - 1), ML = H / RL;
+  const int ilog = pair_lanes_log(st.out.run[0], ML / 2);
 
   build_rowrun<NT>(st.out, rr_out, H + 1, H + 1, 0);
   __syncthreads();
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
-    const bool live = ti.ta * TX + t < st.na;
-    const T2* line = reinterpret_cast<const T2*>(reinterpret_cast<const T*>(rin.base) + (long long)(ti.ta * TX + t) * rin.sa +
-                                                 (long long)ti.b * rin.sb + (long long)ti.c * rin.sc);
+    const T* tbase = reinterpret_cast<const T*>(rin.base) + (long long)ti.b * rin.sb + (long long)ti.c * rin.sc;
     // ---- output row table; L2 prefetch of the real lines of this CTA's next tile ------------
     for (int row = threadIdx.x; row <= H; row += NT) {
       const int g = rr_out[row];
@@ -511,38 +610,42 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
                                                     (long long)tn.b * rin.sb + (long long)tn.c * rin.sc) + j * 128);
       }
     }
-    // ---- pass 1: packed real pairs -> registers -> shared ------------------------------------
+    // ---- pass 1: packed real pairs -> registers -> shared (a warp reads 512 contiguous bytes) ---
     {
       constexpr int R = S::r(0), M = S::m(0), ITEMS = M * TX;
 #pragma unroll
       for (int w0 = 0; w0 < ITEMS; w0 += NT) {
         const int w = w0 + threadIdx.x;
         if (ITEMS % NT == 0 || w < ITEMS) {
-          const int u = w / TX;
+          const int t = w / M, u = w % M;
+          const bool live = ti.ta * TX + t < st.na;
+          const T2* line = reinterpret_cast<const T2*>(tbase + (long long)(ti.ta * TX + t) * rin.sa);
           T2 v[R];
 #pragma unroll
           for (int p = 0; p < R; p++) v[p] = live ? ldg_stream(line + u + p * M) : T2{0, 0};
           Bfly<T, R>::run(v);
-          twiddle_store<T, S, 0, TX, SWZ>(v, s, tw, u, u, t);
+          xtwiddle_store<T, C, 0>(v, s, tw, t, u, u);
         }
       }
     }
     __syncthreads();
-    mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
+    xmid_passes<T, C, 1>(s, tw);
     // ---- pass L on butterfly pairs (kappa, ML-kappa) + Hermitian post-processing -------------
     {
-      constexpr int RL = S::r(L - 1), ML = H / RL, ITEMS = (ML / 2) * TX;
+      constexpr int ITEMS = (ML / 2) * TX;
       static_assert(ML >= 2, "last pass needs at least two butterflies per line");
-      auto put = [&](int k, T2 v) {
-        char* rp = rowptr[k];
-        if (live && rp) stg_stream(reinterpret_cast<T2*>(rp + lout), v);
-      };
 #pragma unroll 1
       for (int w = threadIdx.x; w < ITEMS; w += NT) {
-        const int i = w / TX;
+        const int t = (w >> ilog) % TX, i = (w & ((1 << ilog) - 1)) + (((w >> ilog) / TX) << ilog);
+        const bool live = ti.ta * TX + t < st.na;
+        const long long lout = (long long)t * sao;
+        auto put = [&](int k, T2 v) {
+          char* rp = rowptr[k];
+          if (live && rp) stg_stream(reinterpret_cast<T2*>(rp + lout), v);
+        };
         T2 za[RL], zb[RL];
-        last_bfly<T, S, TX, SWZ>(s, i == 0 ? 0 : i, t, za);
-        last_bfly<T, S, TX, SWZ>(s, i == 0 ? ML / 2 : ML - i, t, zb);
+        xlast_bfly<T, C>(s, t, i, za);
+        xlast_bfly<T, C>(s, t, i == 0 ? ML / 2 : ML - i, zb);
         if (i != 0) {
 #pragma unroll
           for (int q = 0; q < RL; q++) {
@@ -580,7 +683,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
 
 template <typename T, int H> constexpr size_t xstage_smem() {
   using T2 = typename Cx<T>::type;
-  return sizeof(T2) * H * XCfg<T, H>::TX + sizeof(char*) * (H + 1) + (H + 1 + 15) / 16 * 16;
+  return sizeof(T2) * XCfg<T, H>::LP * XCfg<T, H>::TX + sizeof(char*) * (H + 1) + (H + 1 + 15) / 16 * 16;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -606,28 +709,25 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
   using C = XCfg<T, H>;
   using S = typename C::S;
   constexpr int TX = C::TX, NT = C::NT, L = S::L;
-  constexpr bool SWZ = (TX * sizeof(T2) == 64);
-  static_assert(NT % TX == 0, "t must be constant per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T2* s = reinterpret_cast<T2*>(smem_raw);
-  char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * H * TX);      // [H+1] input rows
+  char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * C::LP * TX);      // [H+1] input rows
   unsigned char* rr_in = reinterpret_cast<unsigned char*>(rowptr + H + 1);
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
   const T2* __restrict__ wx = tw + S::twtotal();
 
   const int tiles_a = (st.na + TX - 1) / TX;
   const long long ntiles = tile_count(tiles_a, st.nb, st.nc, st.bord);
-  const int t = threadIdx.x % TX;
   const long long sab = st.in.run[0].sa * (long long)sizeof(T2);
-  const long long lin = (long long)t * sab;
   const FastRun& ro = st.out.run[0];
+  constexpr int R1 = S::r(0), M1 = S::m(0);
+  const int ilog = pair_lanes_log(st.in.run[0], M1 / 2);
 
   build_rowrun<NT>(st.in, rr_in, H + 1, H + 1, 0);
   __syncthreads();
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
-    const bool live = ti.ta * TX + t < st.na;
     const long long nxt = tile + gridDim.x;
     const bool has_next = nxt < ntiles;
     const TileIdx tn = tile_decode(has_next ? nxt : tile, tiles_a, st.nb, st.bord);
@@ -644,17 +744,19 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
       rowptr[row] = p;
     }
     __syncthreads();
-    auto get = [&](int k) -> T2 {
-      const char* rp = rowptr[k];
-      return (live && rp) ? ldg_stream(reinterpret_cast<const T2*>(rp + lin)) : T2{0, 0};
-    };
     // ---- pass 1 on butterfly pairs (u, M-u) with the Hermitian pre-processing ----------------
     {
-      constexpr int R = S::r(0), M = S::m(0), ITEMS = (M / 2) * TX;
+      constexpr int R = R1, M = M1, ITEMS = (M / 2) * TX;
       static_assert(M >= 2, "first pass needs at least two butterflies per line");
 #pragma unroll 1
       for (int w = threadIdx.x; w < ITEMS; w += NT) {
-        const int i = w / TX;
+        const int t = (w >> ilog) % TX, i = (w & ((1 << ilog) - 1)) + (((w >> ilog) / TX) << ilog);
+        const bool live = ti.ta * TX + t < st.na;
+        const long long lin = (long long)t * sab;
+        auto get = [&](int k) -> T2 {
+          const char* rp = rowptr[k];
+          return (live && rp) ? ldg_stream(reinterpret_cast<const T2*>(rp + lin)) : T2{0, 0};
+        };
         T2 za[R], zb[R];
         if (i != 0) {
           T2 xk[R], xm[R];
@@ -681,24 +783,24 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
         }
         const int ua = i, ub = (i == 0) ? M / 2 : M - i;
         Bfly<T, R>::run(za);
-        twiddle_store<T, S, 0, TX, SWZ>(za, s, tw, ua, ua, t);
+        xtwiddle_store<T, C, 0>(za, s, tw, t, ua, ua);
         Bfly<T, R>::run(zb);
-        twiddle_store<T, S, 0, TX, SWZ>(zb, s, tw, ub, ub, t);
+        xtwiddle_store<T, C, 0>(zb, s, tw, t, ub, ub);
       }
     }
     __syncthreads();
-    mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
-    // ---- pass L: shared -> registers -> packed real pairs ---------------------------------------
+    xmid_passes<T, C, 1>(s, tw);
+    // ---- pass L: shared -> registers -> packed real pairs (a warp writes 512 contiguous bytes) ---
     {
-      T2* line = reinterpret_cast<T2*>(const_cast<T*>(reinterpret_cast<const T*>(ro.base)) + (long long)(ti.ta * TX + t) * ro.sa +
-                                       (long long)ti.b * ro.sb + (long long)ti.c * ro.sc);
+      T* tbase = const_cast<T*>(reinterpret_cast<const T*>(ro.base)) + (long long)ti.b * ro.sb + (long long)ti.c * ro.sc;
       constexpr int RL = S::r(L - 1), ML = H / RL, ITEMS = ML * TX;
 #pragma unroll 1
       for (int w = threadIdx.x; w < ITEMS; w += NT) {
-        const int kappa = w / TX;
+        const int t = w / ML, kappa = w % ML;
+        T2* line = reinterpret_cast<T2*>(tbase + (long long)(ti.ta * TX + t) * ro.sa);
         T2 v[RL];
-        last_bfly<T, S, TX, SWZ>(s, kappa, t, v);
-        if (live) {
+        xlast_bfly<T, C>(s, t, kappa, v);
+        if (ti.ta * TX + t < st.na) {
 #pragma unroll
           for (int q = 0; q < RL; q++) stg_stream(line + kappa + q * ML, cswap(v[q]));
         }

@@ -135,15 +135,21 @@ struct Decomp {
       const long long nxb = (iisize + W - 1) / W;
       m = nxb_all * W * jisize * kjsize;                         // X side of the X<->Y buffer
       m = std::max(m, nxb * W * (long long)ny * kjsize);         // Y side of it
-      const int yb = jproc > 1 ? 8 : 1;                          // forward Y->Z blocks pad y to multiples of 8
-      long long nyb_all = 0;
-      for (int p = 0; p < jproc; p++) nyb_all += (jj.sz[p] + yb - 1) / yb;
-      m = std::max(m, nxb * W * nyb_all * yb * kjsize);          // Y side of the Y<->Z buffer
-      m = std::max(m, nxb * W * ((jjsize + yb - 1) / yb) * yb * (long long)nz);   // Z side of it
+      m = std::max(m, nxb * W * (long long)nyc * kjsize);        // Y side of the Y<->Z buffer
+      m = std::max(m, nxb * W * (long long)jjsize * nz);         // Z side of it
     }
     return std::max<long long>(m, 1) * nv;
   }
 };
+
+// Block width W of the tile-blocked internal layouts (lines per tile row) for complex elements of `csize`
+// bytes: 128-byte rows unless the 128-byte tile of the longest Y/Z transform would not fit in shared
+// memory (fft_fast.cuh, CCfg); `force_row_bytes` (64 or 128) overrides the rule.
+inline int pick_W(int ny, int nz, int csize, int force_row_bytes = 0) {
+  const int rb = (force_row_bytes == 64 || force_row_bytes == 128) ? force_row_bytes
+                                                                   : ((ny <= 1024 && nz <= 1024) ? 128 : 64);
+  return rb / csize;
+}
 
 // ------------------------------------------------------------------------------------
 // FFT length factorisation for the on-chip engine
@@ -226,13 +232,17 @@ inline void add_seg_blk(P3dSide& sd, int buf, int peer, long long off, int start
 // exchange is written into the send buffer `snd`, and the rank's own block is written
 // straight to its landing place in the receive buffer `rcv`.
 //
-// W > 0 selects the B200 layouts of the internal buffers: W = 64 bytes / sizeof(complex) lines
-// that are adjacent in x form one row of a kernel tile, and every buffer is ordered so that
-// the tile of the stage that READS it is contiguous in memory --
-//   X<->Y buffer   [z][x/W][y][x%W]   Y-stage tile = (z, x/W), rows y: contiguous
-//   Z->Y buffer    [x/W][y][z][x%W]   Z-stage tile = (x/W, y), rows z: contiguous (backward)
-//   Y->Z buffer    [x/W][y/8][z][y%8][x%W]   Y stage stores 512-byte pieces, 8 Z tiles share a panel (forward)
-// per peer block (blocks padded in x to a multiple of W).  The exchange still moves one
+// W > 0 selects the B200 layouts of the internal buffers: W lines that are adjacent in x (W * sizeof(complex)
+// = 128 bytes, or 64 when a 128-byte tile of the longest transform would not fit in shared memory) form one
+// row of a kernel tile --
+//   X<->Y buffer   [z][x/W][y][x%W]   Y-stage tile = (z, x/W), rows y: contiguous; the X stage stores / loads
+//                                     pieces of (lines per X tile) * W elements
+//   Y->Z buffer    [x/W][z][y][x%W]   forward:  the Y stage WRITES its tile contiguously, the Z stage gathers rows
+//   Z->Y buffer    [x/W][y][z][x%W]   backward: the Z stage WRITES its tile contiguously, the Y stage gathers rows
+// per peer block (blocks padded in x to a multiple of W).  Measured on B200 (tools/membench.cu): scattered
+// WRITES of one row are the slow side (DRAM write locality), scattered READS recover most of the bandwidth
+// when the tiles that share memory lines run at the same time -- hence writer-contiguous layouts and the
+// `bord` tile-order hint on the gathering stage.  The exchange still moves one
 // contiguous block per peer; only the order of the elements inside a block differs from the
 // reference's pack buffers, which no caller can observe.  W = 0 keeps the reference's plain
 // layouts and its exact alltoallv tables (setup.F90:481-518).
@@ -354,31 +364,22 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
                     W, 0, 0, 1, W, nyq * W, nxb * nyq * W, xy_y[q]);
       }
     };
-    // Y<->Z buffer.  Backward (Z stage writes, Y stage reads): [xb][y][z][xi] -- the Z-stage tile
-    // (x/W, y) is one contiguous run per peer.  Forward (Y stage writes, Z stage reads):
-    // [xb][y/YB][z][y%YB][xi] -- the Y stage (tile (z, x/W), rows y) stores YB*64-byte pieces, which is
-    // what NVLink peer stores and HBM writes want, and the YB Z-stage tiles that share one
-    // [z][y%YB][xi] panel run on neighbouring CTAs, so the panel is read from HBM once.
-    // (single column: nothing crosses NVLink and the Z-contiguous order measured faster -> YB = 1)
-    const int YB = M2 > 1 ? 8 : 1;
-    auto nyb = [&](long long n) { return (n + YB - 1) / YB; };
-    std::vector<long long> fz_y(M2), fz_z(M2);       // forward block sizes (y padded to YB)
-    for (int p = 0; p < M2; p++) { fz_y[p] = nxb * nyb(d.jj.sz[p]) * YB * kj * W; fz_z[p] = nxb * nyb(jj) * YB * d.kj.sz[p] * W; }
+    // Y<->Z buffer, writer-contiguous (see the header comment).  Block sizes do not depend on the direction.
     auto yz_yside = [&](P3dSide& sd, bool send) {
       for (int p = 0; p < M2; p++) {
         const long long nyp = d.jj.sz[p];
         const bool self_redirect = send && M2 > 1 && p == d.jpid;
         const bool remote = send && !self_redirect && M2 > 1 && p2p;
         const int buf = send ? ((self_redirect || remote) ? rcv : snd) : cur;
-        if (send) {     // forward: this rank's Y stage writes
-          long long off = self_redirect ? offs(fz_z, d.jpid) : offs(fz_y, p);
+        if (send) {     // forward: this rank's Y stage writes [xb][z][y in jj(p)][xi]
+          long long off = self_redirect ? offs(yz_z, d.jpid) : offs(yz_y, p);
           if (remote) {     // peer p's Z side: block from sender q' holds y in jj(p), z in kj(q')
             off = 0;
-            for (int q = 0; q < d.jpid; q++) off += nv * nxb * nyb(nyp) * YB * d.kj.sz[q] * W;
+            for (int q = 0; q < d.jpid; q++) off += nv * nxb * nyp * d.kj.sz[q] * W;
           }
           add_seg_blk(sd, buf, remote ? d.rank_of(d.ipid, p) : -1, off, d.jj.st[p] - 1, (int)nyp,
-                      YB > 1 ? W : kj * W, YB > 1 ? YB : 0, kj * YB * W, 1, W, nyb(nyp) * kj * YB * W, YB * W, fz_y[p]);
-        } else {        // backward: this rank's Y stage reads what the Z stages stored
+                      W, 0, 0, 1, W, kj * nyp * W, nyp * W, yz_y[p]);
+        } else {        // backward: this rank's Y stage gathers rows y from [xb][y in jj(p)][z][xi]
           add_seg_blk(sd, buf, -1, offs(yz_y, p), d.jj.st[p] - 1, (int)nyp,
                       kj * W, 0, 0, 1, W, nyp * kj * W, W, yz_y[p]);
         }
@@ -390,7 +391,7 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
         const bool self_redirect = send && M2 > 1 && q == d.jpid;
         const bool remote = send && !self_redirect && M2 > 1 && p2p;
         const int buf = send ? ((self_redirect || remote) ? rcv : snd) : cur;
-        if (send) {     // backward: this rank's Z stage writes
+        if (send) {     // backward: this rank's Z stage writes [xb][y][z in kj(q)][xi]
           long long off = self_redirect ? offs(yz_y, d.jpid) : offs(yz_z, q);
           if (remote) {     // peer q's Y side: block from sender p' holds y in jj(p'), z in kj(q)
             off = 0;
@@ -398,14 +399,14 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
           }
           add_seg_blk(sd, buf, remote ? d.rank_of(d.ipid, q) : -1, off, d.kj.st[q] - 1, (int)nzq,
                       W, 0, 0, 1, W, jj * nzq * W, nzq * W, yz_z[q]);
-        } else {        // forward: this rank's Z stage reads; b = y is blocked by YB
-          add_seg_blk(sd, buf, -1, offs(fz_z, q), d.kj.st[q] - 1, (int)nzq,
-                      YB * W, 0, 0, 1, W, nyb(jj) * nzq * YB * W, YB > 1 ? W : nzq * W, fz_z[q]);
-          P3dSeg& g = sd.seg[sd.nseg - 1];
-          if (YB > 1) { g.bw = YB; g.sbh = nzq * YB * W; }
+        } else {        // forward: this rank's Z stage gathers rows z from [xb][z in kj(q)][y][xi]
+          add_seg_blk(sd, buf, -1, offs(yz_z, q), d.kj.st[q] - 1, (int)nzq,
+                      jj * W, 0, 0, 1, W, nzq * jj * W, W, yz_z[q]);
         }
       }
     };
+    // tiles that are adjacent in b share the memory lines of a gathered input: run GATHER_B of them back to back
+    const int GATHER_B = 1;      // measured on B200 (1024^3): the x-fastest tile order wins (the far side of the gathering stage is x-contiguous)
     if (!backward) {
       stage_init(s, P3D_R2C, d.nx, (int)ji, (int)kj, nv, 5); s.layx = 1;
       side_init(s.in, d.nx, d.nx, d.nx);
@@ -422,8 +423,8 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
       rotate();
       yz_yside(s.out, true);
       push_stage(s);
-      if (M2 > 1) { push_exchange_cnt(1, M2, d.jpid, 2, fz_y, fz_z); cur = rcv; } else cur = snd;
-      stage_init(s, zkind, d.nz, (int)ii, (int)jj, nv, 8);
+      if (M2 > 1) { push_exchange_cnt(1, M2, d.jpid, 2, yz_y, yz_z); cur = rcv; } else cur = snd;
+      stage_init(s, zkind, d.nz, (int)ii, (int)jj, nv, 8); s.bord = GATHER_B;
       side_init(s.in, d.nz, d.nz, d.nz);
       yz_zside(s.in, false);
       side_init(s.out, d.nz, d.nzc, d.nzcph);
@@ -440,7 +441,7 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
       yz_zside(s.out, true);
       push_stage(s);
       if (M2 > 1) { push_exchange_cnt(1, M2, d.jpid, 3, yz_z, yz_y); cur = rcv; } else cur = snd;
-      stage_init(s, P3D_C2C_BWD, d.ny, (int)ii, (int)kj, nv, 10);
+      stage_init(s, P3D_C2C_BWD, d.ny, (int)ii, (int)kj, nv, 10); s.bord = GATHER_B;
       side_init(s.in, d.ny, d.nyc, d.nycph);
       yz_yside(s.in, false);
       side_init(s.out, d.ny, d.ny, d.ny);

@@ -67,6 +67,8 @@ struct P3dStage {
   int32_t nfac;
   int32_t fac[P3D_MAXFAC];
   int32_t timer;      // 1-based slot of the reference's timers(12) this stage books into
+  int32_t bord;       // > 1: the input is gathered in rows that tiles adjacent in b share memory lines with ->
+                      // run this many consecutive b back to back (tile order hint for the kernels)
   const void* tw;     // device table exp(-2 pi i k / nfft), k < nfft
   double scale;       // multiplies every output
   P3dSide in, out;

@@ -127,6 +127,19 @@ def test_fast_kernels_double(lib, n, cut):
         lib.force_generic(False)
 
 
+@pytest.mark.parametrize("n,cut", [FAST_CASES[0], FAST_CASES[1], FAST_CASES[8], FAST_CASES[10], ((64, 1024, 1024), None)])
+def test_fast_kernels_row_bytes(lib, n, cut):
+    """Both tile row widths of the internal layouts (64- and 128-byte rows) give the same transform."""
+    for rb in (64, 128):
+        lib.row_bytes(rb)
+        try:
+            lib.fast_launch_count(True)
+            _fwd_bwd(lib, n, cut, device=True)
+            assert lib.fast_launch_count() == 6
+        finally:
+            lib.row_bytes(0)
+
+
 @pytest.mark.parametrize("n,cut", FAST_CASES[:9] + FAST_CASES[10:11])
 def test_fast_kernels_single(libf, n, cut):
     libf.fast_launch_count(True)

@@ -72,11 +72,11 @@ def test_decomp_errors(lib):
 
 
 def _run(lib, n, dims, cut, opf, opb, stride1=False, nv=1, dims_c=False):
-    for plain, p2p in ((False, False), (True, False), (False, True)):
-        _run_layout(lib, n, dims, cut, opf, opb, stride1, nv, dims_c, plain, p2p)
+    for plain, p2p, rb in ((False, False, 0), (True, False, 0), (False, True, 0), (False, True, 64)):
+        _run_layout(lib, n, dims, cut, opf, opb, stride1, nv, dims_c, plain, p2p, rb)
 
 
-def _run_layout(lib, n, dims, cut, opf, opb, stride1, nv, dims_c, plain, p2p=False):
+def _run_layout(lib, n, dims, cut, opf, opb, stride1, nv, dims_c, plain, p2p=False, rb=0):
     nx, ny, nz = n
     c = cut or (None, None, None)
     P = dims[0] * dims[1]
@@ -85,7 +85,7 @@ def _run_layout(lib, n, dims, cut, opf, opb, stride1, nv, dims_c, plain, p2p=Fal
     ds = [po.Decomp(nx, ny, nz, dims, r, *c, stride1=stride1, dims_c=dims_c) for r in range(P)]
     plans, infos = [], []
     for r in range(P):
-        s, inf = lib.plan_steps(dims, nx, ny, nz, r, False, opf, nv, *c, stride1=stride1, dims_c=dims_c, plain=plain, p2p=p2p)
+        s, inf = lib.plan_steps(dims, nx, ny, nz, r, False, opf, nv, *c, stride1=stride1, dims_c=dims_c, plain=plain, p2p=p2p, row_bytes=rb)
         plans.append(s)
         infos.append(inf)
     ins = [np.concatenate([a[po.local_in_slice(d)].ravel(order="F") for a in A]) for d in ds]
@@ -97,7 +97,7 @@ def _run_layout(lib, n, dims, cut, opf, opb, stride1, nv, dims_c, plain, p2p=Fal
     # backward from the oracle's spectrum
     plans, infos = [], []
     for r in range(P):
-        s, inf = lib.plan_steps(dims, nx, ny, nz, r, True, opb, nv, *c, stride1=stride1, dims_c=dims_c, plain=plain, p2p=p2p)
+        s, inf = lib.plan_steps(dims, nx, ny, nz, r, True, opb, nv, *c, stride1=stride1, dims_c=dims_c, plain=plain, p2p=p2p, row_bytes=rb)
         plans.append(s)
         infos.append(inf)
     ins = []

@@ -15,6 +15,7 @@ import p3dfft_b200 as pb
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, nargs="+", default=[1024])
 ap.add_argument("--pairs", type=int, default=2)
+ap.add_argument("--warm", type=int, default=0)
 ap.add_argument("--single", action="store_true")
 ap.add_argument("--opf", default="fft")
 ap.add_argument("--opb", default="tff")
@@ -33,10 +34,15 @@ A = torch.rand(isz[0] * isz[1] * isz[2], dtype=dt, device="cuda")
 F = torch.empty(2 * fsz[0] * fsz[1] * fsz[2], dtype=dt, device="cuda")
 B = torch.empty_like(A)
 torch.cuda.synchronize()
-for _ in range(a.pairs):
+for it in range(a.pairs + a.warm):
+    if it == a.warm:
+        L.set_timers()
     L.p3dfft_ftran_r2c(A, F, a.opf)
     L.p3dfft_btran_c2r(F, B, a.opb)
 torch.cuda.synchronize()
 N = float(nx) * ny * nz
-print("roundtrip max err", float((B / N - A).abs().max()), "timers(ms)", [round(t * 1e3, 3) for t in L.get_timers()])
+t = [x * 1e3 / a.pairs for x in L.get_timers()]
+names = {4: "x_r2c", 6: "y_fwd", 7: "z_fwd", 8: "z_bwd", 9: "y_bwd", 11: "x_c2r"}
+print(os.environ.get("TAG", ""), "roundtrip max err %.2e" % float((B / N - A).abs().max()), "pair ms %.3f" % sum(t),
+      " ".join(f"{names[i]}={t[i]:.3f}" for i in sorted(names)))
 L.p3dfft_clean()
