@@ -232,6 +232,7 @@ static cudaError_t launch_x(const P3dStage& st, const FastStage& f, cudaStream_t
   constexpr size_t smem = xstage_smem<T, HH>();
   const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb * st.nc;
   if (tiles <= 0) return cudaSuccess;
+  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;      // 32-bit tile counters: the generic kernel takes over
   cudaError_t e;
   if (st.kind == P3D_R2C) {
     static bool cfg = false;
@@ -254,6 +255,7 @@ static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t
   const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
   const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
   if (tiles <= 0) return cudaSuccess;
+  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;      // 32-bit tile counters: the generic kernel takes over
   cudaError_t e;
   if (st.kind == P3D_C2C_BWD) {
     static bool cfg = false;

@@ -298,80 +298,81 @@ __device__ __forceinline__ void last_bfly(const typename Cx<T>::type* s, int kap
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// run index of every FFT row on one side (0xFF: row not stored -> zero / dropped); tile independent
-template <int NT>
-__device__ __forceinline__ void build_rowrun(const FastSide& sd, unsigned char* rowrun, int nrows, int nlogical,
-                                             int mirror_nfft) {
+// ---------------------------------------------------------------------------------------
+// row -> address
+//
+// The address of FFT row `row` of line t of a tile is   tb[run] + off(row) + t * line pitch,   where
+// off(row) does not depend on the tile and tb[run] (the run's first row, line 0 of the tile) does not depend
+// on the row.  The kernels therefore keep one tile-invariant entry per row in shared memory, built once per
+// CTA:  (off(row) << 5) | run,  ROW_NONE for rows that are not stored (read as zero / dropped), and a handful
+// of per-run tile bases that a few threads refresh per tile (double buffered by tile parity).
+// ---------------------------------------------------------------------------------------
+constexpr long long ROW_NONE = -1;
+
+template <int NT, int ESZ>
+__device__ __forceinline__ void build_rowent(const FastSide& sd, long long* ent, int nrows, int nlogical, int mirror_nfft) {
   for (int row = threadIdx.x; row < nrows; row += NT) {
     int k = row;
     if (mirror_nfft && row >= nlogical) k = mirror_nfft - row;
-    int g = 0xFF;
+    long long e = ROW_NONE;
     for (int i = 0; i < sd.nrun; i++) {
-      const int ks = sd.run[i].kstart;
-      if (k >= ks && k < ks + sd.run[i].len) g = i;
+      const FastRun& r = sd.run[i];
+      if (k >= r.kstart && k < r.kstart + r.len) {
+        const int j = k - r.korg;
+        const long long ro = r.kw > 1 ? (long long)(j / r.kw) * r.psh + (long long)(j % r.kw) * r.ps : (long long)j * r.ps;
+        e = ((ro * ESZ) << 5) | i;
+      }
     }
-    rowrun[row] = (unsigned char)g;
+    ent[row] = e;
   }
 }
-
-// byte offset of (logical row k, first line of a-tile ta, b, c) inside run r
-template <int ESZ>
-__device__ __forceinline__ long long run_offset(const FastRun& r, int k, int ta, int b, int c) {
-  const int i = k - r.korg;
-  const long long ro = r.kw > 1 ? (long long)(i / r.kw) * r.psh + (long long)(i % r.kw) * r.ps : (long long)i * r.ps;
-  const long long bo = r.bw > 1 ? (long long)(b / r.bw) * r.sbh + (long long)(b % r.bw) * r.sb : (long long)b * r.sb;
-  return (ro + (long long)ta * r.sat + bo + (long long)c * r.sc) * ESZ;
-}
+__device__ __forceinline__ char* row_addr(long long e, char* const* tb) { return tb[(int)e & 31] + (e >> 5); }
 
 // Tile order: a-tiles fastest, then b, then c -- except that bord consecutive b's are innermost when the
-// input is blocked along b (bord Z-stage tiles share one [z][y%bord][xi] panel and must run together).
-// b >= nb marks a padding slot of the last b-block (no work).
+// planner asks for it (stage.h, bord).  b >= nb marks a padding slot of the last b-block (no work).
+// (32-bit arithmetic: the host falls back to the generic kernel for >= 2^31 tiles)
 struct TileIdx { int ta, b, c; };
-__device__ __forceinline__ TileIdx tile_decode(long long tile, int tiles_a, int nb, int bord) {
+__device__ __forceinline__ TileIdx tile_decode(unsigned tile, unsigned tiles_a, unsigned nb, unsigned bord) {
   TileIdx x;
   if (bord <= 1) {
     x.ta = (int)(tile % tiles_a);
-    const long long r = tile / tiles_a;
+    const unsigned r = tile / tiles_a;
     x.b = (int)(r % nb);
     x.c = (int)(r / nb);
   } else {
-    const int nbb = (nb + bord - 1) / bord;
-    const int bl = (int)(tile % bord);
-    long long r = tile / bord;
+    const unsigned nbb = (nb + bord - 1) / bord;
+    const unsigned bl = tile % bord;
+    unsigned r = tile / bord;
     x.ta = (int)(r % tiles_a);
     r /= tiles_a;
-    x.b = (int)(r % nbb) * bord + bl;
+    x.b = (int)((r % nbb) * bord + bl);
     x.c = (int)(r / nbb);
   }
   return x;
 }
-__device__ __forceinline__ long long tile_count(int tiles_a, int nb, int nc, int bord) {
+__host__ __device__ inline long long tile_count(int tiles_a, int nb, int nc, int bord) {
   const long long nbp = bord <= 1 ? nb : (long long)((nb + bord - 1) / bord) * bord;
   return (long long)tiles_a * nbp * nc;
 }
 
-// per-run tile bases: the run-dependent 64-bit arithmetic is done once per run and tile, a row
-// then costs one multiply-add
-struct RunTab {
-  char* tb[2][2][P3D_MAXRUN];      // [tile parity][side][run]: address of the run's first row, line 0 of the tile
-  long long psb[2][P3D_MAXRUN];    // [side][run]: row pitch in bytes
-  long long phb[2][P3D_MAXRUN];    //              pitch of a block of kw rows (rows blocked by kw)
-  int kw[2][P3D_MAXRUN], ks[2][P3D_MAXRUN];
-};
-// byte offset of logical row k inside run g relative to tb
-__device__ __forceinline__ long long row_off(const RunTab& rt, int side, int g, int k) {
-  const int i = k - rt.ks[side][g], kw = rt.kw[side][g];
-  return kw > 1 ? (long long)(i / kw) * rt.phb[side][g] + (long long)(i % kw) * rt.psb[side][g] : (long long)i * rt.psb[side][g];
+// tile bases of every run of one side: tb[g] = run base + tile offset
+template <int ESZ>
+__device__ __forceinline__ char* tile_base(const FastRun& r, TileIdx ti) {
+  const long long bo = r.bw > 1 ? (long long)(ti.b / r.bw) * r.sbh + (long long)(ti.b % r.bw) * r.sb : (long long)ti.b * r.sb;
+  return (char*)r.base + ((long long)ti.ta * r.sat + bo + (long long)ti.c * r.sc) * ESZ;
 }
+
+struct RunTab {
+  char* tb[2][2][P3D_MAXRUN];            // [tile parity][side][run]
+  unsigned char pfmode[P3D_MAXRUN];      // input runs: 0 no L2 prefetch, 1 every row, 2 even rows only (64-byte contiguous rows)
+};
 
 template <int NT, int ESZ>
 __device__ __forceinline__ void fill_tilebase(const FastStage& st, RunTab& rt, int slot, TileIdx ti) {
   const int nin = st.in.nrun, ntot = nin + st.out.nrun;
   for (int i = threadIdx.x; i < ntot; i += NT) {
     const int side = i >= nin, g = side ? i - nin : i;
-    const FastRun& r = side ? st.out.run[g] : st.in.run[g];
-    const long long bo = r.bw > 1 ? (long long)(ti.b / r.bw) * r.sbh + (long long)(ti.b % r.bw) * r.sb : (long long)ti.b * r.sb;
-    rt.tb[slot][side][g] = (char*)r.base + ((long long)ti.ta * r.sat + bo + (long long)ti.c * r.sc) * ESZ;
+    rt.tb[slot][side][g] = tile_base<ESZ>(side ? st.out.run[g] : st.in.run[g], ti);
   }
 }
 
@@ -386,47 +387,37 @@ __global__ void __launch_bounds__(CCfg<T, N, RB>::NT, CCfg<T, N, RB>::MINB) csta
   static_assert(NT % TX == 0, "t must be constant per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T2* s = reinterpret_cast<T2*>(smem_raw);
-  char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * N * TX);     // [N], in side then out side
-  RunTab* rt = reinterpret_cast<RunTab*>(rowptr + N);
-  unsigned char* rr_in = reinterpret_cast<unsigned char*>(rt + 1);
-  unsigned char* rr_out = rr_in + N;
+  long long* ent_in = reinterpret_cast<long long*>(smem_raw + sizeof(T2) * N * TX);     // [N]
+  long long* ent_out = ent_in + N;                                                       // [N]
+  RunTab* rt = reinterpret_cast<RunTab*>(ent_out + N);
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
 
-  const int tiles_a = (st.na + TX - 1) / TX;
-  const long long ntiles = tile_count(tiles_a, st.nb, st.nc, st.bord);
+  const unsigned tiles_a = (st.na + TX - 1) / TX;
+  const unsigned ntiles = (unsigned)tile_count(tiles_a, st.nb, st.nc, st.bord);
   const int t = threadIdx.x % TX;
   const long long lin = (long long)t * st.in.run[0].sa * (long long)sizeof(T2);     // line offsets inside a tile
   const long long lout = (long long)t * st.out.run[0].sa * (long long)sizeof(T2);
 
-  build_rowrun<NT>(st.in, rr_in, N, st.n, st.mirror ? N : 0);
-  build_rowrun<NT>(st.out, rr_out, N, N, 0);
-  for (int i = threadIdx.x; i < st.in.nrun + st.out.nrun; i += NT) {
-    const int side = i >= st.in.nrun, g = side ? i - st.in.nrun : i;
-    const FastRun& r = side ? st.out.run[g] : st.in.run[g];
-    rt->psb[side][g] = r.ps * (long long)sizeof(T2);
-    rt->phb[side][g] = r.psh * (long long)sizeof(T2);
-    rt->kw[side][g] = r.kw;
-    rt->ks[side][g] = r.korg;
+  build_rowent<NT, sizeof(T2)>(st.in, ent_in, N, st.n, st.mirror ? N : 0);
+  build_rowent<NT, sizeof(T2)>(st.out, ent_out, N, N, 0);
+  for (int g = threadIdx.x; g < st.in.nrun; g += NT) {
+    const long long psb = st.in.run[g].ps * (long long)sizeof(T2);
+    rt->pfmode[g] = (st.prefetch && psb <= (long long)st.prefetch) ? (psb == 64 ? 2 : 1) : 0;
   }
-  if ((long long)blockIdx.x < ntiles) fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
+  if (blockIdx.x < ntiles) fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
   __syncthreads();
 
   int slot = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, slot ^= 1) {
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, slot ^= 1) {
     const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
     const bool live = ti.ta * TX + t < st.na && ti.b < st.nb;       // b >= nb: padding slot, nothing loaded or stored
-    const bool has_next = tile + gridDim.x < ntiles;
-    if (has_next) fill_tilebase<NT, sizeof(T2)>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord));
-    // ---- input row table of this tile ---------------------------------------------------------
-    for (int row = threadIdx.x; row < N; row += NT) {
-      const int g = rr_in[row];
-      const int k = (st.mirror && row >= st.n) ? N - row : row;
-      rowptr[row] = g != 0xFF ? rt->tb[slot][0][g] + row_off(*rt, 0, g, k) : nullptr;
-    }
-    __syncthreads();
+    const bool has_next = tile + gridDim.x < ntiles && tile + gridDim.x > tile;
+    if (has_next && threadIdx.x < st.in.nrun + st.out.nrun)
+      fill_tilebase<NT, sizeof(T2)>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord));
     // ---- pass 1: global -> registers -> shared ---------------------------------------------
     {
       constexpr int R = S::r(0), M = S::m(0), ITEMS = M * TX;
+      char* const* tbi = rt->tb[slot][0];
 #pragma unroll
       for (int w0 = 0; w0 < ITEMS; w0 += NT) {
         const int w = w0 + threadIdx.x;
@@ -435,8 +426,8 @@ __global__ void __launch_bounds__(CCfg<T, N, RB>::NT, CCfg<T, N, RB>::MINB) csta
           T2 v[R];
 #pragma unroll
           for (int p = 0; p < R; p++) {
-            const char* rp = rowptr[u + p * M];
-            v[p] = (live && rp) ? ldg_stream(reinterpret_cast<const T2*>(rp + lin)) : T2{0, 0};
+            const long long e = ent_in[u + p * M];
+            v[p] = (live && e >= 0) ? ldg_stream(reinterpret_cast<const T2*>(row_addr(e, tbi) + lin)) : T2{0, 0};
             if (SWAP) v[p] = cswap(v[p]);
           }
           Bfly<T, R>::run(v);
@@ -445,23 +436,21 @@ __global__ void __launch_bounds__(CCfg<T, N, RB>::NT, CCfg<T, N, RB>::MINB) csta
       }
     }
     __syncthreads();
-    // ---- output row table (the input one is dead now); L2 prefetch of the next tile's rows ----
-    for (int row = threadIdx.x; row < N; row += NT) {
-      const int g = rr_out[row];
-      rowptr[row] = g != 0xFF ? rt->tb[slot][1][g] + row_off(*rt, 1, g, row) : nullptr;
-      if (has_next && st.prefetch) {
-        const int gi = rr_in[row];
-        // one request per 128-byte line: contiguous tiles need every other row only
-        if (gi != 0xFF && !(st.mirror && row >= st.n) && rt->psb[0][gi] <= (long long)st.prefetch &&
-            (rt->psb[0][gi] != 64 || !(row & 1)))
-          prefetch_l2(rt->tb[slot ^ 1][0][gi] + row_off(*rt, 0, gi, row));
+    // ---- L2 prefetch of the rows of this CTA's next tile ---------------------------------------
+    if (has_next && st.prefetch) {
+      char* const* tbn = rt->tb[slot ^ 1][0];
+      for (int row = threadIdx.x; row < (st.mirror ? st.n : N); row += NT) {
+        const long long e = ent_in[row];
+        if (e < 0) continue;
+        const int pm = rt->pfmode[(int)e & 31];
+        if (pm == 1 || (pm == 2 && !(row & 1))) prefetch_l2(row_addr(e, tbn));      // one request per 128-byte line
       }
     }
-    if constexpr (L == 2) __syncthreads();
     mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
     // ---- pass L: shared -> registers -> global ----------------------------------------------
     {
       constexpr int RL = S::r(L - 1), ML = N / RL, ITEMS = ML * TX;
+      char* const* tbo = rt->tb[slot][1];
 #pragma unroll 1
       for (int w = threadIdx.x; w < ITEMS; w += NT) {
         const int kappa = w / TX;
@@ -469,18 +458,18 @@ __global__ void __launch_bounds__(CCfg<T, N, RB>::NT, CCfg<T, N, RB>::MINB) csta
         last_bfly<T, S, TX, SWZ>(s, kappa, t, v);
 #pragma unroll
         for (int q = 0; q < RL; q++) {
-          char* rp = rowptr[kappa + q * ML];
-          if (live && rp) stg_stream(reinterpret_cast<T2*>(rp + lout), SWAP ? cswap(v[q]) : v[q]);
+          const long long e = ent_out[kappa + q * ML];
+          if (live && e >= 0) stg_stream(reinterpret_cast<T2*>(row_addr(e, tbo) + lout), SWAP ? cswap(v[q]) : v[q]);
         }
       }
     }
-    __syncthreads();      // tile buffer and row table are reused by the next tile
+    __syncthreads();      // the tile buffer and the tile bases of this parity are reused
   }
 }
 
 template <typename T, int N, int RB> constexpr size_t cstage_smem() {
   using T2 = typename Cx<T>::type;
-  return sizeof(T2) * N * CCfg<T, N, RB>::TX + sizeof(char*) * N + sizeof(RunTab) + 2 * N;
+  return sizeof(T2) * N * CCfg<T, N, RB>::TX + 2 * sizeof(long long) * N + sizeof(RunTab);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -575,30 +564,28 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
   constexpr int TX = C::TX, NT = C::NT, L = S::L;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T2* s = reinterpret_cast<T2*>(smem_raw);
-  char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * C::LP * TX);      // [H+1] output rows
-  unsigned char* rr_out = reinterpret_cast<unsigned char*>(rowptr + H + 1);
+  long long* ent_out = reinterpret_cast<long long*>(smem_raw + sizeof(T2) * C::LP * TX);      // [H+1] output rows (tile invariant)
+  char** rowptr = reinterpret_cast<char**>(ent_out + H + 1);                                   // [H+1] row addresses of this tile
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
   const T2* __restrict__ wx = tw + S::twtotal();
 
-  const int tiles_a = (st.na + TX - 1) / TX;
-  const long long ntiles = tile_count(tiles_a, st.nb, st.nc, st.bord);
+  const unsigned tiles_a = (st.na + TX - 1) / TX;
+  const unsigned ntiles = (unsigned)tile_count(tiles_a, st.nb, st.nc, st.bord);
   const FastRun& rin = st.in.run[0];
   const long long sao = st.out.run[0].sa * (long long)sizeof(T2);
   constexpr int RL = S::r(L - 1), ML = H / RL;
   const int ilog = pair_lanes_log(st.out.run[0], ML / 2);
 
-  build_rowrun<NT>(st.out, rr_out, H + 1, H + 1, 0);
+  build_rowent<NT, sizeof(T2)>(st.out, ent_out, H + 1, H + 1, 0);
   __syncthreads();
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
     const T* tbase = reinterpret_cast<const T*>(rin.base) + (long long)ti.b * rin.sb + (long long)ti.c * rin.sc;
-    // ---- output row table; L2 prefetch of the real lines of this CTA's next tile ------------
+    // ---- output row addresses of this tile (read after the next barrier); L2 prefetch of the next tile's lines
     for (int row = threadIdx.x; row <= H; row += NT) {
-      const int g = rr_out[row];
-      char* p = nullptr;
-      if (g != 0xFF) p = (char*)st.out.run[g].base + run_offset<sizeof(T2)>(st.out.run[g], row, ti.ta, ti.b, ti.c);
-      rowptr[row] = p;
+      const long long e = ent_out[row];
+      rowptr[row] = e >= 0 ? tile_base<sizeof(T2)>(st.out.run[(int)e & 31], ti) + (e >> 5) : nullptr;
     }
     if (st.prefetch && tile + gridDim.x < ntiles) {
       const TileIdx tn = tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord);
@@ -638,7 +625,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
       for (int w = threadIdx.x; w < ITEMS; w += NT) {
         const int t = (w >> ilog) % TX, i = (w & ((1 << ilog) - 1)) + (((w >> ilog) / TX) << ilog);
         const bool live = ti.ta * TX + t < st.na;
-        const long long lout = (long long)t * sao;
+        const int lout = t * (int)sao;
         auto put = [&](int k, T2 v) {
           char* rp = rowptr[k];
           if (live && rp) stg_stream(reinterpret_cast<T2*>(rp + lout), v);
@@ -683,7 +670,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
 
 template <typename T, int H> constexpr size_t xstage_smem() {
   using T2 = typename Cx<T>::type;
-  return sizeof(T2) * XCfg<T, H>::LP * XCfg<T, H>::TX + sizeof(char*) * (H + 1) + (H + 1 + 15) / 16 * 16;
+  return sizeof(T2) * XCfg<T, H>::LP * XCfg<T, H>::TX + (sizeof(long long) + sizeof(char*)) * (H + 1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -711,35 +698,45 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
   constexpr int TX = C::TX, NT = C::NT, L = S::L;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T2* s = reinterpret_cast<T2*>(smem_raw);
-  char** rowptr = reinterpret_cast<char**>(smem_raw + sizeof(T2) * C::LP * TX);      // [H+1] input rows
-  unsigned char* rr_in = reinterpret_cast<unsigned char*>(rowptr + H + 1);
+  long long* ent_in = reinterpret_cast<long long*>(smem_raw + sizeof(T2) * C::LP * TX);      // [H+1] input rows (tile invariant)
+  char** rowptr = reinterpret_cast<char**>(ent_in + H + 1);                                   // [H+1] row addresses of this tile
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
   const T2* __restrict__ wx = tw + S::twtotal();
 
-  const int tiles_a = (st.na + TX - 1) / TX;
-  const long long ntiles = tile_count(tiles_a, st.nb, st.nc, st.bord);
+  const unsigned tiles_a = (st.na + TX - 1) / TX;
+  const unsigned ntiles = (unsigned)tile_count(tiles_a, st.nb, st.nc, st.bord);
   const long long sab = st.in.run[0].sa * (long long)sizeof(T2);
   const FastRun& ro = st.out.run[0];
   constexpr int R1 = S::r(0), M1 = S::m(0);
   const int ilog = pair_lanes_log(st.in.run[0], M1 / 2);
+  // L2 prefetch of the next tile, one request per 128-byte line: in the blocked [xb][y][xi] layout the TX lines
+  // of kw consecutive rows are one contiguous piece, else (plain) every line is contiguous along the rows
+  const int kw = st.in.run[0].kw;
+  const bool pf_blocked = kw > 1 && sab == (long long)sizeof(T2) * kw, pf_plain = !pf_blocked && st.in.run[0].ps == 1;
+  const int pf_per = pf_blocked ? (int)((TX * sab + 127) / 128) : TX;
+  const int pf_mask = pf_blocked ? kw - 1 : (int)(128 / sizeof(T2)) - 1;
 
-  build_rowrun<NT>(st.in, rr_in, H + 1, H + 1, 0);
+  build_rowent<NT, sizeof(T2)>(st.in, ent_in, H + 1, H + 1, 0);
   __syncthreads();
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
-    const long long nxt = tile + gridDim.x;
-    const bool has_next = nxt < ntiles;
+    const unsigned nxt = tile + gridDim.x;
+    const bool has_next = nxt < ntiles && nxt > tile;
     const TileIdx tn = tile_decode(has_next ? nxt : tile, tiles_a, st.nb, st.bord);
-    // ---- input row table; L2 prefetch of the next tile (row k on line k % TX: every 64 bytes) --
+    // ---- input row addresses of this tile; L2 prefetch of the next one ---------------------------
     for (int row = threadIdx.x; row <= H; row += NT) {
-      const int g = rr_in[row];
+      const long long e = ent_in[row];
       char* p = nullptr;
-      if (g != 0xFF) {
-        const FastRun& r = st.in.run[g];
-        p = (char*)r.base + run_offset<sizeof(T2)>(r, row, ti.ta, ti.b, ti.c);
-        if (has_next && st.prefetch && tn.ta * TX + (row % TX) < st.na)
-          prefetch_l2((char*)r.base + run_offset<sizeof(T2)>(r, row, tn.ta, tn.b, tn.c) + (row % TX) * sab);
+      if (e >= 0) {
+        const FastRun& r = st.in.run[(int)e & 31];
+        p = tile_base<sizeof(T2)>(r, ti) + (e >> 5);
+        if (has_next && st.prefetch && (pf_blocked || pf_plain) && ((int)((e >> 5) / (long long)sizeof(T2)) & pf_mask) == 0) {
+          char* q = tile_base<sizeof(T2)>(r, tn) + (e >> 5);
+          for (int j = 0; j < pf_per; j++)
+            if (pf_blocked) prefetch_l2(q + j * 128);
+            else if (tn.ta * TX + j < st.na) prefetch_l2(q + j * sab);
+        }
       }
       rowptr[row] = p;
     }
@@ -752,7 +749,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
       for (int w = threadIdx.x; w < ITEMS; w += NT) {
         const int t = (w >> ilog) % TX, i = (w & ((1 << ilog) - 1)) + (((w >> ilog) / TX) << ilog);
         const bool live = ti.ta * TX + t < st.na;
-        const long long lin = (long long)t * sab;
+        const int lin = t * (int)sab;
         auto get = [&](int k) -> T2 {
           const char* rp = rowptr[k];
           return (live && rp) ? ldg_stream(reinterpret_cast<const T2*>(rp + lin)) : T2{0, 0};
