@@ -139,6 +139,7 @@ template <typename T2> __device__ __forceinline__ T2 cconj(T2 a) { return T2{a.x
 template <typename T2> __device__ __forceinline__ T2 mul_mi(T2 a) { return T2{a.y, -a.x}; }   // * (-i)
 template <typename T2> __device__ __forceinline__ T2 mul_pi(T2 a) { return T2{-a.y, a.x}; }   // * (+i)
 template <typename T2> __device__ __forceinline__ T2 cswap(T2 a) { return T2{a.y, a.x}; }
+template <typename T2> __device__ __forceinline__ T2 sel(bool c, T2 a, T2 b) { return T2{c ? a.x : b.x, c ? a.y : b.y}; }
 
 template <typename T2> __device__ __forceinline__ void bf2(T2& a, T2& b) { T2 t = csub(a, b); a = cadd(a, b); b = t; }
 template <typename T2> __device__ __forceinline__ void bf4(T2& v0, T2& v1, T2& v2, T2& v3) {
@@ -531,12 +532,13 @@ __device__ __forceinline__ void xlast_bfly(const typename Cx<T>::type* s, int t,
   Bfly<T, RL>::run(v);
 }
 
-// Lanes of the (k, H-k) pair pass: `il` consecutive k (one piece of the blocked X<->Y layout, or a whole
-// warp when the complex side is plain), then the TX lines, then the remaining k -- so that a warp touches
-// il * TX * sizeof(complex) contiguous bytes of the [xb][y][xi] buffer.
-// returns log2(il)
-__device__ __forceinline__ int pair_lanes_log(const FastRun& r, int half) {
-  int il = r.kw > 1 ? r.kw : 32;
+// Lanes of the (k, H-k) pair pass: a warp takes 32 consecutive k of ONE line (fewer when the pass has fewer
+// pairs), the lines of the tile go to neighbouring warps.  The k side then touches whole 128-byte rows of the
+// [xb][y][xi] buffer and the H-k side, which is shifted by one element against the row grid, whole rows for
+// three quarters of its accesses -- full rows are what NVLink peer stores and the L1 want.
+// returns log2(lanes along k)
+__device__ __forceinline__ int pair_lanes_log(int half) {
+  int il = 32;
   while (il > half) il >>= 1;
   return 31 - __clz(il);
 }
@@ -574,7 +576,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
   const FastRun& rin = st.in.run[0];
   const long long sao = st.out.run[0].sa * (long long)sizeof(T2);
   constexpr int RL = S::r(L - 1), ML = H / RL;
-  const int ilog = pair_lanes_log(st.out.run[0], ML / 2);
+  const int ilog = pair_lanes_log(ML / 2);
 
   build_rowent<NT, sizeof(T2)>(st.out, ent_out, H + 1, H + 1, 0);
   __syncthreads();
@@ -630,37 +632,38 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
           char* rp = rowptr[k];
           if (live && rp) stg_stream(reinterpret_cast<T2*>(rp + lout), v);
         };
+        // Item i pairs butterflies (i, ML - i).  Butterflies 0 and ML/2 pair with THEMSELVES; the lane with
+        // i == 0 takes both and runs the same instruction stream with other operands (selects, no branch):
+        //   slots q <  RL/2: (zb[q], zb[RL-1-q])        k = ML/2 + q*ML          (butterfly ML/2)
+        //   slots q >= RL/2: (za[j], za[RL-j]), j = q - (RL/2 - 1) = 1..RL/2,  k = j*ML   (butterfly 0)
+        // plus the purely real k = 0 and k = H terms.
+        const bool sp = i == 0;
         T2 za[RL], zb[RL];
         xlast_bfly<T, C>(s, t, i, za);
-        xlast_bfly<T, C>(s, t, i == 0 ? ML / 2 : ML - i, zb);
-        if (i != 0) {
+        xlast_bfly<T, C>(s, t, sp ? ML / 2 : ML - i, zb);
 #pragma unroll
-          for (int q = 0; q < RL; q++) {
-            const int k = i + q * ML;
-            T2 xk, xm;
-            r2c_combine<T>(za[q], zb[RL - 1 - q], __ldg(wx + k), xk, xm);
-            put(k, xk);
-            put(H - k, xm);
+        for (int q = 0; q < RL; q++) {
+          constexpr int OFF = RL / 2 - 1;
+          const int j = q - OFF;                            // only used for q >= RL/2
+          T2 A, B;
+          int k;
+          if (q < RL / 2) {
+            A = sel(sp, zb[q], za[q]);
+            B = zb[RL - 1 - q];
+            k = (sp ? ML / 2 : i) + q * ML;
+          } else {
+            A = sel(sp, za[j], za[q]);
+            B = sel(sp, za[RL - j], zb[RL - 1 - q]);
+            k = sp ? j * ML : i + q * ML;
           }
-        } else {
+          T2 xk, xm;
+          r2c_combine<T>(A, B, __ldg(wx + k), xk, xm);
+          put(k, xk);
+          put(H - k, xm);
+        }
+        if (sp) {
           put(0, T2{za[0].x + za[0].y, 0});
           put(H, T2{za[0].x - za[0].y, 0});
-#pragma unroll
-          for (int q = 1; q <= RL / 2; q++) {          // kappa = 0: k = q*ML pairs with (RL-q)*ML
-            const int k = q * ML;
-            T2 xk, xm;
-            r2c_combine<T>(za[q], za[RL - q], __ldg(wx + k), xk, xm);
-            put(k, xk);
-            if (q != RL / 2) put(H - k, xm);
-          }
-#pragma unroll
-          for (int q = 0; q < RL / 2; q++) {           // kappa = ML/2: k pairs inside the butterfly
-            const int k = ML / 2 + q * ML;
-            T2 xk, xm;
-            r2c_combine<T>(zb[q], zb[RL - 1 - q], __ldg(wx + k), xk, xm);
-            put(k, xk);
-            put(H - k, xm);
-          }
         }
       }
     }
@@ -708,7 +711,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
   const long long sab = st.in.run[0].sa * (long long)sizeof(T2);
   const FastRun& ro = st.out.run[0];
   constexpr int R1 = S::r(0), M1 = S::m(0);
-  const int ilog = pair_lanes_log(st.in.run[0], M1 / 2);
+  const int ilog = pair_lanes_log(M1 / 2);
   // L2 prefetch of the next tile, one request per 128-byte line: in the blocked [xb][y][xi] layout the TX lines
   // of kw consecutive rows are one contiguous piece, else (plain) every line is contiguous along the rows
   const int kw = st.in.run[0].kw;
@@ -754,29 +757,30 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
           const char* rp = rowptr[k];
           return (live && rp) ? ldg_stream(reinterpret_cast<const T2*>(rp + lin)) : T2{0, 0};
         };
+        // same operand selection as the r2c pair pass: the lane with i == 0 builds butterflies 0 and M/2
+        const bool sp = i == 0;
+        T2 x0 = T2{0, 0}, xh = T2{0, 0};
+        if (sp) { x0 = get(0); xh = get(H); }              // issued first: their latency overlaps the loads below
+        T2 xk[R], xm[R];
+        int kk[R];
+#pragma unroll
+        for (int p = 0; p < R; p++) {
+          constexpr int OFF = R / 2 - 1;
+          kk[p] = p < R / 2 ? (sp ? M / 2 : i) + p * M : (sp ? (p - OFF) * M : i + p * M);
+          xk[p] = get(kk[p]);
+          xm[p] = get(H - kk[p]);
+        }
+        T2 zk[R], zm[R];
+#pragma unroll
+        for (int p = 0; p < R; p++) c2r_combine<T>(xk[p], xm[p], __ldg(wx + kk[p]), zk[p], zm[p]);
         T2 za[R], zb[R];
-        if (i != 0) {
-          T2 xk[R], xm[R];
 #pragma unroll
-          for (int p = 0; p < R; p++) { xk[p] = get(i + p * M); xm[p] = get(H - i - p * M); }
-#pragma unroll
-          for (int p = 0; p < R; p++) c2r_combine<T>(xk[p], xm[p], __ldg(wx + i + p * M), za[p], zb[R - 1 - p]);
-        } else {
-          T2 x0 = get(0), xh = get(H);
-          za[0] = cswap(T2{x0.x + xh.x, x0.x - xh.x});
-#pragma unroll
-          for (int p = 1; p <= R / 2; p++) {
-            const int k = p * M;
-            T2 zk, zm;
-            c2r_combine<T>(get(k), get(H - k), __ldg(wx + k), zk, zm);
-            za[p] = zk;
-            if (p != R / 2) za[R - p] = zm;
-          }
-#pragma unroll
-          for (int p = 0; p < R / 2; p++) {
-            const int k = M / 2 + p * M;
-            c2r_combine<T>(get(k), get(H - k), __ldg(wx + k), zb[p], zb[R - 1 - p]);
-          }
+        for (int j = 0; j < R; j++) {
+          constexpr int OFF = R / 2 - 1;
+          // general: za[j] = zk[j], zb[j] = zm[R-1-j]
+          const T2 zs = j == 0 ? cswap(T2{x0.x + xh.x, x0.x - xh.x}) : (j <= R / 2 ? zk[j + OFF] : zm[R + OFF - j]);
+          za[j] = sel(sp, zs, zk[j]);
+          zb[j] = j < R / 2 ? sel(sp, zk[j], zm[R - 1 - j]) : zm[R - 1 - j];
         }
         const int ua = i, ub = (i == 0) ? M / 2 : M - i;
         Bfly<T, R>::run(za);
