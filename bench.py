@@ -266,7 +266,9 @@ def main():
                "z_bwd": (tm[8], sb["z"]), "y_bwd": (tm[9], sb["y"]), "x_c2r": (tm[11], sb["x"])}
     dom = max(stage_t, key=lambda k: stage_t[k][0])
     dt, db = stage_t[dom]
-    kname = {"x_r2c": "xr2c_kernel", "x_c2r": "xc2r_kernel"}.get(dom, "cstage_kernel") + f" ({dom})"
+    # (the Z-backward stage of a 1024-point transform runs the split variant of the c2c kernel, fft_fast.cu)
+    kname = {"x_r2c": "xr2c_kernel", "x_c2r": "xc2r_kernel", "z_bwd": "cstage_split_kernel" if n == 1024 else "cstage_kernel"}.get(
+        dom, "cstage_kernel") + f" ({dom})"
     traffic = None      # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload only)
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:

@@ -70,6 +70,29 @@ def build_all(verbose: bool = False, variants: bool = False, force: bool = False
         return list(ex.map(lambda j: build_one(j[0], j[1], verbose, force), jobs))
 
 
+def build_c_drivers(verbose: bool = False) -> list[str]:
+    """C acceptance drivers (tests/c/*.c) built with gcc against include/p3dfft.h and the MPI stand-in
+    include/mpi_shim/mpi.h, next to the libraries (rpath $ORIGIN) so that they travel with them."""
+    root = os.path.join(HERE, "..")
+    inc = ["-I" + os.path.join(root, "include", "mpi_shim"), "-I" + os.path.join(root, "include")]
+    jobs = [("wave_roundtrip", "wave_roundtrip.c", [], "p3dfft"),
+            ("wave_roundtrip_single", "wave_roundtrip.c", ["-DSINGLE_PREC"], "p3dfft_single"),
+            ("shim_selftest", "shim_selftest.c", [], "p3dfft")]
+    out = []
+    for exe, src, defs, lib in jobs:
+        target = os.path.join(LIBDIR, exe)
+        srcp = os.path.join(root, "tests", "c", src)
+        deps = [srcp, os.path.join(root, "include", "mpi_shim", "mpi.h"), os.path.join(root, "include", "p3dfft.h"),
+                os.path.join(LIBDIR, f"lib{lib}.so")]
+        if _newer(target, deps):
+            cmd = ["gcc", "-O2", "-Wall", *defs, *inc, srcp, "-L" + LIBDIR, "-l" + lib, "-lm", "-Wl,-rpath,$ORIGIN", "-o", target]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+        out.append(target)
+    return out
+
+
 if __name__ == "__main__":
     libs = build_all(verbose="-v" in sys.argv, variants="--variants" in sys.argv, force="-f" in sys.argv)
-    print("\n".join(libs))
+    print("\n".join(libs + build_c_drivers(verbose="-v" in sys.argv)))

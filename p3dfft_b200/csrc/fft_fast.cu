@@ -271,6 +271,30 @@ static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t
   return cudaGetLastError();
 }
 
+// split variant (two half tiles per CTA, two CTAs per SM) for the lengths whose 128-byte tile fills an SM
+template <typename T, int NN>
+static cudaError_t launch_split(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  constexpr int TX = CCfg<T, NN, 128>::TX, NT = SplitCfg<T, NN>::NT;
+  constexpr size_t smem = cstage_split_smem<T, NN>();
+  const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
+  if (tiles <= 0) return cudaSuccess;
+  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
+  cudaError_t e;
+  if (st.kind == P3D_C2C_BWD) {
+    static bool cfg = false;
+    static int per_sm = 0;
+    if ((e = launch_cfg(cstage_split_kernel<T, NN, true>, smem, cfg)) != cudaSuccess) return e;
+    cstage_split_kernel<T, NN, true><<<persistent_grid(cstage_split_kernel<T, NN, true>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
+  } else {
+    static bool cfg = false;
+    static int per_sm = 0;
+    if ((e = launch_cfg(cstage_split_kernel<T, NN, false>, smem, cfg)) != cudaSuccess) return e;
+    cstage_split_kernel<T, NN, false><<<persistent_grid(cstage_split_kernel<T, NN, false>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
+  }
+  return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
   using T2 = typename Cx<T>::type;
@@ -284,8 +308,16 @@ cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t str
   if (is_x(st.kind)) dispatch_x(st.n / 2, [&](auto h) { err = launch_x<T, decltype(h)::value>(st, f, stream); });
   else dispatch_c(st.nfft, [&](auto nn) {
     constexpr int NN = decltype(nn)::value;
+    // Split variant (two CTAs per SM, more loads in flight): measured on B200 it wins when the INPUT rows are far
+    // apart (the user layout: pitch of megabytes, no L2 prefetch) and loses for the other patterns, scattered
+    // writes above all.  P3DFFT_B200_SPLIT = 0 never / 1 always / unset: by that rule.
+    static const int split_env = getenv("P3DFFT_B200_SPLIT") ? atoi(getenv("P3DFFT_B200_SPLIT")) : -1;
     if (f.rowb == 64) err = launch_c<T, NN, 64>(st, f, stream);
-    else if constexpr (ccfg_exists(NN, 128)) { if (f.rowb == 128) err = launch_c<T, NN, 128>(st, f, stream); }
+    else if constexpr (NN == 1024) {
+      const bool far_rows = f.in.nrun > 0 && f.in.run[0].ps * (long long)sizeof(T2) > (long long)(f.prefetch > 0 ? f.prefetch : 131072);
+      const bool split = split_env < 0 ? far_rows : split_env != 0;
+      if (f.rowb == 128) err = split ? launch_split<T, NN>(st, f, stream) : launch_c<T, NN, 128>(st, f, stream);
+    } else if constexpr (ccfg_exists(NN, 128)) { if (f.rowb == 128) err = launch_c<T, NN, 128>(st, f, stream); }
   });
   return err;
 }

@@ -251,10 +251,10 @@ __device__ __forceinline__ void twiddle_store(typename Cx<T>::type* v, typename 
 }
 
 // middle pass PI (0 < PI < L-1): shared -> shared, in place
-template <typename T, class S, int PI, int TX, int NT, bool SWZ>
+template <typename T, class S, int PI, int TX, int NT, bool SWZ, int NROWS = S::N>
 __device__ __forceinline__ void mid_pass(typename Cx<T>::type* s, const typename Cx<T>::type* __restrict__ tw) {
   using T2 = typename Cx<T>::type;
-  constexpr int R = S::r(PI), NCUR = S::ncur(PI), M = S::m(PI), ITEMS = (S::N / R) * TX;
+  constexpr int R = S::r(PI), NCUR = S::ncur(PI), M = S::m(PI), ITEMS = (NROWS / R) * TX;
 #pragma unroll 1
   for (int w = threadIdx.x; w < ITEMS; w += NT) {
     const int t = w % TX, u = w / TX;
@@ -468,6 +468,136 @@ __global__ void __launch_bounds__(CCfg<T, N, RB>::NT, CCfg<T, N, RB>::MINB) csta
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// c2c stage kernel, split variant: the tile (N rows x 128 bytes) is processed in two halves that share one
+// N/2-row buffer, so that TWO CTAs fit on an SM where the whole tile allows only one (N = 1024: 64 KB
+// instead of 128 KB) and one CTA's loads overlap the other's arithmetic.  After the first DIF pass (radix
+// R0) the R0 sub-transforms of length N/R0 are independent: pass 1 runs on the whole tile straight from
+// global memory, the outputs of sub-transforms 0 .. R0/2-1 go to shared memory and are finished first,
+// those of R0/2 .. R0-1 wait in registers (IPT * R0/2 complex values per thread) and follow.
+// Three-pass schedules, 128-byte rows only.
+// ---------------------------------------------------------------------------------------
+template <typename T, int N> struct SplitCfg {
+  static constexpr int NT = 256, MINB = 2;
+};
+
+template <typename T, int N, bool SWAP>
+__global__ void __launch_bounds__(SplitCfg<T, N>::NT, SplitCfg<T, N>::MINB) cstage_split_kernel(const __grid_constant__ FastStage st) {
+  using T2 = typename Cx<T>::type;
+  using S = typename CCfg<T, N, 128>::S;
+  constexpr int TX = CCfg<T, N, 128>::TX, NT = SplitCfg<T, N>::NT, L = S::L;
+  static_assert(L == 3, "split kernel needs a three-pass schedule");
+  constexpr int R0 = S::r(0), M0 = S::m(0), R1 = S::r(1), RL = S::r(2), HB = R0 / 2, NH = N / 2, ML = N / RL;
+  constexpr int ITEMS1 = M0 * TX, IPT = ITEMS1 / NT;
+  static_assert(ITEMS1 % NT == 0 && NT % TX == 0 && R0 % 2 == 0, "split kernel geometry");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T2* s = reinterpret_cast<T2*>(smem_raw);
+  long long* ent_in = reinterpret_cast<long long*>(smem_raw + sizeof(T2) * NH * TX);     // [N]
+  long long* ent_out = ent_in + N;                                                        // [N]
+  RunTab* rt = reinterpret_cast<RunTab*>(ent_out + N);
+  const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
+
+  const unsigned tiles_a = (st.na + TX - 1) / TX;
+  const unsigned ntiles = (unsigned)tile_count(tiles_a, st.nb, st.nc, st.bord);
+  const int t = threadIdx.x % TX;
+  const long long lin = (long long)t * st.in.run[0].sa * (long long)sizeof(T2);
+  const long long lout = (long long)t * st.out.run[0].sa * (long long)sizeof(T2);
+
+  build_rowent<NT, sizeof(T2)>(st.in, ent_in, N, st.n, st.mirror ? N : 0);
+  build_rowent<NT, sizeof(T2)>(st.out, ent_out, N, N, 0);
+  for (int g = threadIdx.x; g < st.in.nrun; g += NT) {
+    const long long psb = st.in.run[g].ps * (long long)sizeof(T2);
+    rt->pfmode[g] = (st.prefetch && psb <= (long long)st.prefetch) ? (psb == 64 ? 2 : 1) : 0;
+  }
+  if (blockIdx.x < ntiles) fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
+  __syncthreads();
+
+  int slot = 0;
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, slot ^= 1) {
+    const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
+    const bool live = ti.ta * TX + t < st.na && ti.b < st.nb;
+    const bool has_next = tile + gridDim.x < ntiles && tile + gridDim.x > tile;
+    if (has_next && threadIdx.x < st.in.nrun + st.out.nrun)
+      fill_tilebase<NT, sizeof(T2)>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord));
+    // ---- pass 1 on the whole tile: lower sub-transforms -> shared, upper ones stay in registers ----
+    T2 hold[IPT][HB];
+    {
+      char* const* tbi = rt->tb[slot][0];
+#pragma unroll
+      for (int it = 0; it < IPT; it++) {
+        const int u = (it * NT + (int)threadIdx.x) / TX;
+        T2 v[R0];
+#pragma unroll
+        for (int p = 0; p < R0; p++) {
+          const long long e = ent_in[u + p * M0];
+          v[p] = (live && e >= 0) ? ldg_stream(reinterpret_cast<const T2*>(row_addr(e, tbi) + lin)) : T2{0, 0};
+          if (SWAP) v[p] = cswap(v[p]);
+        }
+        Bfly<T, R0>::run(v);
+        const T2* twp = tw + S::twoff(0) + u;
+#pragma unroll
+        for (int q = 1; q < R0; q++) v[q] = cmul(v[q], __ldg(twp + (q - 1) * M0));
+#pragma unroll
+        for (int q = 0; q < HB; q++) {
+          s[(u + q * M0) * TX + t] = v[q];
+          hold[it][q] = v[HB + q];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- L2 prefetch of the rows of this CTA's next tile ---------------------------------------
+    if (has_next && st.prefetch) {
+      char* const* tbn = rt->tb[slot ^ 1][0];
+      for (int row = threadIdx.x; row < (st.mirror ? st.n : N); row += NT) {
+        const long long e = ent_in[row];
+        if (e < 0) continue;
+        const int pm = rt->pfmode[(int)e & 31];
+        if (pm == 1 || (pm == 2 && !(row & 1))) prefetch_l2(row_addr(e, tbn));
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      if (half == 1) {
+        __syncthreads();                      // the first half has been read out
+#pragma unroll
+        for (int it = 0; it < IPT; it++) {
+          const int u = (it * NT + (int)threadIdx.x) / TX;
+#pragma unroll
+          for (int q = 0; q < HB; q++) s[(u + q * M0) * TX + t] = hold[it][q];
+        }
+        __syncthreads();
+      }
+      mid_pass<T, S, 1, TX, NT, false, NH>(s, tw);
+      __syncthreads();
+      // ---- pass 3 of this half: physical butterfly kp = q1' + HB*q2  <->  kappa = q1' + HB*half + R0*q2 ----
+      {
+        constexpr int ITEMS = (NH / RL) * TX;
+        char* const* tbo = rt->tb[slot][1];
+#pragma unroll 1
+        for (int w = threadIdx.x; w < ITEMS; w += NT) {
+          const int kp = w / TX, q1 = kp % HB, q2 = kp / HB;
+          const int base = (q1 * R1 + q2) * RL, kappa = q1 + HB * half + R0 * q2;
+          T2 v[RL];
+#pragma unroll
+          for (int p = 0; p < RL; p++) v[p] = s[(base + p) * TX + t];
+          Bfly<T, RL>::run(v);
+#pragma unroll
+          for (int q = 0; q < RL; q++) {
+            const long long e = ent_out[kappa + q * ML];
+            if (live && e >= 0) stg_stream(reinterpret_cast<T2*>(row_addr(e, tbo) + lout), SWAP ? cswap(v[q]) : v[q]);
+          }
+        }
+      }
+    }
+    __syncthreads();      // the tile buffer and the tile bases of this parity are reused
+  }
+}
+
+template <typename T, int N> constexpr size_t cstage_split_smem() {
+  using T2 = typename Cx<T>::type;
+  return sizeof(T2) * (N / 2) * CCfg<T, N, 128>::TX + 2 * sizeof(long long) * N + sizeof(RunTab);
+}
+
 template <typename T, int N, int RB> constexpr size_t cstage_smem() {
   using T2 = typename Cx<T>::type;
   return sizeof(T2) * N * CCfg<T, N, RB>::TX + 2 * sizeof(long long) * N + sizeof(RunTab);
@@ -568,6 +698,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
   T2* s = reinterpret_cast<T2*>(smem_raw);
   long long* ent_out = reinterpret_cast<long long*>(smem_raw + sizeof(T2) * C::LP * TX);      // [H+1] output rows (tile invariant)
   char** rowptr = reinterpret_cast<char**>(ent_out + H + 1);                                   // [H+1] row addresses of this tile
+  char** tbs = rowptr + H + 1;                                                                 // [tile parity][run] tile bases
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
   const T2* __restrict__ wx = tw + S::twtotal();
 
@@ -579,24 +710,36 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
   const int ilog = pair_lanes_log(ML / 2);
 
   build_rowent<NT, sizeof(T2)>(st.out, ent_out, H + 1, H + 1, 0);
+  if (blockIdx.x < ntiles && threadIdx.x < st.out.nrun)
+    tbs[threadIdx.x] = tile_base<sizeof(T2)>(st.out.run[threadIdx.x], tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
   __syncthreads();
 
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  int slot = 0;
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, slot ^= 1) {
     const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
     const T* tbase = reinterpret_cast<const T*>(rin.base) + (long long)ti.b * rin.sb + (long long)ti.c * rin.sc;
-    // ---- output row addresses of this tile (read after the next barrier); L2 prefetch of the next tile's lines
-    for (int row = threadIdx.x; row <= H; row += NT) {
-      const long long e = ent_out[row];
-      rowptr[row] = e >= 0 ? tile_base<sizeof(T2)>(st.out.run[(int)e & 31], ti) + (e >> 5) : nullptr;
+    const unsigned nxt = tile + gridDim.x;
+    const bool has_next = nxt < ntiles && nxt > tile;
+    // ---- output row addresses of this tile (read after the next barrier) from the per-run tile bases;
+    //      tile bases and L2 prefetch of the real lines of this CTA's next tile
+    {
+      char* const* tbo = tbs + slot * P3D_MAXRUN;
+      for (int row = threadIdx.x; row <= H; row += NT) {
+        const long long e = ent_out[row];
+        rowptr[row] = e >= 0 ? row_addr(e, tbo) : nullptr;
+      }
     }
-    if (st.prefetch && tile + gridDim.x < ntiles) {
-      const TileIdx tn = tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord);
-      constexpr int PER_LINE = (int)(H * sizeof(T2) / 128);          // 128-byte lines per real line
-      for (int i = threadIdx.x; i < PER_LINE * TX; i += NT) {
-        const int l = i / PER_LINE, j = i - l * PER_LINE;
-        if (tn.ta * TX + l < st.na)
-          prefetch_l2(reinterpret_cast<const char*>(reinterpret_cast<const T*>(rin.base) + (long long)(tn.ta * TX + l) * rin.sa +
-                                                    (long long)tn.b * rin.sb + (long long)tn.c * rin.sc) + j * 128);
+    if (has_next) {
+      const TileIdx tn = tile_decode(nxt, tiles_a, st.nb, st.bord);
+      if (threadIdx.x < st.out.nrun) tbs[(slot ^ 1) * P3D_MAXRUN + threadIdx.x] = tile_base<sizeof(T2)>(st.out.run[threadIdx.x], tn);
+      if (st.prefetch) {
+        constexpr int PER_LINE = (int)(H * sizeof(T2) / 128);          // 128-byte lines per real line
+        const char* nb = reinterpret_cast<const char*>(reinterpret_cast<const T*>(rin.base) + (long long)(tn.ta * TX) * rin.sa +
+                                                       (long long)tn.b * rin.sb + (long long)tn.c * rin.sc);
+        for (int i = threadIdx.x; i < PER_LINE * TX; i += NT) {
+          const int l = i / PER_LINE, j = i % PER_LINE;
+          if (tn.ta * TX + l < st.na) prefetch_l2(nb + (long long)l * rin.sa * (long long)sizeof(T) + j * 128);
+        }
       }
     }
     // ---- pass 1: packed real pairs -> registers -> shared (a warp reads 512 contiguous bytes) ---
@@ -673,7 +816,8 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
 
 template <typename T, int H> constexpr size_t xstage_smem() {
   using T2 = typename Cx<T>::type;
-  return sizeof(T2) * XCfg<T, H>::LP * XCfg<T, H>::TX + (sizeof(long long) + sizeof(char*)) * (H + 1);
+  return sizeof(T2) * XCfg<T, H>::LP * XCfg<T, H>::TX + (sizeof(long long) + sizeof(char*)) * (H + 1) +
+         sizeof(char*) * 2 * P3D_MAXRUN + sizeof(int) * (H + 2);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -703,6 +847,8 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
   T2* s = reinterpret_cast<T2*>(smem_raw);
   long long* ent_in = reinterpret_cast<long long*>(smem_raw + sizeof(T2) * C::LP * TX);      // [H+1] input rows (tile invariant)
   char** rowptr = reinterpret_cast<char**>(ent_in + H + 1);                                   // [H+1] row addresses of this tile
+  char** tbs = rowptr + H + 1;                                                                 // [tile parity][run] tile bases
+  int* pfrow = reinterpret_cast<int*>(tbs + 2 * P3D_MAXRUN);                                   // [0] = count, then the rows to prefetch
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
   const T2* __restrict__ wx = tw + S::twtotal();
 
@@ -713,37 +859,56 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
   constexpr int R1 = S::r(0), M1 = S::m(0);
   const int ilog = pair_lanes_log(M1 / 2);
   // L2 prefetch of the next tile, one request per 128-byte line: in the blocked [xb][y][xi] layout the TX lines
-  // of kw consecutive rows are one contiguous piece, else (plain) every line is contiguous along the rows
+  // of kw consecutive rows are one contiguous piece of TX * sab bytes, else (plain) every line is contiguous
+  // along the rows.  The rows that start such a piece are listed once per CTA.
   const int kw = st.in.run[0].kw;
   const bool pf_blocked = kw > 1 && sab == (long long)sizeof(T2) * kw, pf_plain = !pf_blocked && st.in.run[0].ps == 1;
   const int pf_per = pf_blocked ? (int)((TX * sab + 127) / 128) : TX;
-  const int pf_mask = pf_blocked ? kw - 1 : (int)(128 / sizeof(T2)) - 1;
 
   build_rowent<NT, sizeof(T2)>(st.in, ent_in, H + 1, H + 1, 0);
+  if (blockIdx.x < ntiles && threadIdx.x < st.in.nrun)
+    tbs[threadIdx.x] = tile_base<sizeof(T2)>(st.in.run[threadIdx.x], tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    if (st.prefetch && (pf_blocked || pf_plain)) {
+      const int mask = pf_blocked ? kw - 1 : (int)(128 / sizeof(T2)) - 1;
+      for (int row = 0; row <= H; row++) {
+        const long long e = ent_in[row];
+        if (e >= 0 && ((int)((e >> 5) / (long long)sizeof(T2)) & mask) == 0) pfrow[1 + n++] = row;
+      }
+    }
+    pfrow[0] = n;
+  }
   __syncthreads();
 
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  int slot = 0;
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, slot ^= 1) {
     const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
     const unsigned nxt = tile + gridDim.x;
     const bool has_next = nxt < ntiles && nxt > tile;
-    const TileIdx tn = tile_decode(has_next ? nxt : tile, tiles_a, st.nb, st.bord);
-    // ---- input row addresses of this tile; L2 prefetch of the next one ---------------------------
-    for (int row = threadIdx.x; row <= H; row += NT) {
-      const long long e = ent_in[row];
-      char* p = nullptr;
-      if (e >= 0) {
-        const FastRun& r = st.in.run[(int)e & 31];
-        p = tile_base<sizeof(T2)>(r, ti) + (e >> 5);
-        if (has_next && st.prefetch && (pf_blocked || pf_plain) && ((int)((e >> 5) / (long long)sizeof(T2)) & pf_mask) == 0) {
-          char* q = tile_base<sizeof(T2)>(r, tn) + (e >> 5);
-          for (int j = 0; j < pf_per; j++)
-            if (pf_blocked) prefetch_l2(q + j * 128);
-            else if (tn.ta * TX + j < st.na) prefetch_l2(q + j * sab);
-        }
+    // ---- input row addresses of this tile from the per-run tile bases --------------------------------
+    {
+      char* const* tbi = tbs + slot * P3D_MAXRUN;
+      for (int row = threadIdx.x; row <= H; row += NT) {
+        const long long e = ent_in[row];
+        rowptr[row] = e >= 0 ? row_addr(e, tbi) : nullptr;
       }
-      rowptr[row] = p;
     }
     __syncthreads();
+    // ---- tile bases of the next tile (read after the next barriers) and its L2 prefetch -----------------
+    if (has_next) {
+      const TileIdx tn = tile_decode(nxt, tiles_a, st.nb, st.bord);
+      if (threadIdx.x < st.in.nrun) tbs[(slot ^ 1) * P3D_MAXRUN + threadIdx.x] = tile_base<sizeof(T2)>(st.in.run[threadIdx.x], tn);
+      const int npf = pfrow[0];
+      for (int i = threadIdx.x; i < npf * pf_per; i += NT) {
+        const int j = i % pf_per;
+        const long long e = ent_in[pfrow[1 + i / pf_per]];
+        char* q = tile_base<sizeof(T2)>(st.in.run[(int)e & 31], tn) + (e >> 5);
+        if (pf_blocked) prefetch_l2(q + j * 128);
+        else if (tn.ta * TX + j < st.na) prefetch_l2(q + j * sab);
+      }
+    }
     // ---- pass 1 on butterfly pairs (u, M-u) with the Hermitian pre-processing ----------------
     {
       constexpr int R = R1, M = M1, ITEMS = (M / 2) * TX;
