@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--grid", type=str, default="")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cufft", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -250,6 +251,28 @@ def main():
                "note": "host pinned buffers through p3dfft_ftran_r2c/p3dfft_btran_c2r; wall clock, max over ranks"}
         del hA, hF, hB
 
+    # ---- cuFFT, comparison only (north_star: "cuFFT is reported only as a comparison"); never on the product path
+    cufft = None
+    if world == 1 and not args.no_cufft:
+        try:
+            x = A.view(n, n, n)                      # same bytes, C order: a [z][y][x] array with x fastest
+            for _ in range(2):
+                y = torch.fft.rfftn(x)
+                z = torch.fft.irfftn(y, s=(n, n, n))
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            for _ in range(3):
+                y = torch.fft.rfftn(x)
+                z = torch.fft.irfftn(y, s=(n, n, n))
+            c1.record(stream)
+            torch.cuda.synchronize()
+            cufft = {"ms_per_pair": c0.elapsed_time(c1) / 3, "what": "torch.fft.rfftn + irfftn (cuFFT D2Z/Z2D, out of place, includes its 1/N scaling)"}
+            del y, z
+        except Exception as e:      # noqa: BLE001 - a comparison line must never fail the bench
+            cufft = {"unavailable": repr(e)[:200]}
+        torch.cuda.empty_cache()
+
     p2p_on = L.p2p_active()
     L.p3dfft_clean()
     L.reset_stream()
@@ -302,6 +325,8 @@ def main():
                       else "grouped ncclSend/ncclRecv")),
         "clocks": clocks, "roundtrip_max_err": err,
     }
+    if cufft:
+        line["cufft_comparison"] = cufft
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu:
