@@ -70,6 +70,40 @@ void p3dfft_b200_plain_layout(int on);
  * 1024), 64 or 128 = forced.  Takes effect at the next p3dfft_setup (also env P3DFFT_B200_ROWB)      */
 void p3dfft_b200_row_bytes(int rb);
 
+/* ---- remaining public routines of the reference's Fortran module (build/module.F90:178-186) ----------
+ * The reference exports these from `module p3dfft` only (no BIND(C) shim); fortran/p3dfft.F90 binds the
+ * module names to the symbols below.  `real` = double, or float in libp3dfft_single.so; arrays may be
+ * host or device pointers like everywhere else.                                                        */
+/* p3dfft_ftran_r2c_1d (build/ftran.F90:787-814): X transform only, real (nx, jisize, kjsize) ->
+ * complex (nxhp, jisize, kjsize), i.e. nx+2 reals per line; no pruning, no transpose                   */
+void p3dfft_ftran_r2c_1d(void* rXgYZ, void* cXgYZ);
+/* rtran_x2y / rtran_y2x / rtran_x2z / rtran_z2x (build/module.F90:1061, 1137, 1214, 1292): real-data pencil
+ * transposes  (nx, jisize, kjsize) <-> (iiisize, ny, kjsize)  over the row communicator and
+ * (nx, jisize, kjsize) <-> (ijsize, jisize, nz)  over the column communicator, iii / ij = MapDataToProc(nx,
+ * iproc / jproc) (build/setup.F90:305-312).  dstart/dend/dsize receive the 1-based extents of `dest` (may be
+ * NULL); *t (may be NULL) is increased by the seconds spent in the exchange, as the reference adds MPI_Wtime
+ * around its alltoallv.  The reference's scratch arguments rbuf1 / rbuf2 do not exist: the library stages the
+ * blocks in its own work buffers (or straight in the peers' buffers over NVLink).                           */
+void p3dfft_b200_rtran_x2y(const void* source, void* dest, int* dstart, int* dend, int* dsize, double* t);
+void p3dfft_b200_rtran_y2x(const void* source, void* dest, int* dstart, int* dend, int* dsize, double* t);
+void p3dfft_b200_rtran_x2z(const void* source, void* dest, int* dstart, int* dend, int* dsize, double* t);
+void p3dfft_b200_rtran_z2x(const void* source, void* dest, int* dstart, int* dend, int* dsize, double* t);
+/* p3dfft_get_mpi_info (build/module.F90:280-297): rank, number of ranks and the communicator handle in use  */
+void p3dfft_get_mpi_info(int* taskid, int* ntasks, int* comm);
+/* proc_id2coords / proc_coords2id / proc_dims tables (build/setup.F90:224-230, 551-577) and proc_neighb
+ * (build/module.F90:788-825).  proc_dims: out9 = start(3), end(3), size(3) of rank `id` in conf 1 or 2.
+ * Return -1 for arguments outside the grid (where the reference reads out of bounds).                       */
+int p3dfft_b200_proc_id2coords(int id, int* ipid, int* jpid);
+int p3dfft_b200_proc_coords2id(int ipid, int jpid);
+int p3dfft_b200_proc_dims(int conf, int id, int* out9);
+int p3dfft_b200_proc_neighb(int base_proc_id, int orient, int direction);
+/* get_proc_parts (build/module.F90:888-1054): which ranks own which part of the box (base, size) of the conf-1
+ * (physical space, X pencils) or conf-2 (wavenumber space, Z pencils) decomposition.  parts = iproc*jproc rows
+ * of 7 ints {proc id, base x, y, z, size x, y, z} as the reference leaves them in proc_parts (unused rows -1).
+ * Returns the number of parts; *ierr as the reference (0, 1 = bad conf, -1 = base point outside the grid).    */
+int p3dfft_b200_get_proc_parts(int base_x, int base_y, int base_z, int size_x, int size_y, int size_z, int conf,
+                               int* parts, int* ierr);
+
 /* ---- host-only planner queries (no GPU needed; used by the CPU test-suite) ------------- */
 typedef struct {
   int32_t nx, ny, nz, nxc, nyc, nzc;
@@ -98,6 +132,17 @@ int p3dfft_b200_plan_steps(const int* dims, int nx, int ny, int nz, int rank, in
                            int elem_bytes, void* steps, int max_steps);
 /* sizeof(P3dStep) as compiled, so bindings can check their struct mirror                  */
 int p3dfft_b200_sizeof_step(void);
+/* step list of p3dfft_ftran_r2c_1d (which = 100) or of a real-data transpose (which = 0 x2y, 1 y2x, 2 x2z,
+ * 3 z2x); flags as above (bit4 = peer-to-peer plan)                                                        */
+int p3dfft_b200_plan_aux_steps(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc, int flags,
+                               int which, int elem_bytes, void* steps, int max_steps);
+/* dims9 = dstart(3), dend(3), dsize(3) of the destination of transpose `which` on `rank`; returns the complex
+ * elements per work buffer the transposes need (the same bound on every rank), -1 on error                */
+long long p3dfft_b200_plan_rtran_info(const int* dims, int nx, int ny, int nz, int rank, int which, int flags, int* dims9);
+/* get_proc_parts / proc_neighb without a plan (any rank count)                                             */
+int p3dfft_b200_plan_proc_parts(const int* dims, int nx, int ny, int nz, int nxc, int nyc, int nzc, int flags, int base_x,
+                                int base_y, int base_z, int size_x, int size_y, int size_z, int conf, int* parts, int* ierr);
+int p3dfft_b200_plan_proc_neighb(const int* dims, int flags, int base_proc_id, int orient, int direction);
 
 #ifdef __cplusplus
 }

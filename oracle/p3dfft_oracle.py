@@ -40,6 +40,7 @@ import scipy.fft as sfft
 __all__ = [
     "map_data_to_proc", "Decomp", "global_forward", "global_backward", "global_cheby",
     "local_forward", "local_backward", "SimWorld", "philox_field", "rel_l2",
+    "rtran_slices", "rtran_local", "forward_r2c_1d", "ProcGrid", "power_spectrum",
 ]
 
 
@@ -119,6 +120,11 @@ class Decomp:
         self.jistart, self.jiend, self.jisize = self.jist[i], self.jien[i], self.jisz[i]
         self.jjstart, self.jjend, self.jjsize = self.jjst[j], self.jjen[j], self.jjsz[j]
         self.kjstart, self.kjend, self.kjsize = self.kjst[j], self.kjen[j], self.kjsz[j]
+        # real-space x blocks of the rtran_* transposes (setup.F90:299-312)
+        self.iiist, self.iiien, self.iiisz = map_data_to_proc(nx, self.iproc)
+        self.ijst, self.ijen, self.ijsz = map_data_to_proc(nx, self.jproc)
+        self.iiistart, self.iiiend, self.iiisize = self.iiist[i], self.iiien[i], self.iiisz[i]
+        self.ijstart, self.ijend, self.ijsize = self.ijst[j], self.ijen[j], self.ijsz[j]
         # work-buffer padding (setup.F90:382-398)
         padd = max(self.iisize * self.jjsize * nz, self.iisize * ny * self.kjsize) \
             - self.nxhp * self.jisize * self.kjsize
@@ -144,6 +150,17 @@ class Decomp:
         self.JrRcvStrt, self.JrRcvCnts = self.KfSndStrt, self.KfSndCnts
         self.KrSndStrt, self.KrSndCnts = self.IfRcvStrt, self.IfRcvCnts
         self.KrRcvStrt, self.KrRcvCnts = self.IfSndStrt, self.IfSndCnts
+        # rtran tables in BYTES (setup.F90:531-549); r = bytes per real
+        r = self.elem
+        iii, ijs = self.iiisize, self.ijsize
+        self.IiStrt = [(self.iiist[p] - 1) * ji * kj * r for p in range(self.iproc)]
+        self.IiCnts = [self.iiisz[p] * ji * kj * r for p in range(self.iproc)]
+        self.JiStrt = [(self.jist[p] - 1) * iii * kj * r for p in range(self.iproc)]
+        self.JiCnts = [self.jisz[p] * iii * kj * r for p in range(self.iproc)]
+        self.IjStrt = [(self.ijst[p] - 1) * ji * kj * r for p in range(self.jproc)]
+        self.IjCnts = [self.ijsz[p] * ji * kj * r for p in range(self.jproc)]
+        self.KjStrt = [(self.kjst[p] - 1) * ji * ijs * r for p in range(self.jproc)]
+        self.KjCnts = [self.kjsz[p] * ji * ijs * r for p in range(self.jproc)]
         # memsize (setup.F90:580-603): real elements needed for an in-place array
         pad1 = 2 * max(nz * jj * ii, ny * kj * ii) - nx * ji * kj
         if pad1 <= 0:
@@ -471,9 +488,274 @@ class SimWorld:
             sfft.irfft(b, n=d.nx, axis=0, norm="forward", workers=_WORKERS).astype(self.rt))
             for d, b in zip(D, xb)]
 
+    # ---- real-data transposes (module.F90:1061-1361) -----------------------------------
+    def _alltoallv_real(self, sendbufs, group_of, snd_strt, snd_cnts, rcv_strt, rcv_cnts, recv_len):
+        r = self.rt.itemsize
+        recv = [np.zeros(recv_len(d), dtype=self.rt) for d in self.d]
+        for d in self.d:
+            grp = group_of(d)
+            me = grp.index(d.rank)
+            for p, peer in enumerate(grp):
+                dp = self.d[peer]
+                s0, n = snd_strt(d)[p] // r, snd_cnts(d)[p] // r
+                r0, m = rcv_strt(dp)[me] // r, rcv_cnts(dp)[me] // r
+                assert n == m, "alltoallv count mismatch"
+                recv[peer][r0:r0 + n] = sendbufs[d.rank][s0:s0 + n]
+        return recv
+
+    def rtran(self, which, parts):
+        """``which`` in {"x2y", "y2x", "x2z", "z2x"}; parts[r] = rank r's source array (Fortran order).
+        Pack loops, MPI_Alltoallv tables and unpack loops as module.F90:1075-1116 (x2y), 1151-1193 (y2x),
+        1228-1271 (x2z), 1306-1347 (z2x)."""
+        D = self.d
+        out = []
+        if which == "x2y":
+            send = []
+            for d, s in zip(D, parts):
+                buf = np.zeros(d.nx * d.jisize * d.kjsize, dtype=self.rt)
+                pos = 0
+                for i in range(d.iproc):
+                    blk = s[d.iiist[i] - 1:d.iiien[i], :, :]
+                    buf[pos:pos + blk.size] = blk.ravel(order="F")
+                    pos += blk.size
+                send.append(buf)
+            recv = self._alltoallv_real(send, lambda d: d.row_ranks(), lambda d: d.IiStrt, lambda d: d.IiCnts,
+                                        lambda d: d.JiStrt, lambda d: d.JiCnts, lambda d: d.iiisize * d.ny * d.kjsize)
+            for d, r in zip(D, recv):
+                dest = np.zeros((d.iiisize, d.ny, d.kjsize), dtype=self.rt, order="F")
+                pos = 0
+                for i in range(d.iproc):
+                    n = d.iiisize * d.jisz[i] * d.kjsize
+                    dest[:, d.jist[i] - 1:d.jien[i], :] = r[pos:pos + n].reshape((d.iiisize, d.jisz[i], d.kjsize), order="F")
+                    pos += n
+                out.append(dest)
+        elif which == "y2x":
+            send = []
+            for d, s in zip(D, parts):
+                buf = np.zeros(d.iiisize * d.ny * d.kjsize, dtype=self.rt)
+                pos = 0
+                for i in range(d.iproc):
+                    blk = s[:, d.jist[i] - 1:d.jien[i], :]
+                    buf[pos:pos + blk.size] = blk.ravel(order="F")
+                    pos += blk.size
+                send.append(buf)
+            recv = self._alltoallv_real(send, lambda d: d.row_ranks(), lambda d: d.JiStrt, lambda d: d.JiCnts,
+                                        lambda d: d.IiStrt, lambda d: d.IiCnts, lambda d: d.nx * d.jisize * d.kjsize)
+            for d, r in zip(D, recv):
+                dest = np.zeros((d.nx, d.jisize, d.kjsize), dtype=self.rt, order="F")
+                pos = 0
+                for i in range(d.iproc):
+                    n = d.iiisz[i] * d.jisize * d.kjsize
+                    dest[d.iiist[i] - 1:d.iiien[i], :, :] = r[pos:pos + n].reshape((d.iiisz[i], d.jisize, d.kjsize), order="F")
+                    pos += n
+                out.append(dest)
+        elif which == "x2z":
+            send = []
+            for d, s in zip(D, parts):
+                buf = np.zeros(d.nx * d.jisize * d.kjsize, dtype=self.rt)
+                pos = 0
+                for i in range(d.jproc):
+                    blk = s[d.ijst[i] - 1:d.ijen[i], :, :]
+                    buf[pos:pos + blk.size] = blk.ravel(order="F")
+                    pos += blk.size
+                send.append(buf)
+            recv = self._alltoallv_real(send, lambda d: d.col_ranks(), lambda d: d.IjStrt, lambda d: d.IjCnts,
+                                        lambda d: d.KjStrt, lambda d: d.KjCnts, lambda d: d.ijsize * d.jisize * d.nz)
+            for d, r in zip(D, recv):
+                dest = np.zeros((d.ijsize, d.jisize, d.nz), dtype=self.rt, order="F")
+                pos = 0
+                for i in range(d.jproc):
+                    n = d.ijsize * d.jisize * d.kjsz[i]
+                    dest[:, :, d.kjst[i] - 1:d.kjen[i]] = r[pos:pos + n].reshape((d.ijsize, d.jisize, d.kjsz[i]), order="F")
+                    pos += n
+                out.append(dest)
+        elif which == "z2x":
+            send = []
+            for d, s in zip(D, parts):
+                buf = np.zeros(d.ijsize * d.jisize * d.nz, dtype=self.rt)
+                pos = 0
+                for i in range(d.jproc):
+                    blk = s[:, :, d.kjst[i] - 1:d.kjen[i]]
+                    buf[pos:pos + blk.size] = blk.ravel(order="F")
+                    pos += blk.size
+                send.append(buf)
+            recv = self._alltoallv_real(send, lambda d: d.col_ranks(), lambda d: d.KjStrt, lambda d: d.KjCnts,
+                                        lambda d: d.IjStrt, lambda d: d.IjCnts, lambda d: d.nx * d.jisize * d.kjsize)
+            for d, r in zip(D, recv):
+                dest = np.zeros((d.nx, d.jisize, d.kjsize), dtype=self.rt, order="F")
+                pos = 0
+                for i in range(d.jproc):
+                    n = d.ijsz[i] * d.jisize * d.kjsize
+                    dest[d.ijst[i] - 1:d.ijen[i], :, :] = r[pos:pos + n].reshape((d.ijsz[i], d.jisize, d.kjsize), order="F")
+                    pos += n
+                out.append(dest)
+        else:
+            raise ValueError(which)
+        return out
+
     def cheby(self, parts, Lz):
         out = self.forward(parts, "ffc")
         return [np.asfortranarray(cheby_epilogue(o, d, Lz).astype(self.ct)) for d, o in zip(self.d, out)]
+
+
+# --------------------------------------------------------------------------------------
+# real-data transposes, X-only transform, process-map queries, power spectrum
+# --------------------------------------------------------------------------------------
+def rtran_slices(d: Decomp, which: str):
+    """(source slice, destination slice) of the GLOBAL real array for one rank: the pencil each side of
+    rtran_x2y / y2x / x2z / z2x holds (module.F90:1064-1065, 1140-1141, 1217-1218, 1295-1296)."""
+    X = (slice(None), slice(d.jistart - 1, d.jiend), slice(d.kjstart - 1, d.kjend))
+    Y = (slice(d.iiistart - 1, d.iiiend), slice(None), slice(d.kjstart - 1, d.kjend))
+    Z = (slice(d.ijstart - 1, d.ijend), slice(d.jistart - 1, d.jiend), slice(None))
+    return {"x2y": (X, Y), "y2x": (Y, X), "x2z": (X, Z), "z2x": (Z, X)}[which]
+
+
+def rtran_local(Aglobal, d: Decomp, which: str):
+    """Destination array of one rank given the global field (the transposes move data, nothing else)."""
+    return np.asfortranarray(Aglobal[rtran_slices(d, which)[1]])
+
+
+def rtran_dims(d: Decomp, which: str):
+    """dstart, dend, dsize returned by the transposes (module.F90:1118-1127, 1195-1204, 1273-1282, 1349-1358)."""
+    if which == "x2y":
+        return ([d.iiistart, 1, d.kjstart], [d.iiiend, d.ny, d.kjend], [d.iiisize, d.ny, d.kjsize])
+    if which == "x2z":
+        return ([d.ijstart, d.jistart, 1], [d.ijend, d.jiend, d.nz], [d.ijsize, d.jisize, d.nz])
+    return ([1, d.jistart, d.kjstart], [d.nx, d.jiend, d.kjend], [d.nx, d.jisize, d.kjsize])
+
+
+def forward_r2c_1d(Alocal):
+    """p3dfft_ftran_r2c_1d (ftran.F90:787-814): r2c along x only, (nx, ji, kj) -> (nxhp, ji, kj)."""
+    A = np.asfortranarray(Alocal)
+    return np.asfortranarray(sfft.rfft(A, axis=0, workers=_WORKERS).astype(_ctype(A.dtype), copy=False))
+
+
+class ProcGrid:
+    """The reference's "trans2proc" tables and queries (module.F90:168-176, 788-1054; setup.F90:224-230, 551-577),
+    restated literally with 1-based proc_parts rows.  Where the reference reads outside its arrays
+    (proc_neighb accepts coord+orient == iproc, module.F90:813-822; the final loop of get_proc_parts starts at
+    row 0, module.F90:1025) the restatement stops at the array bounds instead."""
+
+    def __init__(self, nx, ny, nz, dims, nxc=None, nyc=None, nzc=None, dims_c=False, stride1=False):
+        self.iproc, self.jproc = dims
+        P = self.iproc * self.jproc
+        self.d = [Decomp(nx, ny, nz, tuple(dims), r, nxc, nyc, nzc, dims_c=dims_c, stride1=stride1) for r in range(P)]
+        self.proc_id2coords = []
+        for d in self.d:
+            self.proc_id2coords += [d.ipid, d.jpid]
+        self.proc_coords2id = {(d.ipid, d.jpid): d.rank for d in self.d}
+        # proc_dims(conf, 1..9, id) = start(3), end(3), size(3)
+        self.proc_dims = {}
+        for d in self.d:
+            for conf in (1, 2):
+                st, en, sz = d.get_dims(conf)
+                for k, v in enumerate(list(st) + list(en) + list(sz), start=1):
+                    self.proc_dims[(conf, k, d.rank)] = v
+
+    def proc_neighb(self, base, orient, direction):
+        if base < 0 or base >= self.iproc * self.jproc or orient not in (1, -1) or direction not in (1, 2):
+            return -1
+        ci, cj = self.proc_id2coords[2 * base], self.proc_id2coords[2 * base + 1]
+        if direction == 1:
+            return self.proc_coords2id.get((ci + orient, cj), -1)
+        return self.proc_coords2id.get((ci, cj + orient), -1)
+
+    def search_proc(self, point_i, point_j, di, dj, conf):
+        if not (1 <= di <= 3 and 1 <= dj <= 3 and conf in (1, 2)):
+            return -1
+        pd = self.proc_dims
+        pid = self.proc_coords2id[(0, 0)]
+        while not point_i < pd[(conf, di, pid)] + pd[(conf, di + 6, pid)]:
+            pid = self.proc_neighb(pid, 1, 1)
+            if pid < 0:
+                return -1
+        while not point_j < pd[(conf, dj, pid)] + pd[(conf, dj + 6, pid)]:
+            pid = self.proc_neighb(pid, 1, 2)
+            if pid < 0:
+                return -1
+        return pid
+
+    def get_proc_parts(self, base_x, base_y, base_z, size_x, size_y, size_z, conf):
+        """-> (proc_parts as a list of P rows of 7 ints, no_parts, ierr).  module.F90:888-1054."""
+        P = self.iproc * self.jproc
+        parts = [[-1] * 7 for _ in range(P + 1)]       # row 0 unused (1-based like the reference)
+        pd = self.proc_dims
+        if conf == 1:
+            base_i, base_j, base_k, size_i, size_j, size_k, di, dj = base_y, base_z, base_x, size_y, size_z, size_x, 2, 3
+        elif conf == 2:
+            base_i, base_j, base_k, size_i, size_j, size_k, di, dj = base_x, base_y, base_z, size_x, size_y, size_z, 1, 2
+        else:
+            return parts[1:], 0, 1
+        found = self.search_proc(base_i, base_j, di, dj, conf)
+        if found < 0:
+            return parts[1:], 0, -1
+        hi = lambda off, pid: pd[(conf, off, pid)] + pd[(conf, off + 6, pid)]
+        n = 0
+        end_i = 0
+        while end_i == 0:
+            n += 1
+            parts[n][0] = found
+            start_id_j, start_base_j, start_size_j = found, base_j, size_j
+            if base_i + size_i <= hi(di, found):
+                parts[n][1], parts[n][4] = base_i, size_i
+                end_i = 1
+            else:
+                parts[n][1], parts[n][4] = base_i, hi(di, found) - base_i
+                size_i = base_i + size_i - hi(di, found)
+                base_i = hi(di, found)
+            parts[n][3], parts[n][6] = base_k, size_k
+            end_j, size_i_exist = 0, 1
+            base_j, size_j = start_base_j, start_size_j
+            while end_j == 0:
+                if size_i_exist == 1:
+                    size_i_exist = 0
+                else:
+                    n += 1
+                    parts[n][0] = found
+                    parts[n][3], parts[n][4], parts[n][6] = parts[n - 1][3], parts[n - 1][4], parts[n - 1][6]
+                if base_j + size_j <= hi(dj, found):
+                    parts[n][2], parts[n][5] = base_j, size_j
+                    end_j = 1
+                else:
+                    parts[n][2], parts[n][5] = base_j, hi(dj, found) - base_j
+                    size_j = base_j + size_j - hi(dj, found)
+                    base_j = hi(dj, found)
+                if end_j == 0:
+                    found = self.proc_neighb(found, 1, 2)
+                    if found < 0:
+                        break
+            if end_i == 0:
+                found = self.proc_neighb(start_id_j, 1, 1)
+                if found < 0:
+                    break
+        if conf == 1:
+            for p in range(1, P + 1):
+                bi, bj, bk, si, sj, sk = parts[p][1:7]
+                parts[p][1:7] = [bk, bi, bj, sk, si, sj]
+        return parts[1:], n, 0
+
+
+def power_spectrum(B, fstart, ng, kmax, stride1=False):
+    """compute_spectrum of sample/C/driver_spec.c:298-384 (non-STRIDE1 branch :348-376) on one rank's
+    wavenumber array B (complex, Fortran order, get_dims(2) layout): el[ik] += k2 * (re^2 + im^2) with
+    kx = x + fstart_x - 1 (never folded: the array holds kx <= nx/2), ky, kz folded about ng/2 and
+    ik = int(sqrt(k2) + 0.5).  ``stride1``: B is (nzc, jj, ii) and fstart/ng are given in that order; the result
+    is the same physical shell sum (the reference's STRIDE1 loop, :317-346, walks the same elements)."""
+    B = np.asarray(B)
+    if stride1:
+        B = B.transpose(2, 1, 0)
+        fstart = fstart[::-1]
+        ng = ng[::-1]
+    sx, sy, sz = B.shape
+    kx = np.arange(sx) + fstart[0] - 1
+    ky = np.arange(sy) + fstart[1] - 1
+    ky = np.where(ky > ng[1] // 2, ng[1] - ky, ky)
+    kz = np.arange(sz) + fstart[2] - 1
+    kz = np.where(kz > ng[2] // 2, ng[2] - kz, kz)
+    k2 = kx[:, None, None] ** 2 + ky[None, :, None] ** 2 + kz[None, None, :] ** 2
+    ik = (np.sqrt(k2.astype(np.float64)) + 0.5).astype(np.int64)
+    w = k2 * (B.real.astype(np.float64) ** 2 + B.imag.astype(np.float64) ** 2)
+    return np.bincount(ik.ravel(), weights=w.ravel(), minlength=kmax + 1)[: kmax + 1]
 
 
 # --------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ class Stage(C.Structure):
 
 class Exchange(C.Structure):
     _fields_ = [("comm", C.c_int32), ("npeer", C.c_int32), ("self", C.c_int32), ("sendbuf", C.c_int32),
-                ("recvbuf", C.c_int32), ("timer", C.c_int32), ("p2p", C.c_int32), ("pad_", C.c_int32),
+                ("recvbuf", C.c_int32), ("timer", C.c_int32), ("p2p", C.c_int32), ("ebytes", C.c_int32),
                 ("sndoff", C.c_int64 * MAXSEG), ("sndcnt", C.c_int64 * MAXSEG),
                 ("rcvoff", C.c_int64 * MAXSEG), ("rcvcnt", C.c_int64 * MAXSEG)]
 
@@ -66,7 +66,8 @@ class DecompInfo(C.Structure):
         ("memsize", C.c_int32 * 3), ("nm", C.c_int64), ("work_elems", C.c_int64)]
 
 
-KIND_NAMES = {0: "c2c_fwd", 1: "c2c_bwd", 2: "r2c", 3: "c2r", 4: "dct1", 5: "dst1", 6: "noop"}
+RTRAN_NAMES = ("x2y", "y2x", "x2z", "z2x")      # index = `which` of the planner (csrc/plan.h RtranKind)
+KIND_NAMES = {0: "c2c_fwd", 1: "c2c_bwd", 2: "r2c", 3: "c2r", 4: "dct1", 5: "dst1", 6: "noop", 7: "rcopy"}
 BUF_USER_IN, BUF_USER_OUT, BUF_A, BUF_B, BUF_C = 0, 1, 2, 3, 4
 
 
@@ -121,6 +122,23 @@ class P3DFFT:
         lib.p3dfft_b200_plan_decomp.argtypes = [ip] + [C.c_int] * 8 + [C.POINTER(DecompInfo)]
         lib.p3dfft_b200_plan_steps.argtypes = [ip] + [C.c_int] * 9 + [C.c_char_p, C.c_int, C.c_int64, C.c_int64,
                                                                      C.c_int, vp, C.c_int]
+        lib.p3dfft_ftran_r2c_1d.argtypes = [vp, vp]
+        lib.p3dfft_ftran_r2c_1d.restype = None
+        for w in RTRAN_NAMES:
+            f = getattr(lib, "p3dfft_b200_rtran_" + w)
+            f.argtypes = [vp, vp, ip, ip, ip, C.POINTER(C.c_double)]
+            f.restype = None
+        lib.p3dfft_get_mpi_info.argtypes = [ip, ip, ip]
+        lib.p3dfft_b200_proc_id2coords.argtypes = [C.c_int, ip, ip]
+        lib.p3dfft_b200_proc_coords2id.argtypes = [C.c_int, C.c_int]
+        lib.p3dfft_b200_proc_dims.argtypes = [C.c_int, C.c_int, ip]
+        lib.p3dfft_b200_proc_neighb.argtypes = [C.c_int] * 3
+        lib.p3dfft_b200_get_proc_parts.argtypes = [C.c_int] * 7 + [ip, ip]
+        lib.p3dfft_b200_plan_aux_steps.argtypes = [ip] + [C.c_int] * 10 + [vp, C.c_int]
+        lib.p3dfft_b200_plan_rtran_info.argtypes = [ip] + [C.c_int] * 6 + [ip]
+        lib.p3dfft_b200_plan_rtran_info.restype = C.c_longlong
+        lib.p3dfft_b200_plan_proc_parts.argtypes = [ip] + [C.c_int] * 14 + [ip, ip]
+        lib.p3dfft_b200_plan_proc_neighb.argtypes = [ip] + [C.c_int] * 4
         if lib.p3dfft_b200_sizeof_step() != C.sizeof(Step):
             raise LibraryMissing("ctypes mirror of P3dStep is out of date")
         lib.p3dfft_b200_set_error_mode(1)     # Python callers get exceptions instead of abort()
@@ -187,6 +205,53 @@ class P3DFFT:
 
     def set_timers(self):
         self.lib.set_timers()
+
+    # ---- remaining module routines (module.F90:178-186) ----------------------------------------
+    def p3dfft_ftran_r2c_1d(self, A, B):
+        """``p3dfft_ftran_r2c_1d`` (build/ftran.F90:787): X transform only."""
+        self.lib.p3dfft_ftran_r2c_1d(_addr(A), _addr(B))
+        self._check()
+
+    def rtran(self, which, source, dest, t=0.0):
+        """``rtran_x2y`` / ``rtran_y2x`` / ``rtran_x2z`` / ``rtran_z2x`` (build/module.F90:1061-1361).
+        Returns (dstart, dend, dsize, t)."""
+        a, b, c = (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 3)()
+        tt = C.c_double(t)
+        getattr(self.lib, "p3dfft_b200_rtran_" + which)(_addr(source), _addr(dest), a, b, c, C.byref(tt))
+        self._check()
+        return tuple(a), tuple(b), tuple(c), tt.value
+
+    def p3dfft_get_mpi_info(self):
+        a, b, c = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+        self.lib.p3dfft_get_mpi_info(C.byref(a), C.byref(b), C.byref(c))
+        self._check()
+        return a.value, b.value, c.value
+
+    def proc_id2coords(self, pid):
+        a, b = C.c_int(-1), C.c_int(-1)
+        rc = self.lib.p3dfft_b200_proc_id2coords(pid, C.byref(a), C.byref(b))
+        self._check()
+        return (a.value, b.value) if rc == 0 else None
+
+    def proc_coords2id(self, ipid, jpid):
+        return int(self.lib.p3dfft_b200_proc_coords2id(ipid, jpid))
+
+    def proc_dims(self, conf, pid):
+        o = (C.c_int * 9)()
+        rc = self.lib.p3dfft_b200_proc_dims(conf, pid, o)
+        self._check()
+        return list(o) if rc == 0 else None
+
+    def proc_neighb(self, base, orient, direction):
+        return int(self.lib.p3dfft_b200_proc_neighb(base, orient, direction))
+
+    def get_proc_parts(self, base, size, conf, nproc):
+        """``get_proc_parts`` (build/module.F90:888): (rows of 7 ints, number of parts, ierr)."""
+        parts = (C.c_int * (7 * nproc))()
+        ierr = C.c_int(0)
+        n = self.lib.p3dfft_b200_get_proc_parts(*base, *size, conf, parts, C.byref(ierr))
+        self._check()
+        return [list(parts[7 * i:7 * i + 7]) for i in range(nproc)], n, ierr.value
 
     # ---- extensions ----------------------------------------------------------------------
     def set_layout(self, stride1=False, dims_c=False):
@@ -276,6 +341,48 @@ class P3DFFT:
             self._check()
             raise RuntimeError("plan_steps failed")
         return [arr[i] for i in range(n)], info
+
+
+    def plan_aux_steps(self, dims, nx, ny, nz, rank, which, p2p=False, dims_c=False, nxc=None, nyc=None, nzc=None):
+        """Step list of ``p3dfft_ftran_r2c_1d`` (which = "r2c_1d") or of a real-data transpose ("x2y", ...)."""
+        w = 100 if which == "r2c_1d" else RTRAN_NAMES.index(which)
+        arr = (Step * 8)()
+        d = (C.c_int * 2)(*dims)
+        flags = (4 if dims_c else 0) | (16 if p2p else 0)
+        n = self.lib.p3dfft_b200_plan_aux_steps(d, nx, ny, nz, rank, nxc or nx, nyc or ny, nzc or nz, flags, w,
+                                                4 if self.single else 8, arr, 8)
+        if n < 0:
+            self._check()
+            raise RuntimeError("plan_aux_steps failed")
+        return [arr[i] for i in range(n)]
+
+    def plan_rtran_info(self, dims, nx, ny, nz, rank, which, dims_c=False):
+        """(dstart, dend, dsize) of the destination array and the work-buffer bound (complex elements)."""
+        d = (C.c_int * 2)(*dims)
+        o = (C.c_int * 9)()
+        w = self.lib.p3dfft_b200_plan_rtran_info(d, nx, ny, nz, rank, RTRAN_NAMES.index(which), 4 if dims_c else 0, o)
+        if w < 0:
+            self._check()
+            raise RuntimeError("plan_rtran_info failed")
+        return list(o[0:3]), list(o[3:6]), list(o[6:9]), int(w)
+
+    def plan_proc_parts(self, dims, nx, ny, nz, base, size, conf, nxc=None, nyc=None, nzc=None, stride1=False,
+                        dims_c=False):
+        d = (C.c_int * 2)(*dims)
+        P = dims[0] * dims[1]
+        parts = (C.c_int * (7 * P))()
+        ierr = C.c_int(0)
+        flags = (2 if stride1 else 0) | (4 if dims_c else 0)
+        n = self.lib.p3dfft_b200_plan_proc_parts(d, nx, ny, nz, nxc or nx, nyc or ny, nzc or nz, flags, *base, *size,
+                                                 conf, parts, C.byref(ierr))
+        if n < 0:
+            self._check()
+            raise RuntimeError("plan_proc_parts failed")
+        return [list(parts[7 * i:7 * i + 7]) for i in range(P)], n, ierr.value
+
+    def plan_proc_neighb(self, dims, base, orient, direction, dims_c=False):
+        d = (C.c_int * 2)(*dims)
+        return int(self.lib.p3dfft_b200_plan_proc_neighb(d, 4 if dims_c else 0, base, orient, direction))
 
 
 _cache: dict = {}

@@ -21,7 +21,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 SOURCES = ["fft_kernels.cu", "fft_fast.cu", "api.cpp"]
-HEADERS = ["stage.h", "plan.h", "kernels.h", "fast.h", "fft_fast.cuh"]
+HEADERS = ["stage.h", "plan.h", "kernels.h", "fast.h", "fft_fast.cuh", "rcopy.h", "procmap.h"]
 
 
 def _newer(target, deps):
@@ -90,6 +90,15 @@ def build_c_drivers(verbose: bool = False) -> list[str]:
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
         out.append(target)
+    # test-only host harness of the real-copy address arithmetic (tests/c/rcopy_host.cpp)
+    target = os.path.join(LIBDIR, "librcopy_check.so")
+    srcp = os.path.join(root, "tests", "c", "rcopy_host.cpp")
+    if _newer(target, [srcp, os.path.join(CSRC, "rcopy.h"), os.path.join(CSRC, "stage.h")]):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", srcp, "-o", target]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    out.append(target)
     return out
 
 

@@ -22,6 +22,7 @@
 #include "fast.h"
 #include "kernels.h"
 #include "plan.h"
+#include "procmap.h"
 #include "stage.h"
 
 #ifdef SINGLE_PREC
@@ -132,6 +133,14 @@ struct Lib {
   bool want_p2p = true, p2p = false;
   std::vector<void*> peer_buf;   // [world rank * 3 + (buffer id - P3D_BUF_A)], own entries = own buffers
   float* bar_scratch = nullptr;
+  // dirty[b]: buffer b was the receive buffer of an exchange since the last world barrier, i.e. some rank may still
+  // be reading it.  A peer-to-peer stage must not store into the peers' copies of such a buffer before another
+  // barrier (run_plan).  Derived from the exchange steps only, so every rank takes the same decisions.
+  bool dirty[5] = {false, false, false, false, false};
+  long long work_elems_alloc = 0;   // complex elements per work buffer
+  bool rtran_sized = false;         // the buffers already cover rtran_work_elems()
+  std::map<int, p3d::TransformPlan> aux_plans;     // r2c_1d (key 100) and rtran (key which*2 + p2p) plans
+  p3d::ProcMap procmap;                            // proc_id2coords / proc_dims tables (setup.F90:224-230, 551-577)
   bool plain_layout = false;     // true: the reference's pack-buffer layouts instead of the tile-blocked ones
   int force_row_bytes = 0;       // 64 / 128: override the planner's choice of the tile row width
   int W() const { return plain_layout ? 0 : p3d::pick_W(d.ny, d.nz, (int)CSIZE, force_row_bytes); }
@@ -210,6 +219,7 @@ bool world_barrier(cudaStream_t st) {
   if (!L.comm || !L.comm->world) return true;
   if (!L.bar_scratch) { CUDA_OK(cudaMalloc(&L.bar_scratch, 256)); CUDA_OK(cudaMemset(L.bar_scratch, 0, 256)); }
   NCCL_OK(g_nccl.AllReduce(L.bar_scratch, L.bar_scratch + 32, 1, ncclFloat, ncclSum, L.comm->world, st));
+  for (bool& d : L.dirty) d = false;
   return true;
 }
 
@@ -255,8 +265,12 @@ bool open_peer_maps() {
   return true;
 }
 
-bool alloc_work(int nv) {
-  if (nv <= L.nv_preset) return true;
+// for_rtran: the buffers must also stage the real-data transposes (rtran_work_elems, the same bound on every rank).
+// Both conditions are identical on all ranks, so re-creating the buffers and the peer mappings stays collective.
+bool alloc_work(int nv, bool for_rtran = false) {
+  if (nv <= L.nv_preset && (!for_rtran || L.rtran_sized)) return true;
+  if (nv < L.nv_preset) nv = L.nv_preset;
+  if (for_rtran) L.rtran_sized = true;
   // lazy growth like ftran.F90:133-157 (nv_preset)
   cudaStreamSynchronize(L.stream());
   const bool multi = L.comm && L.comm->size > 1;
@@ -265,7 +279,9 @@ bool alloc_work(int nv) {
     cudaStreamSynchronize(L.stream());
     close_peer_maps();
   }
-  size_t bytes = (size_t)L.d.work_elems(nv, L.W()) * CSIZE;
+  long long elems = L.d.work_elems(nv, L.W());
+  if (L.rtran_sized) elems = std::max(elems, p3d::rtran_work_elems(L.d));
+  size_t bytes = (size_t)elems * CSIZE;
   int nbuf = (L.d.iproc * L.d.jproc > 1) ? 3 : 2;
   for (int b = 0; b < nbuf; b++) {
     int id = P3D_BUF_A + b;
@@ -273,10 +289,26 @@ bool alloc_work(int nv) {
     CUDA_OK(cudaMalloc(&L.buf[id], bytes));
   }
   L.nv_preset = nv;
+  L.work_elems_alloc = elems;
   L.plans.clear();
+  L.aux_plans.clear();
   if (multi && L.want_p2p && L.W() > 0 && nbuf == 3) {
     if (!open_peer_maps() && L.comm->rank == 0 && getenv("P3DFFT_B200_VERBOSE"))
       fprintf(stderr, "P3DFFT(B200): peer mapping unavailable, transposes use ncclSend/ncclRecv\n");
+  }
+  return true;
+}
+
+// tile sizes and twiddle tables of the FFT stages of a freshly built plan
+bool finalize_plan(p3d::TransformPlan& tp) {
+  for (auto& s : tp.steps) {
+    if (s.is_exchange || s.st.kind == P3D_RCOPY) continue;
+    s.st.tile = p3d::choose_tile<real_t>(s.st);
+    if (s.st.tile <= 0) { report(true, "P3DFFT(B200): transform length %d does not fit on chip", s.st.nfft); return false; }
+    if (s.st.kind != P3D_NOOP) {
+      s.st.tw = twiddle_table(s.st.nfft);
+      if (!s.st.tw) { report(true, "P3DFFT(B200): cannot allocate twiddle table"); return false; }
+    }
   }
   return true;
 }
@@ -291,15 +323,7 @@ p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long di
     report(true, "%s", tp.error.c_str());
     return nullptr;
   }
-  for (auto& s : tp.steps) {
-    if (s.is_exchange) continue;
-    s.st.tile = p3d::choose_tile<real_t>(s.st);
-    if (s.st.tile <= 0) { report(true, "P3DFFT(B200): transform length %d does not fit on chip", s.st.nfft); return nullptr; }
-    if (s.st.kind != P3D_NOOP) {
-      s.st.tw = twiddle_table(s.st.nfft);
-      if (!s.st.tw) { report(true, "P3DFFT(B200): cannot allocate twiddle table"); return nullptr; }
-    }
-  }
+  if (!finalize_plan(tp)) return nullptr;
   auto res = L.plans.emplace(key, std::move(tp));
   return &res.first->second;
 }
@@ -314,28 +338,30 @@ bool run_exchange(const P3dExchange& e, cudaStream_t st) {
   ncclComm_t c = e.comm == 0 ? L.row : L.col;
   char* sb = (char*)L.buf[e.sendbuf];
   char* rb = (char*)L.buf[e.recvbuf];
+  const size_t eb = e.ebytes > 0 ? (size_t)e.ebytes : CSIZE;
   NCCL_OK(g_nccl.GroupStart());
   for (int p = 0; p < e.npeer; p++) {
     if (p == e.self) continue;      // own block was written in place by the producing stage
-    if (e.sndcnt[p] > 0) NCCL_OK(g_nccl.Send(sb + e.sndoff[p] * CSIZE, (size_t)e.sndcnt[p] * CSIZE, ncclInt8, p, c, st));
-    if (e.rcvcnt[p] > 0) NCCL_OK(g_nccl.Recv(rb + e.rcvoff[p] * CSIZE, (size_t)e.rcvcnt[p] * CSIZE, ncclInt8, p, c, st));
+    if (e.sndcnt[p] > 0) NCCL_OK(g_nccl.Send(sb + e.sndoff[p] * eb, (size_t)e.sndcnt[p] * eb, ncclInt8, p, c, st));
+    if (e.rcvcnt[p] > 0) NCCL_OK(g_nccl.Recv(rb + e.rcvoff[p] * eb, (size_t)e.rcvcnt[p] * eb, ncclInt8, p, c, st));
   }
   NCCL_OK(g_nccl.GroupEnd());
   return true;
 }
 
-// Runs one transform.  `in`/`out` may be host or device pointers.
-bool run_transform(bool backward, const void* in, void* out, const char* op, int nv, long long dim_real,
-                   long long dim_cplx, bool cheby, double Lz) {
-  if (!alloc_work(nv)) return false;
-  p3d::TransformPlan* tp = get_plan(backward, op, nv, dim_real, dim_cplx);
-  if (!tp) return false;
+// bytes per element of one side (0 = input, 1 = output) of a stage of this kind
+size_t side_elem_bytes(int kind, int side) {
+  if (kind == P3D_RCOPY) return sizeof(real_t);
+  if ((kind == P3D_R2C && side == 0) || (kind == P3D_C2R && side == 1)) return sizeof(real_t);
+  return CSIZE;
+}
+
+// Runs a step list.  `in`/`out` may be host or device pointers (host arrays are staged over PCIe inside the
+// call).  exchange_ms, when given, receives the device time spent in the exchange steps (rtran's `t`).
+bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes, size_t out_bytes, int nv,
+              long long dim_cplx, bool cheby, double Lz, double* exchange_ms) {
   cudaStream_t st = L.stream();
   const p3d::Decomp& d = L.d;
-  const size_t real_elems = (size_t)d.nx * d.jisize * d.kjsize, cplx_elems = (size_t)d.iisize * d.jjsize * d.nzc;
-  const size_t real_bytes = ((size_t)(nv - 1) * dim_real + real_elems) * sizeof(real_t);
-  const size_t cplx_bytes = ((size_t)(nv - 1) * dim_cplx + cplx_elems) * CSIZE;
-  const size_t in_bytes = backward ? cplx_bytes : real_bytes, out_bytes = backward ? real_bytes : cplx_bytes;
   const bool in_dev = is_device_ptr(in), out_dev = is_device_ptr(out);
   const void* din = in; void* dout = out;
   if (!in_dev) {
@@ -353,19 +379,34 @@ bool run_transform(bool backward, const void* in, void* out, const char* op, int
     }
     dout = L.stage_out;
   }
-  const bool timed = !L.async;
+  const bool timed = !L.async || exchange_ms;
   size_t nev = 0;
   std::vector<int> slots;
-  for (auto& s : tp->steps) {
+  std::vector<char> is_ex;
+  const size_t nsteps = tp->steps.size();
+  bool pre_done = false;      // the barrier that protects the receive buffer of the NEXT exchange has been issued
+  for (size_t i = 0; i < nsteps; i++) {
+    auto& s = tp->steps[i];
+    // Peer-to-peer plans: the stage in front of an exchange stores into the peers' receive buffer.  If that buffer
+    // was handed to a consumer stage since the last barrier, a peer may still be reading it (write-after-read
+    // across ranks): barrier first.  Decided from the exchange steps alone, identically on every rank -- a rank
+    // whose producing stage is empty issues the same barrier when it reaches the exchange.
+    const P3dExchange* nex = s.is_exchange ? &s.ex : (i + 1 < nsteps && tp->steps[i + 1].is_exchange ? &tp->steps[i + 1].ex : nullptr);
+    if (nex && nex->p2p && !pre_done && L.dirty[nex->recvbuf]) {
+      if (timed) { cudaEventRecord(get_event(nev++), st); slots.push_back(nex->timer); is_ex.push_back(1); }
+      if (!world_barrier(st)) return false;
+    }
+    if (nex) pre_done = !s.is_exchange;
     if (timed) { cudaEventRecord(get_event(nev++), st); }
     if (s.is_exchange) {
       if (!run_exchange(s.ex, st)) return false;
-      slots.push_back(s.ex.timer);
+      L.dirty[s.ex.recvbuf] = true;
+      slots.push_back(s.ex.timer); is_ex.push_back(1);
     } else {
       P3dStage stg = s.st;
       for (int side = 0; side < 2; side++) {
         P3dSide& sd = side ? stg.out : stg.in;
-        const size_t esz = (stg.kind == P3D_R2C && side == 0) || (stg.kind == P3D_C2R && side == 1) ? sizeof(real_t) : CSIZE;
+        const size_t esz = side_elem_bytes(stg.kind, side);
         for (int g = 0; g < sd.nseg; g++) {
           P3dSeg& sg = sd.seg[g];
           char* base = sg.buf == P3D_BUF_USER_IN ? (char*)din : sg.buf == P3D_BUF_USER_OUT ? (char*)dout : (char*)L.buf[sg.buf];
@@ -374,7 +415,8 @@ bool run_transform(bool backward, const void* in, void* out, const char* op, int
         }
       }
       cudaError_t e = cudaErrorMisalignedAddress;
-      if (!L.force_generic && p3d::fast_supported<real_t>(stg)) {
+      if (stg.kind == P3D_RCOPY) e = p3d::launch_rcopy<real_t>(stg, st);
+      else if (!L.force_generic && p3d::fast_supported<real_t>(stg)) {
         p3d::FastStage fs;
         p3d::to_fast(stg, fs, sizeof(real_t));
         fs.tw = fast_twiddle_block(stg.kind, stg.nfft);
@@ -385,7 +427,7 @@ bool run_transform(bool backward, const void* in, void* out, const char* op, int
       if (e == cudaErrorMisalignedAddress) e = p3d::launch_stage<real_t>(stg, st);   // any length / alignment
       if (e != cudaSuccess) { report(true, "P3DFFT(B200): stage launch failed: %s", cudaGetErrorString(e)); return false; }
       L.launches++;
-      slots.push_back(stg.timer);
+      slots.push_back(stg.timer); is_ex.push_back(0);
     }
   }
   if (cheby) {
@@ -401,20 +443,60 @@ bool run_transform(bool backward, const void* in, void* out, const char* op, int
       if (e != cudaSuccess) { report(true, "P3DFFT(B200): cheby launch failed: %s", cudaGetErrorString(e)); return false; }
       L.launches++;
     }
-    slots.push_back(8);
+    slots.push_back(8); is_ex.push_back(0);
   }
   if (timed) cudaEventRecord(get_event(nev++), st);
   if (!out_dev) CUDA_OK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
-  if (!L.async || !in_dev || !out_dev) {
+  if (!L.async || !in_dev || !out_dev || exchange_ms) {
     CUDA_OK(cudaStreamSynchronize(st));
     if (timed) {
       for (size_t i = 0; i + 1 < nev; i++) {
         float ms = 0; cudaEventElapsedTime(&ms, L.events[i], L.events[i + 1]);
         int slot = slots[i];
         if (slot >= 1 && slot <= 12) L.timers[slot - 1] += ms * 1e-3;
+        if (exchange_ms && is_ex[i]) *exchange_ms += ms;
       }
     }
   }
+  return true;
+}
+
+// Runs one transform.
+bool run_transform(bool backward, const void* in, void* out, const char* op, int nv, long long dim_real,
+                   long long dim_cplx, bool cheby, double Lz) {
+  if (!alloc_work(nv)) return false;
+  p3d::TransformPlan* tp = get_plan(backward, op, nv, dim_real, dim_cplx);
+  if (!tp) return false;
+  const p3d::Decomp& d = L.d;
+  const size_t real_elems = (size_t)d.nx * d.jisize * d.kjsize, cplx_elems = (size_t)d.iisize * d.jjsize * d.nzc;
+  const size_t real_bytes = ((size_t)(nv - 1) * dim_real + real_elems) * sizeof(real_t);
+  const size_t cplx_bytes = ((size_t)(nv - 1) * dim_cplx + cplx_elems) * CSIZE;
+  return run_plan(tp, in, out, backward ? cplx_bytes : real_bytes, backward ? real_bytes : cplx_bytes, nv, dim_cplx,
+                  cheby, Lz, nullptr);
+}
+
+// p3dfft_ftran_r2c_1d and the rtran_* transposes: plans cached by key
+p3d::TransformPlan* get_aux_plan(int key) {
+  auto it = L.aux_plans.find(key);
+  if (it != L.aux_plans.end()) return &it->second;
+  p3d::TransformPlan tp = key == 100 ? p3d::build_r2c_1d_plan(L.d)
+                                     : p3d::build_rtran_plan(L.d, key / 2, (key & 1) != 0, (int)sizeof(real_t));
+  if (!tp.error.empty()) { report(true, "%s", tp.error.c_str()); return nullptr; }
+  if (!finalize_plan(tp)) return nullptr;
+  return &L.aux_plans.emplace(key, std::move(tp)).first->second;
+}
+
+bool run_rtran(int which, const void* src, void* dst, int* dstart, int* dend, int* dsize, double* t) {
+  const bool multi = L.comm && L.comm->size > 1;
+  if (multi && !alloc_work(L.nv_preset, true)) return false;
+  p3d::TransformPlan* tp = get_aux_plan(which * 2 + (L.p2p ? 1 : 0));
+  if (!tp) return false;
+  double ex_ms = 0.0;
+  const size_t ib = (size_t)p3d::rtran_elems(L.d, which, false) * sizeof(real_t);
+  const size_t ob = (size_t)p3d::rtran_elems(L.d, which, true) * sizeof(real_t);
+  if (!run_plan(tp, src, dst, ib, ob, 1, 0, false, 0.0, t ? &ex_ms : nullptr)) return false;
+  if (t) *t += ex_ms * 1e-3;          // the reference adds the MPI_Wtime spent in the alltoallv (module.F90:1085-1095)
+  if (dstart && dend && dsize) p3d::rtran_dims(L.d, which, dstart, dend, dsize);
   return true;
 }
 
@@ -472,6 +554,7 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   if (getenv("P3DFFT_B200_P2P")) L.want_p2p = atoi(getenv("P3DFFT_B200_P2P")) != 0;
   if (getenv("P3DFFT_B200_ROWB")) L.force_row_bytes = atoi(getenv("P3DFFT_B200_ROWB"));
   for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
+  L.procmap.init(L.d);
   L.nv_preset = 0;
   L.set = true;
   if (!alloc_work(1)) { L.set = false; return; }
@@ -569,11 +652,70 @@ void p3dfft_clean(void) {
   if (L.row) { g_nccl.CommDestroy(L.row); L.row = nullptr; }
   if (L.col) { g_nccl.CommDestroy(L.col); L.col = nullptr; }
   L.nv_preset = 0;
+  L.work_elems_alloc = 0;
+  L.rtran_sized = false;
+  L.aux_plans.clear();
+  for (bool& d : L.dirty) d = false;
   L.set = false;
 }
 
 void get_timers(double* timers) { for (int i = 0; i < 12; i++) timers[i] = L.timers[i]; }   // module.F90:726
 void set_timers(void) { for (int i = 0; i < 12; i++) L.timers[i] = 0.0; }                   // module.F90:742
+
+// ======================================================================================
+// remaining public routines of the reference's Fortran module (module.F90:178-186)
+// ======================================================================================
+void p3dfft_ftran_r2c_1d(void* rXgYZ, void* cXgYZ) {      // ftran.F90:787-814
+  if (!check_set()) return;
+  const p3d::Decomp& d = L.d;
+  p3d::TransformPlan* tp = get_aux_plan(100);
+  if (!tp || tp->steps.empty()) return;
+  const size_t lines = (size_t)d.jisize * d.kjsize;
+  run_plan(tp, rXgYZ, cXgYZ, lines * d.nx * sizeof(real_t), lines * d.nxhp * CSIZE, 1, 0, false, 0.0, nullptr);
+}
+
+void p3dfft_b200_rtran_x2y(const void* src, void* dst, int* dstart, int* dend, int* dsize, double* t) {
+  if (check_set()) run_rtran(p3d::RTRAN_X2Y, src, dst, dstart, dend, dsize, t);
+}
+void p3dfft_b200_rtran_y2x(const void* src, void* dst, int* dstart, int* dend, int* dsize, double* t) {
+  if (check_set()) run_rtran(p3d::RTRAN_Y2X, src, dst, dstart, dend, dsize, t);
+}
+void p3dfft_b200_rtran_x2z(const void* src, void* dst, int* dstart, int* dend, int* dsize, double* t) {
+  if (check_set()) run_rtran(p3d::RTRAN_X2Z, src, dst, dstart, dend, dsize, t);
+}
+void p3dfft_b200_rtran_z2x(const void* src, void* dst, int* dstart, int* dend, int* dsize, double* t) {
+  if (check_set()) run_rtran(p3d::RTRAN_Z2X, src, dst, dstart, dend, dsize, t);
+}
+
+void p3dfft_get_mpi_info(int* taskid, int* ntasks, int* comm) {      // module.F90:280-297
+  if (!check_set()) return;
+  *taskid = L.d.rank; *ntasks = L.d.numtasks;
+  *comm = 0;
+  for (auto& kv : g_comms) if (kv.second == L.comm) *comm = kv.first;
+}
+
+int p3dfft_b200_proc_id2coords(int id, int* ipid, int* jpid) {
+  if (!check_set() || id < 0 || id >= L.procmap.nproc()) return -1;
+  *ipid = L.procmap.id2coords[2 * id]; *jpid = L.procmap.id2coords[2 * id + 1];
+  return 0;
+}
+int p3dfft_b200_proc_coords2id(int ipid, int jpid) { return check_set() ? L.procmap.coords2id(ipid, jpid) : -1; }
+int p3dfft_b200_proc_dims(int conf, int id, int* out9) {
+  if (!check_set() || conf < 1 || conf > 2 || id < 0 || id >= L.procmap.nproc()) return -1;
+  for (int k = 1; k <= 9; k++) out9[k - 1] = L.procmap.pd(conf, k, id);
+  return 0;
+}
+int p3dfft_b200_proc_neighb(int base, int orient, int direction) {
+  return check_set() ? L.procmap.neighb(base, orient, direction) : -1;
+}
+int p3dfft_b200_get_proc_parts(int base_x, int base_y, int base_z, int size_x, int size_y, int size_z, int conf,
+                               int* parts, int* ierr) {
+  if (!check_set()) { if (ierr) *ierr = -2; return 0; }
+  int e = 0;
+  const int n = L.procmap.parts(base_x, base_y, base_z, size_x, size_y, size_z, conf, parts, &e);
+  if (ierr) *ierr = e;
+  return n;
+}
 
 // ======================================================================================
 // extensions
@@ -700,6 +842,59 @@ int p3dfft_b200_plan_steps(const int* dims, int nx, int ny, int nz, int rank, in
       out[i].st.tile = elem_bytes == 4 ? p3d::choose_tile<float>(out[i].st) : p3d::choose_tile<double>(out[i].st);
   }
   return (int)tp.steps.size();
+}
+
+int p3dfft_b200_plan_aux_steps(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc, int flags,
+                               int which, int elem_bytes, void* steps, int max_steps) {
+  p3d::Decomp d;
+  std::string err = d.init(nx, ny, nz, dims[0], dims[1], rank, dims[0] * dims[1], nxc, nyc, nzc, (flags & 4) != 0,
+                           (flags & 2) != 0);
+  if (!err.empty()) { g_last_error = err; return -1; }
+  if (which != 100 && (which < 0 || which > 3)) { g_last_error = "unknown auxiliary plan"; return -1; }
+  p3d::TransformPlan tp = which == 100 ? p3d::build_r2c_1d_plan(d) : p3d::build_rtran_plan(d, which, (flags & 16) != 0, elem_bytes);
+  if (!tp.error.empty()) { g_last_error = tp.error; return -1; }
+  if ((int)tp.steps.size() > max_steps) { g_last_error = "step array too small"; return -1; }
+  P3dStepC* out = (P3dStepC*)steps;
+  for (size_t i = 0; i < tp.steps.size(); i++) {
+    memset(&out[i], 0, sizeof out[i]);
+    out[i].is_exchange = tp.steps[i].is_exchange ? 1 : 0;
+    out[i].st = tp.steps[i].st;
+    out[i].ex = tp.steps[i].ex;
+    if (!tp.steps[i].is_exchange && tp.steps[i].st.kind != P3D_RCOPY)
+      out[i].st.tile = elem_bytes == 4 ? p3d::choose_tile<float>(out[i].st) : p3d::choose_tile<double>(out[i].st);
+  }
+  return (int)tp.steps.size();
+}
+
+long long p3dfft_b200_plan_rtran_info(const int* dims, int nx, int ny, int nz, int rank, int which, int flags, int* dims9) {
+  p3d::Decomp d;
+  std::string err = d.init(nx, ny, nz, dims[0], dims[1], rank, dims[0] * dims[1], nx, ny, nz, (flags & 4) != 0, (flags & 2) != 0);
+  if (!err.empty()) { g_last_error = err; return -1; }
+  if (which < 0 || which > 3) { g_last_error = "unknown transpose"; return -1; }
+  if (dims9) p3d::rtran_dims(d, which, dims9, dims9 + 3, dims9 + 6);
+  return p3d::rtran_work_elems(d);
+}
+
+int p3dfft_b200_plan_proc_parts(const int* dims, int nx, int ny, int nz, int nxc, int nyc, int nzc, int flags, int base_x,
+                                int base_y, int base_z, int size_x, int size_y, int size_z, int conf, int* parts, int* ierr) {
+  p3d::Decomp d;
+  std::string err = d.init(nx, ny, nz, dims[0], dims[1], 0, dims[0] * dims[1], nxc, nyc, nzc, (flags & 4) != 0, (flags & 2) != 0);
+  if (!err.empty()) { g_last_error = err; return -1; }
+  p3d::ProcMap pm;
+  pm.init(d);
+  int e = 0;
+  const int n = pm.parts(base_x, base_y, base_z, size_x, size_y, size_z, conf, parts, &e);
+  if (ierr) *ierr = e;
+  return n;
+}
+
+int p3dfft_b200_plan_proc_neighb(const int* dims, int flags, int base, int orient, int direction) {
+  p3d::Decomp d;
+  std::string err = d.init(4, 4, 4, dims[0], dims[1], 0, dims[0] * dims[1], 4, 4, 4, (flags & 4) != 0, false);
+  if (!err.empty()) { g_last_error = err; return -2; }
+  p3d::ProcMap pm;
+  pm.init(d);
+  return pm.neighb(base, orient, direction);
 }
 
 }  // extern "C"

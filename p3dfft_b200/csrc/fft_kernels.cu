@@ -14,6 +14,7 @@
 
 #include "stage.h"
 #include "kernels.h"
+#include "rcopy.h"
 
 namespace p3d {
 
@@ -360,6 +361,7 @@ static cudaError_t launch_kind(const P3dStage& st, cudaStream_t stream) {
 
 template <typename T>
 cudaError_t launch_stage(const P3dStage& st, cudaStream_t stream) {
+  if (st.kind == P3D_RCOPY) return launch_rcopy<T>(st, stream);
   if (st.tile <= 0) return cudaErrorInvalidValue;
   switch (st.kind) {
     case P3D_C2C_FWD: return launch_kind<T, P3D_C2C_FWD>(st, stream);
@@ -369,6 +371,7 @@ cudaError_t launch_stage(const P3dStage& st, cudaStream_t stream) {
     case P3D_DCT1: return launch_kind<T, P3D_DCT1>(st, stream);
     case P3D_DST1: return launch_kind<T, P3D_DST1>(st, stream);
     case P3D_NOOP: return launch_kind<T, P3D_NOOP>(st, stream);
+    default: break;
   }
   return cudaErrorInvalidValue;
 }
@@ -383,7 +386,29 @@ cudaError_t launch_cheby(void* out, long long ncol, int nzc, long long zstride, 
   return cudaGetLastError();
 }
 
+// P3D_RCOPY stages (real-data transposes): one launch copies every (input block, output block) intersection
+template <typename T>
+cudaError_t launch_rcopy(const P3dStage& st, cudaStream_t stream) {
+  RcopyJob job;
+  if (!rcopy_boxes(st, job, sizeof(T))) return cudaErrorInvalidValue;
+  if (job.nbox <= 0 || job.rows_max <= 0) return cudaSuccess;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  // 8 warps per CTA, one row per warp at a time; the grid is a multiple of the SM count unless there is less work
+  long long gx = (job.rows_max + 7) / 8;
+  const long long cap = (long long)sms * 8;
+  if (gx > cap) gx = cap;
+  rcopy_kernel<T><<<dim3((unsigned)gx, (unsigned)job.nbox), 256, 0, stream>>>(job);
+  return cudaGetLastError();
+}
+
 template cudaError_t launch_stage<double>(const P3dStage&, cudaStream_t);
+template cudaError_t launch_rcopy<double>(const P3dStage&, cudaStream_t);
+template cudaError_t launch_rcopy<float>(const P3dStage&, cudaStream_t);
 template cudaError_t launch_stage<float>(const P3dStage&, cudaStream_t);
 template int choose_tile<double>(const P3dStage&);
 template int choose_tile<float>(const P3dStage&);

@@ -42,7 +42,9 @@ struct Decomp {
   int iproc = 1, jproc = 1, ipid = 0, jpid = 0, rank = 0, numtasks = 1;
   bool dims_c = false, stride1 = false;
   BlockMap ii, ji, jj, kj;   // x(nxhpc)/iproc, y(ny)/iproc, y(nyc)/jproc, z(nz)/jproc
+  BlockMap iii, ij;          // real-space x(nx)/iproc and x(nx)/jproc of the rtran_* transposes (setup.F90:299-312)
   int iistart, iiend, iisize, jistart, jiend, jisize, jjstart, jjend, jjsize, kjstart, kjend, kjsize;
+  int iiistart, iiiend, iiisize, ijstart, ijend, ijsize;
   int padi_work = 0, padi = 0;
   long long nm = 0;
   int memsize[3] = {0, 0, 0};
@@ -79,6 +81,10 @@ struct Decomp {
     jistart = ji.st[ipid]; jiend = ji.en[ipid]; jisize = ji.sz[ipid];
     jjstart = jj.st[jpid]; jjend = jj.en[jpid]; jjsize = jj.sz[jpid];
     kjstart = kj.st[jpid]; kjend = kj.en[jpid]; kjsize = kj.sz[jpid];
+    iii = map_data_to_proc(nx, iproc);                             // setup.F90:305-312
+    ij = map_data_to_proc(nx, jproc);
+    iiistart = iii.st[ipid]; iiiend = iii.en[ipid]; iiisize = iii.sz[ipid];
+    ijstart = ij.st[jpid]; ijend = ij.en[jpid]; ijsize = ij.sz[jpid];
     // setup.F90:382-398
     long long padd = std::max((long long)iisize * jjsize * nz, (long long)iisize * ny * kjsize)
                      - (long long)nxhp * jisize * kjsize;
@@ -167,8 +173,8 @@ inline bool factorize(int n, int* fac, int* nfac, int maxprime = 4096) {
 
 struct Step {
   bool is_exchange = false;
-  P3dStage st;
-  P3dExchange ex;
+  P3dStage st{};
+  P3dExchange ex{};
 };
 
 struct TransformPlan {
@@ -530,5 +536,182 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
   }
   return tp;
 }
+
+// ------------------------------------------------------------------------------------
+// p3dfft_ftran_r2c_1d (ftran.F90:787-814): the X stage alone, real (nx, jisize, kjsize) -> complex
+// (nxhp, jisize, kjsize) [= nx+2 reals per line], no pruning, no transpose.
+// ------------------------------------------------------------------------------------
+inline TransformPlan build_r2c_1d_plan(const Decomp& d) {
+  TransformPlan tp;
+  const long long nx = d.nx, ji = d.jisize, kj = d.kjsize, nxhp = d.nxhp;
+  if (ji * kj <= 0) return tp;                                   // ftran.F90:809
+  P3dStage s;
+  stage_init(s, P3D_R2C, d.nx, (int)ji, (int)kj, 1, 5); s.layx = 1;
+  side_init(s.in, d.nx, d.nx, d.nx);
+  add_seg(s.in, P3D_BUF_USER_IN, -1, 0, 0, d.nx, 1, nx, nx * ji, nx * ji * kj);
+  side_init(s.out, d.nxhp, d.nxhp, d.nxhp);
+  add_seg(s.out, P3D_BUF_USER_OUT, -1, 0, 0, d.nxhp, 1, nxhp, nxhp * ji, nxhp * ji * kj);
+  if (!factorize(s.nfft, s.fac, &s.nfac)) {
+    char m[128]; snprintf(m, sizeof m, "transform length %d needs a prime factor > 4096 (unsupported)", s.nfft);
+    tp.error = m; return tp;
+  }
+  Step st; st.is_exchange = false; st.st = s; tp.steps.push_back(st);
+  return tp;
+}
+
+// ------------------------------------------------------------------------------------
+// Real-data pencil transposes rtran_x2y / rtran_y2x / rtran_x2z / rtran_z2x (module.F90:1061-1361):
+//   x2y: (nx, jisize, kjsize)      -> (iiisize, ny, kjsize)     over the row communicator
+//   y2x: (iiisize, ny, kjsize)     -> (nx, jisize, kjsize)
+//   x2z: (nx, jisize, kjsize)      -> (ijsize, jisize, nz)      over the column communicator
+//   z2x: (ijsize, jisize, nz)      -> (nx, jisize, kjsize)
+// Each is pack -> alltoallv -> unpack in the reference (three passes over the data plus the network).  Here
+// the pack is ONE P3D_RCOPY stage that writes every block where its consumer reads it (the peer's receive
+// buffer with peer-to-peer plans, else the send buffer; the rank's own block straight into its own receive
+// buffer) and the unpack is a second one; a 1-rank communicator degenerates to a single direct copy.  Blocks
+// keep the reference's layouts and its Ii/Ji/Ij/Kj counts and displacements (setup.F90:522-549), in REAL
+// elements.
+// ------------------------------------------------------------------------------------
+enum RtranKind { RTRAN_X2Y = 0, RTRAN_Y2X = 1, RTRAN_X2Z = 2, RTRAN_Z2X = 3 };
+
+// real elements of the source / destination array of a transpose on this rank
+inline long long rtran_elems(const Decomp& d, int which, bool dest) {
+  const long long x = (long long)d.nx * d.jisize * d.kjsize;
+  const long long y = (long long)d.iiisize * d.ny * d.kjsize;
+  const long long z = (long long)d.ijsize * d.jisize * d.nz;
+  switch (which) {
+    case RTRAN_X2Y: return dest ? y : x;
+    case RTRAN_Y2X: return dest ? x : y;
+    case RTRAN_X2Z: return dest ? z : x;
+    default:        return dest ? x : z;
+  }
+}
+
+// complex elements a work buffer must hold so that every rank can stage any of the four transposes
+// (the same bound on all ranks, so that growing the buffers is a collective decision)
+inline long long rtran_work_elems(const Decomp& d) {
+  auto mx = [](const BlockMap& m) { int v = 0; for (int x : m.sz) v = std::max(v, x); return (long long)v; };
+  const long long ji = mx(d.ji), kj = mx(d.kj), iii = mx(d.iii), ij = mx(d.ij);
+  long long r = (long long)d.nx * ji * kj;
+  r = std::max(r, iii * d.ny * kj);
+  r = std::max(r, ij * ji * d.nz);
+  return (r + 1) / 2;
+}
+
+// dstart / dend / dsize of the destination array (module.F90:1118-1127, 1195-1204, 1273-1282, 1349-1358)
+inline void rtran_dims(const Decomp& d, int which, int* st, int* en, int* sz) {
+  if (which == RTRAN_X2Y) {
+    st[0] = d.iiistart; en[0] = d.iiiend; sz[0] = d.iiisize;
+    st[1] = 1; en[1] = d.ny; sz[1] = d.ny;
+    st[2] = d.kjstart; en[2] = d.kjend; sz[2] = d.kjsize;
+  } else if (which == RTRAN_X2Z) {
+    st[0] = d.ijstart; en[0] = d.ijend; sz[0] = d.ijsize;
+    st[1] = d.jistart; en[1] = d.jiend; sz[1] = d.jisize;
+    st[2] = 1; en[2] = d.nz; sz[2] = d.nz;
+  } else {
+    st[0] = 1; en[0] = d.nx; sz[0] = d.nx;
+    st[1] = d.jistart; en[1] = d.jiend; sz[1] = d.jisize;
+    st[2] = d.kjstart; en[2] = d.kjend; sz[2] = d.kjsize;
+  }
+}
+
+inline TransformPlan build_rtran_plan(const Decomp& d, int which, bool p2p, int real_bytes) {
+  TransformPlan tp;
+  const bool row = which == RTRAN_X2Y || which == RTRAN_Y2X;      // row communicator (x <-> y), else column (x <-> z)
+  const bool from_x = which == RTRAN_X2Y || which == RTRAN_X2Z;   // the source is the X pencil
+  const int M = row ? d.iproc : d.jproc, me = row ? d.ipid : d.jpid;
+  if (M > P3D_MAXSEG) { tp.error = "processor grid dimension exceeds P3D_MAXSEG"; return tp; }
+  const long long nx = d.nx, ji = d.jisize, kj = d.kjsize;
+  const BlockMap& xb = row ? d.iii : d.ij;          // x blocks of the far pencil
+  const BlockMap& fb = row ? d.ji : d.kj;           // blocks of the far pencil's long axis (y or z) = this rank's peers' shares
+  const long long xs = xb.sz[me];                   // iiisize / ijsize
+  const int nfar = row ? d.ny : d.nz;
+  const int snd = P3D_BUF_A, rcv = P3D_BUF_B;
+  auto world_rank = [&](int p) { return row ? d.rank_of(p, d.jpid) : d.rank_of(d.ipid, p); };
+  // X-pencil side: axis x, lines y (a), planes z (b); block p = (xb.sz[p], ji, kj) at (xb.st[p]-1)*ji*kj
+  auto xside_user = [&](P3dSide& sd, int buf) {
+    side_init(sd, d.nx, d.nx, d.nx);
+    add_seg(sd, buf, -1, 0, 0, d.nx, 1, nx, nx * ji, nx * ji * kj);
+  };
+  auto xside_blocks = [&](P3dSide& sd, bool send) {
+    side_init(sd, d.nx, d.nx, d.nx);
+    for (int p = 0; p < M; p++) {
+      const long long w = xb.sz[p];
+      int buf = send ? snd : rcv, peer = -1;
+      long long off = (long long)(xb.st[p] - 1) * ji * kj;
+      if (send && p == me) { buf = rcv; off = (long long)(fb.st[me] - 1) * xs * (row ? kj : ji); }
+      else if (send && p2p) { buf = rcv; peer = world_rank(p); off = (long long)(fb.st[me] - 1) * w * (row ? kj : ji); }
+      add_seg(sd, buf, peer, off, xb.st[p] - 1, (int)w, 1, w, w * ji, w * ji * kj);
+    }
+  };
+  // far-pencil side: axis = y (row) or z (column).  row: lines x (a, xs of them), planes z (b);
+  // column: lines (x,y) merged (a, xs*ji of them, contiguous), one plane.
+  // block q = (xs, fb.sz[q], kj) [row] / (xs, ji, fb.sz[q]) [column] at (fb.st[q]-1) * xs * (kj | ji)
+  const long long fps = row ? xs : xs * ji;         // stride of the far axis in the user array and inside a block
+  auto fside_user = [&](P3dSide& sd, int buf) {
+    side_init(sd, nfar, nfar, nfar);
+    add_seg(sd, buf, -1, 0, 0, nfar, fps, 1, row ? xs * d.ny : 0, 0);
+  };
+  auto fside_blocks = [&](P3dSide& sd, bool send) {
+    side_init(sd, nfar, nfar, nfar);
+    for (int q = 0; q < M; q++) {
+      const long long w = fb.sz[q];
+      int buf = send ? snd : rcv, peer = -1;
+      long long off = (long long)(fb.st[q] - 1) * xs * (row ? kj : ji);
+      if (send && q == me) { buf = rcv; off = (long long)(xb.st[me] - 1) * ji * kj; }
+      else if (send && p2p) {     // peer q's X side: the block from this rank holds x in xb(me), the peer's y / z share
+        buf = rcv; peer = world_rank(q);
+        off = (long long)(xb.st[me] - 1) * (row ? w * kj : ji * w);
+      }
+      add_seg(sd, buf, peer, off, fb.st[q] - 1, (int)w, fps, 1, row ? xs * w : 0, 0);
+    }
+  };
+  auto push = [&](P3dStage& s) {
+    if ((long long)s.na * s.nb * s.nc <= 0 || s.n <= 0) return;
+    s.nfac = 0;
+    Step st; st.is_exchange = false; st.st = s; tp.steps.push_back(st);
+  };
+  const int fa = row ? (int)xs : (int)(xs * ji), fbn = row ? (int)kj : 1;   // batch extents of the far-axis stages
+  P3dStage s;
+  if (M == 1) {         // one rank along this communicator: the two pencils coincide up to the axis naming
+    stage_init(s, P3D_RCOPY, d.nx, (int)ji, (int)kj, 1, 0); s.layx = 1;
+    xside_user(s.in, P3D_BUF_USER_IN);
+    xside_user(s.out, P3D_BUF_USER_OUT);
+    push(s);
+    return tp;
+  }
+  Step ex; ex.is_exchange = true; P3dExchange& e = ex.ex; memset(&e, 0, sizeof e);
+  e.comm = row ? 0 : 1; e.npeer = M; e.self = me; e.sendbuf = snd; e.recvbuf = rcv; e.timer = 0;
+  e.p2p = p2p ? 1 : 0; e.ebytes = real_bytes;
+  for (int p = 0; p < M; p++) {
+    const long long xo = (long long)(xb.st[p] - 1) * ji * kj, xc = (long long)xb.sz[p] * ji * kj;                  // Ii / Ij
+    const long long fo = (long long)(fb.st[p] - 1) * xs * (row ? kj : ji), fc = (long long)fb.sz[p] * xs * (row ? kj : ji);   // Ji / Kj
+    e.sndoff[p] = from_x ? xo : fo; e.sndcnt[p] = from_x ? xc : fc;
+    e.rcvoff[p] = from_x ? fo : xo; e.rcvcnt[p] = from_x ? fc : xc;
+  }
+  if (from_x) {
+    stage_init(s, P3D_RCOPY, d.nx, (int)ji, (int)kj, 1, 0); s.layx = 1;
+    xside_user(s.in, P3D_BUF_USER_IN);
+    xside_blocks(s.out, true);
+    push(s);
+    tp.steps.push_back(ex);
+    stage_init(s, P3D_RCOPY, nfar, fa, fbn, 1, 0);
+    fside_blocks(s.in, false);
+    fside_user(s.out, P3D_BUF_USER_OUT);
+    push(s);
+  } else {
+    stage_init(s, P3D_RCOPY, nfar, fa, fbn, 1, 0);
+    fside_user(s.in, P3D_BUF_USER_IN);
+    fside_blocks(s.out, true);
+    push(s);
+    tp.steps.push_back(ex);
+    stage_init(s, P3D_RCOPY, d.nx, (int)ji, (int)kj, 1, 0); s.layx = 1;
+    xside_blocks(s.in, false);
+    xside_user(s.out, P3D_BUF_USER_OUT);
+    push(s);
+  }
+  return tp;
+}
+
 
 }  // namespace p3d

@@ -20,7 +20,9 @@ enum P3dKind {
   P3D_C2R = 3,       // exec_b_c2r                   (fft_exec.F90:298)
   P3D_DCT1 = 4,      // exec_ctrans_r2_complex_same  (fft_exec.F90:646)
   P3D_DST1 = 5,      // exec_strans_r2_complex_same  (fft_exec.F90:866)
-  P3D_NOOP = 6       // op letter 'n' / '0': layout change and pruning only
+  P3D_NOOP = 6,      // op letter 'n' / '0': layout change and pruning only
+  P3D_RCOPY = 7      // REAL elements on both sides, no arithmetic: the pack / unpack passes of the real-data
+                     // transposes rtran_x2y / y2x / x2z / z2x (module.F90:1061-1361), run by rcopy_kernel (rcopy.h)
 };
 
 // buffer ids used by the planner; resolved to pointers at execution time
@@ -74,13 +76,14 @@ struct P3dStage {
   P3dSide in, out;
 };
 
-// alltoallv over the row (comm=0) or column (comm=1) communicator; offsets/counts in
-// complex elements.  Mirrors the If/Kf/Jr/Kr tables of setup.F90:481-518.
+// alltoallv over the row (comm=0) or column (comm=1) communicator; offsets/counts in elements of
+// `ebytes` bytes (0: complex elements of the library's precision).  Mirrors the If/Kf/Jr/Kr tables of
+// setup.F90:481-518 and, with real elements, the Ii/Ji/Ij/Kj tables of setup.F90:522-549.
 struct P3dExchange {
   int32_t comm, npeer, self;
   int32_t sendbuf, recvbuf;
   int32_t timer;
   int32_t p2p;       // 1: the producing stage already stored every block at its destination; barrier only
-  int32_t pad_;
+  int32_t ebytes;    // bytes per element of the offsets / counts below; 0 = one complex element
   int64_t sndoff[P3D_MAXSEG], sndcnt[P3D_MAXSEG], rcvoff[P3D_MAXSEG], rcvcnt[P3D_MAXSEG];
 };
