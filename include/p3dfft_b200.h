@@ -104,6 +104,18 @@ int p3dfft_b200_proc_neighb(int base_proc_id, int orient, int direction);
 int p3dfft_b200_get_proc_parts(int base_x, int base_y, int base_z, int size_x, int size_y, int size_z, int conf,
                                int* parts, int* ierr);
 
+/* ---- wave-space epilogues (what the sample drivers do on the host after a transform) -------------------- */
+/* Fused normalisation: every output of p3dfft_ftran_r2c[_many] is multiplied by `forward` and every output of
+ * p3dfft_btran_c2r[_many] by `backward` inside the store of the transform's last stage -- the drivers' mult_array
+ * pass (sample/C/driver_rand.c:265-273, driver_spec.c:223) without a second trip through memory.  Default 1, 1
+ * (the reference's unnormalised transforms).  p3dfft_cheby keeps its own normalisation (ftran.F90:408-413).      */
+void p3dfft_b200_set_scale(double forward, double backward);
+/* Power spectrum of this rank's wavenumber array B (get_dims conf 2 layout; host or device pointer), summed over
+ * all ranks: E[ik] = sum k2 * |factor * B|^2, ik = int(sqrt(k2) + 0.5) <= kmax, k2 = kx^2 + ky^2 + kz^2 with ky,
+ * kz folded about n/2 -- compute_spectrum + MPI_Reduce of sample/C/driver_spec.c:298-384 on the device.  E receives
+ * kmax+1 doubles (host or device) on EVERY rank.  Pruned transforms: stored indices are mapped to their modes.   */
+void p3dfft_b200_spectrum(const void* B, double factor, double* E, int kmax);
+
 /* ---- host-only planner queries (no GPU needed; used by the CPU test-suite) ------------- */
 typedef struct {
   int32_t nx, ny, nz, nxc, nyc, nzc;

@@ -40,7 +40,7 @@ import scipy.fft as sfft
 __all__ = [
     "map_data_to_proc", "Decomp", "global_forward", "global_backward", "global_cheby",
     "local_forward", "local_backward", "SimWorld", "philox_field", "rel_l2",
-    "rtran_slices", "rtran_local", "forward_r2c_1d", "ProcGrid", "power_spectrum",
+    "rtran_slices", "rtran_local", "rtran_dims", "forward_r2c_1d", "ProcGrid", "power_spectrum", "spectrum_kmax",
 ]
 
 
@@ -735,27 +735,33 @@ class ProcGrid:
         return parts[1:], n, 0
 
 
-def power_spectrum(B, fstart, ng, kmax, stride1=False):
-    """compute_spectrum of sample/C/driver_spec.c:298-384 (non-STRIDE1 branch :348-376) on one rank's
-    wavenumber array B (complex, Fortran order, get_dims(2) layout): el[ik] += k2 * (re^2 + im^2) with
-    kx = x + fstart_x - 1 (never folded: the array holds kx <= nx/2), ky, kz folded about ng/2 and
-    ik = int(sqrt(k2) + 0.5).  ``stride1``: B is (nzc, jj, ii) and fstart/ng are given in that order; the result
-    is the same physical shell sum (the reference's STRIDE1 loop, :317-346, walks the same elements)."""
-    B = np.asarray(B)
-    if stride1:
+def spectrum_kmax(nx, ny, nz):
+    """driver_spec.c:228: kmax = sqrt(nx^2 + ny^2 + nz^2) * 0.5 + 0.5 truncated."""
+    return int(np.sqrt(float(nx * nx + ny * ny + nz * nz)) * 0.5 + 0.5)
+
+
+def power_spectrum(Blocal, d: Decomp, kmax=None, factor=1.0):
+    """compute_spectrum of sample/C/driver_spec.c:298-384 on one rank's wavenumber array (get_dims(2) layout,
+    (nzc, jjsize, iisize) with STRIDE1): el[ik] += k2 * (re^2 + im^2) over the block, with kx = global x index
+    (never folded: only kx <= nx/2 is stored), ky and kz the global indices folded about n/2 (:352-358), and
+    ik = int(sqrt(k2) + 0.5) (:364-368).  ``factor`` multiplies B first (the driver's mult_array, :223).
+    For a pruned transform the stored y/z indices are first mapped to the modes they hold (kept_y / kept_z);
+    the reference driver does not prune, where the two agree.  The per-rank results add up to the global
+    spectrum (MPI_Reduce, :381)."""
+    B = np.asarray(Blocal)
+    if d.stride1:
         B = B.transpose(2, 1, 0)
-        fstart = fstart[::-1]
-        ng = ng[::-1]
-    sx, sy, sz = B.shape
-    kx = np.arange(sx) + fstart[0] - 1
-    ky = np.arange(sy) + fstart[1] - 1
-    ky = np.where(ky > ng[1] // 2, ng[1] - ky, ky)
-    kz = np.arange(sz) + fstart[2] - 1
-    kz = np.where(kz > ng[2] // 2, ng[2] - kz, kz)
+    kmax = spectrum_kmax(d.nx, d.ny, d.nz) if kmax is None else kmax
+    kx = np.arange(d.iistart - 1, d.iiend)
+    ky = d.kept_y()[d.jjstart - 1:d.jjend]
+    ky = np.where(ky > d.ny // 2, d.ny - ky, ky)
+    kz = d.kept_z()
+    kz = np.where(kz > d.nz // 2, d.nz - kz, kz)
     k2 = kx[:, None, None] ** 2 + ky[None, :, None] ** 2 + kz[None, None, :] ** 2
     ik = (np.sqrt(k2.astype(np.float64)) + 0.5).astype(np.int64)
-    w = k2 * (B.real.astype(np.float64) ** 2 + B.imag.astype(np.float64) ** 2)
-    return np.bincount(ik.ravel(), weights=w.ravel(), minlength=kmax + 1)[: kmax + 1]
+    w = k2 * (B.real.astype(np.float64) ** 2 + B.imag.astype(np.float64) ** 2) * float(factor) ** 2
+    keep = ik <= kmax
+    return np.bincount(ik[keep].ravel(), weights=w[keep].ravel(), minlength=kmax + 1)[: kmax + 1]
 
 
 # --------------------------------------------------------------------------------------

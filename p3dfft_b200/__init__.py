@@ -129,6 +129,10 @@ class P3DFFT:
             f.argtypes = [vp, vp, ip, ip, ip, C.POINTER(C.c_double)]
             f.restype = None
         lib.p3dfft_get_mpi_info.argtypes = [ip, ip, ip]
+        lib.p3dfft_b200_set_scale.argtypes = [C.c_double, C.c_double]
+        lib.p3dfft_b200_set_scale.restype = None
+        lib.p3dfft_b200_spectrum.argtypes = [vp, C.c_double, vp, C.c_int]
+        lib.p3dfft_b200_spectrum.restype = None
         lib.p3dfft_b200_proc_id2coords.argtypes = [C.c_int, ip, ip]
         lib.p3dfft_b200_proc_coords2id.argtypes = [C.c_int, C.c_int]
         lib.p3dfft_b200_proc_dims.argtypes = [C.c_int, C.c_int, ip]
@@ -252,6 +256,18 @@ class P3DFFT:
         n = self.lib.p3dfft_b200_get_proc_parts(*base, *size, conf, parts, C.byref(ierr))
         self._check()
         return [list(parts[7 * i:7 * i + 7]) for i in range(nproc)], n, ierr.value
+
+    def set_scale(self, forward=1.0, backward=1.0):
+        """Fused normalisation of the transforms' outputs (the drivers' ``mult_array`` pass)."""
+        self.lib.p3dfft_b200_set_scale(float(forward), float(backward))
+
+    def spectrum(self, B, kmax, factor=1.0, out=None):
+        """``compute_spectrum`` of sample/C/driver_spec.c:298-384 on the device; returns kmax+1 doubles."""
+        import numpy as np
+        E = np.zeros(kmax + 1) if out is None else out
+        self.lib.p3dfft_b200_spectrum(_addr(B), float(factor), _addr(E), int(kmax))
+        self._check()
+        return E
 
     # ---- extensions ----------------------------------------------------------------------
     def set_layout(self, stride1=False, dims_c=False):

@@ -140,6 +140,8 @@ struct Lib {
   long long work_elems_alloc = 0;   // complex elements per work buffer
   bool rtran_sized = false;         // the buffers already cover rtran_work_elems()
   std::map<int, p3d::TransformPlan> aux_plans;     // r2c_1d (key 100) and rtran (key which*2 + p2p) plans
+  double scale_fwd = 1.0, scale_bwd = 1.0;          // fused output normalisation (p3dfft_b200_set_scale)
+  double* spec_dev = nullptr; int spec_bins = 0;   // device accumulator of p3dfft_b200_spectrum
   p3d::ProcMap procmap;                            // proc_id2coords / proc_dims tables (setup.F90:224-230, 551-577)
   bool plain_layout = false;     // true: the reference's pack-buffer layouts instead of the tile-blocked ones
   int force_row_bytes = 0;       // 64 / 128: override the planner's choice of the tile row width
@@ -359,7 +361,7 @@ size_t side_elem_bytes(int kind, int side) {
 // Runs a step list.  `in`/`out` may be host or device pointers (host arrays are staged over PCIe inside the
 // call).  exchange_ms, when given, receives the device time spent in the exchange steps (rtran's `t`).
 bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes, size_t out_bytes, int nv,
-              long long dim_cplx, bool cheby, double Lz, double* exchange_ms) {
+              long long dim_cplx, bool cheby, double Lz, double* exchange_ms, double out_scale = 1.0) {
   cudaStream_t st = L.stream();
   const p3d::Decomp& d = L.d;
   const bool in_dev = is_device_ptr(in), out_dev = is_device_ptr(out);
@@ -384,6 +386,8 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
   std::vector<int> slots;
   std::vector<char> is_ex;
   const size_t nsteps = tp->steps.size();
+  size_t last_stage = nsteps;      // out_scale is fused into the stores of the transform's last stage
+  for (size_t i = 0; i < nsteps; i++) if (!tp->steps[i].is_exchange) last_stage = i;
   bool pre_done = false;      // the barrier that protects the receive buffer of the NEXT exchange has been issued
   for (size_t i = 0; i < nsteps; i++) {
     auto& s = tp->steps[i];
@@ -404,6 +408,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
       slots.push_back(s.ex.timer); is_ex.push_back(1);
     } else {
       P3dStage stg = s.st;
+      if (i == last_stage && out_scale != 1.0) stg.scale *= out_scale;
       for (int side = 0; side < 2; side++) {
         P3dSide& sd = side ? stg.out : stg.in;
         const size_t esz = side_elem_bytes(stg.kind, side);
@@ -471,8 +476,10 @@ bool run_transform(bool backward, const void* in, void* out, const char* op, int
   const size_t real_elems = (size_t)d.nx * d.jisize * d.kjsize, cplx_elems = (size_t)d.iisize * d.jjsize * d.nzc;
   const size_t real_bytes = ((size_t)(nv - 1) * dim_real + real_elems) * sizeof(real_t);
   const size_t cplx_bytes = ((size_t)(nv - 1) * dim_cplx + cplx_elems) * CSIZE;
+  // p3dfft_cheby normalises by itself (ftran.F90:408-413): the user scale does not apply to it
+  const double sc = cheby ? 1.0 : (backward ? L.scale_bwd : L.scale_fwd);
   return run_plan(tp, in, out, backward ? cplx_bytes : real_bytes, backward ? real_bytes : cplx_bytes, nv, dim_cplx,
-                  cheby, Lz, nullptr);
+                  cheby, Lz, nullptr, sc);
 }
 
 // p3dfft_ftran_r2c_1d and the rtran_* transposes: plans cached by key
@@ -641,6 +648,7 @@ void p3dfft_clean(void) {
     close_peer_maps();
   }
   if (L.bar_scratch) { cudaFree(L.bar_scratch); L.bar_scratch = nullptr; }
+  if (L.spec_dev) { cudaFree(L.spec_dev); L.spec_dev = nullptr; L.spec_bins = 0; }
   for (int b = P3D_BUF_A; b <= P3D_BUF_C; b++) if (L.buf[b]) { cudaFree(L.buf[b]); L.buf[b] = nullptr; }
   if (L.stage_in) { cudaFree(L.stage_in); L.stage_in = nullptr; L.stage_in_bytes = 0; }
   if (L.stage_out) { cudaFree(L.stage_out); L.stage_out = nullptr; L.stage_out_bytes = 0; }
@@ -768,6 +776,58 @@ void p3dfft_b200_comm_destroy(int handle) {
   if (L.comm == it->second) L.comm = nullptr;
   delete it->second;
   g_comms.erase(it);
+}
+
+void p3dfft_b200_set_scale(double forward, double backward) { L.scale_fwd = forward; L.scale_bwd = backward; }
+
+void p3dfft_b200_spectrum(const void* B, double factor, double* E, int kmax) {
+  if (!check_set()) return;
+  if (kmax < 0 || !E) { report(false, "P3DFFT(B200): spectrum needs kmax >= 0 and an output array"); return; }
+  const p3d::Decomp& d = L.d;
+  cudaStream_t st = L.stream();
+  const size_t cplx_bytes = (size_t)d.iisize * d.jjsize * d.nzc * CSIZE;
+  const void* dB = B;
+  auto run = [&]() -> bool {
+    if (!is_device_ptr(B)) {
+      if (L.stage_in_bytes < cplx_bytes) {
+        if (L.stage_in) cudaFree(L.stage_in);
+        L.stage_in = nullptr; L.stage_in_bytes = 0;
+        CUDA_OK(cudaMalloc(&L.stage_in, cplx_bytes)); L.stage_in_bytes = cplx_bytes;
+      }
+      CUDA_OK(cudaMemcpyAsync(L.stage_in, B, cplx_bytes, cudaMemcpyHostToDevice, st));
+      dB = L.stage_in;
+    }
+    if (L.spec_bins < kmax + 1) {
+      if (L.spec_dev) cudaFree(L.spec_dev);
+      L.spec_dev = nullptr; L.spec_bins = 0;
+      CUDA_OK(cudaMalloc(&L.spec_dev, sizeof(double) * (size_t)(kmax + 1))); L.spec_bins = kmax + 1;
+    }
+    CUDA_OK(cudaMemsetAsync(L.spec_dev, 0, sizeof(double) * (size_t)(kmax + 1), st));
+    p3d::SpecJob j;
+    memset(&j, 0, sizeof j);
+    // physical extents / strides of the wavenumber array (get_dims conf 2)
+    const int ext[3] = {d.iisize, d.jjsize, d.nzc};
+    long long str[3];
+    if (d.stride1) { str[2] = 1; str[1] = d.nzc; str[0] = (long long)d.nzc * d.jjsize; }
+    else { str[0] = 1; str[1] = d.iisize; str[2] = (long long)d.iisize * d.jjsize; }
+    const int order[3] = {d.stride1 ? 2 : 0, 1, d.stride1 ? 0 : 2};      // contiguous axis first
+    for (int i = 0; i < 3; i++) { j.axis[i] = order[i]; j.ext[i] = ext[order[i]]; j.stride[i] = str[order[i]]; }
+    j.start[0] = d.iistart - 1; j.start[1] = d.jjstart - 1; j.start[2] = 0;
+    j.n[0] = d.nx; j.nc[0] = d.nxhpc; j.nch[0] = d.nxhpc;                 // x: the first nxhpc modes, never folded
+    j.n[1] = d.ny; j.nc[1] = d.nyc; j.nch[1] = d.nycph;
+    j.n[2] = d.nz; j.nc[2] = d.nzc; j.nch[2] = d.nzcph;
+    j.kmax = kmax; j.f2 = factor * factor;
+    cudaError_t e = p3d::launch_spectrum<real_t>(dB, j, L.spec_dev, st);
+    if (e != cudaSuccess) { report(true, "P3DFFT(B200): spectrum launch failed: %s", cudaGetErrorString(e)); return false; }
+    L.launches++;
+    if (L.comm && L.comm->size > 1)      // MPI_Reduce(..., MPI_SUM, root) of driver_spec.c:381 -- here every rank gets the sum
+      NCCL_OK(g_nccl.AllReduce(L.spec_dev, L.spec_dev, (size_t)(kmax + 1), ncclDouble, ncclSum, L.comm->world, st));
+    CUDA_OK(cudaMemcpyAsync(E, L.spec_dev, sizeof(double) * (size_t)(kmax + 1),
+                            is_device_ptr(E) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return true;
+  };
+  run();
 }
 
 void p3dfft_b200_set_error_mode(int mode) { g_error_mode = mode; }

@@ -46,6 +46,8 @@ struct FastStage {
   int32_t rowb;          // bytes per tile row (64 or 128) = block width of the internal layouts
   const void* tw;        // device twiddle block of this (kind, nfft), see fast_twiddle_*
   FastSide in, out;
+  double scale;          // multiplies every output (SCALED instantiations only; last member: the unscaled kernels'
+                         // parameter layout does not depend on it)
 };
 
 // true when a specialised kernel exists for this stage (kind, length, strides, alignment)

@@ -109,7 +109,7 @@ static int tile_lines(const P3dStage& st) {
 
 template <typename T>
 bool fast_supported(const P3dStage& st) {
-  if (st.scale != 1.0) return false;
+  if (st.scale != 1.0 && st.kind == P3D_R2C) return false;     // fused scaling: c2c / DCT stages and the X c2r stage
   if (st.in.nseg + 1 > P3D_MAXRUN || st.out.nseg + 1 > P3D_MAXRUN) return false;
   switch (st.kind) {
     case P3D_C2C_FWD: case P3D_C2C_BWD: case P3D_DCT1: {
@@ -194,6 +194,7 @@ void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes) {
   if (!is_x(st.kind) && st.bord > 1) f.bord = bo >= 0 ? (bo > 1 ? bo : 1) : st.bord;
   f.rowb = is_x(st.kind) ? 0 : (real_bytes == 4 ? row_bytes<float>(st) : row_bytes<double>(st));
   f.tw = nullptr;
+  f.scale = st.scale;
   side_to_runs(st.in, f.in, st.kind == P3D_R2C ? real_bytes : 2 * real_bytes, tx);
   side_to_runs(st.out, f.out, st.kind == P3D_C2R ? real_bytes : 2 * real_bytes, tx);
 }
@@ -226,6 +227,15 @@ static unsigned persistent_grid(K kernel, int nt, size_t smem, long long tiles, 
   return (unsigned)(tiles < g ? tiles : g);
 }
 
+// one (configured, CTAs per SM) pair per kernel instantiation; the enclosing function defines smem, tiles, NT, f, stream, e
+#define P3D_LAUNCH(...)                                                                                       \
+  do {                                                                                                        \
+    static bool cfg = false;                                                                                  \
+    static int per_sm = 0;                                                                                    \
+    if ((e = launch_cfg(__VA_ARGS__, smem, cfg)) != cudaSuccess) return e;                                    \
+    __VA_ARGS__<<<persistent_grid(__VA_ARGS__, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);              \
+  } while (0)
+
 template <typename T, int HH>
 static cudaError_t launch_x(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
   constexpr int TX = XCfg<T, HH>::TX, NT = XCfg<T, HH>::NT;
@@ -234,17 +244,9 @@ static cudaError_t launch_x(const P3dStage& st, const FastStage& f, cudaStream_t
   if (tiles <= 0) return cudaSuccess;
   if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;      // 32-bit tile counters: the generic kernel takes over
   cudaError_t e;
-  if (st.kind == P3D_R2C) {
-    static bool cfg = false;
-    static int per_sm = 0;
-    if ((e = launch_cfg(xr2c_kernel<T, HH>, smem, cfg)) != cudaSuccess) return e;
-    xr2c_kernel<T, HH><<<persistent_grid(xr2c_kernel<T, HH>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
-  } else {
-    static bool cfg = false;
-    static int per_sm = 0;
-    if ((e = launch_cfg(xc2r_kernel<T, HH>, smem, cfg)) != cudaSuccess) return e;
-    xc2r_kernel<T, HH><<<persistent_grid(xc2r_kernel<T, HH>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
-  }
+  if (st.kind == P3D_R2C) P3D_LAUNCH(xr2c_kernel<T, HH>);
+  else if (f.scale != 1.0) P3D_LAUNCH(xc2r_kernel<T, HH, true>);
+  else P3D_LAUNCH(xc2r_kernel<T, HH>);
   return cudaGetLastError();
 }
 
@@ -257,16 +259,13 @@ static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t
   if (tiles <= 0) return cudaSuccess;
   if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;      // 32-bit tile counters: the generic kernel takes over
   cudaError_t e;
+  const bool scaled = f.scale != 1.0;
   if (st.kind == P3D_C2C_BWD) {
-    static bool cfg = false;
-    static int per_sm = 0;
-    if ((e = launch_cfg(cstage_kernel<T, NN, RB, true>, smem, cfg)) != cudaSuccess) return e;
-    cstage_kernel<T, NN, RB, true><<<persistent_grid(cstage_kernel<T, NN, RB, true>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
+    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, RB, true, true>);
+    else P3D_LAUNCH(cstage_kernel<T, NN, RB, true>);
   } else {
-    static bool cfg = false;
-    static int per_sm = 0;
-    if ((e = launch_cfg(cstage_kernel<T, NN, RB, false>, smem, cfg)) != cudaSuccess) return e;
-    cstage_kernel<T, NN, RB, false><<<persistent_grid(cstage_kernel<T, NN, RB, false>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
+    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, RB, false, true>);
+    else P3D_LAUNCH(cstage_kernel<T, NN, RB, false>);
   }
   return cudaGetLastError();
 }
@@ -281,16 +280,13 @@ static cudaError_t launch_split(const P3dStage& st, const FastStage& f, cudaStre
   if (tiles <= 0) return cudaSuccess;
   if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
   cudaError_t e;
+  const bool scaled = f.scale != 1.0;
   if (st.kind == P3D_C2C_BWD) {
-    static bool cfg = false;
-    static int per_sm = 0;
-    if ((e = launch_cfg(cstage_split_kernel<T, NN, true>, smem, cfg)) != cudaSuccess) return e;
-    cstage_split_kernel<T, NN, true><<<persistent_grid(cstage_split_kernel<T, NN, true>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
+    if (scaled) P3D_LAUNCH(cstage_split_kernel<T, NN, true, true>);
+    else P3D_LAUNCH(cstage_split_kernel<T, NN, true>);
   } else {
-    static bool cfg = false;
-    static int per_sm = 0;
-    if ((e = launch_cfg(cstage_split_kernel<T, NN, false>, smem, cfg)) != cudaSuccess) return e;
-    cstage_split_kernel<T, NN, false><<<persistent_grid(cstage_split_kernel<T, NN, false>, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);
+    if (scaled) P3D_LAUNCH(cstage_split_kernel<T, NN, false, true>);
+    else P3D_LAUNCH(cstage_split_kernel<T, NN, false>);
   }
   return cudaGetLastError();
 }

@@ -377,7 +377,9 @@ __device__ __forceinline__ void fill_tilebase(const FastStage& st, RunTab& rt, i
   }
 }
 
-template <typename T, int N, int RB, bool SWAP>
+// SCALED: every output is multiplied by st.scale on its way out (the drivers' normalisation pass, mult_array in
+// sample/C/driver_*.c, fused into the store); a separate instantiation, so the unscaled kernels are unchanged.
+template <typename T, int N, int RB, bool SWAP, bool SCALED = false>
 __global__ void __launch_bounds__(CCfg<T, N, RB>::NT, CCfg<T, N, RB>::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
   using C = CCfg<T, N, RB>;
@@ -457,6 +459,11 @@ __global__ void __launch_bounds__(CCfg<T, N, RB>::NT, CCfg<T, N, RB>::MINB) csta
         const int kappa = w / TX;
         T2 v[RL];
         last_bfly<T, S, TX, SWZ>(s, kappa, t, v);
+        if constexpr (SCALED) {
+          const T sc = (T)st.scale;
+#pragma unroll
+          for (int q = 0; q < RL; q++) { v[q].x *= sc; v[q].y *= sc; }
+        }
 #pragma unroll
         for (int q = 0; q < RL; q++) {
           const long long e = ent_out[kappa + q * ML];
@@ -481,7 +488,7 @@ template <typename T, int N> struct SplitCfg {
   static constexpr int NT = 256, MINB = 2;
 };
 
-template <typename T, int N, bool SWAP>
+template <typename T, int N, bool SWAP, bool SCALED = false>
 __global__ void __launch_bounds__(SplitCfg<T, N>::NT, SplitCfg<T, N>::MINB) cstage_split_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
   using S = typename CCfg<T, N, 128>::S;
@@ -581,6 +588,11 @@ __global__ void __launch_bounds__(SplitCfg<T, N>::NT, SplitCfg<T, N>::MINB) csta
 #pragma unroll
           for (int p = 0; p < RL; p++) v[p] = s[(base + p) * TX + t];
           Bfly<T, RL>::run(v);
+          if constexpr (SCALED) {
+            const T sc = (T)st.scale;
+#pragma unroll
+            for (int q = 0; q < RL; q++) { v[q].x *= sc; v[q].y *= sc; }
+          }
 #pragma unroll
           for (int q = 0; q < RL; q++) {
             const long long e = ent_out[kappa + q * ML];
@@ -837,7 +849,7 @@ __device__ __forceinline__ void c2r_combine(T2 xk, T2 xm, T2 w, T2& zk, T2& zm) 
   zm = cswap(bb);
 }
 
-template <typename T, int H>
+template <typename T, int H, bool SCALED = false>
 __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
   using C = XCfg<T, H>;
@@ -966,6 +978,11 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
         T2* line = reinterpret_cast<T2*>(tbase + (long long)(ti.ta * TX + t) * ro.sa);
         T2 v[RL];
         xlast_bfly<T, C>(s, t, kappa, v);
+        if constexpr (SCALED) {
+          const T sc = (T)st.scale;
+#pragma unroll
+          for (int q = 0; q < RL; q++) { v[q].x *= sc; v[q].y *= sc; }
+        }
         if (ti.ta * TX + t < st.na) {
 #pragma unroll
           for (int q = 0; q < RL; q++) stg_stream(line + kappa + q * ML, cswap(v[q]));

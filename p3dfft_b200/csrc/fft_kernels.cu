@@ -314,6 +314,76 @@ __global__ void cheby_kernel(typename Cx<T>::type* out, int64_t ncol, int nzc, i
 }
 
 // ------------------------------------------------------------------------------------
+// Power spectrum (driver_spec.c:298-384): one warp per row of the contiguous direction, per-CTA privatised
+// histograms in shared memory (one copy per group of warps), one global atomic per bin and CTA at the end.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int spec_wavenumber(const SpecJob& j, int ax, int local) {
+  const int s = j.start[ax] + local;                              // stored global index
+  int k = s < j.nch[ax] ? s : s + (j.n[ax] - j.nc[ax]);           // the mode it holds (pruned transforms skip the middle)
+  if (ax != 0 && k > j.n[ax] / 2) k = j.n[ax] - k;                // driver_spec.c:352-358; kx <= nx/2 is never folded
+  return k;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) spectrum_kernel(const typename Cx<T>::type* __restrict__ B,
+                                                       const __grid_constant__ SpecJob j, double* __restrict__ E) {
+  using T2 = typename Cx<T>::type;
+  extern __shared__ double spec_hist[];
+  const int nbin = j.kmax + 1;
+  for (int i = threadIdx.x; i < nbin * j.ncopy; i += blockDim.x) spec_hist[i] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* h = spec_hist + (wib % j.ncopy) * nbin;
+  const long long rows = (long long)j.ext[1] * j.ext[2];
+  const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wib; row < rows; row += nwarp) {
+    const int v = (int)(row % j.ext[1]), w = (int)(row / j.ext[1]);
+    const int kv = spec_wavenumber(j, j.axis[1], v), kw = spec_wavenumber(j, j.axis[2], w);
+    const int kvw2 = kv * kv + kw * kw;
+    const T2* p = B + (long long)v * j.stride[1] + (long long)w * j.stride[2];
+    for (int u = lane; u < j.ext[0]; u += 32) {
+      const int ku = spec_wavenumber(j, j.axis[0], u);
+      const int k2 = ku * ku + kvw2;
+      const int ik = (int)(sqrt((double)k2) + 0.5);
+      const T2 z = p[(long long)u * j.stride[0]];
+      if (ik <= j.kmax) atomicAdd(h + ik, (double)k2 * ((double)z.x * (double)z.x + (double)z.y * (double)z.y) * j.f2);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbin; i += blockDim.x) {
+    double acc = 0.0;
+    for (int c = 0; c < j.ncopy; c++) acc += spec_hist[c * nbin + i];
+    if (acc != 0.0) atomicAdd(E + i, acc);
+  }
+}
+
+template <typename T>
+cudaError_t launch_spectrum(const void* B, const SpecJob& job_in, double* E, cudaStream_t stream) {
+  SpecJob job = job_in;
+  const long long rows = (long long)job.ext[1] * job.ext[2];
+  if (rows <= 0 || job.ext[0] <= 0) return cudaSuccess;
+  const size_t per = (size_t)(job.kmax + 1) * sizeof(double);
+  int ncopy = (int)((96 * 1024) / per);
+  if (ncopy < 1) return cudaErrorInvalidValue;
+  if (ncopy > 8) ncopy = 8;
+  job.ncopy = ncopy;
+  const size_t smem = per * ncopy;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(spectrum_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  long long grid = (rows + 7) / 8;
+  if (grid > (long long)sms * 2) grid = (long long)sms * 2;
+  spectrum_kernel<T><<<(unsigned)grid, 256, smem, stream>>>(reinterpret_cast<const typename Cx<T>::type*>(B), job, E);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------
 static int big_factor(const P3dStage& st) {
@@ -407,6 +477,8 @@ cudaError_t launch_rcopy(const P3dStage& st, cudaStream_t stream) {
 }
 
 template cudaError_t launch_stage<double>(const P3dStage&, cudaStream_t);
+template cudaError_t launch_spectrum<double>(const void*, const SpecJob&, double*, cudaStream_t);
+template cudaError_t launch_spectrum<float>(const void*, const SpecJob&, double*, cudaStream_t);
 template cudaError_t launch_rcopy<double>(const P3dStage&, cudaStream_t);
 template cudaError_t launch_rcopy<float>(const P3dStage&, cudaStream_t);
 template cudaError_t launch_stage<float>(const P3dStage&, cudaStream_t);

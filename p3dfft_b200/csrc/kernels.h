@@ -12,4 +12,18 @@ template <typename T> int choose_tile(const P3dStage& st);
 template <typename T> size_t stage_smem_bytes(const P3dStage& st);
 template <typename T> cudaError_t launch_cheby(void* out, long long ncol, int nzc, long long zstride,
                                                long long colstride, double norm, double lfac, cudaStream_t stream);
+
+// Power-spectrum epilogue (sample/C/driver_spec.c:298-384 compute_spectrum, on the device): shell sums
+// E[ik] += k2 * |B|^2 * f2 over this rank's wavenumber block, ik = int(sqrt(k2) + 0.5).  Loop dimension 0 is the
+// contiguous one; axis[i] names the physical axis (0 x, 1 y, 2 z) of loop dimension i.
+struct SpecJob {
+  int32_t ext[3];          // loop extents
+  int64_t stride[3];       // element strides of the complex array
+  int32_t axis[3];
+  int32_t start[3];        // per PHYSICAL axis: first stored global index held by this rank (0-based)
+  int32_t n[3], nc[3], nch[3];   // per physical axis: logical length, stored count, stored count of the lower half
+  int32_t kmax, ncopy;     // bins 0..kmax; privatised shared-memory copies of the histogram per CTA
+  double f2;               // factor^2
+};
+template <typename T> cudaError_t launch_spectrum(const void* B, const SpecJob& job, double* E, cudaStream_t stream);
 }  // namespace p3d

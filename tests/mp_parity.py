@@ -89,6 +89,57 @@ def run_case(L, comm, dims, rank, case):
     return max(errs)
 
 
+def run_aux(L, comm, dims, rank, n, single):
+    """Remaining module routines on this grid: the four real-data transposes (bit-exact: data movement only),
+    p3dfft_ftran_r2c_1d and the process-map queries.  Returns the worst error (0.0 = exact)."""
+    nx, ny, nz = n
+    rt, ct = (np.float32, np.complex64) if single else (np.float64, np.complex128)
+    tt = torch.float32 if single else torch.float64
+    L.set_layout(False, False)
+    L.p3dfft_setup(dims, nx, ny, nz, comm)
+    d = po.Decomp(nx, ny, nz, dims, rank, elem=4 if single else 8)
+    G = po.philox_field(nx, ny, nz, seed=77).astype(rt)
+    worst = 0.0
+    t_acc = 0.0
+    for which in pb.RTRAN_NAMES * 2:            # twice: the second round reuses the receive buffers (hazard rule)
+        src_sl, dst_sl = po.rtran_slices(d, which)
+        src = torch.from_numpy(np.asfortranarray(G[src_sl]).ravel(order="F").copy()).cuda()
+        exp = po.rtran_local(G, d, which)
+        dst = torch.full((exp.size,), float("nan"), dtype=tt, device="cuda")
+        dstart, dend, dsize, t_acc = L.rtran(which, src, dst, t_acc)
+        if [list(dstart), list(dend), list(dsize)] != [list(x) for x in po.rtran_dims(d, which)]:
+            worst = max(worst, 2.0)       # no assert inside the collective sequence: a rank that raised would hang the others
+        if not np.array_equal(dst.cpu().numpy(), exp.ravel(order="F")):
+            worst = max(worst, 1.0)
+        # host arrays take the staged path
+        dsth = np.full(exp.size, np.nan, dtype=rt)
+        L.rtran(which, np.asfortranarray(G[src_sl]).ravel(order="F").copy(), dsth)
+        if not np.array_equal(dsth, exp.ravel(order="F")):
+            worst = max(worst, 1.0)
+    A = np.asfortranarray(G[po.local_in_slice(d)])
+    tA = torch.from_numpy(A.ravel(order="F").copy()).cuda()
+    tC = torch.zeros(2 * d.nxhp * d.jisize * d.kjsize, dtype=tt, device="cuda")
+    L.p3dfft_ftran_r2c_1d(tA, tC)
+    e = po.rel_l2(tC.cpu().numpy().view(ct), po.forward_r2c_1d(A.astype(np.float64)).ravel(order="F"))
+    worst = max(worst, e / (1e-5 if single else 1e-12) * 1e-12)
+    g = po.ProcGrid(nx, ny, nz, dims)
+    P = dims[0] * dims[1]
+    assert L.p3dfft_get_mpi_info()[:2] == (rank, P)
+    for r in range(P):
+        assert L.proc_id2coords(r) == (g.proc_id2coords[2 * r], g.proc_id2coords[2 * r + 1])
+        assert L.proc_coords2id(*L.proc_id2coords(r)) == r
+        for conf in (1, 2):
+            assert L.proc_dims(conf, r) == [g.proc_dims[(conf, k, r)] for k in range(1, 10)]
+        for o in (-1, 1):
+            for di in (1, 2):
+                assert L.proc_neighb(r, o, di) == g.proc_neighb(r, o, di)
+    for base, size, conf in (((1, 1, 1), (nx, ny, nz), 1), ((2, 3, 1), (3, 4, nz), 2), ((1, 2, 2), (nx, 3, 2), 1)):
+        exp = g.get_proc_parts(*base, *size, conf)
+        assert L.get_proc_parts(base, size, conf, P) == (exp[0][:P], exp[1], exp[2])
+    L.p3dfft_clean()
+    return worst
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grids", default="")
@@ -128,6 +179,21 @@ def main():
                 print(f"grid {dims[0]}x{dims[1]} n={case[0]} cut={case[1]} op={case[2]}/{case[3]} stride1={case[4]} "
                       f"nv={case[5]} {'sp' if single else 'dp'}: max rel-L2 {float(worst):.2e} "
                       f"{'ok' if int(flag) == 0 else 'FAIL'}", flush=True)
+            ok = ok and int(flag) == 0
+        for n, single in (((32, 24, 20), False), ((14, 26, 38), False), ((64, 64, 64), True)):
+            L = pb.load(single)
+            try:
+                err = run_aux(L, comms[single], dims, rank, n, single)
+                good = err <= 1e-12
+            except Exception as e:     # noqa: BLE001 - report and fail
+                err, good = float("nan"), False
+                print(f"rank {rank} grid {dims} aux n={n}: EXCEPTION {e!r}", flush=True)
+                L.p3dfft_clean()
+            flag = torch.tensor([0 if good else 1], device="cuda")
+            dist.all_reduce(flag)
+            if rank == 0:
+                print(f"grid {dims[0]}x{dims[1]} n={n} rtran x2y/y2x/x2z/z2x + r2c_1d + proc queries "
+                      f"{'sp' if single else 'dp'}: {'ok' if int(flag) == 0 else 'FAIL'}", flush=True)
             ok = ok and int(flag) == 0
     for single, h in comms.items():
         pb.load(single).comm_destroy(h)
