@@ -341,12 +341,42 @@ __global__ void __launch_bounds__(256) spectrum_kernel(const typename Cx<T>::typ
     const int kv = spec_wavenumber(j, j.axis[1], v), kw = spec_wavenumber(j, j.axis[2], w);
     const int kvw2 = kv * kv + kw * kw;
     const T2* p = B + (long long)v * j.stride[1] + (long long)w * j.stride[2];
-    for (int u = lane; u < j.ext[0]; u += 32) {
-      const int ku = spec_wavenumber(j, j.axis[0], u);
-      const int k2 = ku * ku + kvw2;
-      const int ik = (int)(sqrt((double)k2) + 0.5);
-      const T2 z = p[(long long)u * j.stride[0]];
-      if (ik <= j.kmax) atomicAdd(h + ik, (double)k2 * ((double)z.x * (double)z.x + (double)z.y * (double)z.y) * j.f2);
+    // Four independent 16-byte loads per lane in flight, then per 32 consecutive u: lanes that fall into the same
+    // shell are adjacent (k grows with u), so their contributions are summed with a segmented warp scan and only
+    // the last lane of each run issues the shared-memory atomic (a 64-bit CAS loop) -- a handful per warp
+    // instead of 32 colliding ones.
+    for (int u0 = 0; u0 < j.ext[0]; u0 += 128) {      // warp-uniform trip count: the shuffles below need all lanes
+      T2 z[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int u = u0 + 32 * i + lane;
+        z[i] = u < j.ext[0] ? p[(long long)u * j.stride[0]] : T2{0, 0};
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int u = u0 + 32 * i + lane;
+        int ik = 0x7fffffff;                            // lanes past the end of the row: a run of their own, value 0
+        double val = 0.0;
+        if (u < j.ext[0]) {
+          const int ku = spec_wavenumber(j, j.axis[0], u);
+          const int k2 = ku * ku + kvw2;
+          // ik = int(sqrt(k2) + 0.5) exactly: float estimate, then ik is the integer with ik(ik-1) < k2 <= ik(ik+1)
+          ik = (int)(sqrtf((float)k2) + 0.5f);
+          if (k2 > ik * (ik + 1)) ik++;
+          else if (ik > 0 && k2 <= ik * (ik - 1)) ik--;
+          val = (double)k2 * ((double)z[i].x * (double)z[i].x + (double)z[i].y * (double)z[i].y) * j.f2;
+        }
+        const int prev = __shfl_up_sync(0xffffffffu, ik, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != ik);
+        const int first = 31 - __clz((int)(heads & ((2u << lane) - 1u)));      // first lane of this lane's run
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+          const double o = __shfl_up_sync(0xffffffffu, val, dd);
+          if (lane - dd >= first) val += o;
+        }
+        const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        if (tail && ik <= j.kmax && val != 0.0) atomicAdd(h + ik, val);
+      }
     }
   }
   __syncthreads();
@@ -363,11 +393,17 @@ cudaError_t launch_spectrum(const void* B, const SpecJob& job_in, double* E, cud
   const long long rows = (long long)job.ext[1] * job.ext[2];
   if (rows <= 0 || job.ext[0] <= 0) return cudaSuccess;
   const size_t per = (size_t)(job.kmax + 1) * sizeof(double);
-  int ncopy = (int)((96 * 1024) / per);
-  if (ncopy < 1) return cudaErrorInvalidValue;
-  if (ncopy > 8) ncopy = 8;
+  // histogram copies per CTA: as many as fit in ~28 KB (at most 4), so that 8 CTAs = 64 warps stay resident per SM
+  // and the loads of one warp hide under the atomics of the others (r1 ncu: 2 CTAs/SM were latency bound)
+  if (per > 200 * 1024) return cudaErrorInvalidValue;
+  int ncopy = (int)((28 * 1024) / per);
+  if (ncopy < 1) ncopy = 1;
+  if (ncopy > 4) ncopy = 4;
   job.ncopy = ncopy;
   const size_t smem = per * ncopy;
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(spectrum_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -378,7 +414,7 @@ cudaError_t launch_spectrum(const void* B, const SpecJob& job_in, double* E, cud
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   long long grid = (rows + 7) / 8;
-  if (grid > (long long)sms * 2) grid = (long long)sms * 2;
+  if (grid > (long long)sms * per_sm) grid = (long long)sms * per_sm;
   spectrum_kernel<T><<<(unsigned)grid, 256, smem, stream>>>(reinterpret_cast<const typename Cx<T>::type*>(B), job, E);
   return cudaGetLastError();
 }
