@@ -107,7 +107,7 @@ int p3dfft_b200_get_proc_parts(int base_x, int base_y, int base_z, int size_x, i
 /* ---- wave-space epilogues (what the sample drivers do on the host after a transform) -------------------- */
 /* Fused normalisation: every output of p3dfft_ftran_r2c[_many] is multiplied by `forward` and every output of
  * p3dfft_btran_c2r[_many] by `backward` inside the store of the transform's last stage -- the drivers' mult_array
- * pass (sample/C/driver_rand.c:265-273, driver_spec.c:223) without a second trip through memory.  Default 1, 1
+ * pass (sample/C/driver_rand.c:224, :298, driver_spec.c:223) without a second trip through memory.  Default 1, 1
  * (the reference's unnormalised transforms).  p3dfft_cheby keeps its own normalisation (ftran.F90:408-413).      */
 void p3dfft_b200_set_scale(double forward, double backward);
 /* Power spectrum of this rank's wavenumber array B (get_dims conf 2 layout; host or device pointer), summed over

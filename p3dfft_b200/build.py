@@ -77,13 +77,15 @@ def build_c_drivers(verbose: bool = False) -> list[str]:
     inc = ["-I" + os.path.join(root, "include", "mpi_shim"), "-I" + os.path.join(root, "include")]
     jobs = [("wave_roundtrip", "wave_roundtrip.c", [], "p3dfft"),
             ("wave_roundtrip_single", "wave_roundtrip.c", ["-DSINGLE_PREC"], "p3dfft_single"),
-            ("shim_selftest", "shim_selftest.c", [], "p3dfft")]
+            ("shim_selftest", "shim_selftest.c", [], "p3dfft"),
+            ("spec_epilogue", "spec_epilogue.c", [], "p3dfft"),
+            ("spec_epilogue_single", "spec_epilogue.c", ["-DSINGLE_PREC"], "p3dfft_single")]
     out = []
     for exe, src, defs, lib in jobs:
         target = os.path.join(LIBDIR, exe)
         srcp = os.path.join(root, "tests", "c", src)
         deps = [srcp, os.path.join(root, "include", "mpi_shim", "mpi.h"), os.path.join(root, "include", "p3dfft.h"),
-                os.path.join(LIBDIR, f"lib{lib}.so")]
+                os.path.join(root, "include", "p3dfft_b200.h"), os.path.join(LIBDIR, f"lib{lib}.so")]
         if _newer(target, deps):
             cmd = ["gcc", "-O2", "-Wall", *defs, *inc, srcp, "-L" + LIBDIR, "-l" + lib, "-lm", "-Wl,-rpath,$ORIGIN", "-o", target]
             if verbose:

@@ -70,3 +70,22 @@ def test_c_driver_multi_rank(ranks, grid):
         pytest.skip(f"needs {ranks} GPUs")
     r = _run(ranks, os.path.join(LIB, "wave_roundtrip"), 64, 48, 80, *grid)
     assert r.returncode == 0 and "Results are correct" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe,n", [("spec_epilogue", (64, 48, 40)), ("spec_epilogue", (128, 64, 64)), ("spec_epilogue", (30, 18, 14)),
+                                   ("spec_epilogue_single", (64, 64, 64))])
+def test_c_epilogue_driver_single_rank(exe, n):
+    """tests/c/spec_epilogue.c: fused normalisation, device power spectrum, rtran_* and r2c_1d from C"""
+    r = _run(1, os.path.join(LIB, exe), *n)
+    assert r.returncode == 0 and "Results are correct" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ranks,grid", [(2, (1, 2)), (2, (2, 1)), (4, (2, 2))])
+def test_c_epilogue_driver_multi_rank(ranks, grid):
+    import torch
+    if torch.cuda.device_count() < ranks:
+        pytest.skip(f"needs {ranks} GPUs")
+    r = _run(ranks, os.path.join(LIB, "spec_epilogue"), 64, 48, 40, *grid)
+    assert r.returncode == 0 and "Results are correct" in r.stdout, r.stdout + r.stderr
