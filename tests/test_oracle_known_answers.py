@@ -180,3 +180,43 @@ def test_philox_field_is_rank_count_independent():
     b = po.philox_field(8, 6, 5, sl=(slice(2, 5), slice(1, 4)))
     assert np.array_equal(a[:, 2:5, 1:4], b)
     assert a.min() >= 0 and a.max() < 1
+
+
+@pytest.mark.parametrize("dims", GRIDS)
+def test_driver_spec_power_spectrum_known_answer(dims):
+    """driver_spec.c:196-203 (sine-product input), :223 (1/N), :298-384 (shell sums, MPI_Reduce): the four spikes of
+    modulus 1/8 stored in the half spectrum (kx = 1, ky = +-1, kz = +-1) have k^2 = 3, i.e. shell int(sqrt(3)+.5) = 2,
+    so E(2) = 4 * 3 / 64 and every other shell is empty.  Summed over the ranks of any grid."""
+    nx, ny, nz = 32, 24, 20
+    A = _sine(nx, ny, nz)
+    kmax = po.spectrum_kmax(nx, ny, nz)
+    assert kmax == int(np.sqrt(nx * nx + ny * ny + nz * nz) * 0.5 + 0.5)
+    E = np.zeros(kmax + 1)
+    for r in range(dims[0] * dims[1]):
+        d = po.Decomp(nx, ny, nz, dims, r)
+        E += po.power_spectrum(po.local_forward(A, d, "fft"), d, kmax, 1.0 / (nx * ny * nz))
+    assert abs(E[2] - 0.1875) < 1e-14
+    E[2] = 0.0
+    assert np.max(np.abs(E)) < 1e-25
+
+
+def test_rtran_restatement_is_a_permutation():
+    """module.F90:1061-1361: the transposes only move data -- the structural restatement (pack, alltoallv with the
+    Ii/Ji/Ij/Kj tables of setup.F90:531-549, unpack) reproduces the global slices and x2y/y2x, x2z/z2x are inverses."""
+    for dims, n in (((2, 3), (14, 26, 38)), ((3, 2), (9, 7, 5)), ((1, 4), (16, 12, 10)), ((4, 1), (16, 12, 10))):
+        w = po.SimWorld(*n, dims)
+        A = np.asfortranarray(np.arange(np.prod(n), dtype=np.float64).reshape(n, order="F"))
+        parts = w.scatter_real(A)
+        for fwd, bwd in (("x2y", "y2x"), ("x2z", "z2x")):
+            o = w.rtran(fwd, parts)
+            for d, x in zip(w.d, o):
+                assert np.array_equal(x, po.rtran_local(A, d, fwd))
+                assert list(x.shape) == po.rtran_dims(d, fwd)[2]
+            for x, y in zip(w.rtran(bwd, o), parts):
+                assert np.array_equal(x, y)
+        # the destination pencils tile the global array exactly once
+        for which in ("x2y", "x2z"):
+            cover = np.zeros(n, dtype=int)
+            for d in w.d:
+                cover[po.rtran_slices(d, which)[1]] += 1
+            assert np.all(cover == 1)
