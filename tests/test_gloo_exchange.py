@@ -97,3 +97,79 @@ def test_two_rank_transform_over_gloo(dims, n, cut, plain):
         assert p.exitcode == 0
     for rank, err in res:
         assert err < 1e-13, (rank, err)
+
+
+def _rtran_worker(rank, world, port, dims, n, q):
+    """real-data transposes on two real processes: RCOPY stages through the test harness (tests/c/rcopy_host.cpp, the
+    address arithmetic the CUDA kernel runs), exchanges over gloo with the plan's Ii/Ji/Ij/Kj counts in REAL elements."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = pb.load(False)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        h = C.CDLL(os.path.join(root, "p3dfft_b200", "lib", "librcopy_check.so"))
+        h.rcopy_host_run.argtypes = [C.POINTER(pb.Stage), C.c_int]
+        nx, ny, nz = n
+        d = po.Decomp(nx, ny, nz, dims, rank)
+        G = po.philox_field(nx, ny, nz, seed=5)
+        bad = 0
+        for which in pb.RTRAN_NAMES:
+            src_sl, dst_sl = po.rtran_slices(d, which)
+            _, _, dsize, welems = lib.plan_rtran_info(dims, nx, ny, nz, rank, which)
+            bufs = {pb.BUF_USER_IN: np.ascontiguousarray(G[src_sl].ravel(order="F")),
+                    pb.BUF_USER_OUT: np.full(int(np.prod(dsize)), np.nan),
+                    pb.BUF_A: np.full(2 * welems, np.nan), pb.BUF_B: np.full(2 * welems, np.nan)}
+            for s in lib.plan_aux_steps(dims, nx, ny, nz, rank, which):
+                if s.is_exchange:
+                    ex = s.ex
+                    assert ex.ebytes == 8 and not ex.p2p
+                    group = [d.rank_of(ip, d.jpid) for ip in range(d.iproc)] if ex.comm == 0 else \
+                        [d.rank_of(d.ipid, jp) for jp in range(d.jproc)]
+                    reqs, landing = [], []
+                    for p in range(ex.npeer):
+                        if p == ex.self:
+                            continue
+                        snd = np.ascontiguousarray(bufs[ex.sendbuf][ex.sndoff[p]:ex.sndoff[p] + ex.sndcnt[p]])
+                        assert not np.any(np.isnan(snd))
+                        reqs.append(dist.isend(torch.from_numpy(snd), group[p]))
+                        r = torch.empty(ex.rcvcnt[p], dtype=torch.float64)
+                        reqs.append(dist.irecv(r, group[p]))
+                        landing.append((p, r))
+                    for rq in reqs:
+                        rq.wait()
+                    for p, r in landing:
+                        bufs[ex.recvbuf][ex.rcvoff[p]:ex.rcvoff[p] + ex.rcvcnt[p]] = r.numpy()
+                else:
+                    st = s.st
+                    for side in (st.inp, st.out):
+                        for g in range(side.nseg):
+                            sg = side.seg[g]
+                            assert sg.peer < 0
+                            sg.base = bufs[sg.buf].ctypes.data + sg.off * 8
+                    assert h.rcopy_host_run(C.byref(st), 8) >= 1
+            exp = po.rtran_local(G, d, which).ravel(order="F")
+            bad += int(not np.array_equal(bufs[pb.BUF_USER_OUT], exp))
+        q.put((rank, bad))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dims,n", [((1, 2), (12, 10, 14)), ((2, 1), (14, 26, 38)), ((2, 1), (9, 7, 5))])
+def test_two_rank_rtran_over_gloo(dims, n):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rtran_worker, args=(r, 2, port, dims, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, bad in res:
+        assert bad == 0, (rank, bad)
