@@ -60,6 +60,8 @@ void p3dfft_b200_force_generic(int on);
  * receive buffer over NVLink and the exchange step is only a barrier.  on = 0 keeps grouped
  * ncclSend/ncclRecv.  Must precede p3dfft_setup (also env P3DFFT_B200_P2P=0/1).               */
 void p3dfft_b200_set_p2p(int on);
+/* env P3DFFT_B200_FLAGBAR=1 (opt-in, experimental): the barrier that orders the peer-to-peer transposes becomes a
+ * one-CTA kernel exchanging epoch flags through peer-mapped memory instead of a one-float NCCL all-reduce.         */
 int p3dfft_b200_p2p_active(void);
 /* on != 0: keep the reference's pack-buffer layouts and exact alltoallv counts in the
  * library's own work buffers instead of the tile-blocked B200 layouts (plan.h); results are

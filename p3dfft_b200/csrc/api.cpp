@@ -133,6 +133,12 @@ struct Lib {
   bool want_p2p = true, p2p = false;
   std::vector<void*> peer_buf;   // [world rank * 3 + (buffer id - P3D_BUF_A)], own entries = own buffers
   float* bar_scratch = nullptr;
+  // opt-in flag barrier over peer-mapped memory (P3DFFT_B200_FLAGBAR=1; not yet run on hardware -- default off)
+  bool want_flagbar = false, flagbar = false;
+  unsigned* bar_flags = nullptr;                 // this rank's slots: one 128-byte slot per world rank, own 2 MiB allocation
+  std::vector<unsigned*> peer_flags;             // [world rank] mapped flag arrays (own entry = bar_flags)
+  unsigned** peer_flags_dev = nullptr;           // the same table on the device
+  unsigned bar_epoch = 0;
   // dirty[b]: buffer b was the receive buffer of an exchange since the last world barrier, i.e. some rank may still
   // be reading it.  A peer-to-peer stage must not store into the peers' copies of such a buffer before another
   // barrier (run_plan).  Derived from the exchange steps only, so every rank takes the same decisions.
@@ -215,13 +221,69 @@ void close_peer_maps() {
     if (L.peer_buf[i] && (int)(i / 3) != me) cudaIpcCloseMemHandle(L.peer_buf[i]);
   L.peer_buf.clear();
   L.p2p = false;
+  for (size_t i = 0; i < L.peer_flags.size(); i++)
+    if (L.peer_flags[i] && (int)i != me) cudaIpcCloseMemHandle(L.peer_flags[i]);
+  L.peer_flags.clear();
+  L.flagbar = false;
 }
 
 bool world_barrier(cudaStream_t st) {
   if (!L.comm || !L.comm->world) return true;
+  if (L.flagbar) {
+    CUDA_OK(p3d::launch_flag_barrier(L.peer_flags_dev, L.comm->rank, L.comm->size, ++L.bar_epoch, st));
+    for (bool& d : L.dirty) d = false;
+    return true;
+  }
   if (!L.bar_scratch) { CUDA_OK(cudaMalloc(&L.bar_scratch, 256)); CUDA_OK(cudaMemset(L.bar_scratch, 0, 256)); }
   NCCL_OK(g_nccl.AllReduce(L.bar_scratch, L.bar_scratch + 32, 1, ncclFloat, ncclSum, L.comm->world, st));
   for (bool& d : L.dirty) d = false;
+  return true;
+}
+
+// Opt-in flag barrier: maps every rank's flag array (collective over the world).  The arrays are zeroed before their
+// handles travel through the all-gather, so nobody can signal into an array that is still being initialised.
+bool open_flag_maps() {
+  const int P = L.comm->size, me = L.comm->rank;
+  cudaStream_t st = L.stream();
+  const size_t bytes = 2u << 20;                 // an allocation of its own (IPC handles name whole allocations)
+  if (!L.bar_flags) {
+    CUDA_OK(cudaMalloc(&L.bar_flags, bytes));
+    CUDA_OK(cudaMemset(L.bar_flags, 0, bytes));
+    L.bar_epoch = 0;
+  }
+  if ((size_t)P * 128 > bytes) return false;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof mine);
+  bool ok = cudaIpcGetMemHandle(&mine, L.bar_flags) == cudaSuccess;
+  if (!ok) cudaGetLastError();
+  cudaIpcMemHandle_t* dev = nullptr;
+  CUDA_OK(cudaMalloc(&dev, sizeof(mine) * (P + 1)));
+  CUDA_OK(cudaMemcpy(dev + P, &mine, sizeof mine, cudaMemcpyHostToDevice));
+  NCCL_OK(g_nccl.AllGather(dev + P, dev, sizeof(mine), ncclInt8, L.comm->world, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<cudaIpcMemHandle_t> all(P);
+  CUDA_OK(cudaMemcpy(all.data(), dev, sizeof(mine) * P, cudaMemcpyDeviceToHost));
+  cudaFree(dev);
+  L.peer_flags.assign(P, nullptr);
+  for (int r = 0; r < P && ok; r++) {
+    if (r == me) { L.peer_flags[r] = L.bar_flags; continue; }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    L.peer_flags[r] = (unsigned*)ptr;
+  }
+  float flag = ok ? 0.f : 1.f, sum = 0.f;
+  CUDA_OK(cudaMemcpy(L.bar_scratch + 3, &flag, sizeof flag, cudaMemcpyHostToDevice));
+  NCCL_OK(g_nccl.AllReduce(L.bar_scratch + 3, L.bar_scratch + 4, 1, ncclFloat, ncclSum, L.comm->world, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaMemcpy(&sum, L.bar_scratch + 4, sizeof sum, cudaMemcpyDeviceToHost));
+  if (sum != 0.f) {
+    for (int r = 0; r < P; r++) if (L.peer_flags[r] && r != me) cudaIpcCloseMemHandle(L.peer_flags[r]);
+    L.peer_flags.clear();
+    return false;
+  }
+  if (!L.peer_flags_dev) CUDA_OK(cudaMalloc(&L.peer_flags_dev, sizeof(unsigned*) * 1024));
+  CUDA_OK(cudaMemcpy(L.peer_flags_dev, L.peer_flags.data(), sizeof(unsigned*) * P, cudaMemcpyHostToDevice));
+  L.flagbar = true;
   return true;
 }
 
@@ -264,6 +326,7 @@ bool open_peer_maps() {
   CUDA_OK(cudaMemcpy(&sum, L.bar_scratch + 2, sizeof sum, cudaMemcpyDeviceToHost));
   if (sum != 0.f) { close_peer_maps(); return false; }
   L.p2p = true;
+  if (L.want_flagbar && !open_flag_maps()) L.flagbar = false;      // the NCCL barrier stays in use
   return true;
 }
 
@@ -560,6 +623,7 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   if (getenv("P3DFFT_B200_PLAIN")) L.plain_layout = true;
   if (getenv("P3DFFT_B200_P2P")) L.want_p2p = atoi(getenv("P3DFFT_B200_P2P")) != 0;
   if (getenv("P3DFFT_B200_ROWB")) L.force_row_bytes = atoi(getenv("P3DFFT_B200_ROWB"));
+  if (getenv("P3DFFT_B200_FLAGBAR")) L.want_flagbar = atoi(getenv("P3DFFT_B200_FLAGBAR")) != 0;
   for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
   L.procmap.init(L.d);
   L.nv_preset = 0;
@@ -648,6 +712,8 @@ void p3dfft_clean(void) {
     close_peer_maps();
   }
   if (L.bar_scratch) { cudaFree(L.bar_scratch); L.bar_scratch = nullptr; }
+  if (L.bar_flags) { cudaFree(L.bar_flags); L.bar_flags = nullptr; }
+  if (L.peer_flags_dev) { cudaFree(L.peer_flags_dev); L.peer_flags_dev = nullptr; }
   if (L.spec_dev) { cudaFree(L.spec_dev); L.spec_dev = nullptr; L.spec_bins = 0; }
   for (int b = P3D_BUF_A; b <= P3D_BUF_C; b++) if (L.buf[b]) { cudaFree(L.buf[b]); L.buf[b] = nullptr; }
   if (L.stage_in) { cudaFree(L.stage_in); L.stage_in = nullptr; L.stage_in_bytes = 0; }

@@ -420,6 +420,35 @@ cudaError_t launch_spectrum(const void* B, const SpecJob& job_in, double* E, cud
 }
 
 // ------------------------------------------------------------------------------------
+// Flag barrier across the GPUs of one NVSwitch box (opt-in replacement of the one-float NCCL all-reduce that
+// orders the peer-to-peer transposes, api.cpp world_barrier).  The preceding stage kernel has completed when
+// this kernel starts (same stream), so its peer stores are performed; thread r publishes this rank's epoch in
+// rank r's array with a system-scope release store and then spins with acquire loads on slot r of the local
+// array.  Epochs only grow, so a rank that is one barrier ahead never unblocks a waiter early.
+// ------------------------------------------------------------------------------------
+__global__ void flag_barrier_kernel(unsigned* const* __restrict__ peers, int me, int nrank, unsigned epoch) {
+  const int r = threadIdx.x;
+  if (r < nrank) {
+    __threadfence_system();
+    unsigned* dst = peers[r] + (size_t)me * 32;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+    const unsigned* src = peers[me] + (size_t)r * 32;
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    } while ((int)(v - epoch) < 0);
+  }
+  __syncthreads();
+}
+
+cudaError_t launch_flag_barrier(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream) {
+  if (nrank > 1024) return cudaErrorInvalidValue;
+  const int nt = nrank <= 32 ? 32 : ((nrank + 31) / 32) * 32;
+  flag_barrier_kernel<<<1, nt, 0, stream>>>(peers, me, nrank, epoch);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------
 static int big_factor(const P3dStage& st) {

@@ -25,5 +25,9 @@ struct SpecJob {
   int32_t kmax, ncopy;     // bins 0..kmax; privatised shared-memory copies of the histogram per CTA
   double f2;               // factor^2
 };
+// Flag barrier over peer-mapped memory (opt-in, P3DFFT_B200_FLAGBAR=1): every rank stores `epoch` into slot `me` of
+// every rank's flag array (128-byte slots) and waits until all slots of its own array have reached it.
+// peers = DEVICE array of nrank pointers (entry `me` = the rank's own array).
+cudaError_t launch_flag_barrier(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream);
 template <typename T> cudaError_t launch_spectrum(const void* B, const SpecJob& job, double* E, cudaStream_t stream);
 }  // namespace p3d
