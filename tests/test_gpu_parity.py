@@ -48,7 +48,8 @@ def _fwd_bwd(L, n, cut=None, opf="fft", opb="tff", stride1=False, single=False, 
     d = po.Decomp(nx, ny, nz, (1, 1), 0, *c, stride1=stride1, elem=4 if single else 8)
     ist, ien, isz = L.p3dfft_get_dims(1)
     fst, fen, fsz = L.p3dfft_get_dims(2)
-    assert (list(ist), list(ien), list(isz)) == tuple(map(list, d.get_dims(1))) or True
+    assert [list(ist), list(ien), list(isz)] == [list(v) for v in d.get_dims(1)]
+    assert [list(fst), list(fen), list(fsz)] == [list(v) for v in d.get_dims(2)]
     assert list(isz) == d.get_dims(1)[2] and list(fsz) == d.get_dims(2)[2]
     A = _rand(n, rt)
     F = np.zeros(fsz, dtype=ct, order="F")
