@@ -101,6 +101,22 @@ def build_c_drivers(verbose: bool = False) -> list[str]:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
     out.append(target)
+    # test-only host emulation of the specialised stage kernels (tests/emu): the product's fft_fast.cu / fft_fast.cuh
+    # compiled by g++ against a CUDA execution-model shim
+    emu = os.path.join(root, "tests", "emu")
+    for name, defs in (("emu_fast", []), ("emu_fast_single", ["-DSINGLE_PREC"])):
+        target = os.path.join(LIBDIR, f"lib{name}.so")
+        deps = [os.path.join(emu, "emu_fast.cpp"), os.path.join(emu, "cuda_emu.h"), os.path.abspath(__file__)] + [os.path.join(CSRC, f) for f in
+                                                                                     ("fft_fast.cu", "fft_fast.cuh", "fast.h", "stage.h")]
+        if _newer(target, deps):
+            # -Bsymbolic: the emulator shares symbol names (p3d::launch_fast ...) with the product library, which the tests
+            # load into the same process with RTLD_GLOBAL; its own calls must bind to its own definitions
+            cmd = ["g++", "-O1", "-std=c++17", "-x", "c++", "-w", "-shared", "-fPIC", "-pthread", "-Wl,-Bsymbolic", *defs, "-I" + os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include"),
+                   os.path.join(emu, "emu_fast.cpp"), "-o", target]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+        out.append(target)
     return out
 
 

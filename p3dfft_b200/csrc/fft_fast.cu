@@ -228,6 +228,7 @@ static unsigned persistent_grid(K kernel, int nt, size_t smem, long long tiles, 
 }
 
 // one (configured, CTAs per SM) pair per kernel instantiation; the enclosing function defines smem, tiles, NT, f, stream, e
+#ifndef P3D_LAUNCH      // (tests/emu/emu_fast.cpp supplies a host emulation of the launch)
 #define P3D_LAUNCH(...)                                                                                       \
   do {                                                                                                        \
     static bool cfg = false;                                                                                  \
@@ -235,6 +236,7 @@ static unsigned persistent_grid(K kernel, int nt, size_t smem, long long tiles, 
     if ((e = launch_cfg(__VA_ARGS__, smem, cfg)) != cudaSuccess) return e;                                    \
     __VA_ARGS__<<<persistent_grid(__VA_ARGS__, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);              \
   } while (0)
+#endif
 
 template <typename T, int HH>
 static cudaError_t launch_x(const P3dStage& st, const FastStage& f, cudaStream_t stream) {

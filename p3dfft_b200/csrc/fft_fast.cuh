@@ -126,7 +126,7 @@ P3D_XCFG(float, 1024, P3D_RS(8, 16, 8), 8, 512, 2, 7, 0)
 #undef P3D_XCFG
 #undef P3D_RS
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(P3D_EMULATE)      // P3D_EMULATE: host emulation of the kernels (tests/emu, CPU tests)
 // ---------------------------------------------------------------------------------------
 // complex helpers and natural-order forward butterflies
 // ---------------------------------------------------------------------------------------
@@ -200,6 +200,7 @@ template <typename T> struct Bfly<T, 16> {
 // ---------------------------------------------------------------------------------------
 // memory access
 // ---------------------------------------------------------------------------------------
+#ifndef P3D_EMULATE
 __device__ __forceinline__ double2 ldg_stream(const double2* p) {
   double2 v;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
@@ -216,6 +217,12 @@ __device__ __forceinline__ void stg_stream(double2* p, double2 v) {
 __device__ __forceinline__ void stg_stream(float2* p, float2 v) {
   asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
+#else
+__device__ __forceinline__ double2 ldg_stream(const double2* p) { return *p; }
+__device__ __forceinline__ float2 ldg_stream(const float2* p) { return *p; }
+__device__ __forceinline__ void stg_stream(double2* p, double2 v) { *p = v; }
+__device__ __forceinline__ void stg_stream(float2* p, float2 v) { *p = v; }
+#endif
 
 constexpr int cpar(int x) { int p = 0; while (x) { p ^= x & 1; x >>= 1; } return p; }
 // swizzle of a row offset that occupies a bit-field disjoint from the rest of the index
@@ -297,7 +304,11 @@ __device__ __forceinline__ void last_bfly(const typename Cx<T>::type* s, int kap
 // into L2, so that tile's pass-1 loads find their data on chip and HBM stays busy while the
 // SM computes.
 // ---------------------------------------------------------------------------------------
+#ifndef P3D_EMULATE
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+__device__ __forceinline__ void prefetch_l2(const void* p) { (void)*reinterpret_cast<const volatile char*>(p); }   // must be a mapped address
+#endif
 
 // ---------------------------------------------------------------------------------------
 // row -> address
@@ -992,7 +1003,7 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(
     __syncthreads();      // tile buffer and row table are reused by the next tile
   }
 }
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || P3D_EMULATE
 
 }  // namespace fast
 }  // namespace p3d

@@ -1,0 +1,200 @@
+"""The specialised CUDA stage kernels, executed on the CPU.
+
+tests/emu compiles the product's own kernel source (p3dfft_b200/csrc/fft_fast.cuh) and its host-side dispatch
+(fft_fast.cu) with g++ against a small emulation of the CUDA execution model: one OS thread per CUDA thread, a
+barrier for __syncthreads(), CTAs one after the other.  These tests run whole transforms stage by stage through the
+emulated kernels (plans from the C-ABI planner, buffers in numpy) and compare with the oracle -- the kernels'
+butterflies, twiddle tables, digit reversal, shared-memory swizzles, row tables, pruning maps, the r2c/c2r pair
+passes and the tile loops are all exercised without a GPU.  What the emulation cannot show: performance, and
+races that need real warp scheduling to appear."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import p3dfft_b200 as pb
+from oracle import p3dfft_oracle as po
+from tests import plan_interp as pi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_libs = {}
+
+
+def emu(single=False):
+    if single not in _libs:
+        h = C.CDLL(os.path.join(ROOT, "p3dfft_b200", "lib", "libemu_fast_single.so" if single else "libemu_fast.so"))
+        h.emu_run_fast.argtypes = [C.POINTER(pb.Stage)]
+        _libs[single] = h
+    return _libs[single]
+
+
+def _esz(kind, side, r):
+    if kind == 7 or (kind == 2 and side == 0) or (kind == 3 and side == 1):
+        return r
+    return 2 * r
+
+
+def run_steps_emulated(steps, bufs, world, single, counts):
+    """one rank's stage steps up to (not including) the next exchange; returns the number of steps consumed"""
+    r = 4 if single else 8
+    n = 0
+    for s in steps:
+        if s.is_exchange:
+            break
+        st = s.st
+        for si, side in enumerate((st.inp, st.out)):
+            for g in range(side.nseg):
+                sg = side.seg[g]
+                tgt = bufs if sg.peer < 0 else world[sg.peer]
+                sg.base = tgt[sg.buf].ctypes.data + sg.off * _esz(st.kind, si, r)
+        rc = emu(single).emu_run_fast(C.byref(st))
+        assert rc in (0, 1), rc
+        if rc == 1:                       # no specialised kernel for this stage: the any-length kernel's job
+            assert not single, "the numpy interpreter of the generic path works in double"
+            pi.run_stage(st, bufs, world)
+        counts[rc] += 1
+        n += 1
+    return n
+
+
+def transform_world(n, dims, cut, opf, opb, stride1=False, single=False, p2p=False, row_bytes=0, nv=1):
+    """forward and backward on P simulated ranks; returns (fast stage count, generic stage count)"""
+    nx, ny, nz = n
+    c = cut or (None, None, None)
+    P = dims[0] * dims[1]
+    rt, ct = (np.float32, np.complex64) if single else (np.float64, np.complex128)
+    L = pb.load(single)
+    D = [po.Decomp(nx, ny, nz, dims, r, *c, stride1=stride1, elem=4 if single else 8) for r in range(P)]
+    A = [np.asfortranarray(np.random.default_rng(7 + v).random(n).astype(rt)) for v in range(nv)]
+    Fg = [po.global_forward(a.astype(np.float64), D[0], opf) for a in A]
+    counts = [0, 0]
+    tol = 2e-6 if single else 1e-13
+    for backward, op in ((False, opf), (True, opb)):
+        plans, world = [], []
+        for r, d in enumerate(D):
+            steps, inf = L.plan_steps(dims, nx, ny, nz, r, backward, op, nv, *c, stride1=stride1, p2p=p2p, row_bytes=row_bytes)
+            plans.append(steps)
+            w = int(inf.work_elems) * nv
+            if backward:
+                parts = []
+                for f in Fg:
+                    loc = f[po.local_out_slice(d)]
+                    parts.append(np.asfortranarray(loc.transpose(2, 1, 0) if stride1 else loc).astype(ct).ravel(order="F"))
+                inp = np.concatenate(parts)
+                out = np.full(nx * d.jisize * d.kjsize * nv, np.nan, dtype=rt)
+            else:
+                inp = np.concatenate([np.asfortranarray(a[po.local_in_slice(d)]).ravel(order="F") for a in A])
+                out = np.full(d.iisize * d.jjsize * d.nzc * nv, np.nan, dtype=ct)
+            world.append({pb.BUF_A: np.zeros(w, dtype=ct), pb.BUF_B: np.zeros(w, dtype=ct), pb.BUF_C: np.zeros(w, dtype=ct),
+                          pb.BUF_USER_IN: inp, pb.BUF_USER_OUT: out})
+        pos = [0] * P
+        while any(pos[r] < len(plans[r]) for r in range(P)):
+            for r in range(P):
+                pos[r] += run_steps_emulated(plans[r][pos[r]:], world[r], world, single, counts)
+            exs = [plans[r][pos[r]].ex if pos[r] < len(plans[r]) else None for r in range(P)]
+            if all(e is None for e in exs):
+                break
+            for r in range(P):
+                ex, me = exs[r], D[r]
+                if not ex.p2p:
+                    for p in range(ex.npeer):
+                        if p == ex.self:
+                            continue
+                        peer = me.rank_of(p, me.jpid) if ex.comm == 0 else me.rank_of(me.ipid, p)
+                        my_idx = me.ipid if ex.comm == 0 else me.jpid
+                        pex = exs[peer]
+                        cnt = ex.sndcnt[p]
+                        assert cnt == pex.rcvcnt[my_idx]
+                        world[peer][pex.recvbuf][pex.rcvoff[my_idx]:pex.rcvoff[my_idx] + cnt] = \
+                            world[r][ex.sendbuf][ex.sndoff[p]:ex.sndoff[p] + cnt]
+                pos[r] += 1
+        for r, d in enumerate(D):
+            if backward:
+                exp = np.concatenate([po.local_backward(f, d, op).ravel(order="F") for f in Fg])
+            else:
+                exp = np.concatenate([np.asfortranarray(po.local_forward(a.astype(np.float64), d, op)).ravel(order="F") for a in A])
+            got = world[r][pb.BUF_USER_OUT]
+            assert not np.any(np.isnan(got)), "output not fully written"
+            assert po.rel_l2(got.astype(np.complex128 if not backward else np.float64), exp) <= tol, (n, dims, cut, op, r)
+    return counts
+
+
+# every specialised length: X stage H = 32 ... 1024 (nx = 64 ... 2048), Y/Z stages 64 ... 2048.  The long axis is paired with
+# short ones to keep the emulation quick; stages shorter than 64 points belong to the any-length kernel (numpy here).
+# (n, cut, number of stages the specialised kernels must take)
+LENGTHS = [((64, 64, 64), None, 6), ((128, 256, 64), None, 6), ((256, 64, 128), None, 6), ((512, 16, 16), None, 2),
+           ((1024, 16, 16), None, 2), ((2048, 16, 16), None, 2), ((16, 512, 16), None, 2), ((16, 16, 1024), None, 2),
+           ((16, 1024, 16), None, 2), ((16, 16, 2048), None, 2), ((16, 2048, 16), None, 2),
+           ((128, 128, 128), (64, 64, 64), 6), ((256, 128, 64), (170, 84, 42), 6), ((16, 1024, 16), (16, 680, 16), 2)]
+
+
+@pytest.mark.parametrize("n,cut,nfast", LENGTHS)
+def test_emulated_kernels_double_all_lengths(n, cut, nfast):
+    fast, generic = transform_world(n, (1, 1), cut, "fft", "tff")
+    assert (fast, generic) == (nfast, 6 - nfast)
+
+
+@pytest.mark.parametrize("n,cut,nfast", [LENGTHS[0], LENGTHS[1], LENGTHS[3]])
+def test_emulated_kernels_single_precision(n, cut, nfast):
+    # (short stages would go to the generic kernel, whose numpy stand-in works in double: all-specialised cases and X only)
+    if nfast < 6:
+        n = (n[0], 64, 64)
+    fast, generic = transform_world(n, (1, 1), cut, "fft", "tff", single=True)
+    assert (fast, generic) == (6, 0)
+
+
+@pytest.mark.parametrize("rb", [64, 128])
+@pytest.mark.parametrize("n,cut", [((64, 64, 64), None), ((64, 256, 64), None), ((128, 64, 64), (84, 42, 42))])
+def test_emulated_kernels_row_widths(n, cut, rb):
+    """both tile row widths of the internal layouts: 64-byte rows use the swizzled shared-memory tile"""
+    fast, generic = transform_world(n, (1, 1), cut, "fft", "tff", row_bytes=rb)
+    assert (fast, generic) == (6, 0)
+
+
+@pytest.mark.parametrize("n,cut", [((64, 64, 33), None), ((64, 64, 65), None), ((128, 64, 129), (64, 32, 65))])
+@pytest.mark.parametrize("stride1", [False, True])
+def test_emulated_kernels_chebyshev_and_stride1(n, cut, stride1):
+    """DCT-I as an even-extended FFT (mirror rows) through the c2c kernel; STRIDE1 output layout"""
+    fast, generic = transform_world(n, (1, 1), cut, "ffc", "cff", stride1=stride1)
+    assert (fast, generic) == (6, 0)
+
+
+def test_emulated_split_kernel(monkeypatch):
+    """the two-half-tiles variant of the 1024-point c2c kernel (taken on the GPU for far-pitch inputs)"""
+    monkeypatch.setenv("P3DFFT_B200_SPLIT", "1")
+    # the environment is read once per process by the dispatch: use a fresh copy of the emulator library
+    import shutil
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        dst = os.path.join(tmp, "libemu_split.so")
+        shutil.copy(os.path.join(ROOT, "p3dfft_b200", "lib", "libemu_fast.so"), dst)
+        h = C.CDLL(dst)
+        h.emu_run_fast.argtypes = [C.POINTER(pb.Stage)]
+        old = _libs.get(False)
+        _libs[False] = h
+        try:
+            fast, generic = transform_world((16, 1024, 16), (1, 1), None, "fft", "tff")
+            assert (fast, generic) == (2, 4)
+            fast, generic = transform_world((16, 16, 1024), (1, 1), (16, 16, 512), "fft", "tff")
+            assert (fast, generic) == (2, 4)
+        finally:
+            if old is not None:
+                _libs[False] = old
+            else:
+                _libs.pop(False, None)
+
+
+@pytest.mark.parametrize("dims", [(1, 2), (2, 1), (2, 2), (2, 4)])
+@pytest.mark.parametrize("p2p", [False, True])
+def test_emulated_kernels_multi_rank(dims, p2p):
+    """P simulated ranks: per-peer blocks, and with p2p the stage kernels store into the peers' buffers"""
+    fast, generic = transform_world((64, 64, 64), dims, None, "fft", "tff", p2p=p2p)
+    assert generic == 0 and fast == 6 * dims[0] * dims[1]
+
+
+def test_emulated_kernels_uneven_multi_rank_and_many():
+    fast, generic = transform_world((64, 64, 64), (2, 3), (42, 42, 42), "fft", "tff", p2p=True)
+    assert generic == 0
+    fast, generic = transform_world((64, 64, 64), (2, 2), None, "fft", "tff", nv=2)
+    assert generic == 0 and fast == 24
