@@ -200,14 +200,14 @@ const void* twiddle_table(int nfft) {
 }
 
 // twiddle block of the specialised kernels (fft_fast.cu), one per (stage class, length)
-const void* fast_twiddle_block(int kind, int nfft) {
+const void* fast_twiddle_block(int kind, int nfft, int variant = 0) {
   const bool xs = kind == P3D_R2C || kind == P3D_C2R;
-  auto key = std::make_pair(xs ? 1 : 0, nfft);
+  auto key = std::make_pair((xs ? 1 : 0) + 2 * variant, nfft);
   auto it = L.fast_twiddles.find(key);
   if (it != L.fast_twiddles.end()) return it->second;
-  const size_t n = p3d::fast_twiddle_elems<real_t>(kind, nfft);
+  const size_t n = p3d::fast_twiddle_elems<real_t>(kind, nfft, variant);
   std::vector<real_t> h(2 * n + 2);
-  p3d::fast_twiddle_fill<real_t>(kind, nfft, h.data());
+  p3d::fast_twiddle_fill<real_t>(kind, nfft, h.data(), variant);
   void* dptr = nullptr;
   if (cudaMalloc(&dptr, h.size() * sizeof(real_t)) != cudaSuccess) return nullptr;
   if (cudaMemcpy(dptr, h.data(), h.size() * sizeof(real_t), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
@@ -487,7 +487,8 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
       else if (!L.force_generic && p3d::fast_supported<real_t>(stg)) {
         p3d::FastStage fs;
         p3d::to_fast(stg, fs, sizeof(real_t));
-        fs.tw = fast_twiddle_block(stg.kind, stg.nfft);
+        fs.variant = p3d::fast_variant<real_t>(stg);
+        fs.tw = fast_twiddle_block(stg.kind, stg.nfft, fs.variant);
         if (!fs.tw) { report(true, "P3DFFT(B200): cannot allocate twiddle table"); return false; }
         e = p3d::launch_fast<real_t>(stg, fs, st);
         if (e == cudaSuccess) L.fast_launches++;

@@ -48,13 +48,17 @@ struct FastStage {
   FastSide in, out;
   double scale;          // multiplies every output (SCALED instantiations only; last member: the unscaled kernels'
                          // parameter layout does not depend on it)
+  int32_t variant;       // 0: default schedules; 1: two-pass radix-32 variant (fast_variant, opt-in)
+  int32_t pad2_;
 };
 
 // true when a specialised kernel exists for this stage (kind, length, strides, alignment)
 template <typename T> bool fast_supported(const P3dStage& st);
 // number of T2 elements of the twiddle block and its host-side fill
-template <typename T> size_t fast_twiddle_elems(int kind, int nfft);
-template <typename T> void fast_twiddle_fill(int kind, int nfft, void* host);
+// experimental kernel variant this stage would run with (0 = default); decides which twiddle block it needs
+template <typename T> int fast_variant(const P3dStage& st);
+template <typename T> size_t fast_twiddle_elems(int kind, int nfft, int variant = 0);
+template <typename T> void fast_twiddle_fill(int kind, int nfft, void* host, int variant = 0);
 // converts resolved segments (seg.base set) into runs; real_bytes = sizeof(real)
 void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes);
 template <typename T> cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t stream);

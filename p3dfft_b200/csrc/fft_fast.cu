@@ -142,16 +142,36 @@ bool fast_supported(const P3dStage& st) {
   }
 }
 
+template <class F>
+bool dispatch_r32(int n, F&& f) {
+  switch (n) {
+    case 512:  f(std::integral_constant<int, 512>{});  return true;
+    case 1024: f(std::integral_constant<int, 1024>{}); return true;
+    default: return false;
+  }
+}
+
+// Opt-in two-pass variant (P3DFFT_B200_R32=1): c2c / DCT stages of 512 or 1024 points with 128-byte rows
 template <typename T>
-size_t fast_twiddle_elems(int kind, int nfft) {
+int fast_variant(const P3dStage& st) {
+  const char* e = getenv("P3DFFT_B200_R32");
+  if (!e || atoi(e) == 0) return 0;
+  if (is_x(st.kind) || !ccfg_r32_exists(st.nfft)) return 0;
+  return row_bytes<T>(st) == 128 ? 1 : 0;
+}
+
+template <typename T>
+size_t fast_twiddle_elems(int kind, int nfft, int variant) {
   size_t n = 0;
+  if (variant == 1 && !is_x(kind)) { dispatch_r32(nfft, [&](auto nn) { n = block_elems<typename CCfgR32<T, decltype(nn)::value>::S>(false); }); return n; }
   if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { n = block_elems<typename XCfg<T, decltype(h)::value>::S>(true); });
   else dispatch_c(nfft, [&](auto nn) { n = block_elems<typename CCfg<T, decltype(nn)::value, 64>::S>(false); });
   return n;
 }
 
 template <typename T>
-void fast_twiddle_fill(int kind, int nfft, void* host) {
+void fast_twiddle_fill(int kind, int nfft, void* host, int variant) {
+  if (variant == 1 && !is_x(kind)) { dispatch_r32(nfft, [&](auto nn) { fill_block<T, typename CCfgR32<T, decltype(nn)::value>::S>(false, host); }); return; }
   if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { fill_block<T, typename XCfg<T, decltype(h)::value>::S>(true, host); });
   else dispatch_c(nfft, [&](auto nn) { fill_block<T, typename CCfg<T, decltype(nn)::value, 64>::S>(false, host); });
 }
@@ -272,6 +292,27 @@ static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t
   return cudaGetLastError();
 }
 
+// two-pass radix-32 variant (opt-in)
+template <typename T, int NN>
+static cudaError_t launch_r32(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  constexpr int TX = CCfgR32<T, NN>::TX, NT = CCfgR32<T, NN>::NT;
+  constexpr size_t smem = cstage_r32_smem<T, NN>();
+  const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
+  if (tiles <= 0) return cudaSuccess;
+  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
+  cudaError_t e;
+  const bool scaled = f.scale != 1.0;
+  if (st.kind == P3D_C2C_BWD) {
+    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 128, true, true, CCfgR32<T, NN>>);
+    else P3D_LAUNCH(cstage_kernel<T, NN, 128, true, false, CCfgR32<T, NN>>);
+  } else {
+    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 128, false, true, CCfgR32<T, NN>>);
+    else P3D_LAUNCH(cstage_kernel<T, NN, 128, false, false, CCfgR32<T, NN>>);
+  }
+  return cudaGetLastError();
+}
+
 // split variant (two half tiles per CTA, two CTAs per SM) for the lengths whose 128-byte tile fills an SM
 template <typename T, int NN>
 static cudaError_t launch_split(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
@@ -303,6 +344,9 @@ cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t str
       if (reinterpret_cast<uintptr_t>(sd.run[g].base) % sizeof(T2)) return cudaErrorMisalignedAddress;
   }
   cudaError_t err = cudaErrorInvalidValue;
+  if (f.variant == 1 && !is_x(st.kind) && f.rowb == 128) {
+    if (dispatch_r32(st.nfft, [&](auto nn) { err = launch_r32<T, decltype(nn)::value>(st, f, stream); })) return err;
+  }
   if (is_x(st.kind)) dispatch_x(st.n / 2, [&](auto h) { err = launch_x<T, decltype(h)::value>(st, f, stream); });
   else dispatch_c(st.nfft, [&](auto nn) {
     constexpr int NN = decltype(nn)::value;
@@ -326,8 +370,9 @@ typedef float fast_real_t;
 typedef double fast_real_t;
 #endif
 template bool fast_supported<fast_real_t>(const P3dStage&);
-template size_t fast_twiddle_elems<fast_real_t>(int, int);
-template void fast_twiddle_fill<fast_real_t>(int, int, void*);
+template int fast_variant<fast_real_t>(const P3dStage&);
+template size_t fast_twiddle_elems<fast_real_t>(int, int, int);
+template void fast_twiddle_fill<fast_real_t>(int, int, void*, int);
 template cudaError_t launch_fast<fast_real_t>(const P3dStage&, const FastStage&, cudaStream_t);
 
 }  // namespace p3d

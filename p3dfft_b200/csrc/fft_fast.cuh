@@ -35,6 +35,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+#include <utility>
+
 #include "fast.h"
 #include "stage.h"
 
@@ -97,6 +100,17 @@ P3D_CCFG(float, 1024, 128, P3D_RS(16, 8, 8), 512, 1)
 #undef P3D_CCFG
 // the 128-byte tile of a 2048-point transform (256 KB) does not fit in shared memory
 constexpr bool ccfg_exists(int n, int rb) { return rb == 64 || (rb == 128 && n <= 1024); }
+
+// Two-pass variants (opt-in, P3DFFT_B200_R32=1): 1024 = 32 x 32 and 512 = 16 x 32 instead of three passes, i.e. ONE round
+// trip through shared memory per element instead of two (r1 ncu: the LSU pipe is busy ~55 % of a 1024-point stage, most
+// of it shared-memory wavefronts).  The price is 32 complex values per thread in registers, hence fewer threads per CTA.
+// 128-byte rows only.  Not yet timed on hardware.
+template <typename T, int N> struct CCfgR32;
+template <> struct CCfgR32<double, 1024> { using S = RS<32, 32>; static constexpr int TX = 8, NT = 256, MINB = 1; };
+template <> struct CCfgR32<double, 512>  { using S = RS<16, 32>; static constexpr int TX = 8, NT = 128, MINB = 3; };
+template <> struct CCfgR32<float, 1024>  { using S = RS<32, 32>; static constexpr int TX = 16, NT = 512, MINB = 1; };
+template <> struct CCfgR32<float, 512>   { using S = RS<16, 32>; static constexpr int TX = 16, NT = 256, MINB = 3; };
+constexpr bool ccfg_r32_exists(int n) { return n == 1024 || n == 512; }
 
 // X-stage configuration per (type, H = nx/2).  The first (c2r) / last (r2c) pass works on
 // butterfly PAIRS, i.e. 2R complex values per thread, so those radices stay <= 8.
@@ -194,6 +208,47 @@ template <typename T> struct Bfly<T, 16> {
     for (int c = 0; c < 4; c++)
 #pragma unroll
       for (int d = c + 1; d < 4; d++) { T2 t = v[4 * c + d]; v[4 * c + d] = v[4 * d + c]; v[4 * d + c] = t; }
+  }
+};
+
+template <int B, int... I, class F>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) { (f(std::integral_constant<int, B + I>{}), ...); }
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) { static_for_impl<B>(f, std::make_integer_sequence<int, E - B>{}); }
+
+// 32 = 4 x 8:  n = 8 n1 + n2,  k = k1 + 4 k2:   X[k1 + 4 k2] = sum_n2 W8^(n2 k2) W32^(n2 k1) sum_n1 W4^(n1 k1) x[8 n1 + n2]
+constexpr double c32tab[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                              0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785, 0.0};
+constexpr double cos32(int m) { m = ((m % 32) + 32) % 32; if (m > 16) m = 32 - m; return m <= 8 ? c32tab[m] : -c32tab[16 - m]; }
+constexpr double sin32(int m) { return cos32(m - 8); }
+template <typename T> struct Bfly<T, 32> {
+  using T2 = typename Cx<T>::type;
+  __device__ __forceinline__ static void run(T2* v) {
+    T2 a[8][4];                                   // a[n2][k1]
+#pragma unroll
+    for (int n2 = 0; n2 < 8; n2++) {
+      T2 x0 = v[n2], x1 = v[8 + n2], x2 = v[16 + n2], x3 = v[24 + n2];
+      bf4(x0, x1, x2, x3);
+      a[n2][0] = x0; a[n2][1] = x1; a[n2][2] = x2; a[n2][3] = x3;
+    }
+    // W32^(n2 k1): the roots are compile-time constants (constexpr evaluation only -- the table above does not exist on the device)
+    static_for<1, 8>([&](auto n2c) {
+      constexpr int n2 = decltype(n2c)::value;
+      static_for<1, 4>([&](auto k1c) {
+        constexpr int k1 = decltype(k1c)::value;
+        constexpr double c = cos32(n2 * k1), sn = sin32(n2 * k1);
+        a[n2][k1] = cmul(a[n2][k1], T2{(T)c, (T)(-sn)});
+      });
+    });
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) {
+      T2 w[8];
+#pragma unroll
+      for (int n2 = 0; n2 < 8; n2++) w[n2] = a[n2][k1];
+      Bfly<T, 8>::run(w);
+#pragma unroll
+      for (int k2 = 0; k2 < 8; k2++) v[k1 + 4 * k2] = w[k2];
+    }
   }
 };
 
@@ -390,10 +445,10 @@ __device__ __forceinline__ void fill_tilebase(const FastStage& st, RunTab& rt, i
 
 // SCALED: every output is multiplied by st.scale on its way out (the drivers' normalisation pass, mult_array in
 // sample/C/driver_*.c, fused into the store); a separate instantiation, so the unscaled kernels are unchanged.
-template <typename T, int N, int RB, bool SWAP, bool SCALED = false>
-__global__ void __launch_bounds__(CCfg<T, N, RB>::NT, CCfg<T, N, RB>::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
+// C: the configuration (schedule, threads); the default is the table above, CCfgR32 selects the two-pass variant
+template <typename T, int N, int RB, bool SWAP, bool SCALED = false, class C = CCfg<T, N, RB>>
+__global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
-  using C = CCfg<T, N, RB>;
   using S = typename C::S;
   constexpr int TX = C::TX, NT = C::NT, L = S::L;
   constexpr bool SWZ = (TX * sizeof(T2) == 64);
@@ -484,6 +539,13 @@ __global__ void __launch_bounds__(CCfg<T, N, RB>::NT, CCfg<T, N, RB>::MINB) csta
     }
     __syncthreads();      // the tile buffer and the tile bases of this parity are reused
   }
+}
+
+// two-pass variant: the same kernel with the CCfgR32 configuration
+
+template <typename T, int N> constexpr size_t cstage_r32_smem() {
+  using T2 = typename Cx<T>::type;
+  return sizeof(T2) * N * CCfgR32<T, N>::TX + 2 * sizeof(long long) * N + sizeof(RunTab);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -59,12 +59,17 @@ typedef double emu_real;
 
 // runs one resolved stage (seg.base set by the caller) with the specialised kernels; returns 0, 1 if no specialised
 // kernel takes this stage (the generic kernel would), or a negative error
+static int g_last_variant = 0;
+extern "C" int emu_last_variant(void) { return g_last_variant; }      // kernel variant of the last stage (fast.h, FastStage.variant)
+
 extern "C" int emu_run_fast(const P3dStage* st) {
+  g_last_variant = 0;
   if (!p3d::fast_supported<emu_real>(*st)) return 1;
   p3d::FastStage fs;
   p3d::to_fast(*st, fs, sizeof(emu_real));
-  std::vector<emu_real> tw(2 * p3d::fast_twiddle_elems<emu_real>(st->kind, st->nfft) + 2);
-  p3d::fast_twiddle_fill<emu_real>(st->kind, st->nfft, tw.data());
+  fs.variant = g_last_variant = p3d::fast_variant<emu_real>(*st);
+  std::vector<emu_real> tw(2 * p3d::fast_twiddle_elems<emu_real>(st->kind, st->nfft, fs.variant) + 2);
+  p3d::fast_twiddle_fill<emu_real>(st->kind, st->nfft, tw.data(), fs.variant);
   fs.tw = tw.data();
   cudaError_t e = p3d::launch_fast<emu_real>(*st, fs, nullptr);
   if (e == cudaErrorMisalignedAddress) return 1;

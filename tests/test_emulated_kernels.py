@@ -198,3 +198,28 @@ def test_emulated_kernels_uneven_multi_rank_and_many():
     assert generic == 0
     fast, generic = transform_world((64, 64, 64), (2, 2), None, "fft", "tff", nv=2)
     assert generic == 0 and fast == 24
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_emulated_two_pass_variant(monkeypatch, single):
+    """opt-in 1024 = 32 x 32 and 512 = 16 x 32 schedules (P3DFFT_B200_R32=1): radix-32 butterfly, their own twiddle blocks"""
+    monkeypatch.setenv("P3DFFT_B200_R32", "1")
+    h = emu(single)
+    nx = 64 if single else 16                 # (single precision: every stage must be a specialised one, see above)
+    for n, cut in (((nx, 1024, 64 if single else 16), None), ((nx, 64 if single else 16, 512), (nx, 64 if single else 16, 340))):
+        fast, generic = transform_world(n, (1, 1), cut, "fft", "tff", single=single)
+        assert fast == (6 if single else 2)
+    # the variant really ran for the last (1024- or 512-point) c2c stage of a transform, and is off without the switch
+    monkeypatch.delenv("P3DFFT_B200_R32")
+    steps, _ = pb.load(single).plan_steps((1, 1), 64, 512, 64, 0, False, "fft")
+    st = steps[1].st
+    w = int(pb.load(single).plan_decomp((1, 1), 64, 512, 64).work_elems)
+    ct = np.complex64 if single else np.complex128
+    bufs = {b: np.zeros(w, dtype=ct) for b in (pb.BUF_A, pb.BUF_B, pb.BUF_C)}
+    for si, side in enumerate((st.inp, st.out)):
+        for g in range(side.nseg):
+            sg = side.seg[g]
+            sg.base = bufs[sg.buf].ctypes.data + sg.off * (8 if single else 16)
+    assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 0
+    monkeypatch.setenv("P3DFFT_B200_R32", "1")
+    assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 1
