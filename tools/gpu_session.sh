@@ -1,0 +1,51 @@
+#!/bin/bash
+# One gpurun call's worth of measurements (1 GPU).  Replaces the per-experiment scratch scripts of round 1.
+#   gpurun --timeout 900 -- 'bash tools/gpu_session.sh all'
+# Sections: tests | ab | sanitize | ncu | aux        (results under gpurun_out/)
+cd "$(dirname "$0")/.." || exit 1
+mkdir -p gpurun_out
+what=${1:-all}
+
+if [[ $what == all || $what == tests ]]; then
+  python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -5 | tee gpurun_out/tests.log
+fi
+
+if [[ $what == all || $what == ab ]]; then
+  # A/B of the switchable kernel variants on the headline size: per-stage times from the library's timers
+  {
+    TAG="default      " python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
+    TAG="R32 two-pass " P3DFFT_B200_R32=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
+    TAG="split always " P3DFFT_B200_SPLIT=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
+    TAG="R32 512^3    " P3DFFT_B200_R32=1 python tools/prof_pair.py --size 512 --pairs 12 --warm 2
+    TAG="default 512^3" python tools/prof_pair.py --size 512 --pairs 12 --warm 2
+    TAG="R32 single   " P3DFFT_B200_R32=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2 --single
+    TAG="default singl" python tools/prof_pair.py --size 1024 --pairs 6 --warm 2 --single
+  } 2>&1 | tee gpurun_out/ab.log
+  # the variants must pass the same parity tests as the defaults
+  P3DFFT_B200_R32=1 python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider -k "fast_kernels or large" 2>&1 | tail -3 | tee -a gpurun_out/ab.log
+fi
+
+if [[ $what == all || $what == sanitize ]]; then
+  {
+    for sz in "64 64 64" "256 128 64" "128 64 1024" "1024 64 128"; do
+      echo "== memcheck $sz"; timeout 120 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/prof_pair.py --size $sz --pairs 1 2>&1 | tail -3
+    done
+    for sz in "64 64 64" "128 32 1024" "1024 16 64"; do
+      echo "== racecheck $sz"; timeout 150 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/prof_pair.py --size $sz --pairs 1 2>&1 | tail -3
+      echo "== racecheck R32 $sz"; P3DFFT_B200_R32=1 timeout 150 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/prof_pair.py --size $sz --pairs 1 2>&1 | tail -3
+    done
+  } | tee gpurun_out/sanitizer.log
+fi
+
+if [[ $what == all || $what == ncu ]]; then
+  ncu --set full --import-source on --clock-control none -k regex:"xr2c|cstage|xc2r" -c 6 -o gpurun_out/stages -f \
+      python tools/prof_pair.py --size 1024 --pairs 1 > gpurun_out/ncu_stages.log 2>&1
+  P3DFFT_B200_R32=1 ncu --set full --import-source on --clock-control none -k regex:"cstage" -c 4 -o gpurun_out/stages_r32 -f \
+      python tools/prof_pair.py --size 1024 --pairs 1 > gpurun_out/ncu_stages_r32.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
+fi
+
+if [[ $what == all || $what == aux ]]; then
+  python tools/bench_aux.py 1024 | tee gpurun_out/aux_bench.json
+fi
