@@ -486,8 +486,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
       if (stg.kind == P3D_RCOPY) e = p3d::launch_rcopy<real_t>(stg, st);
       else if (!L.force_generic && p3d::fast_supported<real_t>(stg)) {
         p3d::FastStage fs;
-        p3d::to_fast(stg, fs, sizeof(real_t));
-        fs.variant = p3d::fast_variant<real_t>(stg);
+        p3d::to_fast(stg, fs, sizeof(real_t), p3d::fast_variant<real_t>(stg));
         fs.tw = fast_twiddle_block(stg.kind, stg.nfft, fs.variant);
         if (!fs.tw) { report(true, "P3DFFT(B200): cannot allocate twiddle table"); return false; }
         e = p3d::launch_fast<real_t>(stg, fs, st);

@@ -48,7 +48,7 @@ struct FastStage {
   FastSide in, out;
   double scale;          // multiplies every output (SCALED instantiations only; last member: the unscaled kernels'
                          // parameter layout does not depend on it)
-  int32_t variant;       // 0: default schedules; 1: two-pass radix-32 variant (fast_variant, opt-in)
+  int32_t variant;       // 0: default; 1: two-pass radix-32 c2c schedules; 2: wide X tiles (fast_variant, opt-in)
   int32_t pad2_;
 };
 
@@ -60,7 +60,7 @@ template <typename T> int fast_variant(const P3dStage& st);
 template <typename T> size_t fast_twiddle_elems(int kind, int nfft, int variant = 0);
 template <typename T> void fast_twiddle_fill(int kind, int nfft, void* host, int variant = 0);
 // converts resolved segments (seg.base set) into runs; real_bytes = sizeof(real)
-void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes);
+void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes, int variant = 0);
 template <typename T> cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t stream);
 
 }  // namespace p3d

@@ -100,8 +100,9 @@ static int row_bytes(const P3dStage& st) {
 }
 
 template <typename T>
-static int tile_lines(const P3dStage& st) {
+static int tile_lines(const P3dStage& st, int variant = 0) {
   int tx = 1;
+  if (is_x(st.kind) && variant == 2) return XCfgWide<double, 512>::TX;
   if (is_x(st.kind)) dispatch_x(st.n / 2, [&](auto h) { tx = XCfg<T, decltype(h)::value>::TX; });
   else tx = row_bytes<T>(st) / (2 * (int)sizeof(T));
   return tx;
@@ -155,8 +156,12 @@ bool dispatch_r32(int n, F&& f) {
 template <typename T>
 int fast_variant(const P3dStage& st) {
   const char* e = getenv("P3DFFT_B200_R32");
+  if (is_x(st.kind)) {          // wide X tiles (variant 2)
+    const char* x = getenv("P3DFFT_B200_XTX8");
+    return (x && atoi(x) != 0 && st.n % 2 == 0 && xcfg_wide_exists(st.n / 2, (int)sizeof(T))) ? 2 : 0;
+  }
   if (!e || atoi(e) == 0) return 0;
-  if (is_x(st.kind) || !ccfg_r32_exists(st.nfft)) return 0;
+  if (!ccfg_r32_exists(st.nfft)) return 0;
   return row_bytes<T>(st) == 128 ? 1 : 0;
 }
 
@@ -202,9 +207,10 @@ static void side_to_runs(const P3dSide& sd, FastSide& f, size_t esz, int tx) {
   }
 }
 
-void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes) {
+void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes, int variant) {
   memset(&f, 0, sizeof f);
-  const int tx = real_bytes == 4 ? tile_lines<float>(st) : tile_lines<double>(st);
+  const int tx = real_bytes == 4 ? tile_lines<float>(st, variant) : tile_lines<double>(st, variant);
+  f.variant = variant;
   f.na = st.na; f.nb = st.nb; f.nc = st.nc; f.n = st.n;
   f.mirror = st.kind == P3D_DCT1;
   static const int pf = getenv("P3DFFT_B200_PREFETCH") ? atoi(getenv("P3DFFT_B200_PREFETCH")) : 131072;
@@ -269,6 +275,22 @@ static cudaError_t launch_x(const P3dStage& st, const FastStage& f, cudaStream_t
   if (st.kind == P3D_R2C) P3D_LAUNCH(xr2c_kernel<T, HH>);
   else if (f.scale != 1.0) P3D_LAUNCH(xc2r_kernel<T, HH, true>);
   else P3D_LAUNCH(xc2r_kernel<T, HH>);
+  return cudaGetLastError();
+}
+
+// wide X tiles (opt-in, double, nx = 1024)
+static cudaError_t launch_x_wide(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  using T = double;
+  using C = XCfgWide<double, 512>;
+  constexpr int TX = C::TX, NT = C::NT, HH = 512;
+  constexpr size_t smem = xstage_smem<T, HH, C>();
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb * st.nc;
+  if (tiles <= 0) return cudaSuccess;
+  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
+  cudaError_t e;
+  if (st.kind == P3D_R2C) P3D_LAUNCH(xr2c_kernel<T, HH, C>);
+  else if (f.scale != 1.0) P3D_LAUNCH(xc2r_kernel<T, HH, true, C>);
+  else P3D_LAUNCH(xc2r_kernel<T, HH, false, C>);
   return cudaGetLastError();
 }
 
@@ -346,6 +368,9 @@ cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t str
   cudaError_t err = cudaErrorInvalidValue;
   if (f.variant == 1 && !is_x(st.kind) && f.rowb == 128) {
     if (dispatch_r32(st.nfft, [&](auto nn) { err = launch_r32<T, decltype(nn)::value>(st, f, stream); })) return err;
+  }
+  if (is_x(st.kind) && f.variant == 2) {
+    if constexpr (std::is_same<T, double>::value) return launch_x_wide(st, f, stream);
   }
   if (is_x(st.kind)) dispatch_x(st.n / 2, [&](auto h) { err = launch_x<T, decltype(h)::value>(st, f, stream); });
   else dispatch_c(st.nfft, [&](auto nn) {

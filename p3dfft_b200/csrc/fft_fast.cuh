@@ -139,6 +139,14 @@ P3D_XCFG(float, 512, P3D_RS(8, 8, 8), 8, 256, 3, 6, 0)
 P3D_XCFG(float, 1024, P3D_RS(8, 16, 8), 8, 512, 2, 7, 0)
 #undef P3D_XCFG
 #undef P3D_RS
+// Wide X tiles (opt-in, P3DFFT_B200_XTX8=1): 8 lines per tile instead of 4 for nx = 1024 in double, so that the pieces the X
+// stage moves on the blocked X<->Y buffer are 1 KB instead of 512 B.  Same schedule and swizzle; not yet timed on hardware.
+template <typename T, int HH> struct XCfgWide;
+template <> struct XCfgWide<double, 512> {
+  using S = RS<8, 8, 8>;
+  static constexpr int H = 512, TX = 8, NT = 256, MINB = 2, SA = 6, SB = 0, LP = 512 + 4;
+};
+constexpr bool xcfg_wide_exists(int h, int real_bytes) { return h == 512 && real_bytes == 8; }
 
 #if defined(__CUDACC__) || defined(P3D_EMULATE)      // P3D_EMULATE: host emulation of the kernels (tests/emu, CPU tests)
 // ---------------------------------------------------------------------------------------
@@ -773,10 +781,9 @@ __device__ __forceinline__ void r2c_combine(T2 zk, T2 zm, T2 w, T2& xk, T2& xm) 
   xm = cconj(csub(e, wo));
 }
 
-template <typename T, int H>
-__global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(const __grid_constant__ FastStage st) {
+template <typename T, int H, class C = XCfg<T, H>>
+__global__ void __launch_bounds__(C::NT, C::MINB) xr2c_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
-  using C = XCfg<T, H>;
   using S = typename C::S;
   constexpr int TX = C::TX, NT = C::NT, L = S::L;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -899,9 +906,9 @@ __global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xr2c_kernel(
   }
 }
 
-template <typename T, int H> constexpr size_t xstage_smem() {
+template <typename T, int H, class C = XCfg<T, H>> constexpr size_t xstage_smem() {
   using T2 = typename Cx<T>::type;
-  return sizeof(T2) * XCfg<T, H>::LP * XCfg<T, H>::TX + (sizeof(long long) + sizeof(char*)) * (H + 1) +
+  return sizeof(T2) * C::LP * C::TX + (sizeof(long long) + sizeof(char*)) * (H + 1) +
          sizeof(char*) * 2 * P3D_MAXRUN + sizeof(int) * (H + 2);
 }
 
@@ -922,10 +929,9 @@ __device__ __forceinline__ void c2r_combine(T2 xk, T2 xm, T2 w, T2& zk, T2& zm) 
   zm = cswap(bb);
 }
 
-template <typename T, int H, bool SCALED = false>
-__global__ void __launch_bounds__(XCfg<T, H>::NT, XCfg<T, H>::MINB) xc2r_kernel(const __grid_constant__ FastStage st) {
+template <typename T, int H, bool SCALED = false, class C = XCfg<T, H>>
+__global__ void __launch_bounds__(C::NT, C::MINB) xc2r_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
-  using C = XCfg<T, H>;
   using S = typename C::S;
   constexpr int TX = C::TX, NT = C::NT, L = S::L;
   extern __shared__ __align__(128) unsigned char smem_raw[];

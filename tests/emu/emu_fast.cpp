@@ -66,8 +66,8 @@ extern "C" int emu_run_fast(const P3dStage* st) {
   g_last_variant = 0;
   if (!p3d::fast_supported<emu_real>(*st)) return 1;
   p3d::FastStage fs;
-  p3d::to_fast(*st, fs, sizeof(emu_real));
-  fs.variant = g_last_variant = p3d::fast_variant<emu_real>(*st);
+  p3d::to_fast(*st, fs, sizeof(emu_real), p3d::fast_variant<emu_real>(*st));
+  g_last_variant = fs.variant;
   std::vector<emu_real> tw(2 * p3d::fast_twiddle_elems<emu_real>(st->kind, st->nfft, fs.variant) + 2);
   p3d::fast_twiddle_fill<emu_real>(st->kind, st->nfft, tw.data(), fs.variant);
   fs.tw = tw.data();

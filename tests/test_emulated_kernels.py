@@ -223,3 +223,15 @@ def test_emulated_two_pass_variant(monkeypatch, single):
     assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 0
     monkeypatch.setenv("P3DFFT_B200_R32", "1")
     assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 1
+
+
+def test_emulated_wide_x_tiles(monkeypatch):
+    """opt-in 8-line X tiles for nx = 1024 in double (P3DFFT_B200_XTX8=1): r2c and c2r, one rank and 2 x 2 with peer stores"""
+    monkeypatch.setenv("P3DFFT_B200_XTX8", "1")
+    fast, generic = transform_world((1024, 16, 16), (1, 1), None, "fft", "tff")
+    assert (fast, generic) == (2, 4) and emu().emu_last_variant() == 2      # the last stage of the backward transform is X c2r
+    fast, generic = transform_world((1024, 20, 12), (2, 2), (680, 20, 12), "fft", "tff", p2p=True)
+    assert fast == 8
+    monkeypatch.delenv("P3DFFT_B200_XTX8")
+    transform_world((1024, 16, 16), (1, 1), None, "fft", "tff")
+    assert emu().emu_last_variant() == 0
