@@ -60,6 +60,10 @@ void p3dfft_b200_force_generic(int on);
  * receive buffer over NVLink and the exchange step is only a barrier.  on = 0 keeps grouped
  * ncclSend/ncclRecv.  Must precede p3dfft_setup (also env P3DFFT_B200_P2P=0/1).               */
 void p3dfft_b200_set_p2p(int on);
+/* env P3DFFT_B200_OVERLAP=C (opt-in, experimental): the last two stages of a peer-to-peer transform run as C chunks, the
+ * local consumer chunks on a second stream beside the NVLink-bound producer (P3DFFT_B200_OVERLAP_SMS = SMs left to them);
+ * the per-stage timers then only cover the producer side.
+ * env P3DFFT_B200_R32=1 / P3DFFT_B200_XTX8=1 (opt-in, experimental): two-pass 512/1024-point schedules / 8-line X tiles.  */
 /* env P3DFFT_B200_FLAGBAR=1 (opt-in, experimental): the barrier that orders the peer-to-peer transposes becomes a
  * one-CTA kernel exchanging epoch flags through peer-mapped memory instead of a one-float NCCL all-reduce.         */
 int p3dfft_b200_p2p_active(void);
@@ -133,7 +137,8 @@ typedef struct {
 
 /* flags: bit0 = single precision (sizes the blocked layouts), bit1 = STRIDE1, bit2 = DIMS_C,
  * bit3 = plain (reference) internal layouts, bit4 = peer-to-peer plan, bit5 / bit6 = force 64- / 128-byte
- * tile rows (default: the planner's rule).  Returns 0, or -1 and records the reference's
+ * tile rows (default: the planner's rule); bits 8-15 (plan_steps only): number of chunks of the pipelined tail
+ * (P3DFFT_B200_OVERLAP, peer-to-peer plans).  Returns 0, or -1 and records the reference's
  * error text (retrievable with p3dfft_b200_last_error).                                   */
 int p3dfft_b200_plan_decomp(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc,
                             int flags, p3dfft_b200_decomp* out);

@@ -107,7 +107,7 @@ int g_next_handle = 1;
 // the plan (module-global state of the reference)
 // ------------------------------------------------------------------------------------
 struct PlanKey {
-  int backward, nv; char op; long long dim_real, dim_cplx; int w, p2p;
+  int backward, nv; char op; long long dim_real, dim_cplx; int w, p2p;      // p2p: bit 0 peer-to-peer, bits 8.. overlap chunks
   bool operator<(const PlanKey& o) const {
     return std::tie(backward, nv, op, dim_real, dim_cplx, w, p2p) <
            std::tie(o.backward, o.nv, o.op, o.dim_real, o.dim_cplx, o.w, o.p2p);
@@ -146,6 +146,12 @@ struct Lib {
   long long work_elems_alloc = 0;   // complex elements per work buffer
   bool rtran_sized = false;         // the buffers already cover rtran_work_elems()
   std::map<int, p3d::TransformPlan> aux_plans;     // r2c_1d (key 100) and rtran (key which*2 + p2p) plans
+  // opt-in pipelined tail of the peer-to-peer plans (P3DFFT_B200_OVERLAP=C chunks; plan.h split_for_overlap): the consumer
+  // chunks run on a side stream, on at most overlap_sms SMs while the producer keeps the rest (not yet run on hardware)
+  int overlap = 0, overlap_sms = 56;
+  cudaStream_t side_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
+  cudaEvent_t side_done = nullptr;
   double scale_fwd = 1.0, scale_bwd = 1.0;          // fused output normalisation (p3dfft_b200_set_scale)
   double* spec_dev = nullptr; int spec_bins = 0;   // device accumulator of p3dfft_b200_spectrum
   p3d::ProcMap procmap;                            // proc_id2coords / proc_dims tables (setup.F90:224-230, 551-577)
@@ -379,7 +385,8 @@ bool finalize_plan(p3d::TransformPlan& tp) {
 }
 
 p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long dim_real, long long dim_cplx) {
-  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx, L.W(), L.p2p ? 1 : 0};
+  const int chunks = (L.p2p && L.overlap > 1) ? L.overlap : 0;
+  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx, L.W(), (L.p2p ? 1 : 0) | (chunks << 8)};
   auto it = L.plans.find(key);
   if (it != L.plans.end()) return &it->second;
   p3d::TransformPlan tp = p3d::build_plan(L.d, backward, op, nv, dim_real, dim_cplx, L.W(), L.p2p);
@@ -388,6 +395,7 @@ p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long di
     report(true, "%s", tp.error.c_str());
     return nullptr;
   }
+  if (chunks > 1) p3d::split_for_overlap(tp, chunks, L.W());
   if (!finalize_plan(tp)) return nullptr;
   auto res = L.plans.emplace(key, std::move(tp));
   return &res.first->second;
@@ -449,17 +457,68 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
   std::vector<int> slots;
   std::vector<char> is_ex;
   const size_t nsteps = tp->steps.size();
-  size_t last_stage = nsteps;      // out_scale is fused into the stores of the transform's last stage
-  for (size_t i = 0; i < nsteps; i++) if (!tp->steps[i].is_exchange) last_stage = i;
+  int nchunks = 0;                 // pipelined tail: chunk ids 0 .. nchunks-1
+  for (auto& s : tp->steps) if (s.chunk + 1 > nchunks) nchunks = s.chunk + 1;
+  bool used_side = false;
+  // resolves the segment bases of a stage and launches it on stream sx; sm_cap > 0 limits a persistent grid to that many SMs
+  auto launch = [&](const P3dStage& planned, cudaStream_t sx, int sm_cap) -> bool {
+    P3dStage stg = planned;
+    if (out_scale != 1.0 && stg.out.nseg > 0 && stg.out.seg[0].buf == P3D_BUF_USER_OUT) stg.scale *= out_scale;   // the transform's last stage
+    for (int side = 0; side < 2; side++) {
+      P3dSide& sd = side ? stg.out : stg.in;
+      const size_t esz = side_elem_bytes(stg.kind, side);
+      for (int g = 0; g < sd.nseg; g++) {
+        P3dSeg& sg = sd.seg[g];
+        char* base = sg.buf == P3D_BUF_USER_IN ? (char*)din : sg.buf == P3D_BUF_USER_OUT ? (char*)dout : (char*)L.buf[sg.buf];
+        if (sg.peer >= 0) base = (char*)L.peer_buf[(size_t)sg.peer * 3 + (sg.buf - P3D_BUF_A)];     // NVLink peer mapping
+        sg.base = base + sg.off * esz;
+      }
+    }
+    cudaError_t e = cudaErrorMisalignedAddress;
+    if (stg.kind == P3D_RCOPY) e = p3d::launch_rcopy<real_t>(stg, sx);
+    else if (!L.force_generic && p3d::fast_supported<real_t>(stg)) {
+      p3d::FastStage fs;
+      p3d::to_fast(stg, fs, sizeof(real_t), p3d::fast_variant<real_t>(stg));
+      fs.tw = fast_twiddle_block(stg.kind, stg.nfft, fs.variant);
+      if (!fs.tw) { report(true, "P3DFFT(B200): cannot allocate twiddle table"); return false; }
+      fs.sm_cap = sm_cap;
+      e = p3d::launch_fast<real_t>(stg, fs, sx);
+      if (e == cudaSuccess) L.fast_launches++;
+    }
+    if (e == cudaErrorMisalignedAddress) e = p3d::launch_stage<real_t>(stg, sx);   // any length / alignment
+    if (e != cudaSuccess) { report(true, "P3DFFT(B200): stage launch failed: %s", cudaGetErrorString(e)); return false; }
+    L.launches++;
+    return true;
+  };
+  int sms = 148;
+  if (nchunks > 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    if (!L.side_stream) CUDA_OK(cudaStreamCreateWithFlags(&L.side_stream, cudaStreamNonBlocking));
+    if (!L.side_done) CUDA_OK(cudaEventCreateWithFlags(&L.side_done, cudaEventDisableTiming));
+    while ((int)L.chunk_events.size() < nchunks) {
+      cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.chunk_events.push_back(ev);
+    }
+  }
+  const int side_sms = L.overlap_sms > 0 && L.overlap_sms < sms ? L.overlap_sms : sms / 3;
   bool pre_done = false;      // the barrier that protects the receive buffer of the NEXT exchange has been issued
   for (size_t i = 0; i < nsteps; i++) {
     auto& s = tp->steps[i];
+    if (!s.is_exchange && s.side) {
+      // consumer chunk of the pipelined tail: side stream, after this chunk's barrier; the last one has the GPU to itself
+      CUDA_OK(cudaStreamWaitEvent(L.side_stream, L.chunk_events[s.chunk], 0));
+      if (!launch(s.st, L.side_stream, s.chunk + 1 < nchunks ? side_sms : 0)) return false;
+      used_side = true;
+      continue;
+    }
     // Peer-to-peer plans: the stage in front of an exchange stores into the peers' receive buffer.  If that buffer
     // was handed to a consumer stage since the last barrier, a peer may still be reading it (write-after-read
     // across ranks): barrier first.  Decided from the exchange steps alone, identically on every rank -- a rank
-    // whose producing stage is empty issues the same barrier when it reaches the exchange.
+    // whose producing stage is empty issues the same barrier when it reaches the exchange.  (Chunks after the first
+    // of a pipelined tail store into other regions of the buffer their group was already cleared for.)
     const P3dExchange* nex = s.is_exchange ? &s.ex : (i + 1 < nsteps && tp->steps[i + 1].is_exchange ? &tp->steps[i + 1].ex : nullptr);
-    if (nex && nex->p2p && !pre_done && L.dirty[nex->recvbuf]) {
+    if (nex && nex->p2p && !pre_done && L.dirty[nex->recvbuf] && s.chunk <= 0) {
       if (timed) { cudaEventRecord(get_event(nev++), st); slots.push_back(nex->timer); is_ex.push_back(1); }
       if (!world_barrier(st)) return false;
     }
@@ -467,36 +526,18 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     if (timed) { cudaEventRecord(get_event(nev++), st); }
     if (s.is_exchange) {
       if (!run_exchange(s.ex, st)) return false;
-      L.dirty[s.ex.recvbuf] = true;
+      if (s.chunk >= 0) CUDA_OK(cudaEventRecord(L.chunk_events[s.chunk], st));
+      if (s.chunk < 0 || s.chunk + 1 == nchunks) L.dirty[s.ex.recvbuf] = true;
       slots.push_back(s.ex.timer); is_ex.push_back(1);
     } else {
-      P3dStage stg = s.st;
-      if (i == last_stage && out_scale != 1.0) stg.scale *= out_scale;
-      for (int side = 0; side < 2; side++) {
-        P3dSide& sd = side ? stg.out : stg.in;
-        const size_t esz = side_elem_bytes(stg.kind, side);
-        for (int g = 0; g < sd.nseg; g++) {
-          P3dSeg& sg = sd.seg[g];
-          char* base = sg.buf == P3D_BUF_USER_IN ? (char*)din : sg.buf == P3D_BUF_USER_OUT ? (char*)dout : (char*)L.buf[sg.buf];
-          if (sg.peer >= 0) base = (char*)L.peer_buf[(size_t)sg.peer * 3 + (sg.buf - P3D_BUF_A)];     // NVLink peer mapping
-          sg.base = base + sg.off * esz;
-        }
-      }
-      cudaError_t e = cudaErrorMisalignedAddress;
-      if (stg.kind == P3D_RCOPY) e = p3d::launch_rcopy<real_t>(stg, st);
-      else if (!L.force_generic && p3d::fast_supported<real_t>(stg)) {
-        p3d::FastStage fs;
-        p3d::to_fast(stg, fs, sizeof(real_t), p3d::fast_variant<real_t>(stg));
-        fs.tw = fast_twiddle_block(stg.kind, stg.nfft, fs.variant);
-        if (!fs.tw) { report(true, "P3DFFT(B200): cannot allocate twiddle table"); return false; }
-        e = p3d::launch_fast<real_t>(stg, fs, st);
-        if (e == cudaSuccess) L.fast_launches++;
-      }
-      if (e == cudaErrorMisalignedAddress) e = p3d::launch_stage<real_t>(stg, st);   // any length / alignment
-      if (e != cudaSuccess) { report(true, "P3DFFT(B200): stage launch failed: %s", cudaGetErrorString(e)); return false; }
-      L.launches++;
-      slots.push_back(stg.timer); is_ex.push_back(0);
+      // producer chunks behind the first leave side_sms SMs to the consumer chunk running beside them
+      if (!launch(s.st, st, s.chunk > 0 ? sms - side_sms : 0)) return false;
+      slots.push_back(s.st.timer); is_ex.push_back(0);
     }
+  }
+  if (used_side) {               // everything behind this point (epilogues, copies, the next call) is ordered after the side stream
+    CUDA_OK(cudaEventRecord(L.side_done, L.side_stream));
+    CUDA_OK(cudaStreamWaitEvent(st, L.side_done, 0));
   }
   if (cheby) {
     // p3dfft_cheby epilogue, ftran.F90:408-451
@@ -624,6 +665,8 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   if (getenv("P3DFFT_B200_P2P")) L.want_p2p = atoi(getenv("P3DFFT_B200_P2P")) != 0;
   if (getenv("P3DFFT_B200_ROWB")) L.force_row_bytes = atoi(getenv("P3DFFT_B200_ROWB"));
   if (getenv("P3DFFT_B200_FLAGBAR")) L.want_flagbar = atoi(getenv("P3DFFT_B200_FLAGBAR")) != 0;
+  if (getenv("P3DFFT_B200_OVERLAP")) L.overlap = atoi(getenv("P3DFFT_B200_OVERLAP"));
+  if (getenv("P3DFFT_B200_OVERLAP_SMS")) L.overlap_sms = atoi(getenv("P3DFFT_B200_OVERLAP_SMS"));
   for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
   L.procmap.init(L.d);
   L.nv_preset = 0;
@@ -715,6 +758,10 @@ void p3dfft_clean(void) {
   if (L.bar_flags) { cudaFree(L.bar_flags); L.bar_flags = nullptr; }
   if (L.peer_flags_dev) { cudaFree(L.peer_flags_dev); L.peer_flags_dev = nullptr; }
   if (L.spec_dev) { cudaFree(L.spec_dev); L.spec_dev = nullptr; L.spec_bins = 0; }
+  if (L.side_stream) { cudaStreamSynchronize(L.side_stream); cudaStreamDestroy(L.side_stream); L.side_stream = nullptr; }
+  for (auto ev : L.chunk_events) cudaEventDestroy(ev);
+  L.chunk_events.clear();
+  if (L.side_done) { cudaEventDestroy(L.side_done); L.side_done = nullptr; }
   for (int b = P3D_BUF_A; b <= P3D_BUF_C; b++) if (L.buf[b]) { cudaFree(L.buf[b]); L.buf[b] = nullptr; }
   if (L.stage_in) { cudaFree(L.stage_in); L.stage_in = nullptr; L.stage_in_bytes = 0; }
   if (L.stage_out) { cudaFree(L.stage_out); L.stage_out = nullptr; L.stage_out_bytes = 0; }
@@ -957,11 +1004,14 @@ int p3dfft_b200_plan_steps(const int* dims, int nx, int ny, int nz, int rank, in
                                           (flags & 8) ? 0 : p3d::pick_W(ny, nz, 2 * elem_bytes, (flags & 32) ? 64 : (flags & 64) ? 128 : 0),
                                           (flags & 16) != 0 && !(flags & 8));
   if (!tp.error.empty()) { g_last_error = tp.error; return -1; }
+  const int nchunk = (flags >> 8) & 0xff;       // pipelined tail (split_for_overlap), peer-to-peer plans only
+  if (nchunk > 1) p3d::split_for_overlap(tp, nchunk, (flags & 8) ? 0 : p3d::pick_W(ny, nz, 2 * elem_bytes, (flags & 32) ? 64 : (flags & 64) ? 128 : 0));
   if ((int)tp.steps.size() > max_steps) { g_last_error = "step array too small"; return -1; }
   P3dStepC* out = (P3dStepC*)steps;
   for (size_t i = 0; i < tp.steps.size(); i++) {
     memset(&out[i], 0, sizeof out[i]);
     out[i].is_exchange = tp.steps[i].is_exchange ? 1 : 0;
+    out[i].pad_ = (tp.steps[i].side ? 1 : 0) | ((tp.steps[i].chunk + 1) << 8);      // bit 0: side stream; bits 8..: chunk + 1
     out[i].st = tp.steps[i].st;
     out[i].ex = tp.steps[i].ex;
     if (!tp.steps[i].is_exchange)

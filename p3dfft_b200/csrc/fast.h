@@ -49,7 +49,7 @@ struct FastStage {
   double scale;          // multiplies every output (SCALED instantiations only; last member: the unscaled kernels'
                          // parameter layout does not depend on it)
   int32_t variant;       // 0: default; 1: two-pass radix-32 c2c schedules; 2: wide X tiles (fast_variant, opt-in)
-  int32_t pad2_;
+  int32_t sm_cap;        // > 0: the persistent grid uses at most this many SMs (pipelined tail, api.cpp); host side only
 };
 
 // true when a specialised kernel exists for this stage (kind, length, strides, alignment)

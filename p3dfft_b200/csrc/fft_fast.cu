@@ -245,11 +245,12 @@ static int sm_count() {
 
 // persistent grid: as many CTAs as stay resident (occupancy query, cached), never more than tiles
 template <typename K>
-static unsigned persistent_grid(K kernel, int nt, size_t smem, long long tiles, int& per_sm) {
+static unsigned persistent_grid(K kernel, int nt, size_t smem, long long tiles, int& per_sm, int sm_cap = 0) {
   if (per_sm <= 0) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem) != cudaSuccess || per_sm <= 0) per_sm = 1;
   }
-  const long long g = (long long)per_sm * sm_count();
+  const int sms = sm_cap > 0 && sm_cap < sm_count() ? sm_cap : sm_count();
+  const long long g = (long long)per_sm * sms;
   return (unsigned)(tiles < g ? tiles : g);
 }
 
@@ -260,7 +261,7 @@ static unsigned persistent_grid(K kernel, int nt, size_t smem, long long tiles, 
     static bool cfg = false;                                                                                  \
     static int per_sm = 0;                                                                                    \
     if ((e = launch_cfg(__VA_ARGS__, smem, cfg)) != cudaSuccess) return e;                                    \
-    __VA_ARGS__<<<persistent_grid(__VA_ARGS__, NT, smem, tiles, per_sm), NT, smem, stream>>>(f);              \
+    __VA_ARGS__<<<persistent_grid(__VA_ARGS__, NT, smem, tiles, per_sm, f.sm_cap), NT, smem, stream>>>(f);              \
   } while (0)
 #endif
 

@@ -173,6 +173,8 @@ inline bool factorize(int n, int* fac, int* nfac, int maxprime = 4096) {
 
 struct Step {
   bool is_exchange = false;
+  int chunk = -1;        // >= 0: this step belongs to chunk `chunk` of a pipelined group (split_for_overlap)
+  bool side = false;     // consumer stage of a pipelined group: runs on the side stream after its chunk's barrier
   P3dStage st{};
   P3dExchange ex{};
 };
@@ -535,6 +537,64 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
     push_stage(s);
   }
   return tp;
+}
+
+// ------------------------------------------------------------------------------------
+// Pipelined tail of a peer-to-peer plan (opt-in, P3DFFT_B200_OVERLAP=C).
+//
+// On a multi-GPU grid the stage in front of the LAST exchange of a transform is bound by NVLink (its stores go to
+// the peers), the stage behind it is local and HBM-bound:  forward  Y -> T2 -> Z,  backward  Y -> T4 -> X.  Both
+// stages are split into C chunks along the batch axis they share (forward: the x blocks, dimension a; backward: the
+// z planes, dimension b); chunk c of the consumer only needs chunk c of the producer from every peer, so the list
+//     P_0  E_0  Q_0   P_1  E_1  Q_1  ...                       (E_c = barrier; Q_c marked `side`)
+// lets the executor run Q_c on a second stream while P_(c+1) is storing.  Chunks are equal on every rank in COUNT
+// (empty ones stay in the list, their barrier is still collective); a chunk is the same stage with smaller batch
+// extents and shifted segment offsets -- the kernels do not know about it.
+// Returns false (plan untouched) when the plan does not end in  stage, p2p exchange, stage.
+// ------------------------------------------------------------------------------------
+inline void shift_side(P3dSide& sd, bool along_a, long long x0) {
+  for (int g = 0; g < sd.nseg; g++) {
+    P3dSeg& s = sd.seg[g];
+    if (along_a) s.off += s.aw > 1 ? (x0 / s.aw) * s.sah + (x0 % s.aw) * s.sa : x0 * s.sa;
+    else         s.off += s.bw > 1 ? (x0 / s.bw) * s.sbh + (x0 % s.bw) * s.sb : x0 * s.sb;
+  }
+}
+
+inline bool split_for_overlap(TransformPlan& tp, int nchunk, int W) {
+  const size_t n = tp.steps.size();
+  if (nchunk < 2 || n < 3) return false;
+  Step& sp = tp.steps[n - 3]; Step& se = tp.steps[n - 2]; Step& sq = tp.steps[n - 1];
+  if (sp.is_exchange || !se.is_exchange || sq.is_exchange || !se.ex.p2p) return false;
+  const P3dStage P = sp.st, Q = sq.st;
+  const P3dExchange E = se.ex;
+  if (P.nc != Q.nc) return false;
+  bool along_a;
+  int total, gran;
+  if (Q.kind == P3D_C2R && P.nb == Q.nb) { along_a = false; total = P.nb; gran = 1; }            // backward: z planes
+  else if (Q.kind != P3D_C2R && P.na == Q.na) { along_a = true; total = P.na; gran = W > 0 ? W : 1; }   // forward: x blocks
+  else return false;
+  for (const P3dStage* st : {&P, &Q})       // blocked line groups must not be cut
+    for (const P3dSide* sd : {&st->in, &st->out})
+      for (int g = 0; g < sd->nseg; g++)
+        if (along_a && sd->seg[g].aw > 1 && gran % sd->seg[g].aw) return false;
+  const long long nblk = (total + gran - 1) / gran;
+  std::vector<Step> tail;
+  for (int c = 0; c < nchunk; c++) {
+    const long long b0 = nblk * c / nchunk * gran, b1 = std::min<long long>(nblk * (c + 1) / nchunk * gran, total);
+    const int cnt = (int)std::max<long long>(b1 - b0, 0);
+    Step a; a.is_exchange = false; a.chunk = c; a.st = P;
+    Step e; e.is_exchange = true;  e.chunk = c; e.ex = E;
+    Step b; b.is_exchange = false; b.chunk = c; b.side = true; b.st = Q;
+    for (P3dStage* st : {&a.st, &b.st}) {
+      if (along_a) st->na = cnt; else st->nb = cnt;
+      shift_side(st->in, along_a, b0);
+      shift_side(st->out, along_a, b0);
+    }
+    tail.push_back(a); tail.push_back(e); tail.push_back(b);
+  }
+  tp.steps.resize(n - 3);
+  tp.steps.insert(tp.steps.end(), tail.begin(), tail.end());
+  return true;
 }
 
 // ------------------------------------------------------------------------------------

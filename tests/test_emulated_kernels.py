@@ -58,7 +58,7 @@ def run_steps_emulated(steps, bufs, world, single, counts):
     return n
 
 
-def transform_world(n, dims, cut, opf, opb, stride1=False, single=False, p2p=False, row_bytes=0, nv=1):
+def transform_world(n, dims, cut, opf, opb, stride1=False, single=False, p2p=False, row_bytes=0, nv=1, overlap=0):
     """forward and backward on P simulated ranks; returns (fast stage count, generic stage count)"""
     nx, ny, nz = n
     c = cut or (None, None, None)
@@ -73,7 +73,8 @@ def transform_world(n, dims, cut, opf, opb, stride1=False, single=False, p2p=Fal
     for backward, op in ((False, opf), (True, opb)):
         plans, world = [], []
         for r, d in enumerate(D):
-            steps, inf = L.plan_steps(dims, nx, ny, nz, r, backward, op, nv, *c, stride1=stride1, p2p=p2p, row_bytes=row_bytes)
+            steps, inf = L.plan_steps(dims, nx, ny, nz, r, backward, op, nv, *c, stride1=stride1, p2p=p2p, row_bytes=row_bytes,
+                                       overlap=overlap)
             plans.append(steps)
             w = int(inf.work_elems) * nv
             if backward:
@@ -235,3 +236,39 @@ def test_emulated_wide_x_tiles(monkeypatch):
     monkeypatch.delenv("P3DFFT_B200_XTX8")
     transform_world((1024, 16, 16), (1, 1), None, "fft", "tff")
     assert emu().emu_last_variant() == 0
+
+
+@pytest.mark.parametrize("dims,n,cut", [((1, 2), (64, 64, 64), None), ((2, 2), (64, 64, 64), (42, 42, 42)), ((2, 4), (64, 64, 64), None),
+                                        ((2, 3), (16, 12, 10), None), ((2, 2), (20, 12, 33), None)])
+@pytest.mark.parametrize("chunks", [2, 3, 5])
+def test_pipelined_tail_plans(dims, n, cut, chunks):
+    """opt-in chunked tail of the peer-to-peer plans (plan.h split_for_overlap): P_c, barrier_c, Q_c ... must give the
+    same transform when every consumer chunk runs right after its own barrier (buffers start zeroed: a consumer that
+    needed a later producer chunk would read zeros).  Power-of-two cases run the emulated CUDA kernels, the others numpy."""
+    L = pb.load(False)
+    opf, opb = ("ffc", "cff") if n[2] % 2 else ("fft", "tff")
+    for backward, op in ((False, opf), (True, opb)):
+        steps, _ = L.plan_steps(dims, *n, 0, backward, op, 1, *(cut or (None, None, None)), p2p=True, overlap=chunks)
+        base, _ = L.plan_steps(dims, *n, 0, backward, op, 1, *(cut or (None, None, None)), p2p=True)
+        if [s.is_exchange for s in base[-3:]] != [0, 1, 0]:       # e.g. backward on a 1 x N grid: no exchange in front of X
+            assert len(steps) == len(base)
+            continue
+        tail = steps[-3 * chunks:]
+        assert [s.is_exchange for s in tail] == [0, 1, 0] * chunks
+        assert [s.pad_ & 1 for s in tail] == [0, 0, 1] * chunks                      # consumers run on the side stream
+        assert [(s.pad_ >> 8) - 1 for s in tail] == [c for c in range(chunks) for _ in range(3)]
+        assert len(steps) == len(base) - 3 + 3 * chunks
+        prod, cons = base[-3].st, base[-1].st                                        # the chunks partition the batch axis
+        if backward:
+            assert sum(s.st.nb for s in tail[0::3]) == prod.nb and sum(s.st.nb for s in tail[2::3]) == cons.nb
+        else:
+            assert sum(s.st.na for s in tail[0::3]) == prod.na and sum(s.st.na for s in tail[2::3]) == cons.na
+    transform_world(n, dims, cut, opf, opb, p2p=True, overlap=chunks)
+
+
+def test_pipelined_tail_needs_a_peer_to_peer_exchange():
+    L = pb.load(False)
+    a, _ = L.plan_steps((1, 1), 64, 64, 64, 0, False, "fft", overlap=4)
+    b, _ = L.plan_steps((2, 2), 64, 64, 64, 0, False, "fft", overlap=4)          # not a p2p plan
+    c, _ = L.plan_steps((2, 1), 64, 64, 64, 0, False, "fft", p2p=True, overlap=4)   # forward on M2 = 1: no exchange in front of Z
+    assert len(a) == 3 and len(b) == 5 and len(c) == 4
