@@ -2,6 +2,7 @@
 # One gpurun call's worth of measurements (1 GPU).  Replaces the per-experiment scratch scripts of round 1.
 #   gpurun --timeout 900 -- 'bash tools/gpu_session.sh all'
 # Sections: tests | ab | sanitize | ncu | aux        (results under gpurun_out/)
+#           mgpu N  -- N-GPU parity and A/B of the multi-GPU switches:  gpurun --gpus N --timeout 900 -- 'bash tools/gpu_session.sh mgpu N'
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 what=${1:-all}
@@ -50,4 +51,20 @@ fi
 
 if [[ $what == all || $what == aux ]]; then
   python tools/bench_aux.py 1024 | tee gpurun_out/aux_bench.json
+fi
+
+if [[ $what == mgpu ]]; then
+  N=${2:-2}
+  run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) "$@"; }
+  {
+    echo "== parity, default";                 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
+    echo "== parity, flag barrier";            P3DFFT_B200_FLAGBAR=1 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
+    echo "== parity, flag barrier + overlap";  P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=4 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
+    for env in "" "P3DFFT_B200_FLAGBAR=1" "P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=4" "P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=4 P3DFFT_B200_OVERLAP_SMS=40" \
+               "P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=8 P3DFFT_B200_OVERLAP_SMS=72"; do
+      echo "== bench [$env]"
+      env $env timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) \
+          bench.py --gpus "$N" --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1
+    done
+  } | tee gpurun_out/mgpu_$N.log
 fi
