@@ -160,9 +160,12 @@ int fast_variant(const P3dStage& st) {
     const char* x = getenv("P3DFFT_B200_XTX8");
     return (x && atoi(x) != 0 && st.n % 2 == 0 && xcfg_wide_exists(st.n / 2, (int)sizeof(T))) ? 2 : 0;
   }
-  if (!e || atoi(e) == 0) return 0;
-  if (!ccfg_r32_exists(st.nfft)) return 0;
-  return row_bytes<T>(st) == 128 ? 1 : 0;
+  const bool r32 = e && atoi(e) != 0 && ccfg_r32_exists(st.nfft);
+  const char* hf = getenv("P3DFFT_B200_HALF");
+  const bool half = hf && atoi(hf) != 0 && st.nfft == 1024;
+  if (!r32 && !half) return 0;
+  if (row_bytes<T>(st) != 128) return 0;
+  return r32 ? 1 : 3;
 }
 
 template <typename T>
@@ -336,6 +339,28 @@ static cudaError_t launch_r32(const P3dStage& st, const FastStage& f, cudaStream
   return cudaGetLastError();
 }
 
+// half-row variant (opt-in): the 64-byte-row kernel on 128-byte-row buffers, two CTAs per tile
+template <typename T, int NN>
+static cudaError_t launch_half(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  using C = CCfg<T, NN, 64>;
+  constexpr int TX = C::TX, NT = C::NT;
+  constexpr size_t smem = cstage_smem<T, NN, 64>();
+  const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
+  if (tiles <= 0) return cudaSuccess;
+  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
+  cudaError_t e;
+  const bool scaled = f.scale != 1.0;
+  if (st.kind == P3D_C2C_BWD) {
+    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 64, true, true, C, 2>);
+    else P3D_LAUNCH(cstage_kernel<T, NN, 64, true, false, C, 2>);
+  } else {
+    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 64, false, true, C, 2>);
+    else P3D_LAUNCH(cstage_kernel<T, NN, 64, false, false, C, 2>);
+  }
+  return cudaGetLastError();
+}
+
 // split variant (two half tiles per CTA, two CTAs per SM) for the lengths whose 128-byte tile fills an SM
 template <typename T, int NN>
 static cudaError_t launch_split(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
@@ -367,6 +392,7 @@ cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t str
       if (reinterpret_cast<uintptr_t>(sd.run[g].base) % sizeof(T2)) return cudaErrorMisalignedAddress;
   }
   cudaError_t err = cudaErrorInvalidValue;
+  if (f.variant == 3 && !is_x(st.kind) && f.rowb == 128 && st.nfft == 1024) return launch_half<T, 1024>(st, f, stream);
   if (f.variant == 1 && !is_x(st.kind) && f.rowb == 128) {
     if (dispatch_r32(st.nfft, [&](auto nn) { err = launch_r32<T, decltype(nn)::value>(st, f, stream); })) return err;
   }

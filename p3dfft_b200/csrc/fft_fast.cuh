@@ -454,7 +454,22 @@ __device__ __forceinline__ void fill_tilebase(const FastStage& st, RunTab& rt, i
 // SCALED: every output is multiplied by st.scale on its way out (the drivers' normalisation pass, mult_array in
 // sample/C/driver_*.c, fused into the store); a separate instantiation, so the unscaled kernels are unchanged.
 // C: the configuration (schedule, threads); the default is the table above, CCfgR32 selects the two-pass variant
-template <typename T, int N, int RB, bool SWAP, bool SCALED = false, class C = CCfg<T, N, RB>>
+// sub-tile bases: the rows of the layout hold TPB * TX lines, this CTA takes lines [sub*TX, sub*TX + TX) of tile ta / TPB
+template <int NT, int ESZ, int TPB, int TX>
+__device__ __forceinline__ void fill_tilebase_sub(const FastStage& st, RunTab& rt, int slot, TileIdx ti) {
+  const int nin = st.in.nrun, ntot = nin + st.out.nrun;
+  const int sub = ti.ta % TPB;
+  ti.ta /= TPB;
+  for (int i = threadIdx.x; i < ntot; i += NT) {
+    const int side = i >= nin, g = side ? i - nin : i;
+    const FastRun& r = side ? st.out.run[g] : st.in.run[g];
+    rt.tb[slot][side][g] = tile_base<ESZ>(r, ti) + (long long)sub * TX * r.sa * ESZ;
+  }
+}
+
+// TPB > 1 (opt-in "half-row" variant, P3DFFT_B200_HALF=1): a kernel built for 64-byte tile rows works on buffers laid out in
+// 128-byte rows, each CTA on one half of the lines of a tile -- two 64 KB CTAs per SM instead of one 128 KB CTA at N = 1024.
+template <typename T, int N, int RB, bool SWAP, bool SCALED = false, class C = CCfg<T, N, RB>, int TPB = 1>
 __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
   using S = typename C::S;
@@ -481,7 +496,10 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
     const long long psb = st.in.run[g].ps * (long long)sizeof(T2);
     rt->pfmode[g] = (st.prefetch && psb <= (long long)st.prefetch) ? (psb == 64 ? 2 : 1) : 0;
   }
-  if (blockIdx.x < ntiles) fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
+  if (blockIdx.x < ntiles) {
+    if constexpr (TPB == 1) fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
+    else fill_tilebase_sub<NT, sizeof(T2), TPB, TX>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
+  }
   __syncthreads();
 
   int slot = 0;
@@ -489,8 +507,10 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
     const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
     const bool live = ti.ta * TX + t < st.na && ti.b < st.nb;       // b >= nb: padding slot, nothing loaded or stored
     const bool has_next = tile + gridDim.x < ntiles && tile + gridDim.x > tile;
-    if (has_next && threadIdx.x < st.in.nrun + st.out.nrun)
-      fill_tilebase<NT, sizeof(T2)>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord));
+    if (has_next && threadIdx.x < st.in.nrun + st.out.nrun) {
+      if constexpr (TPB == 1) fill_tilebase<NT, sizeof(T2)>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord));
+      else fill_tilebase_sub<NT, sizeof(T2), TPB, TX>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord));
+    }
     // ---- pass 1: global -> registers -> shared ---------------------------------------------
     {
       constexpr int R = S::r(0), M = S::m(0), ITEMS = M * TX;

@@ -272,3 +272,29 @@ def test_pipelined_tail_needs_a_peer_to_peer_exchange():
     b, _ = L.plan_steps((2, 2), 64, 64, 64, 0, False, "fft", overlap=4)          # not a p2p plan
     c, _ = L.plan_steps((2, 1), 64, 64, 64, 0, False, "fft", p2p=True, overlap=4)   # forward on M2 = 1: no exchange in front of Z
     assert len(a) == 3 and len(b) == 5 and len(c) == 4
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_emulated_half_row_variant(monkeypatch, single):
+    """opt-in half-row tiles (P3DFFT_B200_HALF=1): the 64-byte-row 1024-point kernel on buffers laid out in 128-byte rows,
+    each CTA on one half of a tile's lines -- Y and Z stages, forward and backward, pruned, 2 x 2 with peer stores"""
+    monkeypatch.setenv("P3DFFT_B200_HALF", "1")
+    h = emu(single)
+    if single:
+        transform_world((64, 1024, 64), (1, 1), None, "fft", "tff", single=True)
+    else:
+        fast, generic = transform_world((16, 1024, 16), (1, 1), None, "fft", "tff")
+        assert (fast, generic) == (2, 4)
+        transform_world((24, 16, 1024), (1, 1), (24, 16, 680), "fft", "tff")
+        assert h.emu_last_variant() == 0          # last stage of the backward transform: X (generic here); check a Y stage below
+        transform_world((32, 1024, 16), (2, 2), None, "fft", "tff", p2p=True)
+    steps, _ = pb.load(single).plan_steps((1, 1), 64, 1024, 64, 0, False, "fft")
+    st = steps[1].st
+    w = int(pb.load(single).plan_decomp((1, 1), 64, 1024, 64).work_elems)
+    ct = np.complex64 if single else np.complex128
+    bufs = {b: np.zeros(w, dtype=ct) for b in (pb.BUF_A, pb.BUF_B, pb.BUF_C)}
+    for si, side in enumerate((st.inp, st.out)):
+        for g in range(side.nseg):
+            sg = side.seg[g]
+            sg.base = bufs[sg.buf].ctypes.data + sg.off * (8 if single else 16)
+    assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 3
