@@ -64,7 +64,7 @@ void p3dfft_b200_set_p2p(int on);
  * local consumer chunks on a second stream beside the NVLink-bound producer (P3DFFT_B200_OVERLAP_SMS = SMs left to them);
  * the per-stage timers then only cover the producer side.
  * env P3DFFT_B200_R32=1 / P3DFFT_B200_XTX8=1 / P3DFFT_B200_HALF=1 (opt-in, experimental): two-pass 512/1024-point schedules /
- * 8-line X tiles / half-row 1024-point tiles.                                                                              */
+ * 8-line X tiles / half-row 1024-point tiles.  P3DFFT_B200_BULK=1: bulk asynchronous (TMA) tile stores.                                                                            */
 /* env P3DFFT_B200_FLAGBAR=1 (opt-in, experimental): the barrier that orders the peer-to-peer transposes becomes a
  * one-CTA kernel exchanging epoch flags through peer-mapped memory instead of a one-float NCCL all-reduce.         */
 int p3dfft_b200_p2p_active(void);

@@ -48,7 +48,7 @@ struct FastStage {
   FastSide in, out;
   double scale;          // multiplies every output (SCALED instantiations only; last member: the unscaled kernels'
                          // parameter layout does not depend on it)
-  int32_t variant;       // 0: default; 1: two-pass radix-32 c2c schedules; 2: wide X tiles; 3: half-row c2c tiles (fast_variant, opt-in)
+  int32_t variant;       // 0: default; 1: two-pass radix-32 c2c schedules; 2: wide X tiles; 3: half-row c2c tiles; 4: bulk-copy stores (fast_variant, opt-in)
   int32_t sm_cap;        // > 0: the persistent grid uses at most this many SMs (pipelined tail, api.cpp); host side only
 };
 

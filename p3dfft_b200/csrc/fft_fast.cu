@@ -163,9 +163,19 @@ int fast_variant(const P3dStage& st) {
   const bool r32 = e && atoi(e) != 0 && ccfg_r32_exists(st.nfft);
   const char* hf = getenv("P3DFFT_B200_HALF");
   const bool half = hf && atoi(hf) != 0 && st.nfft == 1024;
-  if (!r32 && !half) return 0;
+  const char* bk = getenv("P3DFFT_B200_BULK");
+  bool bulk = bk && atoi(bk) != 0 && (st.nfft == 1024 || st.nfft == 512);
+  if (bulk) {      // every output run: whole 128-byte tile rows, consecutive in memory
+    const int tx = 128 / (2 * (int)sizeof(T));
+    for (int g = 0; g < st.out.nseg; g++) {
+      const P3dSeg& sg = st.out.seg[g];
+      if (sg.sa != 1 || sg.kw > 1 || sg.ps != tx || sg.aw != tx) bulk = false;
+    }
+    if (st.out.nseg == 0) bulk = false;
+  }
+  if (!r32 && !half && !bulk) return 0;
   if (row_bytes<T>(st) != 128) return 0;
-  return r32 ? 1 : 3;
+  return r32 ? 1 : half ? 3 : 4;
 }
 
 template <typename T>
@@ -361,6 +371,28 @@ static cudaError_t launch_half(const P3dStage& st, const FastStage& f, cudaStrea
   return cudaGetLastError();
 }
 
+// bulk-store variant (opt-in): default configuration, tile written back through shared memory and cp.async.bulk
+template <typename T, int NN>
+static cudaError_t launch_bulk(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  using C = CCfg<T, NN, 128>;
+  constexpr int TX = C::TX, NT = C::NT;
+  constexpr size_t smem = cstage_smem<T, NN, 128>();
+  const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
+  if (tiles <= 0) return cudaSuccess;
+  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
+  cudaError_t e;
+  const bool scaled = f.scale != 1.0;
+  if (st.kind == P3D_C2C_BWD) {
+    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 128, true, true, C, 1, true>);
+    else P3D_LAUNCH(cstage_kernel<T, NN, 128, true, false, C, 1, true>);
+  } else {
+    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 128, false, true, C, 1, true>);
+    else P3D_LAUNCH(cstage_kernel<T, NN, 128, false, false, C, 1, true>);
+  }
+  return cudaGetLastError();
+}
+
 // split variant (two half tiles per CTA, two CTAs per SM) for the lengths whose 128-byte tile fills an SM
 template <typename T, int NN>
 static cudaError_t launch_split(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
@@ -393,6 +425,10 @@ cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t str
   }
   cudaError_t err = cudaErrorInvalidValue;
   if (f.variant == 3 && !is_x(st.kind) && f.rowb == 128 && st.nfft == 1024) return launch_half<T, 1024>(st, f, stream);
+  if (f.variant == 4 && !is_x(st.kind) && f.rowb == 128) {
+    if (st.nfft == 1024) return launch_bulk<T, 1024>(st, f, stream);
+    if (st.nfft == 512) return launch_bulk<T, 512>(st, f, stream);
+  }
   if (f.variant == 1 && !is_x(st.kind) && f.rowb == 128) {
     if (dispatch_r32(st.nfft, [&](auto nn) { err = launch_r32<T, decltype(nn)::value>(st, f, stream); })) return err;
   }

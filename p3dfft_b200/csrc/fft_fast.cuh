@@ -35,6 +35,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string.h>
+
 #include <type_traits>
 #include <utility>
 
@@ -368,6 +370,23 @@ __device__ __forceinline__ void last_bfly(const typename Cx<T>::type* s, int kap
 // SM computes.
 // ---------------------------------------------------------------------------------------
 #ifndef P3D_EMULATE
+// bulk asynchronous copy shared -> global (TMA, no tensor map): one instruction moves a whole contiguous block of tile rows
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources may be overwritten
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes performed
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }  // generic-proxy writes -> async proxy
+#else
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) { memcpy(gdst, ssrc, bytes); }
+__device__ __forceinline__ void bulk_commit() {}
+__device__ __forceinline__ void bulk_wait_read() {}
+__device__ __forceinline__ void bulk_wait_all() {}
+__device__ __forceinline__ void fence_async_smem() {}
+#endif
+#ifndef P3D_EMULATE
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #else
 __device__ __forceinline__ void prefetch_l2(const void* p) { (void)*reinterpret_cast<const volatile char*>(p); }   // must be a mapped address
@@ -469,7 +488,10 @@ __device__ __forceinline__ void fill_tilebase_sub(const FastStage& st, RunTab& r
 
 // TPB > 1 (opt-in "half-row" variant, P3DFFT_B200_HALF=1): a kernel built for 64-byte tile rows works on buffers laid out in
 // 128-byte rows, each CTA on one half of the lines of a tile -- two 64 KB CTAs per SM instead of one 128 KB CTA at N = 1024.
-template <typename T, int N, int RB, bool SWAP, bool SCALED = false, class C = CCfg<T, N, RB>, int TPB = 1>
+// BULK (opt-in, P3DFFT_B200_BULK=1; 128-byte rows, outputs whose tile rows are contiguous per run -- every stage that
+// feeds an exchange): the last pass puts the tile back into shared memory in natural row order and ONE bulk asynchronous
+// copy per output run (per peer) moves it to HBM or over NVLink, instead of 16-byte stores from registers.
+template <typename T, int N, int RB, bool SWAP, bool SCALED = false, class C = CCfg<T, N, RB>, int TPB = 1, bool BULK = false>
 __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
   using S = typename C::S;
@@ -528,6 +550,13 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
             if (SWAP) v[p] = cswap(v[p]);
           }
           Bfly<T, R>::run(v);
+          if constexpr (BULK) {
+            static_assert(ITEMS % NT == 0, "bulk variant: every thread reaches the barrier");
+            if (w0 == 0 && tile != blockIdx.x) {      // the bulk copies of the previous tile still read the tile buffer
+              bulk_wait_read();                       // (only the threads that issued them have groups outstanding)
+              __syncthreads();
+            }
+          }
           twiddle_store<T, S, 0, TX, SWZ>(v, s, tw, u, u, t);
         }
       }
@@ -545,7 +574,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
     }
     mid_passes<T, S, 1, TX, NT, SWZ>(s, tw);
     // ---- pass L: shared -> registers -> global ----------------------------------------------
-    {
+    if constexpr (!BULK) {
       constexpr int RL = S::r(L - 1), ML = N / RL, ITEMS = ML * TX;
       char* const* tbo = rt->tb[slot][1];
 #pragma unroll 1
@@ -564,9 +593,40 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
           if (live && e >= 0) stg_stream(reinterpret_cast<T2*>(row_addr(e, tbo) + lout), SWAP ? cswap(v[q]) : v[q]);
         }
       }
+    } else {
+      // ---- pass L, bulk variant: shared -> registers -> shared (natural row order) -> one bulk copy per output run ----
+      constexpr int RL = S::r(L - 1), ML = N / RL, ITEMS = ML * TX, IPT = ITEMS / NT;
+      static_assert(ITEMS % NT == 0 && !SWZ, "bulk variant: whole items per thread, unswizzled 128-byte rows");
+      char* const* tbo = rt->tb[slot][1];
+      T2 v[IPT][RL];
+#pragma unroll
+      for (int it = 0; it < IPT; it++) {
+        last_bfly<T, S, TX, SWZ>(s, (it * NT + (int)threadIdx.x) / TX, t, v[it]);
+        if constexpr (SCALED) {
+          const T sc = (T)st.scale;
+#pragma unroll
+          for (int q = 0; q < RL; q++) { v[it][q].x *= sc; v[it][q].y *= sc; }
+        }
+      }
+      __syncthreads();      // every butterfly has read its rows: the buffer may be rewritten
+#pragma unroll
+      for (int it = 0; it < IPT; it++) {
+        const int kappa = (it * NT + (int)threadIdx.x) / TX;
+#pragma unroll
+        for (int q = 0; q < RL; q++) s[(kappa + q * ML) * TX + t] = SWAP ? cswap(v[it][q]) : v[it][q];
+      }
+      fence_async_smem();
+      __syncthreads();
+      if ((int)threadIdx.x < st.out.nrun && ti.b < st.nb) {      // lines past na land in the padding lanes of the blocked layouts
+        const FastRun& r = st.out.run[threadIdx.x];
+        const long long e = ent_out[r.kstart];
+        bulk_store(row_addr(e, tbo), s + (size_t)r.kstart * TX, (unsigned)(r.len * TX * (int)sizeof(T2)));
+        bulk_commit();
+      }
     }
     __syncthreads();      // the tile buffer and the tile bases of this parity are reused
   }
+  if constexpr (BULK) bulk_wait_all();
 }
 
 // two-pass variant: the same kernel with the CCfgR32 configuration

@@ -298,3 +298,34 @@ def test_emulated_half_row_variant(monkeypatch, single):
             sg = side.seg[g]
             sg.base = bufs[sg.buf].ctypes.data + sg.off * (8 if single else 16)
     assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 3
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_emulated_bulk_store_variant(monkeypatch, single):
+    """opt-in bulk-copy stores (P3DFFT_B200_BULK=1): the last pass re-forms the tile in shared memory in natural row order and
+    one cp.async.bulk per output run moves it out (memcpy in the emulation) -- Y forward / Z and Y backward, pruned runs,
+    2 x 2 with the runs landing in the peers' buffers"""
+    monkeypatch.setenv("P3DFFT_B200_BULK", "1")
+    h = emu(single)
+    if single:
+        transform_world((64, 1024, 64), (1, 1), (64, 680, 42), "fft", "tff", single=True)
+    else:
+        fast, generic = transform_world((16, 1024, 16), (1, 1), None, "fft", "tff")
+        assert (fast, generic) == (2, 4)
+        transform_world((24, 512, 16), (1, 1), (24, 340, 16), "fft", "tff")
+        transform_world((16, 16, 1024), (1, 1), (16, 16, 680), "fft", "tff")
+        transform_world((32, 1024, 16), (2, 2), (32, 680, 16), "fft", "tff", p2p=True)
+        transform_world((32, 16, 512), (2, 2), None, "fft", "tff", p2p=True)
+    # the forward Y stage (contiguous rows per run) takes the variant, the forward Z stage (user layout) does not
+    steps, _ = pb.load(single).plan_steps((1, 1), 64, 1024, 64, 0, False, "fft")
+    w = int(pb.load(single).plan_decomp((1, 1), 64, 1024, 64).work_elems)
+    ct = np.complex64 if single else np.complex128
+    bufs = {b: np.zeros(w, dtype=ct) for b in (pb.BUF_A, pb.BUF_B, pb.BUF_C)}
+    bufs[pb.BUF_USER_OUT] = np.zeros(33 * 1024 * 64, dtype=ct)
+    for idx, want in ((1, 4), (2, 0)):
+        st = steps[idx].st
+        for si, side in enumerate((st.inp, st.out)):
+            for g in range(side.nseg):
+                sg = side.seg[g]
+                sg.base = bufs[sg.buf].ctypes.data + sg.off * (8 if single else 16)
+        assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == want

@@ -18,6 +18,7 @@ if [[ $what == all || $what == ab ]]; then
     TAG="R32 two-pass " P3DFFT_B200_R32=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
     TAG="X tiles of 8 " P3DFFT_B200_XTX8=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
     TAG="R32 + XTX8   " P3DFFT_B200_R32=1 P3DFFT_B200_XTX8=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
+    TAG="bulk stores  " P3DFFT_B200_BULK=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
     TAG="half-row c2c " P3DFFT_B200_HALF=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
     TAG="split always " P3DFFT_B200_SPLIT=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
     TAG="R32 512^3    " P3DFFT_B200_R32=1 python tools/prof_pair.py --size 512 --pairs 12 --warm 2
@@ -26,6 +27,7 @@ if [[ $what == all || $what == ab ]]; then
     TAG="default singl" python tools/prof_pair.py --size 1024 --pairs 6 --warm 2 --single
   } 2>&1 | tee gpurun_out/ab.log
   # the variants must pass the same parity tests as the defaults
+  P3DFFT_B200_BULK=1 python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider -k "fast_kernels or large" 2>&1 | tail -3 | tee -a gpurun_out/ab.log
   P3DFFT_B200_HALF=1 python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider -k "fast_kernels or large" 2>&1 | tail -3 | tee -a gpurun_out/ab.log
   P3DFFT_B200_R32=1 P3DFFT_B200_XTX8=1 python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider -k "fast_kernels or large" 2>&1 | tail -3 | tee -a gpurun_out/ab.log
 fi
@@ -61,9 +63,11 @@ if [[ $what == mgpu ]]; then
   {
     echo "== parity, default";                 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
     echo "== parity, flag barrier";            P3DFFT_B200_FLAGBAR=1 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
+    echo "== parity, bulk stores";             P3DFFT_B200_BULK=1 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
     echo "== parity, flag barrier + overlap";  P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=4 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
     for env in "" "P3DFFT_B200_FLAGBAR=1" "P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=4" "P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=4 P3DFFT_B200_OVERLAP_SMS=40" \
-               "P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=8 P3DFFT_B200_OVERLAP_SMS=72"; do
+               "P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=8 P3DFFT_B200_OVERLAP_SMS=72" \
+               "P3DFFT_B200_BULK=1" "P3DFFT_B200_BULK=1 P3DFFT_B200_FLAGBAR=1"; do
       echo "== bench [$env]"
       env $env timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) \
           bench.py --gpus "$N" --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1
