@@ -149,6 +149,10 @@ struct Lib {
   // opt-in pipelined tail of the peer-to-peer plans (P3DFFT_B200_OVERLAP=C chunks; plan.h split_for_overlap): the consumer
   // chunks run on a side stream, on at most overlap_sms SMs while the producer keeps the rest (not yet run on hardware)
   int overlap = 0, overlap_sms = 56;
+  // opt-in X <-> Y pipeline through L2 (P3DFFT_B200_XYPIPE=G planes per chunk; plan.h split_xy_pipeline), M1 = 1 grids
+  int xypipe = 0, xypipe_sms = 0;      // SMs left to the consumer chunks (0: half)
+  bool xypipe_ring = true, xypipe_persist = false;
+  std::vector<cudaEvent_t> chunk_events2;
   cudaStream_t side_stream = nullptr;
   std::vector<cudaEvent_t> chunk_events;
   cudaEvent_t side_done = nullptr;
@@ -386,7 +390,9 @@ bool finalize_plan(p3d::TransformPlan& tp) {
 
 p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long dim_real, long long dim_cplx) {
   const int chunks = (L.p2p && L.overlap > 1) ? L.overlap : 0;
-  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx, L.W(), (L.p2p ? 1 : 0) | (chunks << 8)};
+  const int xyg = (L.xypipe > 0 && L.W() > 0) ? (L.xypipe > 127 ? 127 : L.xypipe) : 0;
+  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx, L.W(),
+              (L.p2p ? 1 : 0) | (chunks << 8) | (xyg << 16) | (L.xypipe_ring ? 1 << 24 : 0)};
   auto it = L.plans.find(key);
   if (it != L.plans.end()) return &it->second;
   p3d::TransformPlan tp = p3d::build_plan(L.d, backward, op, nv, dim_real, dim_cplx, L.W(), L.p2p);
@@ -396,6 +402,7 @@ p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long di
     return nullptr;
   }
   if (chunks > 1) p3d::split_for_overlap(tp, chunks, L.W());
+  if (xyg > 0) p3d::split_xy_pipeline(tp, xyg, L.xypipe_ring, backward);
   if (!finalize_plan(tp)) return nullptr;
   auto res = L.plans.emplace(key, std::move(tp));
   return &res.first->second;
@@ -500,11 +507,58 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     while ((int)L.chunk_events.size() < nchunks) {
       cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.chunk_events.push_back(ev);
     }
+    while ((int)L.chunk_events2.size() < nchunks) {
+      cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.chunk_events2.push_back(ev);
+    }
   }
+  const int pipe_sms = L.xypipe_sms > 0 && L.xypipe_sms < sms ? L.xypipe_sms : sms / 2;
+  bool persist_set = false;
+  auto join_side = [&]() -> bool {       // the main stream waits for everything queued on the side stream
+    if (!used_side) return true;
+    CUDA_OK(cudaEventRecord(L.side_done, L.side_stream));
+    CUDA_OK(cudaStreamWaitEvent(st, L.side_done, 0));
+    used_side = false;
+    if (persist_set) { cudaCtxResetPersistingL2Cache(); persist_set = false; }
+    return true;
+  };
   const int side_sms = L.overlap_sms > 0 && L.overlap_sms < sms ? L.overlap_sms : sms / 3;
   bool pre_done = false;      // the barrier that protects the receive buffer of the NEXT exchange has been issued
   for (size_t i = 0; i < nsteps; i++) {
     auto& s = tp->steps[i];
+    if (!s.is_exchange && s.pipe) {
+      // X <-> Y pipeline chunk: producer on the main stream, consumer on the side stream, ordered by events; with the ring
+      // the producer of chunk c waits for the consumer of chunk c-2 (it overwrites that consumer's slot)
+      const int c = s.chunk;
+      if (s.pipe == 2 && L.xypipe_persist && !persist_set && !s.side) {
+        // keep the two ring slots resident in L2: persisting access window on both streams (reset when the group is joined)
+        const P3dSeg& sg = s.st.out.seg[0];
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        av.accessPolicyWindow.base_ptr = (char*)L.buf[sg.buf] + sg.off * CSIZE;
+        av.accessPolicyWindow.num_bytes = (size_t)2 * (size_t)(L.xypipe > 127 ? 127 : L.xypipe) * (size_t)sg.sb * CSIZE;
+        av.accessPolicyWindow.hitRatio = 1.0f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, av.accessPolicyWindow.num_bytes);
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaStreamSetAttribute(L.side_stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();        // best effort: a refused window only costs the residency hint
+        persist_set = true;
+      }
+      if (!s.side) {
+        if (s.pipe == 2 && c >= 2) CUDA_OK(cudaStreamWaitEvent(st, L.chunk_events2[c - 2], 0));
+        if (timed) { cudaEventRecord(get_event(nev++), st); slots.push_back(s.st.timer); is_ex.push_back(0); }
+        if (!launch(s.st, st, c > 0 ? sms - pipe_sms : 0)) return false;
+        CUDA_OK(cudaEventRecord(L.chunk_events[c], st));
+      } else {
+        CUDA_OK(cudaStreamWaitEvent(L.side_stream, L.chunk_events[c], 0));
+        if (!launch(s.st, L.side_stream, c + 1 < nchunks ? pipe_sms : 0)) return false;
+        CUDA_OK(cudaEventRecord(L.chunk_events2[c], L.side_stream));
+        used_side = true;
+      }
+      continue;
+    }
+    if (used_side && i > 0 && tp->steps[i - 1].pipe && !join_side()) return false;      // the pipeline group is complete
     if (!s.is_exchange && s.side) {
       // consumer chunk of the pipelined tail: side stream, after this chunk's barrier; the last one has the GPU to itself
       CUDA_OK(cudaStreamWaitEvent(L.side_stream, L.chunk_events[s.chunk], 0));
@@ -535,10 +589,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
       slots.push_back(s.st.timer); is_ex.push_back(0);
     }
   }
-  if (used_side) {               // everything behind this point (epilogues, copies, the next call) is ordered after the side stream
-    CUDA_OK(cudaEventRecord(L.side_done, L.side_stream));
-    CUDA_OK(cudaStreamWaitEvent(st, L.side_done, 0));
-  }
+  if (!join_side()) return false;       // everything behind this point (epilogues, copies, the next call) is ordered after the side stream
   if (cheby) {
     // p3dfft_cheby epilogue, ftran.F90:408-451
     const double norm = 1.0 / ((double)d.nx * (double)d.ny * (double)(d.nzc - 1));
@@ -667,6 +718,10 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   if (getenv("P3DFFT_B200_FLAGBAR")) L.want_flagbar = atoi(getenv("P3DFFT_B200_FLAGBAR")) != 0;
   if (getenv("P3DFFT_B200_OVERLAP")) L.overlap = atoi(getenv("P3DFFT_B200_OVERLAP"));
   if (getenv("P3DFFT_B200_OVERLAP_SMS")) L.overlap_sms = atoi(getenv("P3DFFT_B200_OVERLAP_SMS"));
+  if (getenv("P3DFFT_B200_XYPIPE")) L.xypipe = atoi(getenv("P3DFFT_B200_XYPIPE"));
+  if (getenv("P3DFFT_B200_XYPIPE_SMS")) L.xypipe_sms = atoi(getenv("P3DFFT_B200_XYPIPE_SMS"));
+  if (getenv("P3DFFT_B200_XYPIPE_RING")) L.xypipe_ring = atoi(getenv("P3DFFT_B200_XYPIPE_RING")) != 0;
+  if (getenv("P3DFFT_B200_XYPIPE_PERSIST")) L.xypipe_persist = atoi(getenv("P3DFFT_B200_XYPIPE_PERSIST")) != 0;
   for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
   L.procmap.init(L.d);
   L.nv_preset = 0;
@@ -761,6 +816,8 @@ void p3dfft_clean(void) {
   if (L.side_stream) { cudaStreamSynchronize(L.side_stream); cudaStreamDestroy(L.side_stream); L.side_stream = nullptr; }
   for (auto ev : L.chunk_events) cudaEventDestroy(ev);
   L.chunk_events.clear();
+  for (auto ev : L.chunk_events2) cudaEventDestroy(ev);
+  L.chunk_events2.clear();
   if (L.side_done) { cudaEventDestroy(L.side_done); L.side_done = nullptr; }
   for (int b = P3D_BUF_A; b <= P3D_BUF_C; b++) if (L.buf[b]) { cudaFree(L.buf[b]); L.buf[b] = nullptr; }
   if (L.stage_in) { cudaFree(L.stage_in); L.stage_in = nullptr; L.stage_in_bytes = 0; }
@@ -1006,12 +1063,15 @@ int p3dfft_b200_plan_steps(const int* dims, int nx, int ny, int nz, int rank, in
   if (!tp.error.empty()) { g_last_error = tp.error; return -1; }
   const int nchunk = (flags >> 8) & 0xff;       // pipelined tail (split_for_overlap), peer-to-peer plans only
   if (nchunk > 1) p3d::split_for_overlap(tp, nchunk, (flags & 8) ? 0 : p3d::pick_W(ny, nz, 2 * elem_bytes, (flags & 32) ? 64 : (flags & 64) ? 128 : 0));
+  const int xyg = (flags >> 16) & 0x7f;         // X <-> Y pipeline (split_xy_pipeline): planes per chunk; bit 23: no ring
+  if (xyg > 0) p3d::split_xy_pipeline(tp, xyg, !(flags & (1 << 23)), backward != 0);
   if ((int)tp.steps.size() > max_steps) { g_last_error = "step array too small"; return -1; }
   P3dStepC* out = (P3dStepC*)steps;
   for (size_t i = 0; i < tp.steps.size(); i++) {
     memset(&out[i], 0, sizeof out[i]);
     out[i].is_exchange = tp.steps[i].is_exchange ? 1 : 0;
-    out[i].pad_ = (tp.steps[i].side ? 1 : 0) | ((tp.steps[i].chunk + 1) << 8);      // bit 0: side stream; bits 8..: chunk + 1
+    // bit 0: side stream; bits 1-2: X<->Y pipeline chunk (2 = ring); bits 8..: chunk + 1
+    out[i].pad_ = (tp.steps[i].side ? 1 : 0) | (tp.steps[i].pipe << 1) | ((tp.steps[i].chunk + 1) << 8);
     out[i].st = tp.steps[i].st;
     out[i].ex = tp.steps[i].ex;
     if (!tp.steps[i].is_exchange)

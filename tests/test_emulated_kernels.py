@@ -58,7 +58,36 @@ def run_steps_emulated(steps, bufs, world, single, counts):
     return n
 
 
-def transform_world(n, dims, cut, opf, opb, stride1=False, single=False, p2p=False, row_bytes=0, nv=1, overlap=0):
+def _eager_order(steps):
+    """The producer-runs-ahead schedule the events of an X<->Y pipeline allow: every producer chunk as early as legal --
+    without a ring all producers first, with the two-slot ring the producer of chunk c+2 right after the consumer of c."""
+    out, i = [], 0
+    while i < len(steps):
+        if not (steps[i].pad_ >> 1) & 3:
+            out.append(steps[i])
+            i += 1
+            continue
+        j = i
+        while j < len(steps) and (steps[j].pad_ >> 1) & 3:
+            j += 1
+        group = steps[i:j]
+        prod, cons = group[0::2], group[1::2]
+        assert all(not (p.pad_ & 1) for p in prod) and all(c.pad_ & 1 for c in cons)
+        ring = ((group[0].pad_ >> 1) & 3) == 2
+        if not ring:
+            out += prod + cons
+        else:
+            out += prod[:2]
+            for c in range(len(cons)):
+                out.append(cons[c])
+                if c + 2 < len(prod):
+                    out.append(prod[c + 2])
+        i = j
+    return out
+
+
+def transform_world(n, dims, cut, opf, opb, stride1=False, single=False, p2p=False, row_bytes=0, nv=1, overlap=0,
+                    xypipe=0, xyring=True, eager=False):
     """forward and backward on P simulated ranks; returns (fast stage count, generic stage count)"""
     nx, ny, nz = n
     c = cut or (None, None, None)
@@ -74,7 +103,9 @@ def transform_world(n, dims, cut, opf, opb, stride1=False, single=False, p2p=Fal
         plans, world = [], []
         for r, d in enumerate(D):
             steps, inf = L.plan_steps(dims, nx, ny, nz, r, backward, op, nv, *c, stride1=stride1, p2p=p2p, row_bytes=row_bytes,
-                                       overlap=overlap)
+                                       overlap=overlap, xypipe=xypipe, xyring=xyring)
+            if eager:
+                steps = _eager_order(steps)
             plans.append(steps)
             w = int(inf.work_elems) * nv
             if backward:
@@ -329,3 +360,38 @@ def test_emulated_bulk_store_variant(monkeypatch, single):
                 sg = side.seg[g]
                 sg.base = bufs[sg.buf].ctypes.data + sg.off * (8 if single else 16)
         assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == want
+
+
+@pytest.mark.parametrize("ring", [False, True])
+@pytest.mark.parametrize("eager", [False, True])
+@pytest.mark.parametrize("dims,n,cut,G", [((1, 1), (64, 64, 64), None, 8), ((1, 1), (64, 64, 64), (42, 42, 42), 5), ((1, 2), (64, 64, 64), None, 8),
+                                          ((1, 4), (128, 64, 64), None, 3), ((1, 1), (20, 12, 33), None, 4), ((1, 3), (16, 12, 10), None, 1)])
+def test_xy_pipeline_plans(dims, n, cut, G, ring, eager):
+    """opt-in X<->Y pipeline (plan.h split_xy_pipeline): the X and Y stages of a 1 x N grid in chunks of G z-planes, the buffer
+    between them optionally a two-slot ring; in list order and in the producer-runs-ahead order the events allow"""
+    L = pb.load(False)
+    opf, opb = ("ffc", "cff") if n[2] % 2 else ("fft", "tff")
+    c = cut or (None, None, None)
+    for backward, op in ((False, opf), (True, opb)):
+        base, inf = L.plan_steps(dims, *n, 0, backward, op, 1, *c, p2p=dims != (1, 1))
+        steps, _ = L.plan_steps(dims, *n, 0, backward, op, 1, *c, p2p=dims != (1, 1), xypipe=G, xyring=ring)
+        nchunk = -(-inf.kjsize // G)
+        if nchunk < 2:
+            assert len(steps) == len(base)
+            continue
+        assert len(steps) == len(base) - 2 + 2 * nchunk
+        grp = steps[-2 * nchunk:] if backward else steps[:2 * nchunk]
+        assert [(s.pad_ >> 1) & 3 for s in grp] == [2 if ring else 1] * (2 * nchunk)
+        assert [s.pad_ & 1 for s in grp] == [0, 1] * nchunk
+        assert sum(s.st.nb for s in grp[0::2]) == inf.kjsize and sum(s.st.nb for s in grp[1::2]) == inf.kjsize
+        if ring:        # the buffer side of every chunk stays inside the first two slots
+            plane = grp[0].st.out.seg[0].sb
+            assert max(s.st.out.seg[0].off for s in grp[0::2]) <= G * plane + grp[0].st.out.seg[0].off
+    transform_world(n, dims, cut, opf, opb, p2p=dims != (1, 1), xypipe=G, xyring=ring, eager=eager)
+
+
+def test_xy_pipeline_needs_a_single_rank_row():
+    L = pb.load(False)
+    a, _ = L.plan_steps((2, 2), 64, 64, 64, 0, False, "fft", p2p=True, xypipe=8)      # an exchange sits between X and Y
+    b, _ = L.plan_steps((2, 2), 64, 64, 64, 0, False, "fft", p2p=True)
+    assert len(a) == len(b)

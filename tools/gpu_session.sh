@@ -18,6 +18,11 @@ if [[ $what == all || $what == ab ]]; then
     TAG="R32 two-pass " P3DFFT_B200_R32=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
     TAG="X tiles of 8 " P3DFFT_B200_XTX8=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
     TAG="R32 + XTX8   " P3DFFT_B200_R32=1 P3DFFT_B200_XTX8=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
+    TAG="XY pipe G=4  " P3DFFT_B200_XYPIPE=4 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
+    TAG="XY pipe G=4 P" P3DFFT_B200_XYPIPE=4 P3DFFT_B200_XYPIPE_PERSIST=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
+    TAG="XY pipe G=2 P" P3DFFT_B200_XYPIPE=2 P3DFFT_B200_XYPIPE_PERSIST=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
+    TAG="XY pipe G=8  " P3DFFT_B200_XYPIPE=8 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
+    TAG="XY G=4 noring" P3DFFT_B200_XYPIPE=4 P3DFFT_B200_XYPIPE_RING=0 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
     TAG="bulk stores  " P3DFFT_B200_BULK=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
     TAG="half-row c2c " P3DFFT_B200_HALF=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
     TAG="split always " P3DFFT_B200_SPLIT=1 python tools/prof_pair.py --size 1024 --pairs 6 --warm 2
@@ -27,6 +32,7 @@ if [[ $what == all || $what == ab ]]; then
     TAG="default singl" python tools/prof_pair.py --size 1024 --pairs 6 --warm 2 --single
   } 2>&1 | tee gpurun_out/ab.log
   # the variants must pass the same parity tests as the defaults
+  P3DFFT_B200_XYPIPE=4 python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider 2>&1 | tail -3 | tee -a gpurun_out/ab.log
   P3DFFT_B200_BULK=1 python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider -k "fast_kernels or large" 2>&1 | tail -3 | tee -a gpurun_out/ab.log
   P3DFFT_B200_HALF=1 python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider -k "fast_kernels or large" 2>&1 | tail -3 | tee -a gpurun_out/ab.log
   P3DFFT_B200_R32=1 P3DFFT_B200_XTX8=1 python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider -k "fast_kernels or large" 2>&1 | tail -3 | tee -a gpurun_out/ab.log
