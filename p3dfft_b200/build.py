@@ -117,6 +117,25 @@ def build_c_drivers(verbose: bool = False) -> list[str]:
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
         out.append(target)
+    # ... and of the WHOLE library: api.cpp on a mock CUDA runtime + every kernel file (tests/test_emulated_library.py)
+    inc = "-I" + os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include")
+    for name, defs in (("p3dfft_emu", []), ("p3dfft_emu_single", ["-DSINGLE_PREC"])):
+        target = os.path.join(LIBDIR, f"lib{name}.so")
+        objdir = os.path.join(LIBDIR, "obj_" + name)
+        os.makedirs(objdir, exist_ok=True)
+        deps = [os.path.join(emu, f) for f in ("emu_api.cpp", "emu_kernels.cpp", "emu_fast.cpp", "cuda_emu.h", "emu_runtime.inc")] + \
+            [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+        if _newer(target, deps):
+            objs, cmds = [], []
+            for src, extra in (("emu_api.cpp", []), ("emu_kernels.cpp", []), ("emu_fast.cpp", ["-DEMU_NO_RUNTIME"])):
+                obj = os.path.join(objdir, src[:-4] + ".o")
+                objs.append(obj)
+                cmds.append(["g++", "-O1", "-std=c++17", "-x", "c++", "-w", "-c", "-fPIC", "-pthread", *defs, *extra, inc,
+                             os.path.join(emu, src), "-o", obj])
+            with ThreadPoolExecutor(max_workers=len(cmds)) as ex:
+                list(ex.map(subprocess.check_call, cmds))
+            subprocess.check_call(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", *objs, "-o", target, "-ldl"])
+        out.append(target)
     return out
 
 

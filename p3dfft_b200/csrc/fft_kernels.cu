@@ -16,6 +16,11 @@
 #include "kernels.h"
 #include "rcopy.h"
 
+// every kernel launch of this file goes through this macro (tests/emu supplies a host emulation of it)
+#ifndef P3D_KLAUNCH
+#define P3D_KLAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 namespace p3d {
 
 template <typename T> struct Cx;
@@ -415,7 +420,7 @@ cudaError_t launch_spectrum(const void* B, const SpecJob& job_in, double* E, cud
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   long long grid = (rows + 7) / 8;
   if (grid > (long long)sms * per_sm) grid = (long long)sms * per_sm;
-  spectrum_kernel<T><<<(unsigned)grid, 256, smem, stream>>>(reinterpret_cast<const typename Cx<T>::type*>(B), job, E);
+  P3D_KLAUNCH(spectrum_kernel<T>, (unsigned)grid, 256, smem, stream, reinterpret_cast<const typename Cx<T>::type*>(B), job, E);
   return cudaGetLastError();
 }
 
@@ -429,14 +434,19 @@ cudaError_t launch_spectrum(const void* B, const SpecJob& job_in, double* E, cud
 __global__ void flag_barrier_kernel(unsigned* const* __restrict__ peers, int me, int nrank, unsigned epoch) {
   const int r = threadIdx.x;
   if (r < nrank) {
-    __threadfence_system();
     unsigned* dst = peers[r] + (size_t)me * 32;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
     const unsigned* src = peers[me] + (size_t)r * 32;
     unsigned v;
+#ifndef P3D_EMULATE
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
     } while ((int)(v - epoch) < 0);
+#else
+    __atomic_store_n(dst, epoch, __ATOMIC_RELEASE);
+    do { v = __atomic_load_n(src, __ATOMIC_ACQUIRE); } while ((int)(v - epoch) < 0);
+#endif
   }
   __syncthreads();
 }
@@ -444,7 +454,7 @@ __global__ void flag_barrier_kernel(unsigned* const* __restrict__ peers, int me,
 cudaError_t launch_flag_barrier(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream) {
   if (nrank > 1024) return cudaErrorInvalidValue;
   const int nt = nrank <= 32 ? 32 : ((nrank + 31) / 32) * 32;
-  flag_barrier_kernel<<<1, nt, 0, stream>>>(peers, me, nrank, epoch);
+  P3D_KLAUNCH(flag_barrier_kernel, 1, nt, 0, stream, peers, me, nrank, epoch);
   return cudaGetLastError();
 }
 
@@ -490,7 +500,7 @@ static cudaError_t launch_kind(const P3dStage& st, cudaStream_t stream) {
   long long grid = tiles_a * st.nb * st.nc;
   if (grid <= 0) return cudaSuccess;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  stage_kernel<T, KIND><<<(unsigned)grid, 256, smem, stream>>>(st);
+  P3D_KLAUNCH((stage_kernel<T, KIND>), (unsigned)grid, 256, smem, stream, st);
   return cudaGetLastError();
 }
 
@@ -516,8 +526,8 @@ cudaError_t launch_cheby(void* out, long long ncol, int nzc, long long zstride, 
                          double norm, double lfac, cudaStream_t stream) {
   if (ncol <= 0) return cudaSuccess;
   unsigned grid = (unsigned)((ncol + 127) / 128);
-  cheby_kernel<T><<<grid, 128, 0, stream>>>(reinterpret_cast<typename Cx<T>::type*>(out), ncol, nzc, zstride,
-                                            colstride, (T)norm, (T)lfac);
+  P3D_KLAUNCH(cheby_kernel<T>, grid, 128, 0, stream, reinterpret_cast<typename Cx<T>::type*>(out), ncol, nzc, zstride, colstride,
+              (T)norm, (T)lfac);
   return cudaGetLastError();
 }
 
@@ -537,7 +547,7 @@ cudaError_t launch_rcopy(const P3dStage& st, cudaStream_t stream) {
   long long gx = (job.rows_max + 7) / 8;
   const long long cap = (long long)sms * 8;
   if (gx > cap) gx = cap;
-  rcopy_kernel<T><<<dim3((unsigned)gx, (unsigned)job.nbox), 256, 0, stream>>>(job);
+  P3D_KLAUNCH(rcopy_kernel<T>, dim3((unsigned)gx, (unsigned)job.nbox), 256, 0, stream, job);
   return cudaGetLastError();
 }
 

@@ -82,7 +82,7 @@ P3D_HD void rcopy_row(const RcopyBox& bx, int nb, long long row, long long* src_
   *dst_off = v * bx.sv_out + b * bx.sb_out + c * bx.sc_out;
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(P3D_EMULATE)
 // grid = (row groups, boxes); one warp per row at a time, lanes along the contiguous direction u.
 template <typename T>
 __global__ void __launch_bounds__(256) rcopy_kernel(const __grid_constant__ RcopyJob job) {

@@ -1,13 +1,17 @@
 // TEST CODE (CPU only): a minimal functional emulation of the CUDA execution model, enough to run the library's
-// stage kernels (p3dfft_b200/csrc/fft_fast.cuh) on the host: one OS thread per CUDA thread of a CTA, a pthread
-// barrier for __syncthreads(), CTAs one after the other, "shared memory" = one static buffer.  It checks the
-// kernels' index arithmetic, digit reversal, twiddle tables and row tables without a GPU; it says nothing about
-// performance, and memory-model questions (ordering across CTAs, volatile) are outside its reach.
+// kernels (p3dfft_b200/csrc/fft_fast.cuh, fft_kernels.cu, rcopy.h) on the host: one OS thread per CUDA thread of a
+// CTA, a pthread barrier for __syncthreads(), warp shuffles / ballots through a per-warp scratch line, CTAs one
+// after the other, "shared memory" = static buffers.  It checks the kernels' index arithmetic, digit reversal,
+// twiddle tables and row tables without a GPU; it says nothing about performance, and memory-model questions
+// (ordering across CTAs, volatile) are outside its reach.
 #pragma once
 #include <cuda_runtime.h>      // host-side declarations only (double2, dim3, cudaError_t ...)
 #include <pthread.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <functional>
 #include <thread>
 #include <vector>
@@ -15,6 +19,8 @@
 #ifndef __launch_bounds__
 #define __launch_bounds__(...)
 #endif
+// (__noinline__ is defined by the translation unit that needs it, after every standard header: libstdc++ itself
+//  spells __attribute__((__noinline__)))
 
 // ---- built-in variables -----------------------------------------------------------------------------------
 extern thread_local uint3 threadIdx, blockIdx;
@@ -22,13 +28,58 @@ extern thread_local dim3 blockDim, gridDim;
 
 namespace emu {
 extern pthread_barrier_t* cta_barrier;
-// runs kernel body `fn` for a grid of `grid` CTAs of `nt` threads, CTAs sequentially, threads concurrently
-void launch(const std::function<void()>& fn, unsigned grid, unsigned nt);
+extern pthread_barrier_t* warp_barrier;          // [warps of the CTA] (full warps only)
+extern unsigned long long (*warp_scratch)[32];   // [warp][lane]
+// runs kernel body `fn` for a grid of CTAs of `nt` threads, CTAs sequentially, threads concurrently
+void launch(const std::function<void()>& fn, dim3 grid, unsigned nt);
+inline void launch(const std::function<void()>& fn, unsigned grid, unsigned nt) { launch(fn, dim3(grid, 1, 1), nt); }
 unsigned grid_for(long long tiles);      // a few CTAs, so that every CTA walks several tiles
+
+// all 32 lanes of the calling warp exchange one 64-bit word
+inline unsigned long long warp_exchange(unsigned long long mine, int src_lane) {
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  warp_scratch[w][l] = mine;
+  pthread_barrier_wait(&warp_barrier[w]);
+  const unsigned long long v = warp_scratch[w][src_lane & 31];
+  pthread_barrier_wait(&warp_barrier[w]);
+  return v;
+}
 }  // namespace emu
+
+// ---- runtime templates that cuda_runtime.h only provides to nvcc ------------------------------------------------
+template <class F> inline cudaError_t cudaFuncSetAttribute(F*, cudaFuncAttribute, int) { return cudaSuccess; }
 
 // ---- intrinsics the kernels use ------------------------------------------------------------------------------
 inline void __syncthreads() { pthread_barrier_wait(emu::cta_barrier); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
+using std::max;
+using std::min;
+
+template <class T> inline T __shfl_up_sync(unsigned, T val, unsigned delta) {
+  static_assert(sizeof(T) <= 8, "emulated shuffles move up to 8 bytes");
+  unsigned long long bits = 0;
+  memcpy(&bits, &val, sizeof(T));
+  const int lane = (int)(threadIdx.x & 31), src = lane - (int)delta;
+  const unsigned long long got = emu::warp_exchange(bits, src < 0 ? lane : src);
+  T out;
+  memcpy(&out, &got, sizeof(T));
+  return src < 0 ? val : out;
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+  unsigned m = 0;
+  for (int l = 0; l < 32; l++) m |= (emu::warp_exchange(pred ? 1ull : 0ull, l) ? 1u : 0u) << l;
+  return m;
+}
+inline double atomicAdd(double* p, double v) {
+  unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
+  unsigned long long old = __atomic_load_n(q, __ATOMIC_RELAXED), nw;
+  double o;
+  do {
+    memcpy(&o, &old, 8);
+    const double n = o + v;
+    memcpy(&nw, &n, 8);
+  } while (!__atomic_compare_exchange_n(q, &old, nw, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  return o;
+}

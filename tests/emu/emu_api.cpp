@@ -1,0 +1,83 @@
+// TEST CODE (CPU only): the C ABI of the library (p3dfft_b200/csrc/api.cpp, unchanged) on top of a mock CUDA runtime, so
+// that the WHOLE library -- planner, executor, staging of host arrays, scaling, epilogues, the auxiliary routines -- runs in
+// the CPU test-suite through the emulated kernels (emu_fast.cpp, emu_kernels.cpp).  "Device memory" is host memory, streams
+// execute at enqueue time in program order, events are wall-clock stamps.  Single rank only (NCCL is never loaded).
+// Linked with -Bsymbolic: the mock entry points below carry the real CUDA runtime names and must win over an already
+// loaded libcudart inside this library only.
+#define P3D_EMULATE 1
+#include "cuda_emu.h"
+
+#include <chrono>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
+#include "emu_runtime.inc"
+
+namespace {
+std::map<char*, size_t> g_alloc;          // "device" allocations
+std::mutex g_mu;
+struct EmuEvent { std::chrono::steady_clock::time_point t; };
+}  // namespace
+
+extern "C" {
+cudaError_t cudaMalloc(void** p, size_t n) {
+  *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256);
+  if (!*p) return cudaErrorMemoryAllocation;
+  std::lock_guard<std::mutex> l(g_mu);
+  g_alloc[(char*)*p] = n;
+  return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) {
+  if (!p) return cudaSuccess;
+  { std::lock_guard<std::mutex> l(g_mu); g_alloc.erase((char*)p); }
+  free(p);
+  return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaStreamSetAttribute(cudaStream_t, cudaStreamAttrID, const cudaStreamAttrValue*) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t) new EmuEvent; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t) new EmuEvent; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete (EmuEvent*)e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { ((EmuEvent*)e)->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = std::chrono::duration<float, std::milli>(((EmuEvent*)b)->t - ((EmuEvent*)a)->t).count();
+  return cudaSuccess;
+}
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+  memset(a, 0, sizeof *a);
+  a->type = cudaMemoryTypeUnregistered;
+  std::lock_guard<std::mutex> l(g_mu);
+  auto it = g_alloc.upper_bound((char*)p);
+  if (it != g_alloc.begin()) {
+    --it;
+    if ((char*)p < it->first + it->second) { a->type = cudaMemoryTypeDevice; a->devicePointer = (void*)p; }
+  }
+  return cudaSuccess;
+}
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorName(cudaError_t) { return "cudaErrorEmulated"; }
+const char* cudaGetErrorString(cudaError_t) { return "error reported by the emulated runtime"; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }        // a 4-SM "GPU"
+cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
+cudaError_t cudaCtxResetPersistingL2Cache(void) { return cudaSuccess; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+}
+
+// extension for the tests: lets a numpy array play the part of a device array (used in place, not staged)
+extern "C" void emu_register_device_range(void* p, size_t n) { std::lock_guard<std::mutex> l(g_mu); g_alloc[(char*)p] = n; }
+extern "C" void emu_unregister_device_range(void* p) { std::lock_guard<std::mutex> l(g_mu); g_alloc.erase((char*)p); }
+
+#include "../../p3dfft_b200/csrc/api.cpp"

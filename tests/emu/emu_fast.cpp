@@ -5,32 +5,9 @@
 #define P3D_EMULATE 1
 #include "cuda_emu.h"
 
-thread_local uint3 threadIdx, blockIdx;
-thread_local dim3 blockDim, gridDim;
-
-namespace emu {
-pthread_barrier_t* cta_barrier = nullptr;
-
-void launch(const std::function<void()>& fn, unsigned grid, unsigned nt) {
-  pthread_barrier_t bar;
-  for (unsigned b = 0; b < grid; b++) {
-    pthread_barrier_init(&bar, nullptr, nt);
-    cta_barrier = &bar;
-    std::vector<std::thread> th;
-    th.reserve(nt);
-    for (unsigned t = 0; t < nt; t++)
-      th.emplace_back([&, t]() {
-        threadIdx = uint3{t, 0, 0}; blockIdx = uint3{b, 0, 0};
-        blockDim = dim3(nt, 1, 1); gridDim = dim3(grid, 1, 1);
-        fn();
-      });
-    for (auto& x : th) x.join();
-    pthread_barrier_destroy(&bar);
-  }
-}
-
-unsigned grid_for(long long tiles) { return (unsigned)(tiles < 3 ? tiles : 3); }
-}  // namespace emu
+#ifndef EMU_NO_RUNTIME
+#include "emu_runtime.inc"
+#endif
 
 // every launch of fft_fast.cu goes through this macro (the CUDA build defines it with <<< >>>)
 #define P3D_LAUNCH(...)                                                             \

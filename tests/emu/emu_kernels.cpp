@@ -1,0 +1,20 @@
+// TEST CODE (CPU only): the any-length stage kernel, the Chebyshev epilogue, the real-copy kernel, the power-spectrum kernel
+// and the flag barrier of p3dfft_b200/csrc/fft_kernels.cu compiled for the host emulation (cuda_emu.h).  Part of
+// libp3dfft_emu[_single].so only.
+#define P3D_EMULATE 1
+#include "cuda_emu.h"
+
+#define __noinline__ __attribute__((noinline))
+
+#define P3D_KLAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+  do {                                                                                        \
+    (void)(stream); (void)(smem);                                                             \
+    emu::launch([&]() { kernel(__VA_ARGS__); }, dim3(grid), (unsigned)(block));                 \
+  } while (0)
+
+namespace p3d {
+alignas(128) unsigned char smem_raw[232448];
+double spec_hist[232448 / 8];
+}  // namespace p3d
+
+#include "../../p3dfft_b200/csrc/fft_kernels.cu"

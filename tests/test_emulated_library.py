@@ -1,0 +1,218 @@
+"""The whole C-ABI library on the CPU.
+
+libp3dfft_emu[_single].so (tests/emu) is the product's api.cpp, planner and every kernel file compiled by g++ against a
+mock CUDA runtime and the execution-model emulation of tests/emu/cuda_emu.h: "device memory" is host memory, streams run
+at enqueue time, kernels run as OS threads.  These tests drive it through the same Python binding and the same helper
+functions as the GPU parity suite (tests/test_gpu_parity.py), so the executor (run_plan), the staging of host arrays,
+the zero-copy path for "device" arrays, scaling, epilogues, the auxiliary routines and the reference's error behaviour
+are exercised in the CPU test-suite against the oracle -- with small sizes, since every CUDA thread is an OS thread.
+Single rank only; nothing here says anything about speed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import p3dfft_b200 as pb
+from oracle import p3dfft_oracle as po
+from tests import test_gpu_parity as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_cache = {}
+
+
+def emulib(single=False):
+    if single not in _cache:
+        path = os.path.join(ROOT, "p3dfft_b200", "lib", "libp3dfft_emu_single.so" if single else "libp3dfft_emu.so")
+        L = pb.P3DFFT(single, path=path)
+        L.lib.emu_register_device_range.argtypes = [C.c_void_p, C.c_size_t]
+        L.lib.emu_unregister_device_range.argtypes = [C.c_void_p]
+        _cache[single] = L
+    return _cache[single]
+
+
+@pytest.fixture
+def lib():
+    L = emulib(False)
+    L.p3dfft_clean()
+    L.set_layout(False, False)
+    L.set_async(False)
+    L.set_scale(1.0, 1.0)
+    yield L
+    L.p3dfft_clean()
+    L.set_layout(False, False)
+    L.set_scale(1.0, 1.0)
+
+
+class device_arrays:
+    """numpy arrays registered as device memory with the mock runtime: the library uses them in place (no staging)"""
+
+    def __init__(self, L, *arrays):
+        self.L, self.arrays = L, arrays
+
+    def __enter__(self):
+        for a in self.arrays:
+            self.L.lib.emu_register_device_range(a.ctypes.data, a.nbytes)
+        return self.arrays
+
+    def __exit__(self, *exc):
+        for a in self.arrays:
+            self.L.lib.emu_unregister_device_range(a.ctypes.data)
+
+
+@pytest.mark.parametrize("n,cut", [((32, 32, 32), None), ((14, 26, 38), None), ((64, 64, 64), (32, 32, 32)), ((40, 24, 20), (20, 12, 10)),
+                                   ((128, 64, 64), None)])
+def test_forward_backward_host_arrays(lib, n, cut):
+    G._fwd_bwd(lib, n, cut, device=False)
+
+
+@pytest.mark.parametrize("ops", [("ffc", "cff"), ("ffs", "sff"), ("ffn", "nff")])
+@pytest.mark.parametrize("n,cut", [((16, 12, 9), None), ((32, 16, 24), (16, 8, 12))])
+def test_third_dimension_variants(lib, ops, n, cut):
+    G._fwd_bwd(lib, n, cut, *ops)
+
+
+@pytest.mark.parametrize("n,cut", [((32, 32, 32), None), ((64, 32, 48), (32, 16, 24))])
+def test_stride1_layout(lib, n, cut):
+    G._fwd_bwd(lib, n, cut, stride1=True)
+    G._fwd_bwd(lib, n, cut, "ffc", "cff", stride1=True)
+
+
+def test_single_precision():
+    Lf = emulib(True)
+    Lf.p3dfft_clean()
+    Lf.set_layout(False, False)
+    try:
+        G._fwd_bwd(Lf, (64, 64, 64), None, single=True)
+        G._fwd_bwd(Lf, (14, 26, 38), None, single=True)
+    finally:
+        Lf.p3dfft_clean()
+
+
+def test_device_arrays_are_used_in_place(lib):
+    """the zero-copy path: no staging buffers, the input is left untouched, the specialised kernels take every stage"""
+    n = (64, 64, 64)
+    lib.p3dfft_setup((1, 1), *n, 0)
+    d = po.Decomp(*n, (1, 1), 0)
+    A = np.asfortranarray(np.random.default_rng(3).random(n))
+    keep = A.copy()
+    F = np.zeros((d.nxhp, n[1], n[2]), dtype=np.complex128, order="F")
+    B = np.zeros(n, order="F")
+    with device_arrays(lib, A, F, B):
+        lib.fast_launch_count(True)
+        lib.p3dfft_ftran_r2c(A, F, "fft")
+        lib.p3dfft_btran_c2r(F, B, "tff")
+        assert lib.fast_launch_count() == 6
+    assert np.array_equal(A, keep)
+    assert po.rel_l2(F, po.local_forward(A, d, "fft")) <= 1e-13
+    assert np.max(np.abs(B / A.size - A)) <= 1e-13
+
+
+test_driver_sine_known_answer_and_roundtrip = G.test_driver_sine_known_answer_and_roundtrip
+test_driver_inverse_known_answer = G.test_driver_inverse_known_answer
+test_error_behaviour = G.test_error_behaviour
+
+
+@pytest.mark.parametrize("stride1", [False, True])
+def test_driver_cheby_in_place(lib, stride1):
+    G.test_driver_cheby_sin_to_cos(lib, stride1)
+
+
+@pytest.mark.parametrize("stride1", [False, True])
+def test_many_variables(lib, stride1):
+    G.test_many_variables(lib, stride1)
+
+
+@pytest.mark.parametrize("n,cut,stride1", [((64, 64, 64), None, False), ((30, 18, 14), None, False), ((64, 64, 64), (42, 42, 42), True)])
+def test_fused_scale(lib, n, cut, stride1):
+    """p3dfft_b200_set_scale through the executor: the scale lands on the stage that writes the user array, and only there"""
+    nx, ny, nz = n
+    c = cut or (None, None, None)
+    lib.set_layout(stride1, False)
+    lib.p3dfft_setup((1, 1), nx, ny, nz, 0, *c)
+    d = po.Decomp(nx, ny, nz, (1, 1), 0, *c, stride1=stride1)
+    A = np.asfortranarray(np.random.default_rng(8).random(n))
+    N = float(nx * ny * nz)
+    lib.set_scale(1.0 / N, 2.0)
+    exp = po.local_forward(A, d, "fft")
+    F = np.zeros(exp.shape, dtype=np.complex128, order="F")
+    lib.p3dfft_ftran_r2c(A, F, "fft")
+    assert po.rel_l2(F, exp / N) <= 1e-13
+    B = np.zeros(n, order="F")
+    lib.p3dfft_btran_c2r(np.asfortranarray(exp), B, "tff")
+    assert po.rel_l2(B, 2.0 * po.local_backward(po.global_forward(A, d, "fft"), d, "tff")) <= 1e-13
+
+
+@pytest.mark.parametrize("n,cut,stride1", [((16, 16, 16), None, False), ((16, 12, 10), None, True), ((32, 32, 32), (20, 20, 20), False)])
+def test_power_spectrum(lib, n, cut, stride1):
+    """the spectrum kernel (warp shuffles, ballots, shared and global atomics emulated) against the oracle"""
+    nx, ny, nz = n
+    c = cut or (None, None, None)
+    lib.set_layout(stride1, False)
+    lib.p3dfft_setup((1, 1), nx, ny, nz, 0, *c)
+    d = po.Decomp(nx, ny, nz, (1, 1), 0, *c, stride1=stride1)
+    A = np.asfortranarray(np.random.default_rng(4).random(n))
+    F = np.asfortranarray(po.local_forward(A, d, "fft"))
+    kmax = po.spectrum_kmax(nx, ny, nz)
+    factor = 1.0 / (nx * ny * nz)
+    E = lib.spectrum(F, kmax, factor)
+    expE = po.power_spectrum(F, d, kmax, factor)
+    assert np.max(np.abs(E - expE)) <= 1e-12 * np.max(np.abs(expE))
+
+
+def test_r2c_1d_rtran_and_queries(lib):
+    nx, ny, nz = 64, 12, 10
+    lib.p3dfft_setup((1, 1), nx, ny, nz, 0)
+    d = po.Decomp(nx, ny, nz, (1, 1), 0)
+    A = np.asfortranarray(np.random.default_rng(1).random((nx, ny, nz)))
+    exp = po.forward_r2c_1d(A)
+    Cc = np.zeros(exp.size, dtype=np.complex128)
+    lib.p3dfft_ftran_r2c_1d(A, Cc)
+    assert po.rel_l2(Cc, exp.ravel(order="F")) <= 1e-13
+    for which in pb.RTRAN_NAMES:
+        dst = np.full(A.size, np.nan)
+        dstart, dend, dsize, t = lib.rtran(which, A, dst)
+        assert [list(dstart), list(dend), list(dsize)] == [list(x) for x in po.rtran_dims(d, which)]
+        assert np.array_equal(dst, A.ravel(order="F")) and t == 0.0
+    g = po.ProcGrid(nx, ny, nz, (1, 1))
+    assert lib.p3dfft_get_mpi_info()[:2] == (0, 1)
+    assert lib.proc_dims(2, 0) == [g.proc_dims[(2, k, 0)] for k in range(1, 10)]
+    exp_parts = g.get_proc_parts(2, 3, 4, 5, 6, 3, 1)
+    assert lib.get_proc_parts((2, 3, 4), (5, 6, 3), 1, 1) == (exp_parts[0][:1], exp_parts[1], exp_parts[2])
+
+
+def test_opt_in_variants_through_the_executor(lib, monkeypatch):
+    """the switchable kernel variants and the X<->Y pipeline, end to end through api.cpp (sizes whose six stages all run on
+    the specialised kernels: the emulation of the any-length kernel's many small CTAs is slow)"""
+    cases = [({"P3DFFT_B200_R32": "1"}, (64, 512, 64), False), ({"P3DFFT_B200_HALF": "1"}, (64, 1024, 64), False),
+             ({"P3DFFT_B200_BULK": "1"}, (64, 512, 64), True), ({"P3DFFT_B200_XYPIPE": "24"}, (64, 512, 64), True),
+             ({"P3DFFT_B200_XYPIPE": "13", "P3DFFT_B200_XYPIPE_RING": "0"}, (64, 64, 64), True)]
+    for env, n, both in cases:
+        d = po.Decomp(*n, (1, 1), 0)
+        A = np.asfortranarray(np.random.default_rng(5).random(n))
+        exp = po.local_forward(A, d, "fft")
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        try:
+            lib.p3dfft_setup((1, 1), *n, 0)
+            F = np.zeros(exp.shape, dtype=np.complex128, order="F")
+            lib.launch_count(True)
+            lib.fast_launch_count(True)
+            lib.p3dfft_ftran_r2c(A, F, "fft")
+            nl = lib.launch_count()
+            assert lib.fast_launch_count() == nl
+            assert po.rel_l2(F, exp) <= 1e-13, env
+            if both:
+                B = np.zeros(n, order="F")
+                lib.p3dfft_btran_c2r(F, B, "tff")
+                assert np.max(np.abs(B / A.size - A)) <= 1e-13, env
+                assert lib.launch_count() == 2 * nl
+            if "P3DFFT_B200_XYPIPE" in env:
+                chunks = -(-n[2] // int(env["P3DFFT_B200_XYPIPE"]))
+                assert nl == 2 * chunks + 1, (env, nl)       # X and Y in chunks of G planes, one Z stage
+            else:
+                assert nl == 3
+        finally:
+            lib.p3dfft_clean()
+            for k in env:
+                monkeypatch.delenv(k)
