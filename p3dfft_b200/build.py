@@ -19,7 +19,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-gnu-unique", "--expt-relaxed-constexpr"]
+# -fno-gnu-unique: static locals of template functions (launch_spectrum<T>::configured ...) must stay private to each library;
+# the double and single libraries are routinely loaded into one process (tests/mp_parity.py, bench.py)
 SOURCES = ["fft_kernels.cu", "fft_fast.cu", "api.cpp"]
 HEADERS = ["stage.h", "plan.h", "kernels.h", "fast.h", "fft_fast.cuh", "rcopy.h", "procmap.h"]
 
@@ -55,7 +57,9 @@ def build_one(name: str, defines: list[str], verbose: bool = False, force: bool 
         with ThreadPoolExecutor(max_workers=len(cmds)) as ex:
             list(ex.map(run, cmds))
     if force or _newer(target, objs):
-        cmd = [NVCC, *ARCH, "-shared", "-o", target, *objs, "-ldl"]
+        # -Bsymbolic: references inside a library bind to its own definitions even when the double and the single library
+        # (same symbol names, different real type) sit in one process loaded RTLD_GLOBAL
+        cmd = [NVCC, *ARCH, "-shared", "-Xlinker", "-Bsymbolic", "-o", target, *objs, "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
@@ -111,7 +115,7 @@ def build_c_drivers(verbose: bool = False) -> list[str]:
         if _newer(target, deps):
             # -Bsymbolic: the emulator shares symbol names (p3d::launch_fast ...) with the product library, which the tests
             # load into the same process with RTLD_GLOBAL; its own calls must bind to its own definitions
-            cmd = ["g++", "-O1", "-std=c++17", "-x", "c++", "-w", "-shared", "-fPIC", "-pthread", "-Wl,-Bsymbolic", *defs, "-I" + os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include"),
+            cmd = ["g++", "-O1", "-fno-gnu-unique", "-std=c++17", "-x", "c++", "-w", "-shared", "-fPIC", "-pthread", "-Wl,-Bsymbolic", *defs, "-I" + os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include"),
                    os.path.join(emu, "emu_fast.cpp"), "-o", target]
             if verbose:
                 print(" ".join(cmd), flush=True)
@@ -123,18 +127,18 @@ def build_c_drivers(verbose: bool = False) -> list[str]:
         target = os.path.join(LIBDIR, f"lib{name}.so")
         objdir = os.path.join(LIBDIR, "obj_" + name)
         os.makedirs(objdir, exist_ok=True)
-        deps = [os.path.join(emu, f) for f in ("emu_api.cpp", "emu_kernels.cpp", "emu_fast.cpp", "cuda_emu.h", "emu_runtime.inc")] + \
+        deps = [os.path.join(emu, f) for f in ("emu_api.cpp", "emu_kernels.cpp", "emu_fast.cpp", "cuda_emu.h", "emu_runtime.inc", "emu_mp.inc")] + \
             [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
         if _newer(target, deps):
             objs, cmds = [], []
             for src, extra in (("emu_api.cpp", []), ("emu_kernels.cpp", []), ("emu_fast.cpp", ["-DEMU_NO_RUNTIME"])):
                 obj = os.path.join(objdir, src[:-4] + ".o")
                 objs.append(obj)
-                cmds.append(["g++", "-O1", "-std=c++17", "-x", "c++", "-w", "-c", "-fPIC", "-pthread", *defs, *extra, inc,
+                cmds.append(["g++", "-O1", "-fno-gnu-unique", "-std=c++17", "-x", "c++", "-w", "-c", "-fPIC", "-pthread", *defs, *extra, inc,
                              os.path.join(emu, src), "-o", obj])
             with ThreadPoolExecutor(max_workers=len(cmds)) as ex:
                 list(ex.map(subprocess.check_call, cmds))
-            subprocess.check_call(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", *objs, "-o", target, "-ldl"])
+            subprocess.check_call(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", *objs, "-o", target, "-ldl", "-lrt"])
         out.append(target)
     return out
 

@@ -378,6 +378,7 @@ bool alloc_work(int nv, bool for_rtran = false) {
 bool finalize_plan(p3d::TransformPlan& tp) {
   for (auto& s : tp.steps) {
     if (s.is_exchange || s.st.kind == P3D_RCOPY) continue;
+    if (s.st.na <= 0 || s.st.nb <= 0 || s.st.nc <= 0) { s.st.tile = 1; continue; }      // empty chunk of a pipelined tail: never launched
     s.st.tile = p3d::choose_tile<real_t>(s.st);
     if (s.st.tile <= 0) { report(true, "P3DFFT(B200): transform length %d does not fit on chip", s.st.nfft); return false; }
     if (s.st.kind != P3D_NOOP) {

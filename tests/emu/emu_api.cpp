@@ -1,11 +1,15 @@
 // TEST CODE (CPU only): the C ABI of the library (p3dfft_b200/csrc/api.cpp, unchanged) on top of a mock CUDA runtime, so
 // that the WHOLE library -- planner, executor, staging of host arrays, scaling, epilogues, the auxiliary routines -- runs in
 // the CPU test-suite through the emulated kernels (emu_fast.cpp, emu_kernels.cpp).  "Device memory" is host memory, streams
-// execute at enqueue time in program order, events are wall-clock stamps.  Single rank only (NCCL is never loaded).
+// execute at enqueue time in program order, events are wall-clock stamps.  Several ranks = several processes: emu_mp.inc
+// (shared-memory "device" buffers that the mock cudaIpc calls map into the peers, and a mock NCCL bound through dlsym).
 // Linked with -Bsymbolic: the mock entry points below carry the real CUDA runtime names and must win over an already
 // loaded libcudart inside this library only.
 #define P3D_EMULATE 1
 #include "cuda_emu.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <chrono>
 #include <cstdlib>
@@ -13,6 +17,7 @@
 #include <mutex>
 
 #include "emu_runtime.inc"
+#include "emu_mp.inc"
 
 namespace {
 std::map<char*, size_t> g_alloc;          // "device" allocations
@@ -22,7 +27,9 @@ struct EmuEvent { std::chrono::steady_clock::time_point t; };
 
 extern "C" {
 cudaError_t cudaMalloc(void** p, size_t n) {
-  *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256);
+  static bool hooked = false;
+  if (emu_mp::use_shm() && !hooked) { atexit(emu_mp::shm_cleanup); hooked = true; }
+  *p = emu_mp::use_shm() ? emu_mp::shm_create(n) : aligned_alloc(256, (n + 255) / 256 * 256 + 256);
   if (!*p) return cudaErrorMemoryAllocation;
   std::lock_guard<std::mutex> l(g_mu);
   g_alloc[(char*)*p] = n;
@@ -31,7 +38,7 @@ cudaError_t cudaMalloc(void** p, size_t n) {
 cudaError_t cudaFree(void* p) {
   if (!p) return cudaSuccess;
   { std::lock_guard<std::mutex> l(g_mu); g_alloc.erase((char*)p); }
-  free(p);
+  if (!emu_mp::shm_release(p)) free(p);
   return cudaSuccess;
 }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
@@ -71,13 +78,29 @@ cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }        // a 4-SM "GPU"
 cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 cudaError_t cudaCtxResetPersistingL2Cache(void) { return cudaSuccess; }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+// peer mappings: a handle names the shared-memory segment of an allocation (multi-process runs only)
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  static_assert(sizeof(cudaIpcMemHandle_t) >= 64, "handle size");
+  return emu_mp::shm_handle(p, h->reserved) ? cudaSuccess : cudaErrorNotSupported;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  *p = emu_mp::shm_open_peer(h.reserved);
+  if (!*p) return cudaErrorInvalidValue;
+  std::lock_guard<std::mutex> l(g_mu);
+  g_alloc[(char*)*p] = emu_mp::g_shm[(char*)*p].bytes;       // a device pointer of this process from now on
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) {
+  { std::lock_guard<std::mutex> l(g_mu); g_alloc.erase((char*)p); }
+  return emu_mp::shm_release(p) ? cudaSuccess : cudaErrorInvalidValue;
+}
 }
 
 // extension for the tests: lets a numpy array play the part of a device array (used in place, not staged)
 extern "C" void emu_register_device_range(void* p, size_t n) { std::lock_guard<std::mutex> l(g_mu); g_alloc[(char*)p] = n; }
 extern "C" void emu_unregister_device_range(void* p) { std::lock_guard<std::mutex> l(g_mu); g_alloc.erase((char*)p); }
 
+// api.cpp binds NCCL with dlopen/dlsym: hand it the mock
+#define dlopen emu_mp::emu_dlopen
+#define dlsym emu_mp::emu_dlsym
 #include "../../p3dfft_b200/csrc/api.cpp"

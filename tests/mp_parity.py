@@ -11,6 +11,7 @@ Covers the reference's own matrix (extra/makejob.py:122-152): even 32^3 and 128^
 Exit code 0 iff every case passes on every rank.
 """
 import argparse
+import ctypes
 import os
 import sys
 
@@ -18,9 +19,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-
-import torch
-import torch.distributed as dist
 
 import p3dfft_b200 as pb
 from oracle import p3dfft_oracle as po
@@ -41,12 +39,48 @@ CASES = [
 ]
 
 
-def run_case(L, comm, dims, rank, case):
+class TorchArrays:
+    """device arrays of the GPU run: torch CUDA tensors"""
+
+    def dev(self, a):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+    def full(self, n, value, np_dtype):
+        import torch
+        return torch.full((n,), value, dtype=torch.float32 if np_dtype == np.float32 else torch.float64, device="cuda")
+
+    def host(self, t):
+        return t.cpu().numpy()
+
+
+class EmuArrays:
+    """'device' arrays of the CPU emulation (tests/mp_emu.py): numpy arrays registered with the mock runtime, which the
+    library then uses in place like device memory"""
+
+    def __init__(self, L):
+        self.L, self.keep = L, []
+        L.lib.emu_register_device_range.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+
+    def dev(self, a):
+        a = np.ascontiguousarray(a).copy()
+        self.L.lib.emu_register_device_range(a.ctypes.data, a.nbytes)
+        self.keep.append(a)
+        return a
+
+    def full(self, n, value, np_dtype):
+        return self.dev(np.full(n, value, dtype=np_dtype))
+
+    def host(self, t):
+        return t
+
+
+def run_case(L, comm, dims, rank, case, X=None):
+    X = X or TorchArrays()
     n, cut, opf, opb, stride1, nv, single = case
     nx, ny, nz = n
     c = cut or (None, None, None)
     rt, ct = (np.float32, np.complex64) if single else (np.float64, np.complex128)
-    tt = torch.float32 if single else torch.float64
     L.set_layout(stride1, False)
     L.p3dfft_setup(dims, nx, ny, nz, comm, *c)
     d = po.Decomp(nx, ny, nz, dims, rank, *c, stride1=stride1, elem=4 if single else 8)
@@ -56,13 +90,13 @@ def run_case(L, comm, dims, rank, case):
     nreal, ncplx = int(np.prod(isz)), int(np.prod(fsz))
     fields = [po.philox_field(nx, ny, nz, seed=20240229 + v) for v in range(nv)]
     loc = [np.asfortranarray(f[po.local_in_slice(d)]).astype(rt) for f in fields]
-    tA = torch.from_numpy(np.concatenate([a.ravel(order="F") for a in loc])).cuda()
-    tF = torch.zeros(2 * ncplx * nv, dtype=tt, device="cuda")
+    tA = X.dev(np.concatenate([a.ravel(order="F") for a in loc]))
+    tF = X.full(2 * ncplx * nv, 0.0, rt)
     if nv == 1:
         L.p3dfft_ftran_r2c(tA, tF, opf)
     else:
         L.p3dfft_ftran_r2c_many(tA, nreal, tF, ncplx, nv, opf)
-    F = tF.cpu().numpy().view(ct).reshape(nv, ncplx)
+    F = X.host(tF).view(ct).reshape(nv, ncplx)
     errs = []
     for v in range(nv):
         exp = po.local_forward(fields[v].astype(rt).astype(np.float64), d, opf)
@@ -75,13 +109,13 @@ def run_case(L, comm, dims, rank, case):
         if stride1:
             l = l.transpose(2, 1, 0)
         parts.append(np.asfortranarray(l).astype(ct).ravel(order="F"))
-    tFi = torch.from_numpy(np.concatenate(parts).view(rt)).cuda()
-    tB = torch.zeros(nreal * nv, dtype=tt, device="cuda")
+    tFi = X.dev(np.concatenate(parts).view(rt))
+    tB = X.full(nreal * nv, 0.0, rt)
     if nv == 1:
         L.p3dfft_btran_c2r(tFi, tB, opb)
     else:
         L.p3dfft_btran_c2r_many(tFi, ncplx, tB, nreal, nv, opb)
-    B = tB.cpu().numpy().reshape(nv, nreal)
+    B = X.host(tB).reshape(nv, nreal)
     for v in range(nv):
         exp = po.local_backward(Fg[v], d, opb)
         errs.append(po.rel_l2(B[v], np.asfortranarray(exp).ravel(order="F")))
@@ -89,12 +123,12 @@ def run_case(L, comm, dims, rank, case):
     return max(errs)
 
 
-def run_aux(L, comm, dims, rank, n, single):
+def run_aux(L, comm, dims, rank, n, single, X=None):
     """Remaining module routines on this grid: the four real-data transposes (bit-exact: data movement only),
     p3dfft_ftran_r2c_1d and the process-map queries.  Returns the worst error (0.0 = exact)."""
+    X = X or TorchArrays()
     nx, ny, nz = n
     rt, ct = (np.float32, np.complex64) if single else (np.float64, np.complex128)
-    tt = torch.float32 if single else torch.float64
     L.set_layout(False, False)
     L.p3dfft_setup(dims, nx, ny, nz, comm)
     d = po.Decomp(nx, ny, nz, dims, rank, elem=4 if single else 8)
@@ -103,13 +137,13 @@ def run_aux(L, comm, dims, rank, n, single):
     t_acc = 0.0
     for which in pb.RTRAN_NAMES * 2:            # twice: the second round reuses the receive buffers (hazard rule)
         src_sl, dst_sl = po.rtran_slices(d, which)
-        src = torch.from_numpy(np.asfortranarray(G[src_sl]).ravel(order="F").copy()).cuda()
+        src = X.dev(np.asfortranarray(G[src_sl]).ravel(order="F").copy())
         exp = po.rtran_local(G, d, which)
-        dst = torch.full((exp.size,), float("nan"), dtype=tt, device="cuda")
+        dst = X.full(exp.size, float("nan"), rt)
         dstart, dend, dsize, t_acc = L.rtran(which, src, dst, t_acc)
         if [list(dstart), list(dend), list(dsize)] != [list(x) for x in po.rtran_dims(d, which)]:
             worst = max(worst, 2.0)       # no assert inside the collective sequence: a rank that raised would hang the others
-        if not np.array_equal(dst.cpu().numpy(), exp.ravel(order="F")):
+        if not np.array_equal(X.host(dst), exp.ravel(order="F")):
             worst = max(worst, 1.0)
         # host arrays take the staged path
         dsth = np.full(exp.size, np.nan, dtype=rt)
@@ -117,10 +151,10 @@ def run_aux(L, comm, dims, rank, n, single):
         if not np.array_equal(dsth, exp.ravel(order="F")):
             worst = max(worst, 1.0)
     A = np.asfortranarray(G[po.local_in_slice(d)])
-    tA = torch.from_numpy(A.ravel(order="F").copy()).cuda()
-    tC = torch.zeros(2 * d.nxhp * d.jisize * d.kjsize, dtype=tt, device="cuda")
+    tA = X.dev(A.ravel(order="F").copy())
+    tC = X.full(2 * d.nxhp * d.jisize * d.kjsize, 0.0, rt)
     L.p3dfft_ftran_r2c_1d(tA, tC)
-    e = po.rel_l2(tC.cpu().numpy().view(ct), po.forward_r2c_1d(A.astype(np.float64)).ravel(order="F"))
+    e = po.rel_l2(X.host(tC).view(ct), po.forward_r2c_1d(A.astype(np.float64)).ravel(order="F"))
     worst = max(worst, e / (1e-5 if single else 1e-12) * 1e-12)
     g = po.ProcGrid(nx, ny, nz, dims)
     P = dims[0] * dims[1]
@@ -144,6 +178,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grids", default="")
     a = ap.parse_args()
+    import torch                      # (imported here: tests/mp_emu.py reuses this module's cases and checks without torch)
+    import torch.distributed as dist
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
