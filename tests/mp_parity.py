@@ -53,6 +53,10 @@ class TorchArrays:
     def host(self, t):
         return t.cpu().numpy()
 
+    def sync(self):
+        import torch
+        torch.cuda.synchronize()
+
 
 class EmuArrays:
     """'device' arrays of the CPU emulation (tests/mp_emu.py): numpy arrays registered with the mock runtime, which the
@@ -73,6 +77,9 @@ class EmuArrays:
 
     def host(self, t):
         return t
+
+    def sync(self):
+        pass
 
 
 def run_case(L, comm, dims, rank, case, X=None):

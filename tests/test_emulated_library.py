@@ -114,6 +114,15 @@ test_error_behaviour = G.test_error_behaviour
 
 
 @pytest.mark.parametrize("stride1", [False, True])
+@pytest.mark.parametrize("device", [False, True])
+def test_driver_sine_inplace(lib, stride1, device):
+    """driver_sine_inplace.c on the emulated library: host array (staged) and "device" array (used in place)"""
+    from tests import mp_parity as M
+    G._inplace_sine(lib, (64, 64, 64), stride1, M.EmuArrays(lib) if device else None)
+    G._inplace_sine(lib, (30, 18, 50), stride1, M.EmuArrays(lib) if device else None)
+
+
+@pytest.mark.parametrize("stride1", [False, True])
 def test_driver_cheby_in_place(lib, stride1):
     G.test_driver_cheby_sin_to_cos(lib, stride1)
 

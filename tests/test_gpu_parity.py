@@ -205,6 +205,43 @@ def test_driver_inverse_known_answer(lib):
     assert np.max(np.abs(B - exp)) <= 1e-14 * N * 0.25
 
 
+def _inplace_sine(L, n, stride1, arrays=None, iterations=2):
+    """driver_sine_inplace.c:183-232: ONE array of max(real, 2 x complex) elements is input and output of both transforms
+    (Cp3dfft_ftran_r2c(A,A,op_f) ... mult_array ... Cp3dfft_btran_c2r(A,A,op_b)), `iterations` times; the result must be the
+    initial sine field to 1e-14*N/4.  arrays=None: a host array (staged); otherwise the adapter that makes device arrays."""
+    nx, ny, nz = n
+    L.set_layout(stride1, False)
+    L.p3dfft_setup((1, 1), nx, ny, nz, 0, nx, ny, nz, True)
+    _, _, isz = L.p3dfft_get_dims(1)
+    _, _, fsz = L.p3dfft_get_dims(2)
+    nm = max(int(np.prod(isz)), 2 * int(np.prod(fsz)))
+    field = (np.sin(2 * np.pi * np.arange(nx) / nx)[:, None, None] * np.sin(2 * np.pi * np.arange(ny) / ny)[None, :, None]
+             * np.sin(2 * np.pi * np.arange(nz) / nz)[None, None, :])
+    host = np.zeros(nm)
+    host[: nx * ny * nz] = field.ravel(order="F")
+    A = arrays.dev(host) if arrays else host
+    N = nx * ny * nz
+    for _ in range(iterations):
+        L.p3dfft_ftran_r2c(A, A, "fft")
+        if arrays:
+            A *= 1.0 / N                      # mult_array on the device array
+            arrays.sync()
+        else:
+            A[: 2 * int(np.prod(fsz))] *= 1.0 / N
+        L.p3dfft_btran_c2r(A, A, "tff")
+    out = np.asarray(arrays.host(A) if arrays else A)[: nx * ny * nz].reshape((nx, ny, nz), order="F")
+    L.p3dfft_clean()
+    assert np.max(np.abs(out - field)) <= 1e-14 * N * 0.25
+
+
+@pytest.mark.parametrize("stride1", [False, True])
+@pytest.mark.parametrize("device", [False, True])
+def test_driver_sine_inplace(lib, stride1, device):
+    from tests import mp_parity as M
+    _inplace_sine(lib, (64, 64, 64), stride1, M.TorchArrays() if device else None)
+    _inplace_sine(lib, (30, 18, 50), stride1, M.TorchArrays() if device else None)
+
+
 @pytest.mark.parametrize("stride1", [False, True])
 def test_driver_cheby_sin_to_cos(lib, stride1):
     """driver_cheby.F90:218-285 with its in-place call (mem aliased for in and out)."""
