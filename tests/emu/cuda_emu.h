@@ -1,7 +1,7 @@
 // TEST CODE (CPU only): a minimal functional emulation of the CUDA execution model, enough to run the library's
-// kernels (p3dfft_b200/csrc/fft_fast.cuh, fft_kernels.cu, rcopy.h) on the host: one OS thread per CUDA thread of a
-// CTA, a pthread barrier for __syncthreads(), warp shuffles / ballots through a per-warp scratch line, CTAs one
-// after the other, "shared memory" = static buffers.  It checks the kernels' index arithmetic, digit reversal,
+// kernels (p3dfft_b200/csrc/fft_fast.cuh, fft_kernels.cu, rcopy.h) on the host: one fiber per CUDA thread of a
+// CTA (emu_runtime.inc), switched at __syncthreads() and at warp rendezvous, warp shuffles / ballots through a per-warp
+// scratch line, CTAs one after the other, "shared memory" = static buffers.  It checks the kernels' index arithmetic, digit reversal,
 // twiddle tables and row tables without a GPU; it says nothing about performance, and memory-model questions
 // (ordering across CTAs, volatile) are outside its reach.
 #pragma once
@@ -27,21 +27,21 @@ extern thread_local uint3 threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
 
 namespace emu {
-extern pthread_barrier_t* cta_barrier;
-extern pthread_barrier_t* warp_barrier;          // [warps of the CTA] (full warps only)
 extern unsigned long long (*warp_scratch)[32];   // [warp][lane]
-// runs kernel body `fn` for a grid of CTAs of `nt` threads, CTAs sequentially, threads concurrently
+// runs kernel body `fn` for a grid of CTAs of `nt` threads: CTAs one after the other, the threads of a CTA as fibers
 void launch(const std::function<void()>& fn, dim3 grid, unsigned nt);
 inline void launch(const std::function<void()>& fn, unsigned grid, unsigned nt) { launch(fn, dim3(grid, 1, 1), nt); }
 unsigned grid_for(long long tiles);      // a few CTAs, so that every CTA walks several tiles
+void sync_cta();                         // __syncthreads()
+void sync_warp();                        // rendezvous of the calling warp's live threads
 
-// all 32 lanes of the calling warp exchange one 64-bit word
+// all lanes of the calling warp exchange one 64-bit word
 inline unsigned long long warp_exchange(unsigned long long mine, int src_lane) {
   const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
   warp_scratch[w][l] = mine;
-  pthread_barrier_wait(&warp_barrier[w]);
+  sync_warp();
   const unsigned long long v = warp_scratch[w][src_lane & 31];
-  pthread_barrier_wait(&warp_barrier[w]);
+  sync_warp();
   return v;
 }
 }  // namespace emu
@@ -50,7 +50,7 @@ inline unsigned long long warp_exchange(unsigned long long mine, int src_lane) {
 template <class F> inline cudaError_t cudaFuncSetAttribute(F*, cudaFuncAttribute, int) { return cudaSuccess; }
 
 // ---- intrinsics the kernels use ------------------------------------------------------------------------------
-inline void __syncthreads() { pthread_barrier_wait(emu::cta_barrier); }
+inline void __syncthreads() { emu::sync_cta(); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
