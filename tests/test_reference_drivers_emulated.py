@@ -114,3 +114,14 @@ def test_reference_driver_spec(exes, tmp_path, name, ranks, grid, tol):
     assert spec, r.stdout[-3000:]
     assert abs(spec[2] - 3.0 / 16.0) <= tol, spec
     assert all(abs(v) <= tol for k, v in spec.items() if k != 2), spec
+
+
+def test_baseline_config1_driver_inverse_128_cubed_2x2(exes, tmp_path):
+    """BASELINE.json configs[0]: sample/C driver_inverse, 128^3 double, 4 ranks on a 2x2 grid -- the reference's own
+    correctness case, its own binary logic and its own check (four spikes -+N/4 at x = nx, driver_inverse.c:222-258)"""
+    r = run_driver(exes["driver_inverse"], tmp_path, 4, (2, 2), (128, 128, 128))
+    assert r.returncode == 0 and "Results are correct" in r.stdout and "incorrect" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    spikes = re.findall(r"\((\d+),(\d+),(\d+)\) (-?[0-9.]+)", r.stdout)
+    got = sorted((int(a), int(b), int(c), float(v)) for a, b, c, v in spikes)
+    n4 = 128 ** 3 / 4
+    assert got == sorted([(128, 3, 4, -n4), (128, 3, 126, n4), (128, 127, 4, n4), (128, 127, 126, -n4)]), got
