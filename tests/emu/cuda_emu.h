@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <thread>
@@ -32,6 +34,20 @@ extern unsigned long long (*warp_scratch)[32];   // [warp][lane]
 void launch(const std::function<void()>& fn, dim3 grid, unsigned nt);
 inline void launch(const std::function<void()>& fn, unsigned grid, unsigned nt) { launch(fn, dim3(grid, 1, 1), nt); }
 unsigned grid_for(long long tiles);      // a few CTAs, so that every CTA walks several tiles
+// canary behind the dynamic shared memory a launch asked for: a kernel that WRITES past its `smem` bytes (an illegal
+// address on the GPU) is caught after the launch
+inline void canary_set(unsigned char* base, size_t used, size_t total) {
+  const size_t n = std::min<size_t>(total - std::min(used, total), 16384);
+  memset(base + std::min(used, total), 0xA5, n);
+}
+inline void canary_check(const unsigned char* base, size_t used, size_t total, const char* what) {
+  const size_t n = std::min<size_t>(total - std::min(used, total), 16384);
+  for (size_t i = 0; i < n; i++)
+    if (base[std::min(used, total) + i] != 0xA5) {
+      fprintf(stderr, "emulated launch of %s wrote shared memory at byte %zu, beyond the %zu bytes it asked for\n", what, used + i, used);
+      abort();
+    }
+}
 void sync_cta();                         // __syncthreads()
 void sync_warp();                        // rendezvous of the calling warp's live threads
 

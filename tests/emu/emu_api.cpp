@@ -29,7 +29,7 @@ extern "C" {
 cudaError_t cudaMalloc(void** p, size_t n) {
   static bool hooked = false;
   if (emu_mp::use_shm() && !hooked) { atexit(emu_mp::shm_cleanup); hooked = true; }
-  *p = emu_mp::use_shm() ? emu_mp::shm_create(n) : aligned_alloc(256, (n + 255) / 256 * 256 + 256);
+  *p = emu_mp::shm_create(n, emu_mp::use_shm());      // guarded; shared memory in multi-rank runs
   if (!*p) return cudaErrorMemoryAllocation;
   std::lock_guard<std::mutex> l(g_mu);
   g_alloc[(char*)*p] = n;
@@ -38,7 +38,7 @@ cudaError_t cudaMalloc(void** p, size_t n) {
 cudaError_t cudaFree(void* p) {
   if (!p) return cudaSuccess;
   { std::lock_guard<std::mutex> l(g_mu); g_alloc.erase((char*)p); }
-  if (!emu_mp::shm_release(p)) free(p);
+  emu_mp::shm_release(p);
   return cudaSuccess;
 }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
@@ -87,7 +87,7 @@ cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
   *p = emu_mp::shm_open_peer(h.reserved);
   if (!*p) return cudaErrorInvalidValue;
   std::lock_guard<std::mutex> l(g_mu);
-  g_alloc[(char*)*p] = emu_mp::g_shm[(char*)*p].bytes;       // a device pointer of this process from now on
+  g_alloc[(char*)*p] = emu_mp::g_shm[(char*)*p].user_bytes;       // a device pointer of this process from now on
   return cudaSuccess;
 }
 cudaError_t cudaIpcCloseMemHandle(void* p) {

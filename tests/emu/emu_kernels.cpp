@@ -9,7 +9,11 @@
 #define P3D_KLAUNCH(kernel, grid, block, smem, stream, ...)                                   \
   do {                                                                                        \
     (void)(stream); (void)(smem);                                                             \
+    emu::canary_set(p3d::smem_raw, (size_t)(smem), sizeof(p3d::smem_raw));                    \
+    emu::canary_set((unsigned char*)p3d::spec_hist, (size_t)(smem), sizeof(p3d::spec_hist));    \
     emu::launch([&]() { kernel(__VA_ARGS__); }, dim3(grid), (unsigned)(block));                 \
+    emu::canary_check(p3d::smem_raw, (size_t)(smem), sizeof(p3d::smem_raw), #kernel);           \
+    emu::canary_check((const unsigned char*)p3d::spec_hist, (size_t)(smem), sizeof(p3d::spec_hist), #kernel); \
   } while (0)
 
 namespace p3d {

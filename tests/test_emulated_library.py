@@ -225,3 +225,23 @@ def test_opt_in_variants_through_the_executor(lib, monkeypatch):
             lib.p3dfft_clean()
             for k in env:
                 monkeypatch.delenv(k)
+
+
+def test_guard_pages_catch_an_overrun():
+    """the mock cudaMalloc end-aligns every allocation against an inaccessible page (tests/emu/emu_mp.inc): writing 16 bytes
+    past the end of a "device" buffer kills the process, the last 16 bytes inside it are fine"""
+    import subprocess
+    import sys
+    code = ("import ctypes as C, sys\n"
+            f"L = C.CDLL({os.path.join(ROOT, 'p3dfft_b200', 'lib', 'libp3dfft_emu.so')!r})\n"
+            "p = C.c_void_p()\n"
+            "assert L.cudaMalloc(C.byref(p), C.c_size_t(1000 * 16)) == 0\n"
+            "C.memset(p.value + 999 * 16, 1, 16)\n"
+            "print('inside ok', flush=True)\n"
+            "if sys.argv[1] == 'over':\n"
+            "    C.memset(p.value + 1000 * 16, 1, 16)\n"
+            "print('done', flush=True)\n")
+    ok = subprocess.run([sys.executable, "-c", code, "in"], capture_output=True, text=True)
+    assert ok.returncode == 0 and "done" in ok.stdout, ok.stderr
+    bad = subprocess.run([sys.executable, "-c", code, "over"], capture_output=True, text=True)
+    assert bad.returncode < 0 and "inside ok" in bad.stdout and "done" not in bad.stdout, (bad.returncode, bad.stdout, bad.stderr)
