@@ -31,6 +31,12 @@ SUITES = {
              ((64, 64, 64), (32, 32, 32), "fft", "tff", False, 1, False),
              ((64, 64, 64), None, "fft", "tff", False, 2, False),            # _many: the work buffers grow, peers are re-mapped
              ((128, 64, 64), None, "fft", "tff", False, 1, True)],
+    # the headline lengths (1024-point X and Z stages: split kernel, L2 prefetch, blocked tile order) at a thin y extent
+    "long": [((1024, 32, 1024), None, "fft", "tff", False, 1, False),
+             ((2048, 16, 512), None, "fft", "tff", False, 1, True)],
+    "long-light": [((1024, 16, 64), None, "fft", "tff", False, 1, False),
+                   ((64, 16, 1024), None, "fft", "tff", False, 1, False),
+                   ((64, 1024, 16), None, "fft", "tff", False, 1, False)],
     "mixed": [((32, 32, 32), None, "fft", "tff", False, 1, False),
               ((14, 26, 38), None, "fft", "tff", False, 1, False),           # the reference's uneven case
               ((32, 32, 33), None, "ffc", "cff", False, 1, False),

@@ -112,3 +112,14 @@ def test_pipelined_tail_executor(grid, chunks):
 def test_eight_ranks_2x4():
     """the headline grid (BASELINE config 3: 2 x 4) at emulation size"""
     check("2x4", ["--suite", "fast", "--expect-p2p", "1"])
+
+
+def test_headline_lengths_2x4():
+    """1024-point X, Y and Z stages (the lengths of the headline benchmark: split kernel, L2 prefetch, blocked tile order) on
+    the 2x4 grid, one long dimension at a time"""
+    check("2x4", ["--suite", "long-light", "--expect-p2p", "1"])
+
+
+@pytest.mark.skipif(not os.environ.get("P3D_EMU_LONG"), reason="opt-in (P3D_EMU_LONG=1): ~1 min, 1024 x 32 x 1024 double and 2048 x 16 x 512 single on 8 ranks")
+def test_headline_lengths_2x4_full():
+    check("2x4", ["--suite", "long", "--expect-p2p", "1"])
