@@ -17,12 +17,12 @@
 #include <mutex>
 
 #include "emu_runtime.inc"
+#include "emu_streams.inc"
 #include "emu_mp.inc"
 
 namespace {
 std::map<char*, size_t> g_alloc;          // "device" allocations
 std::mutex g_mu;
-struct EmuEvent { std::chrono::steady_clock::time_point t; };
 }  // namespace
 
 extern "C" {
@@ -37,26 +37,37 @@ cudaError_t cudaMalloc(void** p, size_t n) {
 }
 cudaError_t cudaFree(void* p) {
   if (!p) return cudaSuccess;
+  emu_rt::sync_all();                 // cudaFree synchronises the device
   { std::lock_guard<std::mutex> l(g_mu); g_alloc.erase((char*)p); }
   emu_mp::shm_release(p);
   return cudaSuccess;
 }
-cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { emu_rt::sync_legacy(); memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st) {
+  emu_rt::enqueue(st, [=]() { memmove(d, s, n); });
+  return cudaSuccess;
+}
+cudaError_t cudaMemset(void* d, int v, size_t n) { emu_rt::sync_legacy(); memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st) {
+  emu_rt::enqueue(st, [=]() { memset(d, v, n); });
+  return cudaSuccess;
+}
+cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = emu_rt::new_stream(true); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags) { *s = emu_rt::new_stream(!(flags & cudaStreamNonBlocking)); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { emu_rt::sync_stream(s); emu_rt::delete_stream(s); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { emu_rt::sync_stream(s); return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { emu_rt::sync_all(); return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) { emu_rt::wait_event(s, (emu_rt::Event*)e); return cudaSuccess; }
 cudaError_t cudaStreamSetAttribute(cudaStream_t, cudaStreamAttrID, const cudaStreamAttrValue*) { return cudaSuccess; }
-cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t) new EmuEvent; return cudaSuccess; }
-cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t) new EmuEvent; return cudaSuccess; }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { delete (EmuEvent*)e; return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { ((EmuEvent*)e)->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t) new emu_rt::Event; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t) new emu_rt::Event; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { emu_rt::sync_all(); delete (emu_rt::Event*)e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { emu_rt::record_event(s, (emu_rt::Event*)e); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t e) { emu_rt::sync_event((emu_rt::Event*)e); return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
-  *ms = std::chrono::duration<float, std::milli>(((EmuEvent*)b)->t - ((EmuEvent*)a)->t).count();
+  emu_rt::Event *ea = (emu_rt::Event*)a, *eb = (emu_rt::Event*)b;
+  if (ea->done < ea->issued || eb->done < eb->issued) return cudaErrorNotReady;      // like the real runtime: no implicit wait
+  *ms = std::chrono::duration<float, std::milli>(eb->t - ea->t).count();
   return cudaSuccess;
 }
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {

@@ -15,9 +15,11 @@
     (void)stream; (void)smem;                                                       \
     static_assert(smem <= sizeof(p3d::fast::smem_raw), "emulated shared memory");   \
     const FastStage fcopy = f;                                                      \
-    emu::canary_set(p3d::fast::smem_raw, smem, sizeof(p3d::fast::smem_raw));        \
-    emu::launch([&]() { __VA_ARGS__(fcopy); }, emu::grid_for(tiles), NT);           \
-    emu::canary_check(p3d::fast::smem_raw, smem, sizeof(p3d::fast::smem_raw), #__VA_ARGS__); \
+    emu::enqueue(stream, [=]() {                                                    \
+      emu::canary_set(p3d::fast::smem_raw, smem, sizeof(p3d::fast::smem_raw));      \
+      emu::launch([&]() { __VA_ARGS__(fcopy); }, emu::grid_for(tiles), NT);         \
+      emu::canary_check(p3d::fast::smem_raw, smem, sizeof(p3d::fast::smem_raw), #__VA_ARGS__); \
+    });                                                                             \
     e = cudaSuccess;                                                                \
   } while (0)
 

@@ -8,12 +8,16 @@
 
 #define P3D_KLAUNCH(kernel, grid, block, smem, stream, ...)                                   \
   do {                                                                                        \
-    (void)(stream); (void)(smem);                                                             \
-    emu::canary_set(p3d::smem_raw, (size_t)(smem), sizeof(p3d::smem_raw));                    \
-    emu::canary_set((unsigned char*)p3d::spec_hist, (size_t)(smem), sizeof(p3d::spec_hist));    \
-    emu::launch([&]() { kernel(__VA_ARGS__); }, dim3(grid), (unsigned)(block));                 \
-    emu::canary_check(p3d::smem_raw, (size_t)(smem), sizeof(p3d::smem_raw), #kernel);           \
-    emu::canary_check((const unsigned char*)p3d::spec_hist, (size_t)(smem), sizeof(p3d::spec_hist), #kernel); \
+    const size_t smem__ = (size_t)(smem);                                                     \
+    const dim3 grid__ = dim3(grid);                                                           \
+    const unsigned block__ = (unsigned)(block);                                               \
+    emu::enqueue(stream, [=]() {                                                              \
+      emu::canary_set(p3d::smem_raw, smem__, sizeof(p3d::smem_raw));                          \
+      emu::canary_set((unsigned char*)p3d::spec_hist, smem__, sizeof(p3d::spec_hist));        \
+      emu::launch([&]() { kernel(__VA_ARGS__); }, grid__, block__);                           \
+      emu::canary_check(p3d::smem_raw, smem__, sizeof(p3d::smem_raw), #kernel);               \
+      emu::canary_check((const unsigned char*)p3d::spec_hist, smem__, sizeof(p3d::spec_hist), #kernel); \
+    });                                                                                       \
   } while (0)
 
 namespace p3d {

@@ -103,10 +103,18 @@ def test_repeated_direction_hazard_rule(grid, env):
     check(grid, ["--suite", "none", "--repeat"], env)
 
 
-@pytest.mark.parametrize("grid,chunks", [("1x2", 2), ("2x2", 3)])
-def test_pipelined_tail_executor(grid, chunks):
-    """opt-in P3DFFT_B200_OVERLAP=C: chunked producer / barrier / consumer lists through the real executor on several ranks"""
-    check(grid, ["--suite", "fast", "--expect-p2p", "1"], {"P3DFFT_B200_OVERLAP": str(chunks)})
+@pytest.mark.parametrize("grid,chunks,policy", [("1x2", 2, "lazy"), ("2x2", 3, "lazy"), ("2x2", 3, "eager"), ("1x2", 3, "random:5"),
+                                               ("2x2", 2, "random:11")])
+def test_pipelined_tail_executor(grid, chunks, policy):
+    """opt-in P3DFFT_B200_OVERLAP=C: chunked producer / barrier / consumer lists through the real executor on several ranks,
+    the consumers on a side stream -- under every order of execution the mock runtime's stream model allows"""
+    check(grid, ["--suite", "fast", "--expect-p2p", "1"], {"P3DFFT_B200_OVERLAP": str(chunks), "P3D_EMU_STREAMS": policy})
+
+
+@pytest.mark.parametrize("policy", ["eager", "random:3"])
+def test_default_path_under_other_stream_orders(policy):
+    check("2x2", ["--suite", "fast", "--expect-p2p", "1"], {"P3D_EMU_STREAMS": policy})
+    check("1x2", ["--suite", "none", "--repeat"], {"P3D_EMU_STREAMS": policy, "P3D_EMU_DELAY": "1:3:2:250"})
 
 
 def test_eight_ranks_2x4():
