@@ -265,3 +265,38 @@ def test_two_stream_executor_under_every_stream_order(policy, env, n):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_stream_check.py"), *map(str, n)], env=e, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0 and " ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_async_calls_on_a_user_stream(lib):
+    """p3dfft_b200_set_stream + set_async: with device arrays the transform is only ENQUEUED on the caller's stream (the mock
+    runtime, lazy policy, runs nothing before a synchronisation), p3dfft_b200_sync completes it; timers are not touched"""
+    n = (64, 64, 64)
+    st = C.c_void_p()
+    assert lib.lib.cudaStreamCreateWithFlags(C.byref(st), 1) == 0         # a non-blocking stream of the caller
+    lib.set_stream(st.value)
+    lib.p3dfft_setup((1, 1), *n, 0)
+    d = po.Decomp(*n, (1, 1), 0)
+    A = np.asfortranarray(np.random.default_rng(9).random(n))
+    F = np.zeros((d.nxhp, n[1], n[2]), dtype=np.complex128, order="F")
+    B = np.zeros(n, order="F")
+    try:
+        with device_arrays(lib, A, F, B):
+            lib.set_async(True)
+            lib.set_timers()
+            lib.p3dfft_ftran_r2c(A, F, "fft")
+            lib.p3dfft_btran_c2r(F, B, "tff")
+            if os.environ.get("P3D_EMU_STREAMS", "lazy") == "lazy":
+                assert not F.any() and not B.any(), "asynchronous calls must return before the work has run"
+            lib.sync()
+            assert po.rel_l2(F, po.local_forward(A, d, "fft")) <= 1e-13
+            assert np.max(np.abs(B / A.size - A)) <= 1e-13
+            assert not any(lib.get_timers()), "asynchronous calls do not time their stages"
+            # host arrays fall back to a synchronous call even in asynchronous mode (the copy back must have landed)
+            F2 = np.zeros_like(F)
+            lib.p3dfft_ftran_r2c(A.copy(order="F"), F2, "fft")
+            assert po.rel_l2(F2, F) <= 1e-15
+    finally:
+        lib.set_async(False)
+        lib.p3dfft_clean()
+        lib.reset_stream()
+        lib.lib.cudaStreamDestroy(st)
