@@ -39,6 +39,48 @@ def test_library_exports_every_declared_symbol(single):
     assert bool(L.lib.p3dfft_b200_build_flags() & 1) == single
 
 
+def _c_prototypes():
+    """name -> number of parameters, for every function declared in include/*.h"""
+    protos = {}
+    for hdr in ("p3dfft.h", "p3dfft_b200.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        for m in re.finditer(r"^\s*(?:void|int|long long)\s+(\w+)\s*\(([^)]*)\)\s*;", text, flags=re.M | re.S):
+            args = m.group(2).strip()
+            protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return protos
+
+
+def test_fortran_module_binds_the_exported_c_abi():
+    """fortran/p3dfft.F90 cannot be compiled here (no Fortran compiler in the image), so its ISO_C_BINDING interfaces are
+    checked as text: every bind(C,name=...) is a symbol the library exports, with as many dummy arguments as the C prototype
+    in include/*.h has parameters; and the module makes public every name of the reference's public list (module.F90:178-186)."""
+    text = open(os.path.join(ROOT, "fortran", "p3dfft.F90")).read()
+    code = "\n".join(ln.split("!")[0].rstrip() for ln in text.splitlines() if not ln.lstrip().startswith("!"))
+    code = re.sub(r"&\s*\n\s*&?", " ", code)
+    L = pb.P3DFFT(False)
+    protos = _c_prototypes()
+    binds = re.findall(r"(?:subroutine|function)\s+(\w+)\s*\(([^)]*)\)\s*(?:result\s*\(\w+\)\s*)?bind\s*\(\s*C\s*,\s*name\s*=\s*'(\w+)'\s*\)", code, flags=re.I)
+    assert len(binds) >= 19, len(binds)
+    for fname, fargs, cname in binds:
+        assert hasattr(L.lib, cname), f"{fname}: {cname} is not exported by the library"
+        assert cname in protos, f"{cname} is not declared in include/*.h"
+        nf = 0 if not fargs.strip() else fargs.count(",") + 1
+        assert nf == protos[cname], f"{fname} -> {cname}: {nf} Fortran dummies, {protos[cname]} C parameters"
+    bound = {c for _, _, c in binds}
+    assert {"p3dfft_setup", "p3dfft_get_dims", "p3dfft_ftran_r2c", "p3dfft_btran_c2r", "p3dfft_ftran_r2c_many", "p3dfft_btran_c2r_many",
+            "p3dfft_cheby", "p3dfft_cheby_many", "p3dfft_clean", "get_timers", "set_timers"} <= bound
+    public = set()
+    for m in re.finditer(r"public\b[^:\n]*::\s*([^\n]*)", code, flags=re.I):
+        public |= {w.split("(")[0].split("=")[0].strip().lower() for w in re.sub(r"\([^)]*\)", "", m.group(1)).split(",")}
+    for name in ("p3dfft_type", "r8", "i8", "num_thr", "padi", "timers", "real_size", "complex_size", "p3dfft_setup", "p3dfft_get_dims",
+                 "p3dfft_get_mpi_info", "p3dfft_ftran_r2c", "p3dfft_btran_c2r", "p3dfft_ftran_r2c_many", "p3dfft_btran_c2r_many",
+                 "p3dfft_cheby", "p3dfft_cheby_many", "get_timers", "set_timers", "p3dfft_clean", "print_buf", "print_buf_real",
+                 "rtran_x2y", "rtran_y2x", "rtran_x2z", "rtran_z2x", "get_proc_parts", "p3dfft_ftran_r2c_1d", "proc_id2coords",
+                 "proc_coords2id", "proc_dims", "proc_parts"):
+        assert name in public, f"module p3dfft does not make `{name}` public"
+
+
 GRIDS = [(1, 1), (2, 2), (1, 4), (4, 1), (2, 3), (3, 2), (2, 4), (1, 8)]
 SIZES = [((32, 32, 32), None), ((14, 26, 38), None), ((64, 64, 64), (32, 32, 32)), ((128, 128, 128), None),
          ((32, 20, 12), (16, 10, 8)), ((16, 16, 33), None)]
