@@ -1076,8 +1076,11 @@ __global__ void __launch_bounds__(C::NT, C::MINB) xc2r_kernel(const __grid_const
         const int j = i % pf_per;
         const long long e = ent_in[pfrow[1 + i / pf_per]];
         char* q = tile_base<sizeof(T2)>(st.in.run[(int)e & 31], tn) + (e >> 5);
-        if (pf_blocked) prefetch_l2(q + j * 128);
-        else if (tn.ta * TX + j < st.na) prefetch_l2(q + j * sab);
+        if (pf_blocked) {
+          // only the lines of the tile that exist (a partial last tile would otherwise touch memory behind the buffer)
+          const long long have = (long long)st.na - (long long)tn.ta * TX;
+          if ((long long)j * 128 < (have < TX ? have : TX) * sab) prefetch_l2(q + j * 128);
+        } else if (tn.ta * TX + j < st.na) prefetch_l2(q + j * sab);
       }
     }
     // ---- pass 1 on butterfly pairs (u, M-u) with the Hermitian pre-processing ----------------

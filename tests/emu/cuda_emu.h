@@ -51,6 +51,7 @@ inline void canary_check(const unsigned char* base, size_t used, size_t total, c
 // Stream work of the mock runtime: a launch is handed to `enqueue_hook` (emu_api.cpp: per-stream queues run at
 // synchronisation points, in an order only constrained by stream order and events); without a runtime (libemu_fast.so)
 // it runs on the spot.
+extern const char* current_kernel;       // name of the kernel being emulated (for the fault report of emu_api.cpp)
 extern void (*enqueue_hook)(cudaStream_t, std::function<void()>);
 inline void enqueue(cudaStream_t s, std::function<void()> f) {
   if (enqueue_hook) enqueue_hook(s, std::move(f));

@@ -107,6 +107,44 @@ cudaError_t cudaIpcCloseMemHandle(void* p) {
 }
 }
 
+// fault report: which kernel touched which guard page (async-signal-unsafe printing is fine for a test that is about to die)
+#include <signal.h>
+namespace {
+struct sigaction g_prev_segv;
+void on_segv(int sig, siginfo_t* si, void* uc) {
+  char* a = (char*)si->si_addr;
+  if (emu::current_kernel)
+    fprintf(stderr, "emulated runtime: SIGSEGV at %p in kernel %s (block %u,%u thread %u)\n", (void*)a, emu::current_kernel, blockIdx.x,
+            blockIdx.y, threadIdx.x);
+  for (auto& kv : emu_mp::g_shm) {
+    const emu_mp::ShmBlock& b = kv.second;
+    if (a >= b.map && a < b.map + b.map_bytes)
+      fprintf(stderr, "  inside the guarded mapping of a %zu-byte %s allocation: %lld bytes past its end (negative: before its start)\n",
+              b.user_bytes, b.owner ? "own" : "peer", (long long)(a - (kv.first + b.user_bytes)) < 0 && a < kv.first ? (long long)(a - kv.first) : (long long)(a - (kv.first + b.user_bytes)));
+  }
+  // hand over to whoever was there before (the other emulated library, Python's faulthandler, or the default action)
+  if ((g_prev_segv.sa_flags & SA_SIGINFO) && g_prev_segv.sa_sigaction) { g_prev_segv.sa_sigaction(sig, si, uc); return; }
+  if (!(g_prev_segv.sa_flags & SA_SIGINFO) && g_prev_segv.sa_handler != SIG_DFL && g_prev_segv.sa_handler != SIG_IGN) {
+    g_prev_segv.sa_handler(sig);
+    return;
+  }
+  signal(SIGSEGV, SIG_DFL);
+  raise(SIGSEGV);
+}
+struct InstallSegv {
+  InstallSegv() {
+    static char altstack[1 << 16];
+    stack_t ss; ss.ss_sp = altstack; ss.ss_size = sizeof altstack; ss.ss_flags = 0;
+    sigaltstack(&ss, nullptr);
+    struct sigaction sa;
+    memset(&sa, 0, sizeof sa);
+    sa.sa_sigaction = on_segv;
+    sa.sa_flags = SA_SIGINFO | SA_ONSTACK;
+    sigaction(SIGSEGV, &sa, &g_prev_segv);
+  }
+} g_install_segv;
+}  // namespace
+
 // extension for the tests: lets a numpy array play the part of a device array (used in place, not staged)
 extern "C" void emu_register_device_range(void* p, size_t n) { std::lock_guard<std::mutex> l(g_mu); g_alloc[(char*)p] = n; }
 extern "C" void emu_unregister_device_range(void* p) { std::lock_guard<std::mutex> l(g_mu); g_alloc.erase((char*)p); }

@@ -17,7 +17,9 @@
     const FastStage fcopy = f;                                                      \
     emu::enqueue(stream, [=]() {                                                    \
       emu::canary_set(p3d::fast::smem_raw, smem, sizeof(p3d::fast::smem_raw));      \
+      emu::current_kernel = #__VA_ARGS__;                                           \
       emu::launch([&]() { __VA_ARGS__(fcopy); }, emu::grid_for(tiles), NT);         \
+      emu::current_kernel = nullptr;                                                \
       emu::canary_check(p3d::fast::smem_raw, smem, sizeof(p3d::fast::smem_raw), #__VA_ARGS__); \
     });                                                                             \
     e = cudaSuccess;                                                                \

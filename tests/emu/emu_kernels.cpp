@@ -14,7 +14,9 @@
     emu::enqueue(stream, [=]() {                                                              \
       emu::canary_set(p3d::smem_raw, smem__, sizeof(p3d::smem_raw));                          \
       emu::canary_set((unsigned char*)p3d::spec_hist, smem__, sizeof(p3d::spec_hist));        \
+      emu::current_kernel = #kernel;                                                          \
       emu::launch([&]() { kernel(__VA_ARGS__); }, grid__, block__);                           \
+      emu::current_kernel = nullptr;                                                          \
       emu::canary_check(p3d::smem_raw, smem__, sizeof(p3d::smem_raw), #kernel);               \
       emu::canary_check((const unsigned char*)p3d::spec_hist, smem__, sizeof(p3d::spec_hist), #kernel); \
     });                                                                                       \

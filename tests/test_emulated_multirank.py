@@ -131,3 +131,10 @@ def test_headline_lengths_2x4():
 @pytest.mark.skipif(not os.environ.get("P3D_EMU_LONG"), reason="opt-in (P3D_EMU_LONG=1): ~1 min, 1024 x 32 x 1024 double and 2048 x 16 x 512 single on 8 ranks")
 def test_headline_lengths_2x4_full():
     check("2x4", ["--suite", "long", "--expect-p2p", "1"])
+
+
+@pytest.mark.parametrize("grid", ["3x2", "1x3"])
+def test_grids_that_do_not_divide_the_mesh(grid):
+    """64 / 3 pencils: ranks with 21 and 22 lines, partial X tiles, uneven blocks -- under the guard pages of the mock
+    allocator (this is the case that exposed an L2 prefetch of xc2r_kernel reaching behind the work buffer)"""
+    check(grid, ["--suite", "fast", "--expect-p2p", "1", "--aux"])
