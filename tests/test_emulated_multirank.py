@@ -138,3 +138,15 @@ def test_grids_that_do_not_divide_the_mesh(grid):
     """64 / 3 pencils: ranks with 21 and 22 lines, partial X tiles, uneven blocks -- under the guard pages of the mock
     allocator (this is the case that exposed an L2 prefetch of xc2r_kernel reaching behind the work buffer)"""
     check(grid, ["--suite", "fast", "--expect-p2p", "1", "--aux"])
+
+
+SWEEP_ENVS = [{"P3DFFT_B200_BULK": "1"}, {"P3DFFT_B200_HALF": "1"}, {"P3DFFT_B200_R32": "1"}, {"P3DFFT_B200_XTX8": "1"},
+              {"P3DFFT_B200_BULK": "1", "P3DFFT_B200_FLAGBAR": "1", "P3DFFT_B200_OVERLAP": "4"}, {"P3DFFT_B200_ROWB": "64"},
+              {"P3DFFT_B200_GENERIC": "1"}, {"P3DFFT_B200_SPLIT": "1"}]
+
+
+@pytest.mark.skipif(not os.environ.get("P3D_EMU_LONG"), reason="opt-in (P3D_EMU_LONG=1): every switchable variant at the 1024-point lengths on 4 ranks, ~2 min")
+@pytest.mark.parametrize("grid", ["2x2", "1x4"])
+@pytest.mark.parametrize("env", SWEEP_ENVS, ids=lambda e: "+".join(k[12:] for k in e))
+def test_switchable_variants_at_headline_lengths(grid, env):
+    check(grid, ["--suite", "long-light", "--expect-p2p", "1"], env)
