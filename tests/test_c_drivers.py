@@ -89,3 +89,56 @@ def test_c_epilogue_driver_multi_rank(ranks, grid):
         pytest.skip(f"needs {ranks} GPUs")
     r = _run(ranks, os.path.join(LIB, "spec_epilogue"), 64, 48, 40, *grid)
     assert r.returncode == 0 and "Results are correct" in r.stdout, r.stdout + r.stderr
+
+
+# ---- the same acceptance drivers on the CPU-emulated library (tests/emu), 1 / 2 / 4 ranks -----------------------------------
+EMU_OK = os.path.exists(os.path.join(LIB, "libp3dfft_emu.so"))
+
+
+@pytest.fixture(scope="module")
+def emu_exes(tmp_path_factory):
+    out = tmp_path_factory.mktemp("cdrivers_emu")
+    built = {}
+    for exe, src, defs, lib in (("wave_roundtrip", "wave_roundtrip.c", [], "libp3dfft_emu.so"),
+                                ("wave_roundtrip_single", "wave_roundtrip.c", ["-DSINGLE_PREC"], "libp3dfft_emu_single.so"),
+                                ("spec_epilogue", "spec_epilogue.c", [], "libp3dfft_emu.so"),
+                                ("spec_epilogue_single", "spec_epilogue.c", ["-DSINGLE_PREC"], "libp3dfft_emu_single.so")):
+        target = out / exe
+        cmd = ["gcc", "-O2", "-Wall", *defs, f"-I{ROOT}/include/mpi_shim", f"-I{ROOT}/include", os.path.join(ROOT, "tests", "c", src),
+               f"-L{LIB}", f"-l:{lib}", "-lm", f"-Wl,-rpath,{LIB}", "-o", str(target)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        built[exe] = str(target)
+    return built
+
+
+def _run_emu(n, exe, *args, env=None):
+    _port[0] += 2
+    e = {k: v for k, v in os.environ.items() if not k.startswith("P3DFFT_B200_")}
+    e.update({"P3D_EMU_SHM": "1", "P3D_EMU_TIMEOUT": "60"})
+    e.update(env or {})
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "p3drun.py"), "-n", str(n), "--port", str(_port[0]), "--timeout", "240", exe, *map(str, args)]
+    try:
+        return subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=e)
+    finally:
+        from tests.test_reference_drivers_emulated import sweep_shm
+        sweep_shm()
+
+
+@pytest.mark.skipif(not EMU_OK, reason="emulated library not built")
+@pytest.mark.parametrize("exe,ranks,args", [("wave_roundtrip", 1, (64, 64, 64)), ("wave_roundtrip", 2, (64, 48, 80, 1, 2)),
+                                            ("wave_roundtrip", 4, (64, 48, 80, 2, 2)), ("wave_roundtrip_single", 2, (64, 64, 64, 2, 1)),
+                                            ("wave_roundtrip", 2, (20, 12, 36, 1, 2))])
+def test_c_driver_on_emulated_ranks(emu_exes, exe, ranks, args):
+    r = _run_emu(ranks, emu_exes[exe], *args)
+    assert r.returncode == 0 and "Results are correct" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not EMU_OK, reason="emulated library not built")
+@pytest.mark.parametrize("exe,ranks,args", [("spec_epilogue", 1, (64, 48, 40)), ("spec_epilogue", 2, (64, 48, 40, 1, 2)),
+                                            ("spec_epilogue", 2, (64, 48, 40, 2, 1)), ("spec_epilogue", 4, (64, 48, 40, 2, 2)),
+                                            ("spec_epilogue_single", 4, (64, 64, 64, 2, 2)), ("spec_epilogue", 4, (30, 18, 14, 2, 2))])
+def test_c_epilogue_driver_on_emulated_ranks(emu_exes, exe, ranks, args):
+    """fused normalisation, device power spectrum (NCCL all-reduce over the ranks), rtran_* and r2c_1d from C, several ranks"""
+    r = _run_emu(ranks, emu_exes[exe], *args)
+    assert r.returncode == 0 and "Results are correct" in r.stdout, r.stdout + r.stderr
