@@ -96,53 +96,10 @@ def build_c_drivers(verbose: bool = False) -> list[str]:
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
         out.append(target)
-    # test-only host harness of the real-copy address arithmetic (tests/c/rcopy_host.cpp)
-    target = os.path.join(LIBDIR, "librcopy_check.so")
-    srcp = os.path.join(root, "tests", "c", "rcopy_host.cpp")
-    if _newer(target, [srcp, os.path.join(CSRC, "rcopy.h"), os.path.join(CSRC, "stage.h")]):
-        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", srcp, "-o", target]
-        if verbose:
-            print(" ".join(cmd), flush=True)
-        subprocess.check_call(cmd)
-    out.append(target)
-    # test-only host emulation of the specialised stage kernels (tests/emu): the product's fft_fast.cu / fft_fast.cuh
-    # compiled by g++ against a CUDA execution-model shim
-    emu = os.path.join(root, "tests", "emu")
-    for name, defs in (("emu_fast", []), ("emu_fast_single", ["-DSINGLE_PREC"])):
-        target = os.path.join(LIBDIR, f"lib{name}.so")
-        deps = [os.path.join(emu, "emu_fast.cpp"), os.path.join(emu, "cuda_emu.h"), os.path.abspath(__file__)] + [os.path.join(CSRC, f) for f in
-                                                                                     ("fft_fast.cu", "fft_fast.cuh", "fast.h", "stage.h")]
-        if _newer(target, deps):
-            # -Bsymbolic: the emulator shares symbol names (p3d::launch_fast ...) with the product library, which the tests
-            # load into the same process with RTLD_GLOBAL; its own calls must bind to its own definitions
-            cmd = ["g++", "-O1", "-fno-gnu-unique", "-std=c++17", "-x", "c++", "-w", "-shared", "-fPIC", "-pthread", "-Wl,-Bsymbolic", *defs, "-I" + os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include"),
-                   os.path.join(emu, "emu_fast.cpp"), "-o", target]
-            if verbose:
-                print(" ".join(cmd), flush=True)
-            subprocess.check_call(cmd)
-        out.append(target)
-    # ... and of the WHOLE library: api.cpp on a mock CUDA runtime + every kernel file (tests/test_emulated_library.py)
-    inc = "-I" + os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include")
-    for name, defs in (("p3dfft_emu", []), ("p3dfft_emu_single", ["-DSINGLE_PREC"])):
-        target = os.path.join(LIBDIR, f"lib{name}.so")
-        objdir = os.path.join(LIBDIR, "obj_" + name)
-        os.makedirs(objdir, exist_ok=True)
-        deps = [os.path.join(emu, f) for f in ("emu_api.cpp", "emu_kernels.cpp", "emu_fast.cpp", "cuda_emu.h", "emu_runtime.inc", "emu_mp.inc")] + \
-            [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-        if _newer(target, deps):
-            objs, cmds = [], []
-            for src, extra in (("emu_api.cpp", []), ("emu_kernels.cpp", []), ("emu_fast.cpp", ["-DEMU_NO_RUNTIME"])):
-                obj = os.path.join(objdir, src[:-4] + ".o")
-                objs.append(obj)
-                cmds.append(["g++", "-O1", "-fno-gnu-unique", "-std=c++17", "-x", "c++", "-w", "-c", "-fPIC", "-pthread", *defs, *extra, inc,
-                             os.path.join(emu, src), "-o", obj])
-            with ThreadPoolExecutor(max_workers=len(cmds)) as ex:
-                list(ex.map(subprocess.check_call, cmds))
-            subprocess.check_call(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", *objs, "-o", target, "-ldl", "-lrt"])
-        out.append(target)
     return out
 
 
 if __name__ == "__main__":
     libs = build_all(verbose="-v" in sys.argv, variants="--variants" in sys.argv, force="-f" in sys.argv)
     print("\n".join(libs + build_c_drivers(verbose="-v" in sys.argv)))
+    # (the test-only host builds -- kernel emulation, mock runtime -- live in tests/emu/build.py)

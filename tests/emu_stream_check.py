@@ -17,7 +17,7 @@ from oracle import p3dfft_oracle as po  # noqa: E402
 
 def main():
     n = tuple(int(x) for x in sys.argv[1:4])
-    path = os.environ.get("P3D_EMU_LIB") or os.path.join(ROOT, "p3dfft_b200", "lib", "libp3dfft_emu.so")
+    path = os.environ.get("P3D_EMU_LIB") or os.path.join(ROOT, "tests", "emu", "lib", "libp3dfft_emu.so")
     lib = pb.P3DFFT(False, path=path)
     d = po.Decomp(*n, (1, 1), 0)
     A = np.asfortranarray(np.random.default_rng(5).random(n))

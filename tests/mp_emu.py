@@ -47,7 +47,7 @@ SUITES = {
 
 
 def emulib(single):
-    path = os.path.join(ROOT, "p3dfft_b200", "lib", "libp3dfft_emu_single.so" if single else "libp3dfft_emu.so")
+    path = os.path.join(ROOT, "tests", "emu", "lib", "libp3dfft_emu_single.so" if single else "libp3dfft_emu.so")
     if not single and os.environ.get("P3D_EMU_LIB"):      # mutation checks of the tests themselves (a deliberately broken build)
         path = os.environ["P3D_EMU_LIB"]
     return pb.P3DFFT(single, path=path)

@@ -92,7 +92,8 @@ def test_c_epilogue_driver_multi_rank(ranks, grid):
 
 
 # ---- the same acceptance drivers on the CPU-emulated library (tests/emu), 1 / 2 / 4 ranks -----------------------------------
-EMU_OK = os.path.exists(os.path.join(LIB, "libp3dfft_emu.so"))
+EMULIB = os.path.join(ROOT, "tests", "emu", "lib")
+EMU_OK = os.path.exists(os.path.join(EMULIB, "libp3dfft_emu.so"))
 
 
 @pytest.fixture(scope="module")
@@ -105,7 +106,7 @@ def emu_exes(tmp_path_factory):
                                 ("spec_epilogue_single", "spec_epilogue.c", ["-DSINGLE_PREC"], "libp3dfft_emu_single.so")):
         target = out / exe
         cmd = ["gcc", "-O2", "-Wall", *defs, f"-I{ROOT}/include/mpi_shim", f"-I{ROOT}/include", os.path.join(ROOT, "tests", "c", src),
-               f"-L{LIB}", f"-l:{lib}", "-lm", f"-Wl,-rpath,{LIB}", "-o", str(target)]
+               f"-L{EMULIB}", f"-l:{lib}", "-lm", f"-Wl,-rpath,{EMULIB}", "-o", str(target)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         built[exe] = str(target)

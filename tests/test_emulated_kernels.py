@@ -23,7 +23,7 @@ _libs = {}
 
 def emu(single=False):
     if single not in _libs:
-        h = C.CDLL(os.path.join(ROOT, "p3dfft_b200", "lib", "libemu_fast_single.so" if single else "libemu_fast.so"))
+        h = C.CDLL(os.path.join(ROOT, "tests", "emu", "lib", "libemu_fast_single.so" if single else "libemu_fast.so"))
         h.emu_run_fast.argtypes = [C.POINTER(pb.Stage)]
         _libs[single] = h
     return _libs[single]
@@ -200,7 +200,7 @@ def test_emulated_split_kernel(monkeypatch):
     import tempfile
     with tempfile.TemporaryDirectory() as tmp:
         dst = os.path.join(tmp, "libemu_split.so")
-        shutil.copy(os.path.join(ROOT, "p3dfft_b200", "lib", "libemu_fast.so"), dst)
+        shutil.copy(os.path.join(ROOT, "tests", "emu", "lib", "libemu_fast.so"), dst)
         h = C.CDLL(dst)
         h.emu_run_fast.argtypes = [C.POINTER(pb.Stage)]
         old = _libs.get(False)

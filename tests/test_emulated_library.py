@@ -23,7 +23,7 @@ _cache = {}
 
 def emulib(single=False):
     if single not in _cache:
-        path = os.path.join(ROOT, "p3dfft_b200", "lib", "libp3dfft_emu_single.so" if single else "libp3dfft_emu.so")
+        path = os.path.join(ROOT, "tests", "emu", "lib", "libp3dfft_emu_single.so" if single else "libp3dfft_emu.so")
         L = pb.P3DFFT(single, path=path)
         L.lib.emu_register_device_range.argtypes = [C.c_void_p, C.c_size_t]
         L.lib.emu_unregister_device_range.argtypes = [C.c_void_p]
@@ -233,7 +233,7 @@ def test_guard_pages_catch_an_overrun():
     import subprocess
     import sys
     code = ("import ctypes as C, sys\n"
-            f"L = C.CDLL({os.path.join(ROOT, 'p3dfft_b200', 'lib', 'libp3dfft_emu.so')!r})\n"
+            f"L = C.CDLL({os.path.join(ROOT, 'tests', 'emu', 'lib', 'libp3dfft_emu.so')!r})\n"
             "p = C.c_void_p()\n"
             "assert L.cudaMalloc(C.byref(p), C.c_size_t(1000 * 16)) == 0\n"
             "C.memset(p.value + 999 * 16, 1, 16)\n"

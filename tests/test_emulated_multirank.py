@@ -14,9 +14,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU = os.path.join(ROOT, "p3dfft_b200", "lib", "libp3dfft_emu.so")
+EMU = os.path.join(ROOT, "tests", "emu", "lib", "libp3dfft_emu.so")
 
-pytestmark = pytest.mark.skipif(not os.path.exists(EMU), reason="emulated library not built (python -m p3dfft_b200.build)")
+pytestmark = pytest.mark.skipif(not os.path.exists(EMU), reason="emulated library not built (python tests/emu/build.py)")
 
 
 def launch(grid, args=(), env=None, timeout=600):

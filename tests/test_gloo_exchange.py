@@ -111,7 +111,7 @@ def _rtran_worker(rank, world, port, dims, n, q):
     try:
         lib = pb.load(False)
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        h = C.CDLL(os.path.join(root, "p3dfft_b200", "lib", "librcopy_check.so"))
+        h = C.CDLL(os.path.join(root, "tests", "emu", "lib", "librcopy_check.so"))
         h.rcopy_host_run.argtypes = [C.POINTER(pb.Stage), C.c_int]
         nx, ny, nz = n
         d = po.Decomp(nx, ny, nz, dims, rank)

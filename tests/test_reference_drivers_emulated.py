@@ -18,7 +18,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "p3dfft_b200", "lib")
+LIB = os.path.join(ROOT, "tests", "emu", "lib")
 REF = "/root/reference/sample/C"
 _port = [31750 + (os.getpid() % 89) * 2]
 

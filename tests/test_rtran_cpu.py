@@ -26,7 +26,7 @@ def lib():
 
 @pytest.fixture(scope="module")
 def harness():
-    h = C.CDLL(os.path.join(ROOT, "p3dfft_b200", "lib", "librcopy_check.so"))
+    h = C.CDLL(os.path.join(ROOT, "tests", "emu", "lib", "librcopy_check.so"))
     h.rcopy_host_run.argtypes = [C.POINTER(pb.Stage), C.c_int]
     h.rcopy_host_contiguous_boxes.argtypes = [C.POINTER(pb.Stage), C.c_int]
     return h
