@@ -59,7 +59,7 @@ def nccl_counts(L):
     return list(out)      # sends, receives, all-reduces, all-gathers
 
 
-def run_repeat(L, comm, dims, rank, n, X):
+def run_repeat(L, comm, dims, rank, n, X, asynchronous=False):
     """forward, forward, backward, backward on the same plan: on one-dimensional grids the second call of a pair stores
     into a receive buffer a slower peer may still be reading -- the executor's extra barrier (api.cpp run_plan) is what
     keeps the results right.  Ranks are desynchronised on purpose."""
@@ -74,10 +74,12 @@ def run_repeat(L, comm, dims, rank, n, X):
     ins = [X.dev(np.asfortranarray(f[po.local_in_slice(d)]).ravel(order="F")) for f in fields]
     outs = [X.full(2 * int(np.prod(fsz)), 0.0, np.float64) for _ in fields]
     worst = 0.0
+    L.set_async(asynchronous)       # asynchronous: the three calls are only enqueued (device arrays), one sync at the end
     for i in range(3):
         if rank == i % (dims[0] * dims[1]):
             time.sleep(0.05)
         L.p3dfft_ftran_r2c(ins[i], outs[i], "fft")
+    L.sync()
     for i in range(3):
         exp = np.asfortranarray(po.local_forward(fields[i], d, "fft")).ravel(order="F")
         worst = max(worst, po.rel_l2(X.host(outs[i]).view(np.complex128), exp))
@@ -86,6 +88,8 @@ def run_repeat(L, comm, dims, rank, n, X):
         if rank == (i + 1) % (dims[0] * dims[1]):
             time.sleep(0.05)
         L.p3dfft_btran_c2r(outs[i], backs[i], "tff")
+    L.sync()
+    L.set_async(False)
     for i in range(3):
         worst = max(worst, float(np.abs(X.host(backs[i]) / (nx * ny * nz) - X.host(ins[i])).max()))
     L.p3dfft_clean()
@@ -98,6 +102,7 @@ def main():
     ap.add_argument("--suite", default="fast")
     ap.add_argument("--aux", action="store_true")
     ap.add_argument("--repeat", action="store_true")
+    ap.add_argument("--async", dest="asynchronous", action="store_true")
     ap.add_argument("--expect-p2p", type=int, default=-1)
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -152,13 +157,13 @@ def main():
         L = libs[False]
         for n in ((64, 64, 64), (32, 32, 32)):
             try:
-                err = run_repeat(L, comms[False], dims, rank, n, M.EmuArrays(L))
+                err = run_repeat(L, comms[False], dims, rank, n, M.EmuArrays(L), a.asynchronous)
             except Exception as e:     # noqa: BLE001
                 err = float("nan")
                 print(f"rank {rank} grid {dims} repeat n={n}: EXCEPTION {e!r}", flush=True)
                 L.p3dfft_clean()
             good = err <= 1e-12
-            print(f"rank {rank} grid {a.grid} n={n} fwd x3, bwd x3: {err:.2e} {'ok' if good else 'FAIL'}", flush=True)
+            print(f"rank {rank} grid {a.grid} n={n} fwd x3, bwd x3{' (asynchronous)' if a.asynchronous else ''}: {err:.2e} {'ok' if good else 'FAIL'}", flush=True)
             ok = ok and good
     for single in (False, True):
         libs[single].comm_destroy(comms[single])

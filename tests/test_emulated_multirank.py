@@ -150,3 +150,10 @@ SWEEP_ENVS = [{"P3DFFT_B200_BULK": "1"}, {"P3DFFT_B200_HALF": "1"}, {"P3DFFT_B20
 @pytest.mark.parametrize("env", SWEEP_ENVS, ids=lambda e: "+".join(k[12:] for k in e))
 def test_switchable_variants_at_headline_lengths(grid, env):
     check(grid, ["--suite", "long-light", "--expect-p2p", "1"], env)
+
+
+@pytest.mark.parametrize("grid,policy", [("1x2", "lazy"), ("2x2", "random:4")])
+def test_asynchronous_calls_on_several_ranks(grid, policy):
+    """p3dfft_b200_set_async: three forward and three backward transforms are only enqueued (device arrays), one
+    p3dfft_b200_sync at the end; barriers and exchanges are stream work like the kernels"""
+    check(grid, ["--suite", "none", "--repeat", "--async"], {"P3D_EMU_STREAMS": policy, "P3D_EMU_DELAY": "1:3:2:100"})
