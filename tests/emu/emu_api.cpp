@@ -145,6 +145,14 @@ struct InstallSegv {
 } g_install_segv;
 }  // namespace
 
+// test hook: number (and bytes) of live mock cudaMalloc blocks + peer mappings -- p3dfft_clean must leave none behind
+extern "C" long long emu_live_allocations(long long* bytes) {
+  long long n = 0, b = 0;
+  for (auto& kv : emu_mp::g_shm) { n++; b += (long long)kv.second.user_bytes; }
+  if (bytes) *bytes = b;
+  return n;
+}
+
 // extension for the tests: lets a numpy array play the part of a device array (used in place, not staged)
 extern "C" void emu_register_device_range(void* p, size_t n) { std::lock_guard<std::mutex> l(g_mu); g_alloc[(char*)p] = n; }
 extern "C" void emu_unregister_device_range(void* p) { std::lock_guard<std::mutex> l(g_mu); g_alloc.erase((char*)p); }

@@ -167,6 +167,12 @@ def main():
             ok = ok and good
     for single in (False, True):
         libs[single].comm_destroy(comms[single])
+        # every p3dfft_clean above must have released its work buffers AND closed its mappings of the peers' buffers
+        libs[single].lib.emu_live_allocations.restype = ctypes.c_longlong
+        live = libs[single].lib.emu_live_allocations(None)
+        if live != 0:
+            print(f"rank {rank}: {live} device allocations / peer mappings still live after p3dfft_clean: FAIL", flush=True)
+            ok = False
     sys.exit(0 if ok else 1)
 
 

@@ -300,3 +300,29 @@ def test_async_calls_on_a_user_stream(lib):
         lib.p3dfft_clean()
         lib.reset_stream()
         lib.lib.cudaStreamDestroy(st)
+
+
+def test_clean_releases_every_device_allocation(lib):
+    """p3dfft_clean (module.F90:309) frees work buffers, staging buffers, twiddle tables, the spectrum accumulator ...: the mock
+    allocator counts live blocks, none may survive; a second setup / clean cycle must not accumulate any either"""
+    nb = C.c_longlong()
+    lib.lib.emu_live_allocations.restype = C.c_longlong
+    base = lib.lib.emu_live_allocations(C.byref(nb))
+    for cycle in range(2):
+        n = (64, 32, 33)
+        lib.p3dfft_setup((1, 1), *n, 0)
+        d = po.Decomp(*n, (1, 1), 0)
+        A = np.asfortranarray(np.random.default_rng(1).random(n))
+        F = np.zeros((d.nxhp, n[1], n[2]), dtype=np.complex128, order="F")
+        lib.p3dfft_ftran_r2c(A, F, "fft")
+        lib.p3dfft_btran_c2r(F, A.copy(order="F"), "tff")
+        lib.p3dfft_ftran_r2c(A, F, "ffc")
+        A2 = np.asfortranarray(np.random.default_rng(2).random((2,) + n)).ravel()
+        F2 = np.zeros(2 * F.size, dtype=np.complex128)
+        lib.p3dfft_ftran_r2c_many(A2, A.size, F2, F.size, 2, "fft")          # the work buffers grow
+        lib.spectrum(F, 20)
+        dst = np.zeros(A.size)
+        lib.rtran("x2y", A.ravel(order="F").copy(), dst)
+        assert lib.lib.emu_live_allocations(C.byref(nb)) > base
+        lib.p3dfft_clean()
+        assert lib.lib.emu_live_allocations(C.byref(nb)) == base, (cycle, nb.value)
