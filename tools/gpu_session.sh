@@ -40,7 +40,7 @@ fi
 
 if [[ $what == all || $what == sanitize ]]; then
   {
-    for sz in "64 64 64" "256 128 64" "128 64 1024" "1024 64 128"; do
+    for sz in "64 64 64" "256 128 64" "128 64 1024" "1024 64 128" "64 26 38" "128 22 18"; do   # (the last two: partial X tiles, the case of the r1 prefetch fix)
       echo "== memcheck $sz"; timeout 120 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/prof_pair.py --size $sz --pairs 1 2>&1 | tail -3
     done
     for sz in "64 64 64" "128 32 1024" "1024 16 64"; do
