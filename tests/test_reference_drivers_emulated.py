@@ -125,3 +125,20 @@ def test_baseline_config1_driver_inverse_128_cubed_2x2(exes, tmp_path):
     got = sorted((int(a), int(b), int(c), float(v)) for a, b, c, v in spikes)
     n4 = 128 ** 3 / 4
     assert got == sorted([(128, 3, 4, -n4), (128, 3, 126, n4), (128, 127, 4, n4), (128, 127, 126, -n4)]), got
+
+
+def test_shipped_reference_binaries_run_on_the_emulation(tmp_path):
+    """oracle/_ref/drivers/* are the binaries that travel to the GPU box (linked with the PRODUCT library, run there by
+    tests/test_zzzz_reference_binaries.py).  Here the very same files run on the CPU: LD_LIBRARY_PATH, which the loader
+    searches before their RUNPATH, presents the emulated library under the product's name."""
+    drv = os.path.join(ROOT, "oracle", "_ref", "drivers")
+    if not os.path.exists(os.path.join(drv, "driver_inverse")):
+        pytest.skip("oracle/_ref/drivers not built (python oracle/build_ref_drivers.py)")
+    link = tmp_path / "lib"
+    link.mkdir()
+    os.symlink(os.path.join(LIB, "libp3dfft_emu.so"), link / "libp3dfft.so")
+    os.symlink(os.path.join(LIB, "libp3dfft_emu_single.so"), link / "libp3dfft_single.so")
+    for name, ranks, grid in (("driver_inverse", 4, (2, 2)), ("driver_sine_sp", 1, (1, 1)), ("driver_rand_many", 2, (1, 2))):
+        r = run_driver(os.path.join(drv, name), tmp_path, ranks, grid, (64, 64, 64), nv=2 if "many" in name else None,
+                       env={"LD_LIBRARY_PATH": str(link)})
+        assert r.returncode == 0 and "Results are correct" in r.stdout and "incorrect" not in r.stdout, name + r.stdout[-2000:] + r.stderr[-2000:]
