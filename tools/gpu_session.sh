@@ -68,6 +68,8 @@ if [[ $what == mgpu ]]; then
   run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) "$@"; }
   {
     echo "== parity, default";                 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
+    echo "== the reference's own driver binaries and our C drivers on $N GPUs"
+    timeout 600 python -m pytest tests/test_zzzz_reference_binaries.py tests/test_c_drivers.py -m gpu -q -p no:cacheprovider 2>&1 | tail -4
     echo "== parity, flag barrier";            P3DFFT_B200_FLAGBAR=1 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
     echo "== parity, bulk stores";             P3DFFT_B200_BULK=1 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
     echo "== parity, flag barrier + overlap";  P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=4 timeout 600 run tests/mp_parity.py 2>&1 | tail -4
