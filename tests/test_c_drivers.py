@@ -136,9 +136,9 @@ def test_c_driver_on_emulated_ranks(emu_exes, exe, ranks, args):
 
 
 @pytest.mark.skipif(not EMU_OK, reason="emulated library not built")
-@pytest.mark.parametrize("exe,ranks,args", [("spec_epilogue", 1, (64, 48, 40)), ("spec_epilogue", 2, (64, 48, 40, 1, 2)),
-                                            ("spec_epilogue", 2, (64, 48, 40, 2, 1)), ("spec_epilogue", 4, (64, 48, 40, 2, 2)),
-                                            ("spec_epilogue_single", 4, (64, 64, 64, 2, 2)), ("spec_epilogue", 4, (30, 18, 14, 2, 2))])
+@pytest.mark.parametrize("exe,ranks,args", [("spec_epilogue", 1, (64, 24, 20)), ("spec_epilogue", 2, (32, 24, 20, 1, 2)),
+                                            ("spec_epilogue", 2, (64, 16, 12, 2, 1)), ("spec_epilogue_single", 4, (64, 32, 16, 2, 2)),
+                                            ("spec_epilogue", 4, (30, 18, 14, 2, 2))])
 def test_c_epilogue_driver_on_emulated_ranks(emu_exes, exe, ranks, args):
     """fused normalisation, device power spectrum (NCCL all-reduce over the ranks), rtran_* and r2c_1d from C, several ranks"""
     r = _run_emu(ranks, emu_exes[exe], *args)

@@ -309,7 +309,7 @@ def test_clean_releases_every_device_allocation(lib):
     lib.lib.emu_live_allocations.restype = C.c_longlong
     base = lib.lib.emu_live_allocations(C.byref(nb))
     for cycle in range(2):
-        n = (64, 32, 33)
+        n = (64, 16, 17)
         lib.p3dfft_setup((1, 1), *n, 0)
         d = po.Decomp(*n, (1, 1), 0)
         A = np.asfortranarray(np.random.default_rng(1).random(n))
@@ -320,7 +320,7 @@ def test_clean_releases_every_device_allocation(lib):
         A2 = np.asfortranarray(np.random.default_rng(2).random((2,) + n)).ravel()
         F2 = np.zeros(2 * F.size, dtype=np.complex128)
         lib.p3dfft_ftran_r2c_many(A2, A.size, F2, F.size, 2, "fft")          # the work buffers grow
-        lib.spectrum(F, 20)
+        lib.spectrum(F, 12)
         dst = np.zeros(A.size)
         lib.rtran("x2y", A.ravel(order="F").copy(), dst)
         assert lib.lib.emu_live_allocations(C.byref(nb)) > base
