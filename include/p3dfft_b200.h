@@ -63,10 +63,10 @@ void p3dfft_b200_set_p2p(int on);
 /* env P3DFFT_B200_OVERLAP=C (opt-in, experimental): the last two stages of a peer-to-peer transform run as C chunks, the
  * local consumer chunks on a second stream beside the NVLink-bound producer (P3DFFT_B200_OVERLAP_SMS = SMs left to them);
  * the per-stage timers then only cover the producer side.
- * env P3DFFT_B200_XYPIPE=G (opt-in, experimental; grids with M1 = 1): the X and Y stages run as a pipeline of chunks of G z-planes
- * whose intermediate planes stay in L2 (two-slot ring; _RING=0 / _SMS=k / _PERSIST=1 tune it).
- * env P3DFFT_B200_R32=1 / P3DFFT_B200_XTX8=1 / P3DFFT_B200_HALF=1 (opt-in, experimental): two-pass 512/1024-point schedules /
- * 8-line X tiles / half-row 1024-point tiles.  P3DFFT_B200_BULK=1: bulk asynchronous (TMA) tile stores.                                                                            */
+ * env P3DFFT_B200_R32 = 0 / 1 / unset: two-pass (radix-32) 512/1024-point c2c schedules never / wherever they exist / by the
+ * measured rule (1024-point stages that write whole tiles contiguously).  P3DFFT_B200_BULK = 0 / 1 / unset: bulk asynchronous
+ * (TMA, cp.async.bulk) tile stores never / wherever the output rows allow / for stages storing into a peer's memory.
+ * Both are read at p3dfft_setup.                                                                                          */
 /* env P3DFFT_B200_FLAGBAR=1 (opt-in, experimental): the barrier that orders the peer-to-peer transposes becomes a
  * one-CTA kernel exchanging epoch flags through peer-mapped memory instead of a one-float NCCL all-reduce.         */
 int p3dfft_b200_p2p_active(void);
@@ -141,8 +141,7 @@ typedef struct {
 /* flags: bit0 = single precision (sizes the blocked layouts), bit1 = STRIDE1, bit2 = DIMS_C,
  * bit3 = plain (reference) internal layouts, bit4 = peer-to-peer plan, bit5 / bit6 = force 64- / 128-byte
  * tile rows (default: the planner's rule); bits 8-15 (plan_steps only): number of chunks of the pipelined tail
- * (P3DFFT_B200_OVERLAP, peer-to-peer plans), bits 16-22: planes per chunk of the X <-> Y pipeline (P3DFFT_B200_XYPIPE), bit 23:
- * without the two-slot ring.  Returns 0, or -1 and records the reference's
+ * (P3DFFT_B200_OVERLAP, peer-to-peer plans).  Returns 0, or -1 and records the reference's
  * error text (retrievable with p3dfft_b200_last_error).                                   */
 int p3dfft_b200_plan_decomp(const int* dims, int nx, int ny, int nz, int rank, int nxc, int nyc, int nzc,
                             int flags, p3dfft_b200_decomp* out);

@@ -836,3 +836,138 @@ def cpu_pair_sampled(nx, ny, nz, frac_planes, dtype=np.float64, workers=None, se
             f"z-planes, Z stage on {nxs}/{nxhp} x-columns, all 1D lines at full length; linearly extrapolated")
     del R, zc
     return full, meas_xy + meas_z, desc
+
+
+def _kept(n, nc):
+    """stored index -> logical mode index of a pruned axis (lower half, then the upper modes)"""
+    h = (nc + 1) // 2
+    return np.concatenate([np.arange(h), np.arange(n - (nc - h), n)]).astype(np.int64)
+
+
+def cpu_pair_measured(nx, ny, nz, dtype="f64", op="fft", workers=None, budget_s=150.0, max_steps=20, cut=None,
+                      warmup=0, min_fraction=0.125, seed=1):
+    """The reference's P=1 forward+backward stage sequence (ftran.F90:530,554,581-583,756-757,605-683;
+    btran.F90:437-466,471-509,618-623,655-671: the FFT executes plus the seg_copy / ar_copy passes), restated with
+    pocketfft and run on COMPLETE fields: the X and Y stages over z-slabs, the Z stage over x-slabs, `workers`
+    slabs in flight (one thread each -- the parallelism the reference gets from its MPI ranks), thread count fixed
+    here and independent of OMP_NUM_THREADS.
+
+    op: 'fft' (forward fft, backward tff), 'cheby' (forward ffc + the Chebyshev epilogue ftran.F90:408-451, backward
+    cff) or 'pruned' (fft/tff with `cut`).  Steps are whole pairs; as many as fit `budget_s` (at least one, at most
+    `max_steps`).  When one pair is predicted (from a probe of 1/32 of the slabs) not to fit the budget, only every
+    k-th slab of each stage is executed (fraction >= `min_fraction`) and the pair time is extrapolated linearly --
+    the returned description says which.  Returns a dict."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    w = int(workers or os.cpu_count() or 1)
+    rt = np.dtype(np.float32 if dtype in ("f32", np.float32) else np.float64)
+    ct = np.dtype(_ctype(rt))
+    nxc, nyc, nzc = cut if (cut and op == "pruned") else (nx, ny, nz)
+    nxhp, nxhpc = nx // 2 + 1, nxc // 2 + 1
+    ky, kz = _kept(ny, nyc), _kept(nz, nzc)
+    zch = "c" if op == "cheby" else "f"
+    SZ = max(1, min(8, nz // (2 * w) or 1))            # z-planes per slab of the X/Y stages
+    SX = max(1, min(8, nxhpc // (2 * w) or 1))         # x-columns per slab of the Z stage
+    zslabs = [(z, min(z + SZ, nz)) for z in range(0, nz, SZ)]
+    xslabs = [(x, min(x + SX, nxhpc)) for x in range(0, nxhpc, SX)]
+    pool = ThreadPoolExecutor(max_workers=w)
+    A = np.empty((nx, ny, nz), dtype=rt, order="F")
+
+    def fill(sl):
+        A[:, :, sl[0]:sl[1]] = np.random.default_rng(seed + sl[0]).random((nx, ny, sl[1] - sl[0]), dtype=np.float64).astype(rt, copy=False)
+    list(pool.map(fill, zslabs))
+    Y = np.empty((nxhpc, nyc, nz), dtype=ct, order="F")       # buf after the Y stage (y-pruned), then XYZg (z-pruned view)
+    F = Y if nzc == nz else np.empty((nxhpc, nyc, nzc), dtype=ct, order="F")
+    B = np.empty((nx, ny, nz), dtype=rt, order="F")
+    Lz = 2.0
+
+    def fwd_xy(sl):
+        a = A[:, :, sl[0]:sl[1]]
+        b = sfft.rfft(a, axis=0, workers=1)                    # exec_f_r2c (ftran.F90:530)
+        b = np.array(b[:nxhpc], order="F", copy=True)          # seg_copy_x (ftran.F90:554)
+        b = sfft.fft(b, axis=1, workers=1, overwrite_x=True)   # Y stage, one z-plane at a time (ftran.F90:581-583)
+        Y[:, :, sl[0]:sl[1]] = b if nyc == ny else b[:, ky, :]   # seg_copy_y (ftran.F90:756-757)
+
+    def fwd_z(sl):
+        v = Y[sl[0]:sl[1]]
+        if zch == "c":                                         # exec_ctrans_r2_complex_same: re and im apart (fft_exec.F90:646-701)
+            r = sfft.dct(v.real, type=1, axis=2, workers=1) + 1j * sfft.dct(v.imag, type=1, axis=2, workers=1)
+        else:
+            r = sfft.fft(v, axis=2, workers=1)                 # exec_f_c2_same on the user array (ftran.F90:605-683)
+        if op == "cheby":
+            r = cheby_epilogue(r, _ChebyDims(nx, ny, nzc), Lz)
+        F[sl[0]:sl[1]] = r if nzc == nz else r[:, :, kz]        # seg_copy_z (ftran.F90:645-646)
+
+    def bwd_z(sl):
+        if nzc == nz:
+            v = F[sl[0]:sl[1]]
+        else:                                                  # zero-fill of the pruned band (btran.F90:471-509)
+            v = np.zeros((sl[1] - sl[0], nyc, nz), dtype=ct, order="F")
+            v[:, :, kz] = F[sl[0]:sl[1]]
+        if zch == "c":
+            r = sfft.dct(v.real, type=1, axis=2, workers=1) + 1j * sfft.dct(v.imag, type=1, axis=2, workers=1)
+        else:
+            r = sfft.ifft(v, axis=2, norm="forward", workers=1)     # exec_b_c2_same (btran.F90:437-466)
+        Y[sl[0]:sl[1]] = r                                     # ar_copy into buf
+
+    def bwd_yx(sl):
+        if nyc == ny and nxhpc == nxhp:
+            v = Y[:, :, sl[0]:sl[1]]
+        else:                                                  # seg_copy_x / seg_zero_x, zero-fill of the pruned Y band (bcomm1.F90:367-374)
+            v = np.zeros((nxhp, ny, sl[1] - sl[0]), dtype=ct, order="F")
+            v[:nxhpc, ky, :] = Y[:, :, sl[0]:sl[1]]
+        yb = sfft.ifft(v, axis=1, norm="forward", workers=1)    # Y inverse per z-plane (btran.F90:618-623)
+        xb = np.array(yb, order="F", copy=True)                # unpack copy into buf1 (btran.F90:663-671)
+        B[:, :, sl[0]:sl[1]] = sfft.irfft(xb, n=nx, axis=0, norm="forward", workers=1)   # exec_b_c2r (btran.F90:655)
+
+    stages = (("fwd_xy", fwd_xy, zslabs), ("fwd_z", fwd_z, xslabs), ("bwd_z", bwd_z, xslabs), ("bwd_yx", bwd_yx, zslabs))
+
+    def run_pair(stride):
+        ts = {}
+        for name, fn, slabs in stages:
+            t0 = time.perf_counter()
+            sub = slabs[::stride]
+            list(pool.map(fn, sub))
+            ts[name] = (time.perf_counter() - t0) * (len(slabs) / len(sub))
+        return ts
+
+    # probe: 1/32 of the slabs of every stage -> estimated seconds per complete pair (also warms the thread pool)
+    probe = max(1, min(32, len(zslabs) // w, len(xslabs) // w))
+    est = sum(run_pair(probe).values()) if probe > 1 else None
+    stride = 1
+    if est is not None and est > budget_s:
+        stride = 2
+        while est / stride > budget_s and 1.0 / (2 * stride) >= min_fraction:
+            stride *= 2
+    per = (est / stride) if est is not None else None
+    steps = 1 if per is None else int(max(1, min(max_steps, budget_s // max(per, 1e-9))))
+    for _ in range(warmup):
+        run_pair(stride)
+    t_steps, acc = [], {}
+    wall0 = time.perf_counter()
+    for _ in range(steps):
+        ts = run_pair(stride)
+        t_steps.append(sum(ts.values()))
+        for k, v in ts.items():
+            acc[k] = acc.get(k, 0.0) + v / steps
+    wall = time.perf_counter() - wall0
+    pool.shutdown()
+    size = f"{nx}^3" if nx == ny == nz else f"{nx}x{ny}x{nz}"
+    whole = stride == 1
+    # self-check on the first slab (always executed): backward(forward(A)) = N * A for the band the transform keeps
+    rt_err = None
+    if op == "fft" and whole:
+        sl = zslabs[0]
+        rt_err = float(np.abs(B[:, :, sl[0]:sl[1]] / (float(nx) * ny * nz) - A[:, :, sl[0]:sl[1]]).max())
+    sample = (f"reference P=1 stage sequence restated with scipy/pocketfft, {w} threads (one slab per thread): "
+              + (f"{steps} complete {size} pair(s) on a complete field" if whole else
+                 f"every {stride}-th slab of every stage of a {size} pair (fraction 1/{stride}), linearly extrapolated; {steps} step(s)"))
+    return {"ms_per_pair": 1e3 * sum(t_steps) / steps, "ms_per_executed_step": 1e3 * wall / steps, "steps": steps,
+            "warmup": warmup, "fraction": 1.0 / stride, "executed": "complete pairs" if whole else f"1/{stride} of the slabs per step",
+            "sample": sample, "stage_s": acc, "cores": w, "roundtrip_max_err": rt_err}
+
+
+class _ChebyDims:
+    """the three integers cheby_epilogue reads"""
+    def __init__(self, nx, ny, nzc):
+        self.nx, self.ny, self.nzc = nx, ny, nzc

@@ -340,7 +340,7 @@ class P3DFFT:
         return info
 
     def plan_steps(self, dims, nx, ny, nz, rank, backward, op, nv=1, nxc=None, nyc=None, nzc=None, stride1=False,
-                   dims_c=False, dim_real=None, dim_cplx=None, plain=False, p2p=False, row_bytes=0, overlap=0, xypipe=0, xyring=True):
+                   dims_c=False, dim_real=None, dim_cplx=None, plain=False, p2p=False, row_bytes=0, overlap=0):
         info = self.plan_decomp(dims, nx, ny, nz, rank, nxc, nyc, nzc, stride1, dims_c, plain, row_bytes)
         if dim_real is None:
             dim_real = info.nx * info.jisize * info.kjsize
@@ -351,7 +351,6 @@ class P3DFFT:
         flags = (2 if stride1 else 0) | (4 if dims_c else 0) | (8 if plain else 0) | (16 if p2p else 0)
         flags |= 32 if row_bytes == 64 else 64 if row_bytes == 128 else 0
         flags |= (int(overlap) & 0xff) << 8
-        flags |= ((int(xypipe) & 0x7f) << 16) | (0 if xyring else 1 << 23)
         n = self.lib.p3dfft_b200_plan_steps(d, nx, ny, nz, rank, nxc or nx, nyc or ny, nzc or nz, flags,
                                             1 if backward else 0, op.encode() + b"\0", nv, dim_real, dim_cplx,
                                             4 if self.single else 8, arr, 512)

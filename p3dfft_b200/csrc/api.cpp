@@ -32,6 +32,17 @@ typedef double real_t;
 #endif
 static const size_t CSIZE = 2 * sizeof(real_t);
 
+// defaults of the multi-GPU switches (decided by the A/B runs under profiles/)
+#ifndef P3D_DEFAULT_FLAGBAR
+#define P3D_DEFAULT_FLAGBAR 0
+#endif
+#ifndef P3D_DEFAULT_OVERLAP
+#define P3D_DEFAULT_OVERLAP 0
+#endif
+#ifndef P3D_DEFAULT_OVERLAP_SMS
+#define P3D_DEFAULT_OVERLAP_SMS 56
+#endif
+
 namespace {
 
 // ------------------------------------------------------------------------------------
@@ -130,6 +141,7 @@ struct Lib {
   bool force_generic = false;
   // peer-to-peer transposes: stage kernels store each block straight into the destination rank's
   // receive buffer over NVLink (CUDA IPC mappings of the peers' work buffers); exchange = barrier
+  bool api_p2p = true;           // p3dfft_b200_set_p2p; the environment variable, when present at setup, wins
   bool want_p2p = true, p2p = false;
   std::vector<void*> peer_buf;   // [world rank * 3 + (buffer id - P3D_BUF_A)], own entries = own buffers
   float* bar_scratch = nullptr;
@@ -148,11 +160,7 @@ struct Lib {
   std::map<int, p3d::TransformPlan> aux_plans;     // r2c_1d (key 100) and rtran (key which*2 + p2p) plans
   // opt-in pipelined tail of the peer-to-peer plans (P3DFFT_B200_OVERLAP=C chunks; plan.h split_for_overlap): the consumer
   // chunks run on a side stream, on at most overlap_sms SMs while the producer keeps the rest (not yet run on hardware)
-  int overlap = 0, overlap_sms = 56;
-  // opt-in X <-> Y pipeline through L2 (P3DFFT_B200_XYPIPE=G planes per chunk; plan.h split_xy_pipeline), M1 = 1 grids
-  int xypipe = 0, xypipe_sms = 0;      // SMs left to the consumer chunks (0: half)
-  bool xypipe_ring = true, xypipe_persist = false;
-  std::vector<cudaEvent_t> chunk_events2;
+  int overlap = P3D_DEFAULT_OVERLAP, overlap_sms = P3D_DEFAULT_OVERLAP_SMS;
   cudaStream_t side_stream = nullptr;
   std::vector<cudaEvent_t> chunk_events;
   cudaEvent_t side_done = nullptr;
@@ -160,8 +168,9 @@ struct Lib {
   double* spec_dev = nullptr; int spec_bins = 0;   // device accumulator of p3dfft_b200_spectrum
   p3d::ProcMap procmap;                            // proc_id2coords / proc_dims tables (setup.F90:224-230, 551-577)
   bool plain_layout = false;     // true: the reference's pack-buffer layouts instead of the tile-blocked ones
-  int force_row_bytes = 0;       // 64 / 128: override the planner's choice of the tile row width
-  int W() const { return plain_layout ? 0 : p3d::pick_W(d.ny, d.nz, (int)CSIZE, force_row_bytes); }
+  int force_row_bytes = 0;       // 64 / 128: override the planner's choice of the tile row width (p3dfft_b200_row_bytes)
+  int row_bytes_plan = 0;        // ... as latched by p3dfft_setup: the live plan and its buffers never see a later change
+  int W() const { return plain_layout ? 0 : p3d::pick_W(d.ny, d.nz, (int)CSIZE, row_bytes_plan); }
   long long fast_launches = 0;
   std::map<std::pair<int, int>, void*> fast_twiddles;   // (x-stage?, nfft) -> device block
   double timers[12] = {0};
@@ -353,6 +362,9 @@ bool alloc_work(int nv, bool for_rtran = false) {
     if (!world_barrier(L.stream())) return false;
     cudaStreamSynchronize(L.stream());
     close_peer_maps();
+    // an exported allocation must not be freed before every importer has closed its mapping of it (cudaIpcCloseMemHandle)
+    if (!world_barrier(L.stream())) return false;
+    cudaStreamSynchronize(L.stream());
   }
   long long elems = L.d.work_elems(nv, L.W());
   if (L.rtran_sized) elems = std::max(elems, p3d::rtran_work_elems(L.d));
@@ -391,9 +403,7 @@ bool finalize_plan(p3d::TransformPlan& tp) {
 
 p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long dim_real, long long dim_cplx) {
   const int chunks = (L.p2p && L.overlap > 1) ? L.overlap : 0;
-  const int xyg = (L.xypipe > 0 && L.W() > 0) ? (L.xypipe > 127 ? 127 : L.xypipe) : 0;
-  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx, L.W(),
-              (L.p2p ? 1 : 0) | (chunks << 8) | (xyg << 16) | (L.xypipe_ring ? 1 << 24 : 0)};
+  PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx, L.W(), (L.p2p ? 1 : 0) | (chunks << 8)};
   auto it = L.plans.find(key);
   if (it != L.plans.end()) return &it->second;
   p3d::TransformPlan tp = p3d::build_plan(L.d, backward, op, nv, dim_real, dim_cplx, L.W(), L.p2p);
@@ -403,7 +413,6 @@ p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long di
     return nullptr;
   }
   if (chunks > 1) p3d::split_for_overlap(tp, chunks, L.W());
-  if (xyg > 0) p3d::split_xy_pipeline(tp, xyg, L.xypipe_ring, backward);
   if (!finalize_plan(tp)) return nullptr;
   auto res = L.plans.emplace(key, std::move(tp));
   return &res.first->second;
@@ -487,7 +496,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     else if (!L.force_generic && p3d::fast_supported<real_t>(stg)) {
       p3d::FastStage fs;
       p3d::to_fast(stg, fs, sizeof(real_t), p3d::fast_variant<real_t>(stg));
-      fs.tw = fast_twiddle_block(stg.kind, stg.nfft, fs.variant);
+      fs.tw = fast_twiddle_block(stg.kind, stg.nfft, fs.variant & 1);      // the block depends on the schedule only
       if (!fs.tw) { report(true, "P3DFFT(B200): cannot allocate twiddle table"); return false; }
       fs.sm_cap = sm_cap;
       e = p3d::launch_fast<real_t>(stg, fs, sx);
@@ -508,58 +517,18 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     while ((int)L.chunk_events.size() < nchunks) {
       cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.chunk_events.push_back(ev);
     }
-    while ((int)L.chunk_events2.size() < nchunks) {
-      cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.chunk_events2.push_back(ev);
-    }
   }
-  const int pipe_sms = L.xypipe_sms > 0 && L.xypipe_sms < sms ? L.xypipe_sms : sms / 2;
-  bool persist_set = false;
   auto join_side = [&]() -> bool {       // the main stream waits for everything queued on the side stream
     if (!used_side) return true;
     CUDA_OK(cudaEventRecord(L.side_done, L.side_stream));
     CUDA_OK(cudaStreamWaitEvent(st, L.side_done, 0));
     used_side = false;
-    if (persist_set) { cudaCtxResetPersistingL2Cache(); persist_set = false; }
     return true;
   };
   const int side_sms = L.overlap_sms > 0 && L.overlap_sms < sms ? L.overlap_sms : sms / 3;
   bool pre_done = false;      // the barrier that protects the receive buffer of the NEXT exchange has been issued
   for (size_t i = 0; i < nsteps; i++) {
     auto& s = tp->steps[i];
-    if (!s.is_exchange && s.pipe) {
-      // X <-> Y pipeline chunk: producer on the main stream, consumer on the side stream, ordered by events; with the ring
-      // the producer of chunk c waits for the consumer of chunk c-2 (it overwrites that consumer's slot)
-      const int c = s.chunk;
-      if (s.pipe == 2 && L.xypipe_persist && !persist_set && !s.side) {
-        // keep the two ring slots resident in L2: persisting access window on both streams (reset when the group is joined)
-        const P3dSeg& sg = s.st.out.seg[0];
-        cudaStreamAttrValue av;
-        memset(&av, 0, sizeof av);
-        av.accessPolicyWindow.base_ptr = (char*)L.buf[sg.buf] + sg.off * CSIZE;
-        av.accessPolicyWindow.num_bytes = (size_t)2 * (size_t)(L.xypipe > 127 ? 127 : L.xypipe) * (size_t)sg.sb * CSIZE;
-        av.accessPolicyWindow.hitRatio = 1.0f;
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, av.accessPolicyWindow.num_bytes);
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-        cudaStreamSetAttribute(L.side_stream, cudaStreamAttributeAccessPolicyWindow, &av);
-        cudaGetLastError();        // best effort: a refused window only costs the residency hint
-        persist_set = true;
-      }
-      if (!s.side) {
-        if (s.pipe == 2 && c >= 2) CUDA_OK(cudaStreamWaitEvent(st, L.chunk_events2[c - 2], 0));
-        if (timed) { cudaEventRecord(get_event(nev++), st); slots.push_back(s.st.timer); is_ex.push_back(0); }
-        if (!launch(s.st, st, c > 0 ? sms - pipe_sms : 0)) return false;
-        CUDA_OK(cudaEventRecord(L.chunk_events[c], st));
-      } else {
-        CUDA_OK(cudaStreamWaitEvent(L.side_stream, L.chunk_events[c], 0));
-        if (!launch(s.st, L.side_stream, c + 1 < nchunks ? pipe_sms : 0)) return false;
-        CUDA_OK(cudaEventRecord(L.chunk_events2[c], L.side_stream));
-        used_side = true;
-      }
-      continue;
-    }
-    if (used_side && i > 0 && tp->steps[i - 1].pipe && !join_side()) return false;      // the pipeline group is complete
     if (!s.is_exchange && s.side) {
       // consumer chunk of the pipelined tail: side stream, after this chunk's barrier; the last one has the GPU to itself
       CUDA_OK(cudaStreamWaitEvent(L.side_stream, L.chunk_events[s.chunk], 0));
@@ -689,6 +658,14 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   }
   CommCtx* cc = nullptr;
   if (comm) { auto it = g_comms.find(*comm); if (it != g_comms.end()) cc = it->second; }
+  if (comm && *comm != 0 && !cc) {
+    // not a handle of p3dfft_b200_comm_create (0 is reserved for the implicit one-rank communicator): e.g. a real Fortran
+    // MPI handle from code that was not ported.  Running on as one rank would silently give every process its own
+    // full-size transform, so this is an error (INTEGRATION.md section 1 shows the four lines a real-MPI driver adds).
+    report(true, "P3DFFT(B200) setup error: communicator %d is not a handle created by p3dfft_b200_comm_create "
+                 "(a Fortran MPI handle is not understood by this build; see INTEGRATION.md)", *comm);
+    return;
+  }
   const int rank = cc ? cc->rank : 0, ntasks = cc ? cc->size : 1;
   std::string err = L.d.init(*nx, *ny, *nz, dims[0], dims[1], rank, ntasks, nxc ? *nxc : *nx, nyc ? *nyc : *ny,
                              nzc ? *nzc : *nz, L.dims_c != 0, L.stride1 != 0);
@@ -712,17 +689,18 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
       report(true, "P3DFFT(B200): ncclCommSplit(col) failed"); return;
     }
   }
+  // switches: an environment variable wins; without it the value set through the API stays (generic, plain, p2p, row bytes)
+  // or the default applies (barrier kind, pipelined tail) -- so a later setup in the same process starts from the defaults
+  auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
   if (getenv("P3DFFT_B200_GENERIC")) L.force_generic = true;
   if (getenv("P3DFFT_B200_PLAIN")) L.plain_layout = true;
-  if (getenv("P3DFFT_B200_P2P")) L.want_p2p = atoi(getenv("P3DFFT_B200_P2P")) != 0;
+  L.want_p2p = env_int("P3DFFT_B200_P2P", L.api_p2p ? 1 : 0) != 0;
   if (getenv("P3DFFT_B200_ROWB")) L.force_row_bytes = atoi(getenv("P3DFFT_B200_ROWB"));
-  if (getenv("P3DFFT_B200_FLAGBAR")) L.want_flagbar = atoi(getenv("P3DFFT_B200_FLAGBAR")) != 0;
-  if (getenv("P3DFFT_B200_OVERLAP")) L.overlap = atoi(getenv("P3DFFT_B200_OVERLAP"));
-  if (getenv("P3DFFT_B200_OVERLAP_SMS")) L.overlap_sms = atoi(getenv("P3DFFT_B200_OVERLAP_SMS"));
-  if (getenv("P3DFFT_B200_XYPIPE")) L.xypipe = atoi(getenv("P3DFFT_B200_XYPIPE"));
-  if (getenv("P3DFFT_B200_XYPIPE_SMS")) L.xypipe_sms = atoi(getenv("P3DFFT_B200_XYPIPE_SMS"));
-  if (getenv("P3DFFT_B200_XYPIPE_RING")) L.xypipe_ring = atoi(getenv("P3DFFT_B200_XYPIPE_RING")) != 0;
-  if (getenv("P3DFFT_B200_XYPIPE_PERSIST")) L.xypipe_persist = atoi(getenv("P3DFFT_B200_XYPIPE_PERSIST")) != 0;
+  L.want_flagbar = env_int("P3DFFT_B200_FLAGBAR", P3D_DEFAULT_FLAGBAR) != 0;
+  L.overlap = env_int("P3DFFT_B200_OVERLAP", P3D_DEFAULT_OVERLAP);
+  L.overlap_sms = env_int("P3DFFT_B200_OVERLAP_SMS", P3D_DEFAULT_OVERLAP_SMS);
+  L.row_bytes_plan = L.force_row_bytes;
+  p3d::fast_reload_switches();
   for (int i = 0; i < 12; i++) L.timers[i] = 0.0;      // setup.F90:144
   L.procmap.init(L.d);
   L.nv_preset = 0;
@@ -809,6 +787,8 @@ void p3dfft_clean(void) {
     world_barrier(L.stream());
     cudaStreamSynchronize(L.stream());
     close_peer_maps();
+    world_barrier(L.stream());     // ... nor before every importer has closed its mapping of them
+    cudaStreamSynchronize(L.stream());
   }
   if (L.bar_scratch) { cudaFree(L.bar_scratch); L.bar_scratch = nullptr; }
   if (L.bar_flags) { cudaFree(L.bar_flags); L.bar_flags = nullptr; }
@@ -817,8 +797,6 @@ void p3dfft_clean(void) {
   if (L.side_stream) { cudaStreamSynchronize(L.side_stream); cudaStreamDestroy(L.side_stream); L.side_stream = nullptr; }
   for (auto ev : L.chunk_events) cudaEventDestroy(ev);
   L.chunk_events.clear();
-  for (auto ev : L.chunk_events2) cudaEventDestroy(ev);
-  L.chunk_events2.clear();
   if (L.side_done) { cudaEventDestroy(L.side_done); L.side_done = nullptr; }
   for (int b = P3D_BUF_A; b <= P3D_BUF_C; b++) if (L.buf[b]) { cudaFree(L.buf[b]); L.buf[b] = nullptr; }
   if (L.stage_in) { cudaFree(L.stage_in); L.stage_in = nullptr; L.stage_in_bytes = 0; }
@@ -1013,7 +991,7 @@ int p3dfft_b200_last_error(char* buf, int buflen) {
 void p3dfft_b200_set_stream(void* s) { L.user_stream = (cudaStream_t)s; L.has_user_stream = true; }
 void p3dfft_b200_reset_stream(void) { L.user_stream = nullptr; L.has_user_stream = false; }
 void p3dfft_b200_force_generic(int on) { L.force_generic = on != 0; }
-void p3dfft_b200_set_p2p(int on) { L.want_p2p = on != 0; }
+void p3dfft_b200_set_p2p(int on) { L.api_p2p = L.want_p2p = on != 0; }
 int p3dfft_b200_p2p_active(void) { return L.p2p ? 1 : 0; }
 void p3dfft_b200_row_bytes(int rb) {      // 0: planner's rule; 64 / 128: forced.  Takes effect at the next p3dfft_setup
   L.force_row_bytes = (rb == 64 || rb == 128) ? rb : 0;
@@ -1064,15 +1042,13 @@ int p3dfft_b200_plan_steps(const int* dims, int nx, int ny, int nz, int rank, in
   if (!tp.error.empty()) { g_last_error = tp.error; return -1; }
   const int nchunk = (flags >> 8) & 0xff;       // pipelined tail (split_for_overlap), peer-to-peer plans only
   if (nchunk > 1) p3d::split_for_overlap(tp, nchunk, (flags & 8) ? 0 : p3d::pick_W(ny, nz, 2 * elem_bytes, (flags & 32) ? 64 : (flags & 64) ? 128 : 0));
-  const int xyg = (flags >> 16) & 0x7f;         // X <-> Y pipeline (split_xy_pipeline): planes per chunk; bit 23: no ring
-  if (xyg > 0) p3d::split_xy_pipeline(tp, xyg, !(flags & (1 << 23)), backward != 0);
   if ((int)tp.steps.size() > max_steps) { g_last_error = "step array too small"; return -1; }
   P3dStepC* out = (P3dStepC*)steps;
   for (size_t i = 0; i < tp.steps.size(); i++) {
     memset(&out[i], 0, sizeof out[i]);
     out[i].is_exchange = tp.steps[i].is_exchange ? 1 : 0;
-    // bit 0: side stream; bits 1-2: X<->Y pipeline chunk (2 = ring); bits 8..: chunk + 1
-    out[i].pad_ = (tp.steps[i].side ? 1 : 0) | (tp.steps[i].pipe << 1) | ((tp.steps[i].chunk + 1) << 8);
+    // bit 0: side stream; bits 8..: chunk + 1
+    out[i].pad_ = (tp.steps[i].side ? 1 : 0) | ((tp.steps[i].chunk + 1) << 8);
     out[i].st = tp.steps[i].st;
     out[i].ex = tp.steps[i].ex;
     if (!tp.steps[i].is_exchange)

@@ -48,15 +48,17 @@ struct FastStage {
   FastSide in, out;
   double scale;          // multiplies every output (SCALED instantiations only; last member: the unscaled kernels'
                          // parameter layout does not depend on it)
-  int32_t variant;       // 0: default; 1: two-pass radix-32 c2c schedules; 2: wide X tiles; 3: half-row c2c tiles; 4: bulk-copy stores (fast_variant, opt-in)
+  int32_t variant;       // bit 0: two-pass radix-32 c2c schedule; bit 2: bulk-copy stores (fast_variant)
   int32_t sm_cap;        // > 0: the persistent grid uses at most this many SMs (pipelined tail, api.cpp); host side only
 };
 
 // true when a specialised kernel exists for this stage (kind, length, strides, alignment)
 template <typename T> bool fast_supported(const P3dStage& st);
 // number of T2 elements of the twiddle block and its host-side fill
-// experimental kernel variant this stage would run with (0 = default); decides which twiddle block it needs
+// kernel variant this stage runs with (0 = default; bit 0 decides which twiddle block it needs)
 template <typename T> int fast_variant(const P3dStage& st);
+// re-reads the P3DFFT_B200_R32 / P3DFFT_B200_BULK switches (p3dfft_setup calls it; launches never touch the environment)
+void fast_reload_switches();
 template <typename T> size_t fast_twiddle_elems(int kind, int nfft, int variant = 0);
 template <typename T> void fast_twiddle_fill(int kind, int nfft, void* host, int variant = 0);
 // converts resolved segments (seg.base set) into runs; real_bytes = sizeof(real)

@@ -102,7 +102,6 @@ static int row_bytes(const P3dStage& st) {
 template <typename T>
 static int tile_lines(const P3dStage& st, int variant = 0) {
   int tx = 1;
-  if (is_x(st.kind) && variant == 2) return XCfgWide<double, 512>::TX;
   if (is_x(st.kind)) dispatch_x(st.n / 2, [&](auto h) { tx = XCfg<T, decltype(h)::value>::TX; });
   else tx = row_bytes<T>(st) / (2 * (int)sizeof(T));
   return tx;
@@ -152,36 +151,48 @@ bool dispatch_r32(int n, F&& f) {
   }
 }
 
-// Opt-in two-pass variant (P3DFFT_B200_R32=1): c2c / DCT stages of 512 or 1024 points with 128-byte rows
+// Kernel variant of a c2c / DCT stage (bit 0: two-pass radix-32 schedule, bit 2: bulk-copy stores), decided from the stage's
+// geometry and two switches read at p3dfft_setup (fast_reload_switches), never per launch:
+//   P3DFFT_B200_R32  = 0 never / 1 wherever a two-pass schedule exists / unset: the measured rule below
+//   P3DFFT_B200_BULK = 0 never / 1 wherever the output rows allow it   / unset: stages that store into a peer's memory
+// Measured on B200 (profiles/r2_ab_1gpu_optin_variants.log, 1024^3): the two-pass schedule 1024 = 32 x 32 wins where the
+// stage WRITES whole tiles contiguously (Y forward 3.54 -> 3.32 ms, Y backward 3.67 -> 3.56 ms; single 1.87 -> 1.70 ms) and
+// loses where the rows are scattered into the user layout or gathered from it (Z stages), and at 512 points.
+struct FastSwitches { int r32, bulk; bool loaded; };
+static FastSwitches g_switches = {-1, -1, false};
+void fast_reload_switches() {
+  g_switches.r32 = getenv("P3DFFT_B200_R32") ? atoi(getenv("P3DFFT_B200_R32")) : -1;
+  g_switches.bulk = getenv("P3DFFT_B200_BULK") ? atoi(getenv("P3DFFT_B200_BULK")) : -1;
+  g_switches.loaded = true;
+}
+static const FastSwitches& fast_switches() {
+  if (!g_switches.loaded) fast_reload_switches();
+  return g_switches;
+}
+
 template <typename T>
 int fast_variant(const P3dStage& st) {
-  const char* e = getenv("P3DFFT_B200_R32");
-  if (is_x(st.kind)) {          // wide X tiles (variant 2)
-    const char* x = getenv("P3DFFT_B200_XTX8");
-    return (x && atoi(x) != 0 && st.n % 2 == 0 && xcfg_wide_exists(st.n / 2, (int)sizeof(T))) ? 2 : 0;
+  if (is_x(st.kind) || st.out.nseg == 0 || st.in.nseg == 0) return 0;
+  if (!(st.nfft == 1024 || st.nfft == 512) || row_bytes<T>(st) != 128) return 0;
+  const FastSwitches& sw = fast_switches();
+  const int tx = 128 / (2 * (int)sizeof(T));
+  // every output run: whole 128-byte tile rows, consecutive in memory (the writer-contiguous internal layouts)
+  bool out_contig = true, out_peer = false;
+  for (int g = 0; g < st.out.nseg; g++) {
+    const P3dSeg& sg = st.out.seg[g];
+    if (sg.sa != 1 || sg.kw > 1 || sg.ps != tx || sg.aw != tx) out_contig = false;
+    if (sg.peer >= 0) out_peer = true;
   }
-  const bool r32 = e && atoi(e) != 0 && ccfg_r32_exists(st.nfft);
-  const char* hf = getenv("P3DFFT_B200_HALF");
-  const bool half = hf && atoi(hf) != 0 && st.nfft == 1024;
-  const char* bk = getenv("P3DFFT_B200_BULK");
-  bool bulk = bk && atoi(bk) != 0 && (st.nfft == 1024 || st.nfft == 512);
-  if (bulk) {      // every output run: whole 128-byte tile rows, consecutive in memory
-    const int tx = 128 / (2 * (int)sizeof(T));
-    for (int g = 0; g < st.out.nseg; g++) {
-      const P3dSeg& sg = st.out.seg[g];
-      if (sg.sa != 1 || sg.kw > 1 || sg.ps != tx || sg.aw != tx) bulk = false;
-    }
-    if (st.out.nseg == 0) bulk = false;
-  }
-  if (!r32 && !half && !bulk) return 0;
-  if (row_bytes<T>(st) != 128) return 0;
-  return r32 ? 1 : half ? 3 : 4;
+  const bool far_in = st.in.seg[0].ps * 2 * (long long)sizeof(T) > 131072;      // the split kernel's case (launch_fast)
+  const bool r32 = ccfg_r32_exists(st.nfft) && (sw.r32 > 0 || (sw.r32 < 0 && st.nfft == 1024 && out_contig && !far_in));
+  const bool bulk = out_contig && (sw.bulk > 0 || (sw.bulk < 0 && out_peer));
+  return (r32 ? 1 : 0) | (bulk ? 4 : 0);
 }
 
 template <typename T>
 size_t fast_twiddle_elems(int kind, int nfft, int variant) {
   size_t n = 0;
-  if (variant == 1 && !is_x(kind)) { dispatch_r32(nfft, [&](auto nn) { n = block_elems<typename CCfgR32<T, decltype(nn)::value>::S>(false); }); return n; }
+  if ((variant & 1) && !is_x(kind)) { dispatch_r32(nfft, [&](auto nn) { n = block_elems<typename CCfgR32<T, decltype(nn)::value>::S>(false); }); return n; }
   if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { n = block_elems<typename XCfg<T, decltype(h)::value>::S>(true); });
   else dispatch_c(nfft, [&](auto nn) { n = block_elems<typename CCfg<T, decltype(nn)::value, 64>::S>(false); });
   return n;
@@ -189,7 +200,7 @@ size_t fast_twiddle_elems(int kind, int nfft, int variant) {
 
 template <typename T>
 void fast_twiddle_fill(int kind, int nfft, void* host, int variant) {
-  if (variant == 1 && !is_x(kind)) { dispatch_r32(nfft, [&](auto nn) { fill_block<T, typename CCfgR32<T, decltype(nn)::value>::S>(false, host); }); return; }
+  if ((variant & 1) && !is_x(kind)) { dispatch_r32(nfft, [&](auto nn) { fill_block<T, typename CCfgR32<T, decltype(nn)::value>::S>(false, host); }); return; }
   if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { fill_block<T, typename XCfg<T, decltype(h)::value>::S>(true, host); });
   else dispatch_c(nfft, [&](auto nn) { fill_block<T, typename CCfg<T, decltype(nn)::value, 64>::S>(false, host); });
 }
@@ -292,22 +303,6 @@ static cudaError_t launch_x(const P3dStage& st, const FastStage& f, cudaStream_t
   return cudaGetLastError();
 }
 
-// wide X tiles (opt-in, double, nx = 1024)
-static cudaError_t launch_x_wide(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
-  using T = double;
-  using C = XCfgWide<double, 512>;
-  constexpr int TX = C::TX, NT = C::NT, HH = 512;
-  constexpr size_t smem = xstage_smem<T, HH, C>();
-  const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb * st.nc;
-  if (tiles <= 0) return cudaSuccess;
-  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
-  cudaError_t e;
-  if (st.kind == P3D_R2C) P3D_LAUNCH(xr2c_kernel<T, HH, C>);
-  else if (f.scale != 1.0) P3D_LAUNCH(xc2r_kernel<T, HH, true, C>);
-  else P3D_LAUNCH(xc2r_kernel<T, HH, false, C>);
-  return cudaGetLastError();
-}
-
 template <typename T, int NN, int RB>
 static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
   constexpr int TX = CCfg<T, NN, RB>::TX, NT = CCfg<T, NN, RB>::NT;
@@ -328,33 +323,12 @@ static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t
   return cudaGetLastError();
 }
 
-// two-pass radix-32 variant (opt-in)
-template <typename T, int NN>
-static cudaError_t launch_r32(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
-  constexpr int TX = CCfgR32<T, NN>::TX, NT = CCfgR32<T, NN>::NT;
-  constexpr size_t smem = cstage_r32_smem<T, NN>();
-  const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
-  const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
-  if (tiles <= 0) return cudaSuccess;
-  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
-  cudaError_t e;
-  const bool scaled = f.scale != 1.0;
-  if (st.kind == P3D_C2C_BWD) {
-    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 128, true, true, CCfgR32<T, NN>>);
-    else P3D_LAUNCH(cstage_kernel<T, NN, 128, true, false, CCfgR32<T, NN>>);
-  } else {
-    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 128, false, true, CCfgR32<T, NN>>);
-    else P3D_LAUNCH(cstage_kernel<T, NN, 128, false, false, CCfgR32<T, NN>>);
-  }
-  return cudaGetLastError();
-}
-
-// half-row variant (opt-in): the 64-byte-row kernel on 128-byte-row buffers, two CTAs per tile
-template <typename T, int NN>
-static cudaError_t launch_half(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
-  using C = CCfg<T, NN, 64>;
+// variants of the 128-byte-row c2c kernel: C = CCfg (three passes) or CCfgR32 (two passes); BULK = tile stored by cp.async.bulk
+template <typename T, int NN, class C, bool BULK>
+static cudaError_t launch_cv(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  using T2 = typename Cx<T>::type;
   constexpr int TX = C::TX, NT = C::NT;
-  constexpr size_t smem = cstage_smem<T, NN, 64>();
+  constexpr size_t smem = sizeof(T2) * NN * TX + 2 * sizeof(long long) * NN + sizeof(RunTab);
   const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
   const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
   if (tiles <= 0) return cudaSuccess;
@@ -362,33 +336,11 @@ static cudaError_t launch_half(const P3dStage& st, const FastStage& f, cudaStrea
   cudaError_t e;
   const bool scaled = f.scale != 1.0;
   if (st.kind == P3D_C2C_BWD) {
-    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 64, true, true, C, 2>);
-    else P3D_LAUNCH(cstage_kernel<T, NN, 64, true, false, C, 2>);
+    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 128, true, true, C, BULK>);
+    else P3D_LAUNCH(cstage_kernel<T, NN, 128, true, false, C, BULK>);
   } else {
-    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 64, false, true, C, 2>);
-    else P3D_LAUNCH(cstage_kernel<T, NN, 64, false, false, C, 2>);
-  }
-  return cudaGetLastError();
-}
-
-// bulk-store variant (opt-in): default configuration, tile written back through shared memory and cp.async.bulk
-template <typename T, int NN>
-static cudaError_t launch_bulk(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
-  using C = CCfg<T, NN, 128>;
-  constexpr int TX = C::TX, NT = C::NT;
-  constexpr size_t smem = cstage_smem<T, NN, 128>();
-  const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
-  const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
-  if (tiles <= 0) return cudaSuccess;
-  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
-  cudaError_t e;
-  const bool scaled = f.scale != 1.0;
-  if (st.kind == P3D_C2C_BWD) {
-    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 128, true, true, C, 1, true>);
-    else P3D_LAUNCH(cstage_kernel<T, NN, 128, true, false, C, 1, true>);
-  } else {
-    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 128, false, true, C, 1, true>);
-    else P3D_LAUNCH(cstage_kernel<T, NN, 128, false, false, C, 1, true>);
+    if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, 128, false, true, C, BULK>);
+    else P3D_LAUNCH(cstage_kernel<T, NN, 128, false, false, C, BULK>);
   }
   return cudaGetLastError();
 }
@@ -424,16 +376,17 @@ cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t str
       if (reinterpret_cast<uintptr_t>(sd.run[g].base) % sizeof(T2)) return cudaErrorMisalignedAddress;
   }
   cudaError_t err = cudaErrorInvalidValue;
-  if (f.variant == 3 && !is_x(st.kind) && f.rowb == 128 && st.nfft == 1024) return launch_half<T, 1024>(st, f, stream);
-  if (f.variant == 4 && !is_x(st.kind) && f.rowb == 128) {
-    if (st.nfft == 1024) return launch_bulk<T, 1024>(st, f, stream);
-    if (st.nfft == 512) return launch_bulk<T, 512>(st, f, stream);
-  }
-  if (f.variant == 1 && !is_x(st.kind) && f.rowb == 128) {
-    if (dispatch_r32(st.nfft, [&](auto nn) { err = launch_r32<T, decltype(nn)::value>(st, f, stream); })) return err;
-  }
-  if (is_x(st.kind) && f.variant == 2) {
-    if constexpr (std::is_same<T, double>::value) return launch_x_wide(st, f, stream);
+  if (f.variant != 0 && !is_x(st.kind) && f.rowb == 128) {
+    const bool r32 = (f.variant & 1) != 0, bulk = (f.variant & 4) != 0;
+    if (st.nfft == 1024) {
+      if (r32 && bulk) return launch_cv<T, 1024, CCfgR32<T, 1024>, true>(st, f, stream);
+      if (r32) return launch_cv<T, 1024, CCfgR32<T, 1024>, false>(st, f, stream);
+      if (bulk) return launch_cv<T, 1024, CCfg<T, 1024, 128>, true>(st, f, stream);
+    } else if (st.nfft == 512) {
+      if (r32 && bulk) return launch_cv<T, 512, CCfgR32<T, 512>, true>(st, f, stream);
+      if (r32) return launch_cv<T, 512, CCfgR32<T, 512>, false>(st, f, stream);
+      if (bulk) return launch_cv<T, 512, CCfg<T, 512, 128>, true>(st, f, stream);
+    }
   }
   if (is_x(st.kind)) dispatch_x(st.n / 2, [&](auto h) { err = launch_x<T, decltype(h)::value>(st, f, stream); });
   else dispatch_c(st.nfft, [&](auto nn) {

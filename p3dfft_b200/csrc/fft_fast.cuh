@@ -141,15 +141,6 @@ P3D_XCFG(float, 512, P3D_RS(8, 8, 8), 8, 256, 3, 6, 0)
 P3D_XCFG(float, 1024, P3D_RS(8, 16, 8), 8, 512, 2, 7, 0)
 #undef P3D_XCFG
 #undef P3D_RS
-// Wide X tiles (opt-in, P3DFFT_B200_XTX8=1): 8 lines per tile instead of 4 for nx = 1024 in double, so that the pieces the X
-// stage moves on the blocked X<->Y buffer are 1 KB instead of 512 B.  Same schedule and swizzle; not yet timed on hardware.
-template <typename T, int HH> struct XCfgWide;
-template <> struct XCfgWide<double, 512> {
-  using S = RS<8, 8, 8>;
-  static constexpr int H = 512, TX = 8, NT = 256, MINB = 2, SA = 6, SB = 0, LP = 512 + 4;
-};
-constexpr bool xcfg_wide_exists(int h, int real_bytes) { return h == 512 && real_bytes == 8; }
-
 #if defined(__CUDACC__) || defined(P3D_EMULATE)      // P3D_EMULATE: host emulation of the kernels (tests/emu, CPU tests)
 // ---------------------------------------------------------------------------------------
 // complex helpers and natural-order forward butterflies
@@ -473,25 +464,10 @@ __device__ __forceinline__ void fill_tilebase(const FastStage& st, RunTab& rt, i
 // SCALED: every output is multiplied by st.scale on its way out (the drivers' normalisation pass, mult_array in
 // sample/C/driver_*.c, fused into the store); a separate instantiation, so the unscaled kernels are unchanged.
 // C: the configuration (schedule, threads); the default is the table above, CCfgR32 selects the two-pass variant
-// sub-tile bases: the rows of the layout hold TPB * TX lines, this CTA takes lines [sub*TX, sub*TX + TX) of tile ta / TPB
-template <int NT, int ESZ, int TPB, int TX>
-__device__ __forceinline__ void fill_tilebase_sub(const FastStage& st, RunTab& rt, int slot, TileIdx ti) {
-  const int nin = st.in.nrun, ntot = nin + st.out.nrun;
-  const int sub = ti.ta % TPB;
-  ti.ta /= TPB;
-  for (int i = threadIdx.x; i < ntot; i += NT) {
-    const int side = i >= nin, g = side ? i - nin : i;
-    const FastRun& r = side ? st.out.run[g] : st.in.run[g];
-    rt.tb[slot][side][g] = tile_base<ESZ>(r, ti) + (long long)sub * TX * r.sa * ESZ;
-  }
-}
-
-// TPB > 1 (opt-in "half-row" variant, P3DFFT_B200_HALF=1): a kernel built for 64-byte tile rows works on buffers laid out in
-// 128-byte rows, each CTA on one half of the lines of a tile -- two 64 KB CTAs per SM instead of one 128 KB CTA at N = 1024.
 // BULK (opt-in, P3DFFT_B200_BULK=1; 128-byte rows, outputs whose tile rows are contiguous per run -- every stage that
 // feeds an exchange): the last pass puts the tile back into shared memory in natural row order and ONE bulk asynchronous
 // copy per output run (per peer) moves it to HBM or over NVLink, instead of 16-byte stores from registers.
-template <typename T, int N, int RB, bool SWAP, bool SCALED = false, class C = CCfg<T, N, RB>, int TPB = 1, bool BULK = false>
+template <typename T, int N, int RB, bool SWAP, bool SCALED = false, class C = CCfg<T, N, RB>, bool BULK = false>
 __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
   using S = typename C::S;
@@ -519,8 +495,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
     rt->pfmode[g] = (st.prefetch && psb <= (long long)st.prefetch) ? (psb == 64 ? 2 : 1) : 0;
   }
   if (blockIdx.x < ntiles) {
-    if constexpr (TPB == 1) fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
-    else fill_tilebase_sub<NT, sizeof(T2), TPB, TX>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
+    fill_tilebase<NT, sizeof(T2)>(st, *rt, 0, tile_decode(blockIdx.x, tiles_a, st.nb, st.bord));
   }
   __syncthreads();
 
@@ -530,8 +505,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
     const bool live = ti.ta * TX + t < st.na && ti.b < st.nb;       // b >= nb: padding slot, nothing loaded or stored
     const bool has_next = tile + gridDim.x < ntiles && tile + gridDim.x > tile;
     if (has_next && threadIdx.x < st.in.nrun + st.out.nrun) {
-      if constexpr (TPB == 1) fill_tilebase<NT, sizeof(T2)>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord));
-      else fill_tilebase_sub<NT, sizeof(T2), TPB, TX>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord));
+      fill_tilebase<NT, sizeof(T2)>(st, *rt, slot ^ 1, tile_decode(tile + gridDim.x, tiles_a, st.nb, st.bord));
     }
     // ---- pass 1: global -> registers -> shared ---------------------------------------------
     {

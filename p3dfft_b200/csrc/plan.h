@@ -175,8 +175,6 @@ struct Step {
   bool is_exchange = false;
   int chunk = -1;        // >= 0: this step belongs to chunk `chunk` of a pipelined group (split_for_overlap)
   bool side = false;     // consumer stage of a pipelined group: runs on the side stream after its chunk's barrier
-  int pipe = 0;          // 1: chunk of an X<->Y pipeline (split_xy_pipeline): ordered by events, no exchange in between;
-                         // 2: ... whose buffer side lives in a two-slot ring (the producer of chunk c+2 waits for consumer c)
   P3dStage st{};
   P3dExchange ex{};
 };
@@ -596,55 +594,6 @@ inline bool split_for_overlap(TransformPlan& tp, int nchunk, int W) {
   }
   tp.steps.resize(n - 3);
   tp.steps.insert(tp.steps.end(), tail.begin(), tail.end());
-  return true;
-}
-
-// ------------------------------------------------------------------------------------
-// X <-> Y pipeline through L2 (opt-in, P3DFFT_B200_XYPIPE=G).
-//
-// When the row communicator has one rank (M1 = 1: 1 x N grids, a single GPU) the X stage and the Y stage exchange
-// their data through a work buffer on the same GPU: 8.6 GB written and 8.6 GB read again per 1024^3 transform, a
-// third of the traffic.  A z plane of that buffer is only ~8.5 MB, so the pair is cut into chunks of G planes
-//     forward   X_0  Y_0  X_1  Y_1 ...          backward   Y_0  X_0  Y_1  X_1 ...        (second stage of a pair: `side`)
-// and the consumer of chunk c runs on the side stream as soon as its producer has finished, while the producer
-// works on chunk c+1: the planes are read back while they are still in the 126 MB L2.  With `ring` the buffer side
-// of every chunk is one of two slots of G planes at the start of the buffer (chunk c -> slot c mod 2), so the same
-// ~2 G planes are rewritten over and over and need never reach HBM; the producer of chunk c+2 then waits for the
-// consumer of chunk c.  A chunk is the same stage with nb = planes of the chunk and shifted offsets.
-// Returns false (plan untouched) unless the plan starts (forward) / ends (backward) with two stages in a row.
-// ------------------------------------------------------------------------------------
-inline bool split_xy_pipeline(TransformPlan& tp, int G, bool ring, bool backward) {
-  const size_t n = tp.steps.size();
-  if (G < 1 || n < 2) return false;
-  const size_t ip = backward ? n - 2 : 0, iq = ip + 1;
-  if (tp.steps[ip].is_exchange || tp.steps[iq].is_exchange) return false;
-  if (tp.steps[ip].chunk >= 0 || tp.steps[iq].chunk >= 0) return false;      // already part of a pipelined tail
-  const P3dStage P = tp.steps[ip].st, Q = tp.steps[iq].st;
-  const bool ok_kinds = backward ? (Q.kind == P3D_C2R) : (P.kind == P3D_R2C);
-  if (!ok_kinds || P.nb != Q.nb || P.nc != Q.nc || P.nb < 2) return false;
-  if (P.out.nseg != 1 || Q.in.nseg != 1 || P.out.seg[0].buf != Q.in.seg[0].buf || P.out.seg[0].peer >= 0) return false;
-  if (P.out.seg[0].sb != Q.in.seg[0].sb || P.out.seg[0].bw > 1 || Q.in.seg[0].bw > 1) return false;
-  const int nb = P.nb, nchunk = (nb + G - 1) / G;
-  if (nchunk < 2) return false;
-  std::vector<Step> seq;
-  for (int c = 0; c < nchunk; c++) {
-    const int b0 = c * G, cnt = std::min(G, nb - b0);
-    Step a; a.is_exchange = false; a.chunk = c; a.pipe = ring ? 2 : 1; a.st = P;
-    Step b; b.is_exchange = false; b.chunk = c; b.pipe = ring ? 2 : 1; b.side = true; b.st = Q;
-    a.st.nb = b.st.nb = cnt;
-    shift_side(a.st.in, false, b0);                                   // far sides: the planes themselves
-    shift_side(b.st.out, false, b0);
-    const long long slot = ring ? (long long)(c & 1) * G : b0;        // buffer side: ring slot or the planes' own place
-    shift_side(a.st.out, false, slot);
-    shift_side(b.st.in, false, slot);
-    seq.push_back(a); seq.push_back(b);
-  }
-  std::vector<Step> out;
-  for (size_t i = 0; i < n; i++) {
-    if (i == ip) out.insert(out.end(), seq.begin(), seq.end());
-    else if (i != iq) out.push_back(tp.steps[i]);
-  }
-  tp.steps.swap(out);
   return true;
 }
 

@@ -49,6 +49,7 @@ extern "C" int emu_run_fast(const P3dStage* st) {
   g_last_variant = 0;
   if (!p3d::fast_supported<emu_real>(*st)) return 1;
   p3d::FastStage fs;
+  p3d::fast_reload_switches();      // the kernel-only test library has no p3dfft_setup: tests flip the switches between runs
   p3d::to_fast(*st, fs, sizeof(emu_real), p3d::fast_variant<emu_real>(*st));
   g_last_variant = fs.variant;
   std::vector<emu_real> tw(2 * p3d::fast_twiddle_elems<emu_real>(st->kind, st->nfft, fs.variant) + 2);

@@ -87,7 +87,7 @@ def _eager_order(steps):
 
 
 def transform_world(n, dims, cut, opf, opb, stride1=False, single=False, p2p=False, row_bytes=0, nv=1, overlap=0,
-                    xypipe=0, xyring=True, eager=False):
+                    eager=False):
     """forward and backward on P simulated ranks; returns (fast stage count, generic stage count)"""
     nx, ny, nz = n
     c = cut or (None, None, None)
@@ -103,7 +103,7 @@ def transform_world(n, dims, cut, opf, opb, stride1=False, single=False, p2p=Fal
         plans, world = [], []
         for r, d in enumerate(D):
             steps, inf = L.plan_steps(dims, nx, ny, nz, r, backward, op, nv, *c, stride1=stride1, p2p=p2p, row_bytes=row_bytes,
-                                       overlap=overlap, xypipe=xypipe, xyring=xyring)
+                                       overlap=overlap)
             if eager:
                 steps = _eager_order(steps)
             plans.append(steps)
@@ -241,7 +241,7 @@ def test_emulated_two_pass_variant(monkeypatch, single):
     for n, cut in (((nx, 1024, 64 if single else 16), None), ((nx, 64 if single else 16, 512), (nx, 64 if single else 16, 340))):
         fast, generic = transform_world(n, (1, 1), cut, "fft", "tff", single=single)
         assert fast == (6 if single else 2)
-    # the variant really ran for the last (1024- or 512-point) c2c stage of a transform, and is off without the switch
+    # the variant really ran for the (512-point) Y stage of a transform; at 512 points it is off without the switch
     monkeypatch.delenv("P3DFFT_B200_R32")
     steps, _ = pb.load(single).plan_steps((1, 1), 64, 512, 64, 0, False, "fft")
     st = steps[1].st
@@ -255,18 +255,6 @@ def test_emulated_two_pass_variant(monkeypatch, single):
     assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 0
     monkeypatch.setenv("P3DFFT_B200_R32", "1")
     assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 1
-
-
-def test_emulated_wide_x_tiles(monkeypatch):
-    """opt-in 8-line X tiles for nx = 1024 in double (P3DFFT_B200_XTX8=1): r2c and c2r, one rank and 2 x 2 with peer stores"""
-    monkeypatch.setenv("P3DFFT_B200_XTX8", "1")
-    fast, generic = transform_world((1024, 16, 16), (1, 1), None, "fft", "tff")
-    assert (fast, generic) == (2, 4) and emu().emu_last_variant() == 2      # the last stage of the backward transform is X c2r
-    fast, generic = transform_world((1024, 20, 12), (2, 2), (680, 20, 12), "fft", "tff", p2p=True)
-    assert fast == 8
-    monkeypatch.delenv("P3DFFT_B200_XTX8")
-    transform_world((1024, 16, 16), (1, 1), None, "fft", "tff")
-    assert emu().emu_last_variant() == 0
 
 
 @pytest.mark.parametrize("dims,n,cut", [((1, 2), (64, 64, 64), None), ((2, 2), (64, 64, 64), (42, 42, 42)), ((2, 4), (64, 64, 64), None),
@@ -306,32 +294,6 @@ def test_pipelined_tail_needs_a_peer_to_peer_exchange():
 
 
 @pytest.mark.parametrize("single", [False, True])
-def test_emulated_half_row_variant(monkeypatch, single):
-    """opt-in half-row tiles (P3DFFT_B200_HALF=1): the 64-byte-row 1024-point kernel on buffers laid out in 128-byte rows,
-    each CTA on one half of a tile's lines -- Y and Z stages, forward and backward, pruned, 2 x 2 with peer stores"""
-    monkeypatch.setenv("P3DFFT_B200_HALF", "1")
-    h = emu(single)
-    if single:
-        transform_world((64, 1024, 64), (1, 1), None, "fft", "tff", single=True)
-    else:
-        fast, generic = transform_world((16, 1024, 16), (1, 1), None, "fft", "tff")
-        assert (fast, generic) == (2, 4)
-        transform_world((24, 16, 1024), (1, 1), (24, 16, 680), "fft", "tff")
-        assert h.emu_last_variant() == 0          # last stage of the backward transform: X (generic here); check a Y stage below
-        transform_world((32, 1024, 16), (2, 2), None, "fft", "tff", p2p=True)
-    steps, _ = pb.load(single).plan_steps((1, 1), 64, 1024, 64, 0, False, "fft")
-    st = steps[1].st
-    w = int(pb.load(single).plan_decomp((1, 1), 64, 1024, 64).work_elems)
-    ct = np.complex64 if single else np.complex128
-    bufs = {b: np.zeros(w, dtype=ct) for b in (pb.BUF_A, pb.BUF_B, pb.BUF_C)}
-    for si, side in enumerate((st.inp, st.out)):
-        for g in range(side.nseg):
-            sg = side.seg[g]
-            sg.base = bufs[sg.buf].ctypes.data + sg.off * (8 if single else 16)
-    assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 3
-
-
-@pytest.mark.parametrize("single", [False, True])
 def test_emulated_bulk_store_variant(monkeypatch, single):
     """opt-in bulk-copy stores (P3DFFT_B200_BULK=1): the last pass re-forms the tile in shared memory in natural row order and
     one cp.async.bulk per output run moves it out (memcpy in the emulation) -- Y forward / Z and Y backward, pruned runs,
@@ -347,51 +309,17 @@ def test_emulated_bulk_store_variant(monkeypatch, single):
         transform_world((16, 16, 1024), (1, 1), (16, 16, 680), "fft", "tff")
         transform_world((32, 1024, 16), (2, 2), (32, 680, 16), "fft", "tff", p2p=True)
         transform_world((32, 16, 512), (2, 2), None, "fft", "tff", p2p=True)
-    # the forward Y stage (contiguous rows per run) takes the variant, the forward Z stage (user layout) does not
+    # the forward Y stage (contiguous rows per run) takes the variant -- together with the two-pass schedule, which a 1024-point
+    # stage with contiguous output rows runs by default (bits 0 and 2) --, the forward Z stage (user layout) takes neither
     steps, _ = pb.load(single).plan_steps((1, 1), 64, 1024, 64, 0, False, "fft")
     w = int(pb.load(single).plan_decomp((1, 1), 64, 1024, 64).work_elems)
     ct = np.complex64 if single else np.complex128
     bufs = {b: np.zeros(w, dtype=ct) for b in (pb.BUF_A, pb.BUF_B, pb.BUF_C)}
     bufs[pb.BUF_USER_OUT] = np.zeros(33 * 1024 * 64, dtype=ct)
-    for idx, want in ((1, 4), (2, 0)):
+    for idx, want in ((1, 5), (2, 0)):
         st = steps[idx].st
         for si, side in enumerate((st.inp, st.out)):
             for g in range(side.nseg):
                 sg = side.seg[g]
                 sg.base = bufs[sg.buf].ctypes.data + sg.off * (8 if single else 16)
         assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == want
-
-
-@pytest.mark.parametrize("ring", [False, True])
-@pytest.mark.parametrize("eager", [False, True])
-@pytest.mark.parametrize("dims,n,cut,G", [((1, 1), (64, 64, 64), None, 8), ((1, 1), (64, 64, 64), (42, 42, 42), 5), ((1, 2), (64, 64, 64), None, 8),
-                                          ((1, 4), (128, 64, 64), None, 3), ((1, 1), (20, 12, 33), None, 4), ((1, 3), (16, 12, 10), None, 1)])
-def test_xy_pipeline_plans(dims, n, cut, G, ring, eager):
-    """opt-in X<->Y pipeline (plan.h split_xy_pipeline): the X and Y stages of a 1 x N grid in chunks of G z-planes, the buffer
-    between them optionally a two-slot ring; in list order and in the producer-runs-ahead order the events allow"""
-    L = pb.load(False)
-    opf, opb = ("ffc", "cff") if n[2] % 2 else ("fft", "tff")
-    c = cut or (None, None, None)
-    for backward, op in ((False, opf), (True, opb)):
-        base, inf = L.plan_steps(dims, *n, 0, backward, op, 1, *c, p2p=dims != (1, 1))
-        steps, _ = L.plan_steps(dims, *n, 0, backward, op, 1, *c, p2p=dims != (1, 1), xypipe=G, xyring=ring)
-        nchunk = -(-inf.kjsize // G)
-        if nchunk < 2:
-            assert len(steps) == len(base)
-            continue
-        assert len(steps) == len(base) - 2 + 2 * nchunk
-        grp = steps[-2 * nchunk:] if backward else steps[:2 * nchunk]
-        assert [(s.pad_ >> 1) & 3 for s in grp] == [2 if ring else 1] * (2 * nchunk)
-        assert [s.pad_ & 1 for s in grp] == [0, 1] * nchunk
-        assert sum(s.st.nb for s in grp[0::2]) == inf.kjsize and sum(s.st.nb for s in grp[1::2]) == inf.kjsize
-        if ring:        # the buffer side of every chunk stays inside the first two slots
-            plane = grp[0].st.out.seg[0].sb
-            assert max(s.st.out.seg[0].off for s in grp[0::2]) <= G * plane + grp[0].st.out.seg[0].off
-    transform_world(n, dims, cut, opf, opb, p2p=dims != (1, 1), xypipe=G, xyring=ring, eager=eager)
-
-
-def test_xy_pipeline_needs_a_single_rank_row():
-    L = pb.load(False)
-    a, _ = L.plan_steps((2, 2), 64, 64, 64, 0, False, "fft", p2p=True, xypipe=8)      # an exchange sits between X and Y
-    b, _ = L.plan_steps((2, 2), 64, 64, 64, 0, False, "fft", p2p=True)
-    assert len(a) == len(b)

@@ -191,11 +191,10 @@ def test_r2c_1d_rtran_and_queries(lib):
 
 
 def test_opt_in_variants_through_the_executor(lib, monkeypatch):
-    """the switchable kernel variants and the X<->Y pipeline, end to end through api.cpp (sizes whose six stages all run on
-    the specialised kernels: the emulation of the any-length kernel's many small CTAs is slow)"""
-    cases = [({"P3DFFT_B200_R32": "1"}, (64, 512, 64), False), ({"P3DFFT_B200_HALF": "1"}, (64, 1024, 64), False),
-             ({"P3DFFT_B200_BULK": "1"}, (64, 512, 64), True), ({"P3DFFT_B200_XYPIPE": "24"}, (64, 512, 64), True),
-             ({"P3DFFT_B200_XYPIPE": "13", "P3DFFT_B200_XYPIPE_RING": "0"}, (64, 64, 64), True)]
+    """the switchable kernel variants end to end through api.cpp (sizes whose six stages all run on the specialised
+    kernels: the emulation of the any-length kernel's many small CTAs is slow)"""
+    cases = [({"P3DFFT_B200_R32": "1"}, (64, 512, 64), False), ({"P3DFFT_B200_R32": "0"}, (64, 1024, 64), False),
+             ({"P3DFFT_B200_BULK": "1"}, (64, 512, 64), True), ({"P3DFFT_B200_BULK": "1", "P3DFFT_B200_R32": "1"}, (64, 512, 64), True)]
     for env, n, both in cases:
         d = po.Decomp(*n, (1, 1), 0)
         A = np.asfortranarray(np.random.default_rng(5).random(n))
@@ -216,11 +215,7 @@ def test_opt_in_variants_through_the_executor(lib, monkeypatch):
                 lib.p3dfft_btran_c2r(F, B, "tff")
                 assert np.max(np.abs(B / A.size - A)) <= 1e-13, env
                 assert lib.launch_count() == 2 * nl
-            if "P3DFFT_B200_XYPIPE" in env:
-                chunks = -(-n[2] // int(env["P3DFFT_B200_XYPIPE"]))
-                assert nl == 2 * chunks + 1, (env, nl)       # X and Y in chunks of G planes, one Z stage
-            else:
-                assert nl == 3
+            assert nl == 3
         finally:
             lib.p3dfft_clean()
             for k in env:
@@ -245,26 +240,6 @@ def test_guard_pages_catch_an_overrun():
     assert ok.returncode == 0 and "done" in ok.stdout, ok.stderr
     bad = subprocess.run([sys.executable, "-c", code, "over"], capture_output=True, text=True)
     assert bad.returncode < 0 and "inside ok" in bad.stdout and "done" not in bad.stdout, (bad.returncode, bad.stdout, bad.stderr)
-
-
-@pytest.mark.parametrize("policy", ["lazy", "eager", "random:1", "random:7"])
-@pytest.mark.parametrize("env,n", [({"P3DFFT_B200_XYPIPE": "24"}, (64, 512, 64)),
-                                   ({"P3DFFT_B200_XYPIPE": "13", "P3DFFT_B200_XYPIPE_RING": "0"}, (64, 64, 64)),
-                                   ({"P3DFFT_B200_XYPIPE": "8", "P3DFFT_B200_XYPIPE_PERSIST": "1"}, (64, 64, 64))])
-def test_two_stream_executor_under_every_stream_order(policy, env, n):
-    """The mock runtime queues stream work and runs it at synchronisation points in an order constrained only by stream order
-    and events (tests/emu/emu_streams.inc).  The X<->Y pipeline (producer on the main stream, consumer on a side stream, ring
-    slots recycled through events) must give the right answer under every policy.  Checked by hand when written: removing
-    the final join, the consumer's wait for its producer, or the ring wait from run_plan (api.cpp) each makes one of these
-    policies return errors of order 1."""
-    import subprocess
-    import sys
-    e = {k: v for k, v in os.environ.items() if not k.startswith("P3DFFT_B200_")}
-    e.update(env)
-    e["P3D_EMU_STREAMS"] = policy
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_stream_check.py"), *map(str, n)], env=e, capture_output=True,
-                       text=True, timeout=300)
-    assert r.returncode == 0 and " ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_async_calls_on_a_user_stream(lib):

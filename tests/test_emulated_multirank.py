@@ -140,7 +140,7 @@ def test_grids_that_do_not_divide_the_mesh(grid):
     check(grid, ["--suite", "fast", "--expect-p2p", "1", "--aux"])
 
 
-SWEEP_ENVS = [{"P3DFFT_B200_BULK": "1"}, {"P3DFFT_B200_HALF": "1"}, {"P3DFFT_B200_R32": "1"}, {"P3DFFT_B200_XTX8": "1"},
+SWEEP_ENVS = [{"P3DFFT_B200_BULK": "1"}, {"P3DFFT_B200_BULK": "0"}, {"P3DFFT_B200_R32": "1"}, {"P3DFFT_B200_R32": "0"},
               {"P3DFFT_B200_BULK": "1", "P3DFFT_B200_FLAGBAR": "1", "P3DFFT_B200_OVERLAP": "4"}, {"P3DFFT_B200_ROWB": "64"},
               {"P3DFFT_B200_GENERIC": "1"}, {"P3DFFT_B200_SPLIT": "1"}]
 
