@@ -14,8 +14,8 @@
 !   (setup.F90:224-230, 551-577) filled at setup, print_buf / print_buf_real module.F90:747 / :765.
 ! The external (non-module) wrappers of build/wrap.F90:82-150 follow the module.
 !
-! NOT COMPILED IN THE BUILD IMAGE (no Fortran compiler there); shipped as source because a .mod
-! file is compiler specific.  Build with  -DSINGLE_PREC  to bind libp3dfft_single.so.
+! NOT COMPILED IN THE BUILD IMAGE (no Fortran compiler there: `gfortran -cpp -c p3dfft.F90` is the check to run where
+! one exists); shipped as source because a .mod file is compiler specific.  Build with  -DSINGLE_PREC  to bind libp3dfft_single.so.
       module p3dfft
       use iso_c_binding
       implicit none
@@ -157,6 +157,7 @@
         logical, optional, intent(in) :: overwrite
         integer, optional, intent(out) :: memsize(3)
         integer(c_int) :: nxc, nyc, nzc, ow, mem(3)
+        integer(c_int) :: me, np, cm, i, ip, jp, k, rc, d9(9)
         nxc = nx; nyc = ny; nzc = nz; ow = 1
         if (present(nxcut)) nxc = nxcut
         if (present(nycut)) nyc = nycut
@@ -164,7 +165,6 @@
         if (present(overwrite)) then
           if (.not. overwrite) ow = 0
         end if
-        integer(c_int) :: me, np, cm, i, ip, jp, k, rc, d9(9)
         call c_setup(dims, nx, ny, nz, mpi_comm_in, nxc, nyc, nzc, ow, mem)
         if (present(memsize)) memsize = mem
         ! public variables the reference sets in setup (setup.F90:143-147, 224-230, 551-577, 597)
@@ -272,18 +272,20 @@
         call c_get_dims(istart, iend, isize, conf)
       end subroutine
 
-      ! assumed-size arguments: the reference's explicit-shape dummies (ftran.F90:494-499) accept any
-      ! contiguous actual argument, including real arrays posing as complex (in-place calls)
+      ! Dummy types as in the reference (ftran.F90:494-499, btran.F90:401-406): the real-space array is real, the
+      ! wavenumber array complex -- the drivers pass complex arrays (driver_rand.F90:61,219).  Callers that pass a real
+      ! array posing as complex (in-place calls) go through the external wrappers behind the module (wrap.F90:82-150),
+      ! which have an implicit interface.
       subroutine p3dfft_ftran_r2c(XgYZ,XYZg,op)
         real(p3dfft_type), target :: XgYZ(*)
-        real(p3dfft_type), target :: XYZg(*)
+        complex(p3dfft_type), target :: XYZg(*)
         character(len=3) :: op
         call c_ftran(c_loc(XgYZ), c_loc(XYZg), op//c_null_char)
         call c_get_timers(timers)
       end subroutine
 
       subroutine p3dfft_btran_c2r(XYZg,XgYZ,op)
-        real(p3dfft_type), target :: XYZg(*)
+        complex(p3dfft_type), target :: XYZg(*)
         real(p3dfft_type), target :: XgYZ(*)
         character(len=3) :: op
         call c_btran(c_loc(XYZg), c_loc(XgYZ), op//c_null_char)
@@ -292,7 +294,8 @@
 
       subroutine p3dfft_ftran_r2c_many(XgYZ,dim_in,XYZg,dim_out,nv,op)
         integer :: dim_in, dim_out, nv
-        real(p3dfft_type), target :: XgYZ(*), XYZg(*)
+        real(p3dfft_type), target :: XgYZ(*)
+        complex(p3dfft_type), target :: XYZg(*)
         character(len=3) :: op
         call c_ftran_many(c_loc(XgYZ), dim_in, c_loc(XYZg), dim_out, nv, op//c_null_char)
         call c_get_timers(timers)
@@ -300,21 +303,24 @@
 
       subroutine p3dfft_btran_c2r_many(XYZg,dim_in,XgYZ,dim_out,nv,op)
         integer :: dim_in, dim_out, nv
-        real(p3dfft_type), target :: XYZg(*), XgYZ(*)
+        complex(p3dfft_type), target :: XYZg(*)
+        real(p3dfft_type), target :: XgYZ(*)
         character(len=3) :: op
         call c_btran_many(c_loc(XYZg), dim_in, c_loc(XgYZ), dim_out, nv, op//c_null_char)
         call c_get_timers(timers)
       end subroutine
 
       subroutine p3dfft_cheby(in,out,Lz)
-        real(p3dfft_type), target :: in(*), out(*)
+        real(p3dfft_type), target :: in(*)
+        complex(p3dfft_type), target :: out(*)
         real(p3dfft_type) :: Lz
         call c_cheby(c_loc(in), c_loc(out), Lz)
       end subroutine
 
       subroutine p3dfft_cheby_many(in,dim_in,out,dim_out,nv,Lz)
         integer :: dim_in, dim_out, nv
-        real(p3dfft_type), target :: in(*), out(*)
+        real(p3dfft_type), target :: in(*)
+        complex(p3dfft_type), target :: out(*)
         real(p3dfft_type) :: Lz
         call c_cheby_many(c_loc(in), dim_in, c_loc(out), dim_out, nv, Lz)
       end subroutine
@@ -336,32 +342,72 @@
       end module p3dfft
 
 ! ---- external wrappers of build/wrap.F90:82-150 (real arrays posing as complex, in-place calls) ----
+! Not module procedures: callers reach them through an implicit interface, so any array type is accepted (that is what
+! the reference's wrap.F90 is for).  They bind the C ABI themselves and refresh the module's public timers.
       subroutine ftran_r2c(IN,OUT,op)
-        use p3dfft
-        real(p3dfft_type) :: IN(*), OUT(*)
+        use iso_c_binding
+        use p3dfft, only : p3dfft_type, timers, get_timers
+        real(p3dfft_type), target :: IN(*), OUT(*)
         character(len=3) :: op
-        call p3dfft_ftran_r2c(IN, OUT, op)
+        interface
+          subroutine c_ftran(a,b,op) bind(C,name='p3dfft_ftran_r2c')
+            import :: c_ptr, c_char
+            type(c_ptr), value :: a, b
+            character(kind=c_char) :: op(*)
+          end subroutine
+        end interface
+        call c_ftran(c_loc(IN), c_loc(OUT), op//c_null_char)
+        call get_timers(timers)
       end subroutine
 
       subroutine btran_c2r(IN,OUT,op)
-        use p3dfft
-        real(p3dfft_type) :: IN(*), OUT(*)
+        use iso_c_binding
+        use p3dfft, only : p3dfft_type, timers, get_timers
+        real(p3dfft_type), target :: IN(*), OUT(*)
         character(len=3) :: op
-        call p3dfft_btran_c2r(IN, OUT, op)
+        interface
+          subroutine c_btran(a,b,op) bind(C,name='p3dfft_btran_c2r')
+            import :: c_ptr, c_char
+            type(c_ptr), value :: a, b
+            character(kind=c_char) :: op(*)
+          end subroutine
+        end interface
+        call c_btran(c_loc(IN), c_loc(OUT), op//c_null_char)
+        call get_timers(timers)
       end subroutine
 
       subroutine ftran_r2c_many(IN,dim_in,OUT,dim_out,nv,op)
-        use p3dfft
+        use iso_c_binding
+        use p3dfft, only : p3dfft_type, timers, get_timers
         integer :: dim_in, dim_out, nv
-        real(p3dfft_type) :: IN(*), OUT(*)
+        real(p3dfft_type), target :: IN(*), OUT(*)
         character(len=3) :: op
-        call p3dfft_ftran_r2c_many(IN, dim_in, OUT, dim_out, nv, op)
+        interface
+          subroutine c_ftran_many(a,dim_in,b,dim_out,nv,op) bind(C,name='p3dfft_ftran_r2c_many')
+            import :: c_ptr, c_char, c_int
+            type(c_ptr), value :: a, b
+            integer(c_int) :: dim_in, dim_out, nv
+            character(kind=c_char) :: op(*)
+          end subroutine
+        end interface
+        call c_ftran_many(c_loc(IN), dim_in, c_loc(OUT), dim_out, nv, op//c_null_char)
+        call get_timers(timers)
       end subroutine
 
       subroutine btran_c2r_many(IN,dim_in,OUT,dim_out,nv,op)
-        use p3dfft
+        use iso_c_binding
+        use p3dfft, only : p3dfft_type, timers, get_timers
         integer :: dim_in, dim_out, nv
-        real(p3dfft_type) :: IN(*), OUT(*)
+        real(p3dfft_type), target :: IN(*), OUT(*)
         character(len=3) :: op
-        call p3dfft_btran_c2r_many(IN, dim_in, OUT, dim_out, nv, op)
+        interface
+          subroutine c_btran_many(a,dim_in,b,dim_out,nv,op) bind(C,name='p3dfft_btran_c2r_many')
+            import :: c_ptr, c_char, c_int
+            type(c_ptr), value :: a, b
+            integer(c_int) :: dim_in, dim_out, nv
+            character(kind=c_char) :: op(*)
+          end subroutine
+        end interface
+        call c_btran_many(c_loc(IN), dim_in, c_loc(OUT), dim_out, nv, op//c_null_char)
+        call get_timers(timers)
       end subroutine

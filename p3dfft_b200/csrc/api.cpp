@@ -476,6 +476,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
   const size_t nsteps = tp->steps.size();
   int nchunks = 0;                 // pipelined tail: chunk ids 0 .. nchunks-1
   for (auto& s : tp->steps) if (s.chunk + 1 > nchunks) nchunks = s.chunk + 1;
+  std::vector<unsigned> chunk_epoch((size_t)nchunks, 0u);   // flag-barrier epoch of every chunk of a pipelined group
   bool used_side = false;
   // resolves the segment bases of a stage and launches it on stream sx; sm_cap > 0 limits a persistent grid to that many SMs
   auto launch = [&](const P3dStage& planned, cudaStream_t sx, int sm_cap) -> bool {
@@ -496,7 +497,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     else if (!L.force_generic && p3d::fast_supported<real_t>(stg)) {
       p3d::FastStage fs;
       p3d::to_fast(stg, fs, sizeof(real_t), p3d::fast_variant<real_t>(stg));
-      fs.tw = fast_twiddle_block(stg.kind, stg.nfft, fs.variant & 1);      // the block depends on the schedule only
+      fs.tw = fast_twiddle_block(stg.kind, stg.nfft, fs.variant & 9);      // the block depends on the schedule only
       if (!fs.tw) { report(true, "P3DFFT(B200): cannot allocate twiddle table"); return false; }
       fs.sm_cap = sm_cap;
       e = p3d::launch_fast<real_t>(stg, fs, sx);
@@ -525,13 +526,17 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     used_side = false;
     return true;
   };
-  const int side_sms = L.overlap_sms > 0 && L.overlap_sms < sms ? L.overlap_sms : sms / 3;
+  // pipelined group (plan.h split_for_overlap): producer chunks P_c on the main stream on `sms - side_sms` SMs (they are bound by
+  // NVLink, not by SMs), consumer chunks Q_c on the side stream on the other `side_sms`; the last consumer has the GPU to itself
+  const int side_sms = L.overlap_sms > 0 && L.overlap_sms < sms ? L.overlap_sms : sms / 2;
   bool pre_done = false;      // the barrier that protects the receive buffer of the NEXT exchange has been issued
   for (size_t i = 0; i < nsteps; i++) {
     auto& s = tp->steps[i];
+    if (s.chunk < 0 && used_side && !join_side()) return false;      // a step behind the pipelined group: the group is complete
     if (!s.is_exchange && s.side) {
-      // consumer chunk of the pipelined tail: side stream, after this chunk's barrier; the last one has the GPU to itself
-      CUDA_OK(cudaStreamWaitEvent(L.side_stream, L.chunk_events[s.chunk], 0));
+      // consumer chunk: after every rank's producer chunk (flag wait on this stream, or the event behind the NCCL barrier)
+      CUDA_OK(cudaStreamWaitEvent(L.side_stream, L.chunk_events[s.chunk], 0));      // this rank's own chunk (and signal) first
+      if (L.flagbar) CUDA_OK(p3d::launch_flag_wait(L.peer_flags_dev, L.comm->rank, L.comm->size, chunk_epoch[s.chunk], L.side_stream));
       if (!launch(s.st, L.side_stream, s.chunk + 1 < nchunks ? side_sms : 0)) return false;
       used_side = true;
       continue;
@@ -540,7 +545,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     // was handed to a consumer stage since the last barrier, a peer may still be reading it (write-after-read
     // across ranks): barrier first.  Decided from the exchange steps alone, identically on every rank -- a rank
     // whose producing stage is empty issues the same barrier when it reaches the exchange.  (Chunks after the first
-    // of a pipelined tail store into other regions of the buffer their group was already cleared for.)
+    // of a pipelined group store into other regions of the buffer their group was already cleared for.)
     const P3dExchange* nex = s.is_exchange ? &s.ex : (i + 1 < nsteps && tp->steps[i + 1].is_exchange ? &tp->steps[i + 1].ex : nullptr);
     if (nex && nex->p2p && !pre_done && L.dirty[nex->recvbuf] && s.chunk <= 0) {
       if (timed) { cudaEventRecord(get_event(nev++), st); slots.push_back(nex->timer); is_ex.push_back(1); }
@@ -549,13 +554,17 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     if (nex) pre_done = !s.is_exchange;
     if (timed) { cudaEventRecord(get_event(nev++), st); }
     if (s.is_exchange) {
-      if (!run_exchange(s.ex, st)) return false;
+      if (s.chunk >= 0 && s.ex.p2p && L.flagbar) {
+        // chunk barrier, first half: tell every rank that this rank's producer chunk has been stored; the main stream goes
+        // straight on to the next producer chunk, the consumer waits for all ranks' flags on the side stream
+        chunk_epoch[s.chunk] = ++L.bar_epoch;
+        CUDA_OK(p3d::launch_flag_signal(L.peer_flags_dev, L.comm->rank, L.comm->size, chunk_epoch[s.chunk], st));
+      } else if (!run_exchange(s.ex, st)) return false;
       if (s.chunk >= 0) CUDA_OK(cudaEventRecord(L.chunk_events[s.chunk], st));
       if (s.chunk < 0 || s.chunk + 1 == nchunks) L.dirty[s.ex.recvbuf] = true;
       slots.push_back(s.ex.timer); is_ex.push_back(1);
     } else {
-      // producer chunks behind the first leave side_sms SMs to the consumer chunk running beside them
-      if (!launch(s.st, st, s.chunk > 0 ? sms - side_sms : 0)) return false;
+      if (!launch(s.st, st, s.chunk >= 0 ? sms - side_sms : 0)) return false;
       slots.push_back(s.st.timer); is_ex.push_back(0);
     }
   }

@@ -158,11 +158,15 @@ bool dispatch_r32(int n, F&& f) {
 // Measured on B200 (profiles/r2_ab_1gpu_optin_variants.log, 1024^3): the two-pass schedule 1024 = 32 x 32 wins where the
 // stage WRITES whole tiles contiguously (Y forward 3.54 -> 3.32 ms, Y backward 3.67 -> 3.56 ms; single 1.87 -> 1.70 ms) and
 // loses where the rows are scattered into the user layout or gathered from it (Z stages), and at 512 points.
-struct FastSwitches { int r32, bulk; bool loaded; };
-static FastSwitches g_switches = {-1, -1, false};
+#ifndef P3D_DEFAULT_ASYNC
+#define P3D_DEFAULT_ASYNC 0
+#endif
+struct FastSwitches { int r32, bulk, async; bool loaded; };
+static FastSwitches g_switches = {-1, -1, -1, false};
 void fast_reload_switches() {
   g_switches.r32 = getenv("P3DFFT_B200_R32") ? atoi(getenv("P3DFFT_B200_R32")) : -1;
   g_switches.bulk = getenv("P3DFFT_B200_BULK") ? atoi(getenv("P3DFFT_B200_BULK")) : -1;
+  g_switches.async = getenv("P3DFFT_B200_ASYNC") ? atoi(getenv("P3DFFT_B200_ASYNC")) : -1;
   g_switches.loaded = true;
 }
 static const FastSwitches& fast_switches() {
@@ -184,14 +188,33 @@ int fast_variant(const P3dStage& st) {
     if (sg.peer >= 0) out_peer = true;
   }
   const bool far_in = st.in.seg[0].ps * 2 * (long long)sizeof(T) > 131072;      // the split kernel's case (launch_fast)
+  // asynchronously staged 1024-point kernel (bit 3; P3DFFT_B200_ASYNC = 0 never / 1 always / unset: P3D_DEFAULT_ASYNC)
+  if (acfg_exists(st.nfft) && (sw.async > 0 || (sw.async < 0 && P3D_DEFAULT_ASYNC))) return 8;
   const bool r32 = ccfg_r32_exists(st.nfft) && (sw.r32 > 0 || (sw.r32 < 0 && st.nfft == 1024 && out_contig && !far_in));
   const bool bulk = out_contig && (sw.bulk > 0 || (sw.bulk < 0 && out_peer));
   return (r32 ? 1 : 0) | (bulk ? 4 : 0);
 }
 
+// twiddle block of the asynchronously staged kernel: pass table of the M-point schedule, then the outer twiddles
+template <typename T>
+static void fill_async_block(void* host) {
+  using C = ACfg<T>;
+  std::vector<long double> re, im;
+  fill_pass_tables<typename C::S>(C::M, re, im);
+  const long double twopi = 6.283185307179586476925286766559L;
+  for (int q = 1; q < C::Q; q++)
+    for (int k = 0; k < C::M; k++) {
+      long double ang = -twopi * (long double)((long long)q * k % C::N) / (long double)C::N;
+      re.push_back(cosl(ang)); im.push_back(sinl(ang));
+    }
+  T* o = reinterpret_cast<T*>(host);
+  for (size_t i = 0; i < re.size(); i++) { o[2 * i] = (T)re[i]; o[2 * i + 1] = (T)im[i]; }
+}
+
 template <typename T>
 size_t fast_twiddle_elems(int kind, int nfft, int variant) {
   size_t n = 0;
+  if ((variant & 8) && !is_x(kind) && acfg_exists(nfft)) return (size_t)ACfg<T>::S::twtotal() + (ACfg<T>::Q - 1) * ACfg<T>::M;
   if ((variant & 1) && !is_x(kind)) { dispatch_r32(nfft, [&](auto nn) { n = block_elems<typename CCfgR32<T, decltype(nn)::value>::S>(false); }); return n; }
   if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { n = block_elems<typename XCfg<T, decltype(h)::value>::S>(true); });
   else dispatch_c(nfft, [&](auto nn) { n = block_elems<typename CCfg<T, decltype(nn)::value, 64>::S>(false); });
@@ -200,6 +223,7 @@ size_t fast_twiddle_elems(int kind, int nfft, int variant) {
 
 template <typename T>
 void fast_twiddle_fill(int kind, int nfft, void* host, int variant) {
+  if ((variant & 8) && !is_x(kind) && acfg_exists(nfft)) { fill_async_block<T>(host); return; }
   if ((variant & 1) && !is_x(kind)) { dispatch_r32(nfft, [&](auto nn) { fill_block<T, typename CCfgR32<T, decltype(nn)::value>::S>(false, host); }); return; }
   if (is_x(kind)) dispatch_x(nfft / 2, [&](auto h) { fill_block<T, typename XCfg<T, decltype(h)::value>::S>(true, host); });
   else dispatch_c(nfft, [&](auto nn) { fill_block<T, typename CCfg<T, decltype(nn)::value, 64>::S>(false, host); });
@@ -345,6 +369,27 @@ static cudaError_t launch_cv(const P3dStage& st, const FastStage& f, cudaStream_
   return cudaGetLastError();
 }
 
+// asynchronously staged variant of the 1024-point stages (cp.async input staging, one CTA per SM)
+template <typename T>
+static cudaError_t launch_async(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  constexpr int TX = ACfg<T>::TX, NT = ACfg<T>::NT;
+  constexpr size_t smem = cstage_async_smem<T>();
+  const long long nbp = f.bord > 1 ? (long long)((st.nb + f.bord - 1) / f.bord) * f.bord : st.nb;
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * nbp * st.nc;
+  if (tiles <= 0) return cudaSuccess;
+  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
+  cudaError_t e;
+  const bool scaled = f.scale != 1.0;
+  if (st.kind == P3D_C2C_BWD) {
+    if (scaled) P3D_LAUNCH(cstage_async_kernel<T, true, true>);
+    else P3D_LAUNCH(cstage_async_kernel<T, true>);
+  } else {
+    if (scaled) P3D_LAUNCH(cstage_async_kernel<T, false, true>);
+    else P3D_LAUNCH(cstage_async_kernel<T, false>);
+  }
+  return cudaGetLastError();
+}
+
 // split variant (two half tiles per CTA, two CTAs per SM) for the lengths whose 128-byte tile fills an SM
 template <typename T, int NN>
 static cudaError_t launch_split(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
@@ -376,6 +421,7 @@ cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t str
       if (reinterpret_cast<uintptr_t>(sd.run[g].base) % sizeof(T2)) return cudaErrorMisalignedAddress;
   }
   cudaError_t err = cudaErrorInvalidValue;
+  if ((f.variant & 8) && !is_x(st.kind) && f.rowb == 128 && acfg_exists(st.nfft)) return launch_async<T>(st, f, stream);
   if (f.variant != 0 && !is_x(st.kind) && f.rowb == 128) {
     const bool r32 = (f.variant & 1) != 0, bulk = (f.variant & 4) != 0;
     if (st.nfft == 1024) {

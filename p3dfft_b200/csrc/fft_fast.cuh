@@ -740,6 +740,188 @@ __global__ void __launch_bounds__(SplitCfg<T, N>::NT, SplitCfg<T, N>::MINB) csta
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// c2c stage kernel, asynchronously staged variant for the 1024-point stages (128-byte rows: one tile = 128 KB, so
+// only ONE tile fits on an SM and the plain kernel's load, arithmetic and store phases of a tile run one after the
+// other).  Here the input rows reach shared memory by cp.async (LDGSTS: no registers held, no warp waiting) while the
+// previous tile is transformed, and the transform is arranged so that the tile can arrive in quarters:
+//
+//   N = 4 M:   X[k + M m] = sum_q  w_N^(q k) (-i)^(q m)  S_q[k],     S_q = FFT_M of the rows r = q (mod 4)
+//
+// (decimation in time by 4 on the outside).  Shared memory holds SIX units of M rows (6 x 32 KB): the four quarters of
+// the tile being transformed and two quarters of the next one.  Per tile:
+//   wait Q0,Q1 -> passes A, B (the M = 16 x 16 sub-transforms, in place) on them
+//   wait Q2,Q3 -> passes A, B on them                      (their loads were issued after the previous tile's pass C)
+//   pass C: radix-4 combine with the outer twiddles, registers -> global (one HBM write per element)
+//   issue the loads of Q2,Q3 of the next tile and Q0,Q1 of the one after it into the four units just freed
+// so about one tile (128 KB) of loads is in flight per SM all the time, and every quarter has at least the time of
+// half a tile's arithmetic to land.  Shared-memory traffic equals the three-pass kernel's (three writes, three reads
+// per element).  Twiddle block: the pass table of RS<16,16>, then wo[(q-1) M + k] = exp(-2 pi i q k / N), q = 1..3.
+// ---------------------------------------------------------------------------------------
+#ifndef P3D_EMULATE
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc, bool valid) {      // !valid: 16 zero bytes
+  const unsigned sz = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc, bool valid) {
+  const unsigned sz = valid ? 8u : 0u;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+#else
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc, bool valid) { if (valid) memcpy(sdst, gsrc, 16); else memset(sdst, 0, 16); }
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc, bool valid) { if (valid) memcpy(sdst, gsrc, 8); else memset(sdst, 0, 8); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() {}
+#endif
+
+template <typename T> struct ACfg {
+  using S = RS<16, 16>;                          // schedule of the four M-point sub-transforms
+  static constexpr int N = 1024, Q = 4, M = N / Q, TX = 128 / (2 * (int)sizeof(T)), NT = 256, UNITS = 6;
+};
+constexpr bool acfg_exists(int n) { return n == 1024; }
+
+struct RunTab3 {
+  char* tb[3][2][P3D_MAXRUN];            // [tile counter mod 3][side][run]
+};
+
+template <typename T, bool SWAP, bool SCALED = false>
+__global__ void __launch_bounds__(ACfg<T>::NT, 1) cstage_async_kernel(const __grid_constant__ FastStage st) {
+  using T2 = typename Cx<T>::type;
+  using C = ACfg<T>;
+  using S = typename C::S;
+  constexpr int N = C::N, Q = C::Q, M = C::M, TX = C::TX, NT = C::NT, UNITS = C::UNITS;
+  constexpr int RA = S::r(0), MA = S::m(0), RB = S::r(1);      // inner passes: RA x RB = M
+  static_assert(S::L == 2 && RA * RB == M && Q == 4, "async kernel: two inner passes, radix-4 outside");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T2* s = reinterpret_cast<T2*>(smem_raw);                                                   // [UNITS][M][TX]
+  long long* ent_in = reinterpret_cast<long long*>(smem_raw + sizeof(T2) * UNITS * M * TX);  // [N]
+  long long* ent_out = ent_in + N;                                                           // [N]
+  RunTab3* rt = reinterpret_cast<RunTab3*>(ent_out + N);
+  const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
+  const T2* __restrict__ wo = tw + S::twtotal();
+
+  const unsigned tiles_a = (st.na + TX - 1) / TX;
+  const unsigned ntiles = (unsigned)tile_count(tiles_a, st.nb, st.nc, st.bord);
+  if (blockIdx.x >= ntiles) return;
+  const int t = threadIdx.x % TX;
+  const long long lin = (long long)t * st.in.run[0].sa * (long long)sizeof(T2);     // line offsets inside a tile
+  const long long lout = (long long)t * st.out.run[0].sa * (long long)sizeof(T2);
+  const int nrun_all = st.in.nrun + st.out.nrun;
+
+  build_rowent<NT, sizeof(T2)>(st.in, ent_in, N, st.n, st.mirror ? N : 0);
+  build_rowent<NT, sizeof(T2)>(st.out, ent_out, N, N, 0);
+  auto fill_tb = [&](unsigned tile, int slot) {
+    if ((int)threadIdx.x < nrun_all) {
+      const int side = (int)threadIdx.x >= st.in.nrun, g = side ? (int)threadIdx.x - st.in.nrun : (int)threadIdx.x;
+      rt->tb[slot][side][g] = tile_base<sizeof(T2)>(side ? st.out.run[g] : st.in.run[g], tile_decode(tile, tiles_a, st.nb, st.bord));
+    }
+  };
+  auto unit_of = [&](int slot, int q) -> T2* { return s + (size_t)((4 * slot + q) % UNITS) * M * TX; };      // slot = tile counter mod 3
+  // loads of quarters 2 qp and 2 qp + 1 of a tile (one commit group; an empty group when the tile does not exist)
+  auto issue = [&](bool exists, unsigned tile, int slot, int qp) {
+    if (exists) {
+      const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
+      const bool live = ti.ta * TX + t < st.na && ti.b < st.nb;
+      char* const* tbi = rt->tb[slot][0];
+#pragma unroll 4
+      for (int w = threadIdx.x; w < 2 * M * TX; w += NT) {
+        const int rr = (w / TX) % M, q = 2 * qp + w / (TX * M);
+        const long long e = ent_in[Q * rr + q];
+        const bool ok = live && e >= 0;
+        const char* src = ok ? row_addr(e, tbi) + lin : reinterpret_cast<const char*>(tw);
+        T2* dst = unit_of(slot, q) + rr * TX + t;
+        if constexpr (sizeof(T2) == 16) cp_async16(dst, src, ok);
+        else cp_async8(dst, src, ok);
+      }
+    }
+    cp_async_commit();
+  };
+  // passes A and B of the sub-transforms of quarters 2 qp, 2 qp + 1 (in place)
+  auto inner = [&](int slot, int qp) {
+#pragma unroll 1
+    for (int w = threadIdx.x; w < 2 * MA * TX; w += NT) {
+      const int u = (w / TX) % MA;
+      T2* U = unit_of(slot, 2 * qp + w / (TX * MA));
+      T2 v[RA];
+#pragma unroll
+      for (int p = 0; p < RA; p++) { v[p] = U[(u + p * MA) * TX + t]; if (SWAP) v[p] = cswap(v[p]); }
+      Bfly<T, RA>::run(v);
+      twiddle_store<T, S, 0, TX, false>(v, U, tw, u, u, t);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int w = threadIdx.x; w < 2 * (M / RB) * TX; w += NT) {
+      const int kap = (w / TX) % (M / RB);
+      T2* U = unit_of(slot, 2 * qp + w / (TX * (M / RB))) + (size_t)kap * RB * TX + t;
+      T2 v[RB];
+#pragma unroll
+      for (int p = 0; p < RB; p++) v[p] = U[p * TX];
+      Bfly<T, RB>::run(v);                                    // v[j] = S_q[kap + (M / RB) j], kept at row kap * RB + j
+#pragma unroll
+      for (int p = 0; p < RB; p++) U[p * TX] = v[p];
+    }
+  };
+
+  const unsigned first = blockIdx.x, step = gridDim.x;
+  fill_tb(first, 0);
+  if (first + step < ntiles && first + step > first) fill_tb(first + step, 1);
+  __syncthreads();
+  issue(true, first, 0, 0);
+  issue(true, first, 0, 1);
+  issue(first + step < ntiles && first + step > first, first + step, 1, 0);
+
+  int slot = 0;
+  for (unsigned tile = first;; slot = (slot + 1) % 3) {
+    const unsigned t1 = tile + step, t2 = tile + 2 * step;
+    const bool has1 = t1 < ntiles && t1 > tile, has2 = has1 && t2 < ntiles && t2 > t1;
+    const TileIdx ti = tile_decode(tile, tiles_a, st.nb, st.bord);
+    const bool live = ti.ta * TX + t < st.na && ti.b < st.nb;
+    if (has2) fill_tb(t2, (slot + 2) % 3);        // read by issue() below, behind several barriers
+    cp_async_wait<2>();
+    __syncthreads();                              // quarters 0, 1 have landed (every thread's copies)
+    inner(slot, 0);
+    cp_async_wait<1>();
+    __syncthreads();                              // quarters 2, 3 have landed; passes A, B of 0, 1 are complete
+    inner(slot, 1);
+    __syncthreads();
+    // ---- pass C: X[k + M m] = sum_q wo_q[k] (-i)^(q m) S_q[k];  S_q[k] sits at row (k % (M/RB)) * RB + k / (M/RB) of unit q
+    {
+      char* const* tbo = rt->tb[slot][1];
+      const T2* U0 = unit_of(slot, 0); const T2* U1 = unit_of(slot, 1); const T2* U2 = unit_of(slot, 2); const T2* U3 = unit_of(slot, 3);
+#pragma unroll 2
+      for (int w = threadIdx.x; w < M * TX; w += NT) {
+        const int k = w / TX;
+        const int pos = ((k % (M / RB)) * RB + k / (M / RB)) * TX + t;
+        T2 a0 = U0[pos];
+        T2 a1 = cmul(U1[pos], __ldg(wo + k));
+        T2 a2 = cmul(U2[pos], __ldg(wo + M + k));
+        T2 a3 = cmul(U3[pos], __ldg(wo + 2 * M + k));
+        bf4(a0, a1, a2, a3);
+        T2 o[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          if constexpr (SCALED) { const T sc = (T)st.scale; o[m].x *= sc; o[m].y *= sc; }
+          const long long e = ent_out[k + m * M];
+          if (live && e >= 0) stg_stream(reinterpret_cast<T2*>(row_addr(e, tbo) + lout), SWAP ? cswap(o[m]) : o[m]);
+        }
+      }
+    }
+    __syncthreads();                              // the four units of this tile are free
+    issue(has1, t1, (slot + 1) % 3, 1);
+    issue(has2, t2, (slot + 2) % 3, 0);
+    if (!has1) break;
+    tile = t1;
+  }
+  cp_async_wait<0>();
+}
+
+template <typename T> constexpr size_t cstage_async_smem() {
+  using T2 = typename Cx<T>::type;
+  return sizeof(T2) * ACfg<T>::UNITS * ACfg<T>::M * ACfg<T>::TX + 2 * sizeof(long long) * ACfg<T>::N + sizeof(RunTab3);
+}
+
 template <typename T, int N> constexpr size_t cstage_split_smem() {
   using T2 = typename Cx<T>::type;
   return sizeof(T2) * (N / 2) * CCfg<T, N, 128>::TX + 2 * sizeof(long long) * N + sizeof(RunTab);

@@ -451,10 +451,54 @@ __global__ void flag_barrier_kernel(unsigned* const* __restrict__ peers, int me,
   __syncthreads();
 }
 
+// The two halves of the barrier as kernels of their own, for the pipelined groups (api.cpp): `signal` follows a
+// producer chunk on the main stream (its stores are complete when it runs), `wait` precedes the consumer chunk on the
+// side stream -- so the next producer chunk need not wait for the slowest peer.
+__global__ void flag_signal_kernel(unsigned* const* __restrict__ peers, int me, int nrank, unsigned epoch) {
+  const int r = threadIdx.x;
+  if (r < nrank) {
+    unsigned* dst = peers[r] + (size_t)me * 32;
+#ifndef P3D_EMULATE
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+#else
+    __atomic_store_n(dst, epoch, __ATOMIC_RELEASE);
+#endif
+  }
+}
+__global__ void flag_wait_kernel(unsigned* const* __restrict__ peers, int me, int nrank, unsigned epoch) {
+  const int r = threadIdx.x;
+  if (r < nrank) {
+    const unsigned* src = peers[me] + (size_t)r * 32;
+    unsigned v;
+#ifndef P3D_EMULATE
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    } while ((int)(v - epoch) < 0);
+#else
+    do { v = __atomic_load_n(src, __ATOMIC_ACQUIRE); } while ((int)(v - epoch) < 0);
+#endif
+  }
+  __syncthreads();
+}
+
+static int flag_threads(int nrank) { return nrank <= 32 ? 32 : ((nrank + 31) / 32) * 32; }
 cudaError_t launch_flag_barrier(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream) {
   if (nrank > 1024) return cudaErrorInvalidValue;
-  const int nt = nrank <= 32 ? 32 : ((nrank + 31) / 32) * 32;
+  const int nt = flag_threads(nrank);
   P3D_KLAUNCH(flag_barrier_kernel, 1, nt, 0, stream, peers, me, nrank, epoch);
+  return cudaGetLastError();
+}
+cudaError_t launch_flag_signal(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream) {
+  if (nrank > 1024) return cudaErrorInvalidValue;
+  const int nt = flag_threads(nrank);
+  P3D_KLAUNCH(flag_signal_kernel, 1, nt, 0, stream, peers, me, nrank, epoch);
+  return cudaGetLastError();
+}
+cudaError_t launch_flag_wait(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream) {
+  if (nrank > 1024) return cudaErrorInvalidValue;
+  const int nt = flag_threads(nrank);
+  P3D_KLAUNCH(flag_wait_kernel, 1, nt, 0, stream, peers, me, nrank, epoch);
   return cudaGetLastError();
 }
 

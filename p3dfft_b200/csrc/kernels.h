@@ -29,5 +29,8 @@ struct SpecJob {
 // every rank's flag array (128-byte slots) and waits until all slots of its own array have reached it.
 // peers = DEVICE array of nrank pointers (entry `me` = the rank's own array).
 cudaError_t launch_flag_barrier(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream);
+// the barrier's two halves as separate launches (pipelined groups): store `epoch` into every rank's slot `me` / wait for all
+cudaError_t launch_flag_signal(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream);
+cudaError_t launch_flag_wait(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream);
 template <typename T> cudaError_t launch_spectrum(const void* B, const SpecJob& job, double* E, cudaStream_t stream);
 }  // namespace p3d

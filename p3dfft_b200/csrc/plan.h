@@ -540,7 +540,7 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
 }
 
 // ------------------------------------------------------------------------------------
-// Pipelined tail of a peer-to-peer plan (opt-in, P3DFFT_B200_OVERLAP=C).
+// Pipelined group of a peer-to-peer plan (P3DFFT_B200_OVERLAP=C).
 //
 // On a multi-GPU grid the stage in front of the LAST exchange of a transform is bound by NVLink (its stores go to
 // the peers), the stage behind it is local and HBM-bound:  forward  Y -> T2 -> Z,  backward  Y -> T4 -> X.  Both
@@ -550,7 +550,7 @@ inline TransformPlan build_plan(const Decomp& d, bool backward, const char* op, 
 // lets the executor run Q_c on a second stream while P_(c+1) is storing.  Chunks are equal on every rank in COUNT
 // (empty ones stay in the list, their barrier is still collective); a chunk is the same stage with smaller batch
 // extents and shifted segment offsets -- the kernels do not know about it.
-// Returns false (plan untouched) when the plan does not end in  stage, p2p exchange, stage.
+// Returns false (plan untouched) when the plan holds no  stage, p2p exchange, stage  triple.
 // ------------------------------------------------------------------------------------
 inline void shift_side(P3dSide& sd, bool along_a, long long x0) {
   for (int g = 0; g < sd.nseg; g++) {
@@ -563,22 +563,33 @@ inline void shift_side(P3dSide& sd, bool along_a, long long x0) {
 inline bool split_for_overlap(TransformPlan& tp, int nchunk, int W) {
   const size_t n = tp.steps.size();
   if (nchunk < 2 || n < 3) return false;
-  Step& sp = tp.steps[n - 3]; Step& se = tp.steps[n - 2]; Step& sq = tp.steps[n - 1];
-  if (sp.is_exchange || !se.is_exchange || sq.is_exchange || !se.ex.p2p) return false;
-  const P3dStage P = sp.st, Q = sq.st;
-  const P3dExchange E = se.ex;
+  // the LAST  stage, peer-to-peer exchange, stage  triple of the plan (forward: Y T2 Z; backward: Y T4 X, or Z T3 Y
+  // when the row communicator has one rank and no exchange precedes the X stage)
+  size_t at = n;
+  for (size_t i = n - 3;; i--) {
+    if (!tp.steps[i].is_exchange && tp.steps[i + 1].is_exchange && tp.steps[i + 1].ex.p2p && !tp.steps[i + 2].is_exchange &&
+        tp.steps[i].chunk < 0 && tp.steps[i + 2].chunk < 0) { at = i; break; }
+    if (i == 0) break;
+  }
+  if (at == n) return false;
+  const P3dStage P = tp.steps[at].st, Q = tp.steps[at + 2].st;
+  const P3dExchange E = tp.steps[at + 1].ex;
   if (P.nc != Q.nc) return false;
+  // the batch axis the two stages share, by their places in the transform (timer slots of the reference, module.F90:106):
+  //   X -> Y (5, 7) and Y -> X (10, 12): the z planes, dimension b;   Y -> Z (7, 8) and Z -> Y (9, 10): the x lines, dimension a
   bool along_a;
   int total, gran;
-  if (Q.kind == P3D_C2R && P.nb == Q.nb) { along_a = false; total = P.nb; gran = 1; }            // backward: z planes
-  else if (Q.kind != P3D_C2R && P.na == Q.na) { along_a = true; total = P.na; gran = W > 0 ? W : 1; }   // forward: x blocks
+  const bool zplanes = (P.timer == 5 && Q.timer == 7) || (P.timer == 10 && Q.timer == 12);
+  const bool xlines = (P.timer == 7 && Q.timer == 8) || (P.timer == 9 && Q.timer == 10);
+  if (zplanes && P.nb == Q.nb) { along_a = false; total = P.nb; gran = 1; }
+  else if (xlines && P.na == Q.na) { along_a = true; total = P.na; gran = W > 0 ? W : 1; }
   else return false;
   for (const P3dStage* st : {&P, &Q})       // blocked line groups must not be cut
     for (const P3dSide* sd : {&st->in, &st->out})
       for (int g = 0; g < sd->nseg; g++)
         if (along_a && sd->seg[g].aw > 1 && gran % sd->seg[g].aw) return false;
   const long long nblk = (total + gran - 1) / gran;
-  std::vector<Step> tail;
+  std::vector<Step> group;
   for (int c = 0; c < nchunk; c++) {
     const long long b0 = nblk * c / nchunk * gran, b1 = std::min<long long>(nblk * (c + 1) / nchunk * gran, total);
     const int cnt = (int)std::max<long long>(b1 - b0, 0);
@@ -590,10 +601,12 @@ inline bool split_for_overlap(TransformPlan& tp, int nchunk, int W) {
       shift_side(st->in, along_a, b0);
       shift_side(st->out, along_a, b0);
     }
-    tail.push_back(a); tail.push_back(e); tail.push_back(b);
+    group.push_back(a); group.push_back(e); group.push_back(b);
   }
-  tp.steps.resize(n - 3);
-  tp.steps.insert(tp.steps.end(), tail.begin(), tail.end());
+  std::vector<Step> out(tp.steps.begin(), tp.steps.begin() + at);
+  out.insert(out.end(), group.begin(), group.end());
+  out.insert(out.end(), tp.steps.begin() + at + 3, tp.steps.end());
+  tp.steps.swap(out);
   return true;
 }
 

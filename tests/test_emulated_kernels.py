@@ -269,19 +269,23 @@ def test_pipelined_tail_plans(dims, n, cut, chunks):
     for backward, op in ((False, opf), (True, opb)):
         steps, _ = L.plan_steps(dims, *n, 0, backward, op, 1, *(cut or (None, None, None)), p2p=True, overlap=chunks)
         base, _ = L.plan_steps(dims, *n, 0, backward, op, 1, *(cut or (None, None, None)), p2p=True)
-        if [s.is_exchange for s in base[-3:]] != [0, 1, 0]:       # e.g. backward on a 1 x N grid: no exchange in front of X
+        # the LAST  stage, exchange, stage  triple of the plan is pipelined (backward on a 1 x N grid: Z T3 Y, in front of X)
+        ex = [s.is_exchange for s in base]
+        at = max((i for i in range(len(base) - 2) if ex[i:i + 3] == [0, 1, 0]), default=None)
+        if at is None:
             assert len(steps) == len(base)
             continue
-        tail = steps[-3 * chunks:]
-        assert [s.is_exchange for s in tail] == [0, 1, 0] * chunks
-        assert [s.pad_ & 1 for s in tail] == [0, 0, 1] * chunks                      # consumers run on the side stream
-        assert [(s.pad_ >> 8) - 1 for s in tail] == [c for c in range(chunks) for _ in range(3)]
+        grp = steps[at:at + 3 * chunks]
+        assert [s.is_exchange for s in grp] == [0, 1, 0] * chunks
+        assert [s.pad_ & 1 for s in grp] == [0, 0, 1] * chunks                       # consumers run on the side stream
+        assert [(s.pad_ >> 8) - 1 for s in grp] == [c for c in range(chunks) for _ in range(3)]
         assert len(steps) == len(base) - 3 + 3 * chunks
-        prod, cons = base[-3].st, base[-1].st                                        # the chunks partition the batch axis
-        if backward:
-            assert sum(s.st.nb for s in tail[0::3]) == prod.nb and sum(s.st.nb for s in tail[2::3]) == cons.nb
+        assert [(s.pad_ >> 8) for s in steps[at + 3 * chunks:]] == [0] * (len(base) - at - 3)   # what follows is not chunked
+        prod, cons = base[at].st, base[at + 2].st                                    # the chunks partition the batch axis
+        if cons.kind == 3:        # X c2r consumer: z planes
+            assert sum(s.st.nb for s in grp[0::3]) == prod.nb and sum(s.st.nb for s in grp[2::3]) == cons.nb
         else:
-            assert sum(s.st.na for s in tail[0::3]) == prod.na and sum(s.st.na for s in tail[2::3]) == cons.na
+            assert sum(s.st.na for s in grp[0::3]) == prod.na and sum(s.st.na for s in grp[2::3]) == cons.na
     transform_world(n, dims, cut, opf, opb, p2p=True, overlap=chunks)
 
 
@@ -289,8 +293,9 @@ def test_pipelined_tail_needs_a_peer_to_peer_exchange():
     L = pb.load(False)
     a, _ = L.plan_steps((1, 1), 64, 64, 64, 0, False, "fft", overlap=4)
     b, _ = L.plan_steps((2, 2), 64, 64, 64, 0, False, "fft", overlap=4)          # not a p2p plan
-    c, _ = L.plan_steps((2, 1), 64, 64, 64, 0, False, "fft", p2p=True, overlap=4)   # forward on M2 = 1: no exchange in front of Z
-    assert len(a) == 3 and len(b) == 5 and len(c) == 4
+    c, _ = L.plan_steps((2, 1), 64, 64, 64, 0, False, "fft", p2p=True, overlap=4)   # forward on M2 = 1: X T1 Y is pipelined (z planes), Z follows
+    assert len(a) == 3 and len(b) == 5 and len(c) == 3 * 4 + 1
+    assert [s.is_exchange for s in c] == [0, 1, 0] * 4 + [0] and [(s.pad_ >> 8) for s in c] == [1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 0]
 
 
 @pytest.mark.parametrize("single", [False, True])
@@ -323,3 +328,34 @@ def test_emulated_bulk_store_variant(monkeypatch, single):
                 sg = side.seg[g]
                 sg.base = bufs[sg.buf].ctypes.data + sg.off * (8 if single else 16)
         assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == want
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_emulated_async_staged_kernel(monkeypatch, single):
+    """asynchronously staged 1024-point kernel (P3DFFT_B200_ASYNC=1): cp.async input staging through six 256-row units,
+    decimation in time by 4 on the outside, 16 x 16 sub-transforms -- Y and Z stages, forward and backward, pruned rows
+    (zero-filled copies), the DCT-I mirror rows, STRIDE1 output, 2 x 2 with peer stores, CTAs that walk 1, 2, 3 and more tiles"""
+    monkeypatch.setenv("P3DFFT_B200_ASYNC", "1")
+    h = emu(single)
+    if single:
+        transform_world((64, 1024, 64), (1, 1), (64, 680, 42), "fft", "tff", single=True)
+        transform_world((64, 64, 1024), (1, 1), None, "fft", "tff", single=True, stride1=True)
+    else:
+        fast, generic = transform_world((16, 1024, 16), (1, 1), None, "fft", "tff")
+        assert (fast, generic) == (2, 4)
+        transform_world((24, 1024, 16), (1, 1), (24, 680, 16), "fft", "tff")
+        transform_world((16, 16, 1024), (1, 1), (16, 16, 680), "fft", "tff")
+        transform_world((16, 16, 513), (1, 1), None, "ffc", "cff")
+        transform_world((16, 40, 1024), (1, 1), None, "fft", "tff", stride1=True)
+        transform_world((32, 1024, 16), (2, 2), (32, 680, 16), "fft", "tff", p2p=True)
+        transform_world((48, 8, 1024), (1, 2), None, "fft", "tff", p2p=True, overlap=3)
+    steps, _ = pb.load(single).plan_steps((1, 1), 64, 1024, 64, 0, False, "fft")
+    w = int(pb.load(single).plan_decomp((1, 1), 64, 1024, 64).work_elems)
+    ct = np.complex64 if single else np.complex128
+    bufs = {b: np.zeros(w, dtype=ct) for b in (pb.BUF_A, pb.BUF_B, pb.BUF_C)}
+    st = steps[1].st
+    for si, side in enumerate((st.inp, st.out)):
+        for g in range(side.nseg):
+            sg = side.seg[g]
+            sg.base = bufs[sg.buf].ctypes.data + sg.off * (8 if single else 16)
+    assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 8

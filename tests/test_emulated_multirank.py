@@ -111,6 +111,16 @@ def test_pipelined_tail_executor(grid, chunks, policy):
     check(grid, ["--suite", "fast", "--expect-p2p", "1"], {"P3DFFT_B200_OVERLAP": str(chunks), "P3D_EMU_STREAMS": policy})
 
 
+@pytest.mark.parametrize("grid,chunks,policy", [("1x2", 3, "lazy"), ("2x2", 2, "eager"), ("2x2", 4, "random:7"), ("2x1", 2, "random:2")])
+def test_pipelined_group_with_the_split_flag_barrier(grid, chunks, policy):
+    """P3DFFT_B200_OVERLAP=C with the flag barrier: every chunk barrier is a `signal` kernel on the main stream and a `wait`
+    kernel in front of the consumer chunk on the side stream (api.cpp run_plan) -- also with a delayed rank and with the
+    transforms repeated (the write-after-read rule across calls)"""
+    env = {"P3DFFT_B200_OVERLAP": str(chunks), "P3DFFT_B200_FLAGBAR": "1", "P3D_EMU_STREAMS": policy}
+    check(grid, ["--suite", "fast", "--expect-p2p", "1"], env)
+    check(grid, ["--suite", "none", "--repeat"], dict(env, P3D_EMU_DELAY="1:3:2:250"))
+
+
 @pytest.mark.parametrize("policy", ["eager", "random:3"])
 def test_default_path_under_other_stream_orders(policy):
     check("2x2", ["--suite", "fast", "--expect-p2p", "1"], {"P3D_EMU_STREAMS": policy})

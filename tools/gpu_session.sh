@@ -5,7 +5,7 @@
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 what=${1:-tests}
-run() { local n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) "$@"; }
+run() { local n=$1; shift; timeout "${TMO:-600}" python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) "$@"; }
 
 if [[ $what == tests ]]; then
   python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -8 | tee gpurun_out/tests.log
@@ -57,25 +57,25 @@ if [[ $what == mgpu ]]; then
   for part in $parts; do
     case $part in
       parity)     # every grid of N ranks: the reference's own matrix against the oracle, rtran_*, r2c_1d, proc queries
-        timeout 900 run "$N" tests/mp_parity.py 2>&1 | grep -v "^W\|^\[W\|Warning\|warn" | tee gpurun_out/mp_parity_${N}gpu.log | tail -5 ;;
+        TMO=900 run "$N" tests/mp_parity.py 2>&1 | grep -v "^W\|^\[W\|Warning\|warn" | tee gpurun_out/mp_parity_${N}gpu.log | tail -5 ;;
       stress)     # determinism under a delayed rank, NCCL barrier and flag barrier (+ pipelined tail)
-        { timeout 300 run "$N" tests/mp_stress.py --iters 1000 2>&1 | tail -2
-          P3DFFT_B200_FLAGBAR=1 timeout 300 run "$N" tests/mp_stress.py --iters 1000 2>&1 | tail -2
-          P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=4 timeout 300 run "$N" tests/mp_stress.py --iters 1000 2>&1 | tail -2
+        { TMO=300 run "$N" tests/mp_stress.py --iters 1000 2>&1 | tail -2
+          P3DFFT_B200_FLAGBAR=1 TMO=300 run "$N" tests/mp_stress.py --iters 1000 2>&1 | tail -2
+          P3DFFT_B200_FLAGBAR=1 P3DFFT_B200_OVERLAP=4 TMO=300 run "$N" tests/mp_stress.py --iters 1000 2>&1 | tail -2
         } | tee gpurun_out/mp_stress_${N}gpu.log ;;
       ab)         # the multi-GPU switches on the headline size, one job
-        timeout 900 run "$N" tools/ab_multi.py --size 1024 2>&1 | grep "^\[\|EXCEPTION" | tee gpurun_out/ab_multi_${N}gpu.log ;;
+        TMO=900 run "$N" tools/ab_multi.py --size 1024 2>&1 | grep "^\[\|EXCEPTION" | tee gpurun_out/ab_multi_${N}gpu.log ;;
       refbin)     # the reference's own driver binaries and our C drivers on N GPUs
         timeout 600 python -m pytest tests/test_zzzz_reference_binaries.py tests/test_c_drivers.py -m gpu -q -p no:cacheprovider -rA 2>&1 | grep -v "^$" | tail -40 | tee gpurun_out/refbin_${N}gpu.log ;;
       bench)
-        timeout 600 run "$N" bench.py --gpus "$N" --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench_${N}gpu.json ;;
+        TMO=600 run "$N" bench.py --gpus "$N" --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench_${N}gpu.json ;;
       configs)    # BASELINE configs 4 and 5 (8 GPUs: 2048^3 single on 1x8 and 2x4; Chebyshev and pruned at the run's grid)
         { if [[ $N == 8 ]]; then
-            timeout 600 run 8 bench.py --gpus 8 --nx 2048 --ny 2048 --nz 2048 --dtype f32 --grid 1x8 --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1
-            timeout 600 run 8 bench.py --gpus 8 --nx 2048 --ny 2048 --nz 2048 --dtype f32 --grid 2x4 --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1
+            TMO=600 run 8 bench.py --gpus 8 --nx 2048 --ny 2048 --nz 2048 --dtype f32 --grid 1x8 --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1
+            TMO=600 run 8 bench.py --gpus 8 --nx 2048 --ny 2048 --nz 2048 --dtype f32 --grid 2x4 --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1
           fi
-          timeout 600 run "$N" bench.py --gpus "$N" --nx 2048 --ny 512 --nz 513 --op cheby --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1
-          timeout 600 run "$N" bench.py --gpus "$N" --nx 2048 --ny 512 --nz 512 --op pruned --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1
+          TMO=600 run "$N" bench.py --gpus "$N" --nx 2048 --ny 512 --nz 513 --op cheby --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1
+          TMO=600 run "$N" bench.py --gpus "$N" --nx 2048 --ny 512 --nz 512 --op pruned --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1
         } | tee gpurun_out/bench_configs_${N}gpu.json ;;
     esac
   done
