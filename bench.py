@@ -255,7 +255,7 @@ def main():
     ap.add_argument("--no-cufft", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU work the reference arm may spend")
+    ap.add_argument("--ref-budget", type=float, default=100.0, help="seconds of CPU work the reference arm may spend")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work of the cpu_baseline leg")
     args = ap.parse_args()
     args.nx, args.ny, args.nz = args.nx or args.size, args.ny or args.size, args.nz or args.size
@@ -495,6 +495,7 @@ def main():
             tj = json.load(f)
         if world == 1 and (nx, ny, nz) == (1024, 1024, 1024) and not single and args.op == "fft":
             traffic = tj["per_launch"][dom]["dram_bytes"]
+            kname = tj["per_launch"][dom]["kernel"] + f" ({dom})"      # the instantiation ncu saw for this stage
     except Exception:
         traffic = None
     ach = db / dt / 1e9 if dt > 0 else 0.0

@@ -33,14 +33,24 @@ typedef double real_t;
 static const size_t CSIZE = 2 * sizeof(real_t);
 
 // defaults of the multi-GPU switches (decided by the A/B runs under profiles/)
+// Measured on 8 B200s, 1024^3 double, 2x4 (profiles/r2_ab_multi_8gpu.log): NCCL barrier, no pipelining 5.67 ms; flag barrier
+// 5.62; flag barrier + the last stage-exchange-stage triple in 4 chunks with 74 SMs for the consumer 5.29 (2 chunks 5.34,
+// 8 chunks 5.50, 56 SMs 5.41, 92 SMs 5.56); 1x8: 5.02 -> 4.87; 1x2: 14.58 -> 14.07; 2x1: 15.48 -> 13.63.
 #ifndef P3D_DEFAULT_FLAGBAR
-#define P3D_DEFAULT_FLAGBAR 0
+#define P3D_DEFAULT_FLAGBAR 1
 #endif
 #ifndef P3D_DEFAULT_OVERLAP
-#define P3D_DEFAULT_OVERLAP 0
+#define P3D_DEFAULT_OVERLAP 4
 #endif
 #ifndef P3D_DEFAULT_OVERLAP_SMS
-#define P3D_DEFAULT_OVERLAP_SMS 56
+#define P3D_DEFAULT_OVERLAP_SMS 74
+#endif
+#ifndef P3D_DEFAULT_OVERLAP_SHAPE
+#define P3D_DEFAULT_OVERLAP_SHAPE ""
+#endif
+// the pipelined group pays a few launches and barriers per chunk: only for stages of at least this many bytes per rank
+#ifndef P3D_OVERLAP_MIN_BYTES
+#define P3D_OVERLAP_MIN_BYTES (48ll << 20)
 #endif
 
 namespace {
@@ -161,6 +171,9 @@ struct Lib {
   // opt-in pipelined tail of the peer-to-peer plans (P3DFFT_B200_OVERLAP=C chunks; plan.h split_for_overlap): the consumer
   // chunks run on a side stream, on at most overlap_sms SMs while the producer keeps the rest (not yet run on hardware)
   int overlap = P3D_DEFAULT_OVERLAP, overlap_sms = P3D_DEFAULT_OVERLAP_SMS;
+  bool overlap_forced = false;   // P3DFFT_B200_OVERLAP given in the environment: also for small transforms (tests)
+  int overlap_sms_dir[2] = {0, 0};      // per direction (forward, backward); 0: overlap_sms
+  std::vector<int> overlap_shape;       // relative chunk sizes (P3DFFT_B200_OVERLAP_SHAPE=1,3,3,3,1); empty: equal chunks
   cudaStream_t side_stream = nullptr;
   std::vector<cudaEvent_t> chunk_events;
   cudaEvent_t side_done = nullptr;
@@ -402,7 +415,9 @@ bool finalize_plan(p3d::TransformPlan& tp) {
 }
 
 p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long dim_real, long long dim_cplx) {
-  const int chunks = (L.p2p && L.overlap > 1) ? L.overlap : 0;
+  // (decided from the global sizes, so that every rank cuts its plan the same way)
+  const long long stage_bytes = (long long)(L.d.nxhpc / L.d.iproc + 1) * L.d.ny * (L.d.nz / L.d.jproc + 1) * (long long)CSIZE * nv;
+  const int chunks = (L.p2p && L.overlap > 1 && (stage_bytes >= P3D_OVERLAP_MIN_BYTES || L.overlap_forced)) ? L.overlap : 0;
   PlanKey key{backward ? 1 : 0, nv, backward ? op[0] : op[2], dim_real, dim_cplx, L.W(), (L.p2p ? 1 : 0) | (chunks << 8)};
   auto it = L.plans.find(key);
   if (it != L.plans.end()) return &it->second;
@@ -412,7 +427,7 @@ p3d::TransformPlan* get_plan(bool backward, const char* op, int nv, long long di
     report(true, "%s", tp.error.c_str());
     return nullptr;
   }
-  if (chunks > 1) p3d::split_for_overlap(tp, chunks, L.W());
+  if (chunks > 1) p3d::split_for_overlap(tp, chunks, L.W(), L.overlap_shape);
   if (!finalize_plan(tp)) return nullptr;
   auto res = L.plans.emplace(key, std::move(tp));
   return &res.first->second;
@@ -528,7 +543,9 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
   };
   // pipelined group (plan.h split_for_overlap): producer chunks P_c on the main stream on `sms - side_sms` SMs (they are bound by
   // NVLink, not by SMs), consumer chunks Q_c on the side stream on the other `side_sms`; the last consumer has the GPU to itself
-  const int side_sms = L.overlap_sms > 0 && L.overlap_sms < sms ? L.overlap_sms : sms / 2;
+  const int dir = (!tp->steps.empty() && !tp->steps[0].is_exchange && tp->steps[0].st.timer >= 9) ? 1 : 0;      // 9..12: backward stages
+  const int want_sms = L.overlap_sms_dir[dir] > 0 ? L.overlap_sms_dir[dir] : L.overlap_sms;
+  const int side_sms = want_sms > 0 && want_sms < sms ? want_sms : sms / 2;
   bool pre_done = false;      // the barrier that protects the receive buffer of the NEXT exchange has been issued
   for (size_t i = 0; i < nsteps; i++) {
     auto& s = tp->steps[i];
@@ -707,6 +724,21 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   if (getenv("P3DFFT_B200_ROWB")) L.force_row_bytes = atoi(getenv("P3DFFT_B200_ROWB"));
   L.want_flagbar = env_int("P3DFFT_B200_FLAGBAR", P3D_DEFAULT_FLAGBAR) != 0;
   L.overlap = env_int("P3DFFT_B200_OVERLAP", P3D_DEFAULT_OVERLAP);
+  L.overlap_forced = getenv("P3DFFT_B200_OVERLAP") != nullptr;
+  L.overlap_sms_dir[0] = env_int("P3DFFT_B200_OVERLAP_SMS_FWD", 0);
+  L.overlap_sms_dir[1] = env_int("P3DFFT_B200_OVERLAP_SMS_BWD", 0);
+  L.overlap_shape.clear();
+  {
+    const char* sh = getenv("P3DFFT_B200_OVERLAP_SHAPE");
+    if (!sh) sh = P3D_DEFAULT_OVERLAP_SHAPE;
+    for (const char* q = sh; q && *q;) {
+      L.overlap_shape.push_back(atoi(q));
+      q = strchr(q, ',');
+      if (q) q++;
+    }
+    if (L.overlap_shape.size() == 1) L.overlap_shape.clear();
+    if (!L.overlap_shape.empty() && L.overlap > 1) L.overlap = (int)L.overlap_shape.size();
+  }
   L.overlap_sms = env_int("P3DFFT_B200_OVERLAP_SMS", P3D_DEFAULT_OVERLAP_SMS);
   L.row_bytes_plan = L.force_row_bytes;
   p3d::fast_reload_switches();

@@ -161,12 +161,13 @@ bool dispatch_r32(int n, F&& f) {
 #ifndef P3D_DEFAULT_ASYNC
 #define P3D_DEFAULT_ASYNC 0
 #endif
-struct FastSwitches { int r32, bulk, async; bool loaded; };
-static FastSwitches g_switches = {-1, -1, -1, false};
+struct FastSwitches { int r32, bulk, async, xstage; bool loaded; };
+static FastSwitches g_switches = {-1, -1, -1, -1, false};
 void fast_reload_switches() {
   g_switches.r32 = getenv("P3DFFT_B200_R32") ? atoi(getenv("P3DFFT_B200_R32")) : -1;
   g_switches.bulk = getenv("P3DFFT_B200_BULK") ? atoi(getenv("P3DFFT_B200_BULK")) : -1;
   g_switches.async = getenv("P3DFFT_B200_ASYNC") ? atoi(getenv("P3DFFT_B200_ASYNC")) : -1;
+  g_switches.xstage = getenv("P3DFFT_B200_XSTAGE") ? atoi(getenv("P3DFFT_B200_XSTAGE")) : -1;
   g_switches.loaded = true;
 }
 static const FastSwitches& fast_switches() {
@@ -176,9 +177,14 @@ static const FastSwitches& fast_switches() {
 
 template <typename T>
 int fast_variant(const P3dStage& st) {
+  const FastSwitches& sw = fast_switches();
+  if (st.kind == P3D_R2C) {      // bit 4: whole-row stores through a staging buffer (P3DFFT_B200_XSTAGE = 0 / 1 / unset: peers)
+    bool peer = false;
+    for (int g = 0; g < st.out.nseg; g++) if (st.out.seg[g].peer >= 0) peer = true;
+    return (sw.xstage > 0 || (sw.xstage < 0 && peer)) ? 16 : 0;
+  }
   if (is_x(st.kind) || st.out.nseg == 0 || st.in.nseg == 0) return 0;
   if (!(st.nfft == 1024 || st.nfft == 512) || row_bytes<T>(st) != 128) return 0;
-  const FastSwitches& sw = fast_switches();
   const int tx = 128 / (2 * (int)sizeof(T));
   // every output run: whole 128-byte tile rows, consecutive in memory (the writer-contiguous internal layouts)
   bool out_contig = true, out_peer = false;
@@ -314,12 +320,25 @@ static unsigned persistent_grid(K kernel, int nt, size_t smem, long long tiles, 
 #endif
 
 template <typename T, int HH>
+static cudaError_t launch_x_staged(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
+  constexpr int TX = XCfg<T, HH>::TX, NT = XCfg<T, HH>::NT;
+  constexpr size_t smem = xstage_smem<T, HH>(true);
+  const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb * st.nc;
+  if (tiles <= 0) return cudaSuccess;
+  if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
+  cudaError_t e;
+  P3D_LAUNCH(xr2c_kernel<T, HH, true>);
+  return cudaGetLastError();
+}
+
+template <typename T, int HH>
 static cudaError_t launch_x(const P3dStage& st, const FastStage& f, cudaStream_t stream) {
   constexpr int TX = XCfg<T, HH>::TX, NT = XCfg<T, HH>::NT;
   constexpr size_t smem = xstage_smem<T, HH>();
   const long long tiles = (long long)((st.na + TX - 1) / TX) * st.nb * st.nc;
   if (tiles <= 0) return cudaSuccess;
   if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;      // 32-bit tile counters: the generic kernel takes over
+  if (st.kind == P3D_R2C && (f.variant & 16)) return launch_x_staged<T, HH>(st, f, stream);
   cudaError_t e;
   if (st.kind == P3D_R2C) P3D_LAUNCH(xr2c_kernel<T, HH>);
   else if (f.scale != 1.0) P3D_LAUNCH(xc2r_kernel<T, HH, true>);

@@ -1006,6 +1006,12 @@ __device__ __forceinline__ int pair_lanes_log(int half) {
 // X stage, forward: real line (N = 2H) -> H+1 complex, exec_f_r2c (fft_exec.F90:495)
 // twiddle block: pass tables of the H-point schedule, then wx[k] = exp(-2 pi i k / N), k < H
 // ---------------------------------------------------------------------------------------
+// dynamic shared memory of an X-stage CTA without the staging buffer (16-byte aligned)
+template <typename T, int H, class C = XCfg<T, H>> constexpr size_t xstage_smem_base() {
+  using T2 = typename Cx<T>::type;
+  return (sizeof(T2) * C::LP * C::TX + (sizeof(long long) + sizeof(char*)) * (H + 1) + sizeof(char*) * 2 * P3D_MAXRUN +
+          sizeof(int) * (H + 2) + 15) / 16 * 16;
+}
 // E = (Zk + conj Zm)/2, O = -(i/2)(Zk - conj Zm);  X[k] = E + w O,  X[H-k] = conj(E - w O)
 template <typename T, typename T2>
 __device__ __forceinline__ void r2c_combine(T2 zk, T2 zm, T2 w, T2& xk, T2& xm) {
@@ -1017,7 +1023,12 @@ __device__ __forceinline__ void r2c_combine(T2 zk, T2 zm, T2 w, T2& xk, T2& xm) 
   xm = cconj(csub(e, wo));
 }
 
-template <typename T, int H, class C = XCfg<T, H>>
+// STAGED (stages whose output goes to a peer over NVLink): the last pass puts the H+1 outputs of every line into a second
+// shared-memory buffer in natural order and the CTA then stores whole 128-byte rows of the blocked X<->Y buffer.  Straight
+// from registers the mirrored half (H - k) of every pair is shifted by one element against the row grid, i.e. two partial
+// rows (112 + 16 bytes) per quarter warp -- two NVLink packets where one would do (measured 2x4, 1024^3: the X stage moved
+// 542 GB/s to its row peer where the Y and Z stages reach 630-640 GB/s).
+template <typename T, int H, bool STAGED = false, class C = XCfg<T, H>>
 __global__ void __launch_bounds__(C::NT, C::MINB) xr2c_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
   using S = typename C::S;
@@ -1027,6 +1038,8 @@ __global__ void __launch_bounds__(C::NT, C::MINB) xr2c_kernel(const __grid_const
   long long* ent_out = reinterpret_cast<long long*>(smem_raw + sizeof(T2) * C::LP * TX);      // [H+1] output rows (tile invariant)
   char** rowptr = reinterpret_cast<char**>(ent_out + H + 1);                                   // [H+1] row addresses of this tile
   char** tbs = rowptr + H + 1;                                                                 // [tile parity][run] tile bases
+  constexpr int LPO = H + 8;                                                                   // line pitch of the staging buffer
+  T2* so = reinterpret_cast<T2*>(smem_raw + xstage_smem_base<T, H, C>());                      // [TX][LPO], STAGED only
   const T2* __restrict__ tw = reinterpret_cast<const T2*>(st.tw);
   const T2* __restrict__ wx = tw + S::twtotal();
 
@@ -1100,8 +1113,11 @@ __global__ void __launch_bounds__(C::NT, C::MINB) xr2c_kernel(const __grid_const
         const bool live = ti.ta * TX + t < st.na;
         const int lout = t * (int)sao;
         auto put = [&](int k, T2 v) {
-          char* rp = rowptr[k];
-          if (live && rp) stg_stream(reinterpret_cast<T2*>(rp + lout), v);
+          if constexpr (STAGED) so[t * LPO + k] = v;
+          else {
+            char* rp = rowptr[k];
+            if (live && rp) stg_stream(reinterpret_cast<T2*>(rp + lout), v);
+          }
         };
         // Item i pairs butterflies (i, ML - i).  Butterflies 0 and ML/2 pair with THEMSELVES; the lane with
         // i == 0 takes both and runs the same instruction stream with other operands (selects, no branch):
@@ -1137,15 +1153,27 @@ __global__ void __launch_bounds__(C::NT, C::MINB) xr2c_kernel(const __grid_const
           put(H, T2{za[0].x - za[0].y, 0});
         }
       }
+      if constexpr (STAGED) {
+        // whole rows: WB consecutive k of one line are one 128-byte row, the TX lines of a row group are adjacent in memory
+        constexpr int WB = 128 / (int)sizeof(T2), NG = (H + 1 + WB - 1) / WB;
+        __syncthreads();
+#pragma unroll 2
+        for (int idx = threadIdx.x; idx < NG * TX * WB; idx += NT) {
+          const int xi = idx % WB, t = (idx / WB) % TX, k = (idx / (WB * TX)) * WB + xi;
+          if (k <= H && ti.ta * TX + t < st.na) {
+            char* rp = rowptr[k];
+            if (rp) stg_stream(reinterpret_cast<T2*>(rp + (long long)t * sao), so[t * LPO + k]);
+          }
+        }
+      }
     }
     __syncthreads();      // tile buffer and row table are reused by the next tile
   }
 }
 
-template <typename T, int H, class C = XCfg<T, H>> constexpr size_t xstage_smem() {
+template <typename T, int H, class C = XCfg<T, H>> constexpr size_t xstage_smem(bool staged = false) {
   using T2 = typename Cx<T>::type;
-  return sizeof(T2) * C::LP * C::TX + (sizeof(long long) + sizeof(char*)) * (H + 1) +
-         sizeof(char*) * 2 * P3D_MAXRUN + sizeof(int) * (H + 2);
+  return xstage_smem_base<T, H, C>() + (staged ? sizeof(T2) * (H + 8) * C::TX : 0);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -308,12 +308,26 @@ __global__ void cheby_kernel(typename Cx<T>::type* out, int64_t ncol, int nzc, i
   T2 o_k1 = T2{lfac * (T)(nzc - 1) * a_hi.x * (T)0.5, lfac * (T)(nzc - 1) * a_hi.y * (T)0.5};  // out(nzc-1)
   at(nzc) = o_k2;
   at(nzc - 1) = o_k1;
-  for (int k = nzc - 2; k >= 1; k--) {
-    T2 nw = at(k); nw.x *= norm; nw.y *= norm;                // a(k)
-    T2 o = T2{lfac * (T)k * old.x + o_k2.x, lfac * (T)k * old.y + o_k2.y};
-    if (k == 1) { o.x *= (T)0.5; o.y *= (T)0.5; }
-    at(k) = o;
-    o_k2 = o_k1; o_k1 = o; old = nw;
+  // The recurrence is sequential in k, its loads are not: U coefficients are fetched at once (U independent loads in flight
+  // per thread), then U steps run in registers.  With one dependent load per step a column costs nzc DRAM latencies, which is
+  // what a rank of a multi-GPU grid pays in full (few columns per GPU: 1.3 ms of the 1.7 ms Z stage of config 5a on 2x4).
+  constexpr int U = 16;
+  for (int k = nzc - 2; k >= 1; k -= U) {
+    const int cnt = k < U ? k : U;                            // steps k, k-1, ..., k-cnt+1
+    T2 a[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) if (u < cnt) a[u] = at(k - u);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (u < cnt) {
+        const int kk = k - u;
+        T2 nw = a[u]; nw.x *= norm; nw.y *= norm;             // a(kk)
+        T2 o = T2{lfac * (T)kk * old.x + o_k2.x, lfac * (T)kk * old.y + o_k2.y};
+        if (kk == 1) { o.x *= (T)0.5; o.y *= (T)0.5; }
+        at(kk) = o;
+        o_k2 = o_k1; o_k1 = o; old = nw;
+      }
+    }
   }
   if (nzc == 2) { T2 o = at(1); o.x *= (T)0.5; o.y *= (T)0.5; at(1) = o; }
 }

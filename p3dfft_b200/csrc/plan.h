@@ -560,8 +560,11 @@ inline void shift_side(P3dSide& sd, bool along_a, long long x0) {
   }
 }
 
-inline bool split_for_overlap(TransformPlan& tp, int nchunk, int W) {
+// `shape` (optional): relative sizes of the chunks, e.g. {1, 3, 3, 3, 1} -- a small first chunk lets the consumer start early,
+// a small last one shortens the tail that nothing overlaps; empty = equal chunks.
+inline bool split_for_overlap(TransformPlan& tp, int nchunk, int W, const std::vector<int>& shape = std::vector<int>()) {
   const size_t n = tp.steps.size();
+  if (!shape.empty()) nchunk = (int)shape.size();
   if (nchunk < 2 || n < 3) return false;
   // the LAST  stage, peer-to-peer exchange, stage  triple of the plan (forward: Y T2 Z; backward: Y T4 X, or Z T3 Y
   // when the row communicator has one rank and no exchange precedes the X stage)
@@ -589,9 +592,11 @@ inline bool split_for_overlap(TransformPlan& tp, int nchunk, int W) {
       for (int g = 0; g < sd->nseg; g++)
         if (along_a && sd->seg[g].aw > 1 && gran % sd->seg[g].aw) return false;
   const long long nblk = (total + gran - 1) / gran;
+  std::vector<long long> cum(nchunk + 1, 0);      // cumulative weights: chunk c covers blocks [nblk cum[c] / cum[C], nblk cum[c+1] / cum[C])
+  for (int c = 0; c < nchunk; c++) cum[c + 1] = cum[c] + (shape.empty() ? 1 : std::max(shape[c], 1));
   std::vector<Step> group;
   for (int c = 0; c < nchunk; c++) {
-    const long long b0 = nblk * c / nchunk * gran, b1 = std::min<long long>(nblk * (c + 1) / nchunk * gran, total);
+    const long long b0 = nblk * cum[c] / cum[nchunk] * gran, b1 = std::min<long long>(nblk * cum[c + 1] / cum[nchunk] * gran, total);
     const int cnt = (int)std::max<long long>(b1 - b0, 0);
     Step a; a.is_exchange = false; a.chunk = c; a.st = P;
     Step e; e.is_exchange = true;  e.chunk = c; e.ex = E;

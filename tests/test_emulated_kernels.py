@@ -359,3 +359,21 @@ def test_emulated_async_staged_kernel(monkeypatch, single):
             sg = side.seg[g]
             sg.base = bufs[sg.buf].ctypes.data + sg.off * (8 if single else 16)
     assert h.emu_run_fast(C.byref(st)) == 0 and h.emu_last_variant() == 8
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_emulated_staged_x_stores(monkeypatch, single):
+    """X r2c with whole-row stores through a staging buffer (the rule for stages that store into a peer's memory;
+    P3DFFT_B200_XSTAGE=1 forces it everywhere): every specialised X length, pruned in x, partial tiles, 2 x 2 with peer stores"""
+    monkeypatch.setenv("P3DFFT_B200_XSTAGE", "1")
+    h = emu(single)
+    for nx in (64, 128, 256, 512, 1024, 2048):
+        fast, generic = transform_world((nx, 64, 64) if single else (nx, 16, 16), (1, 1), None, "fft", "tff", single=single)
+        assert fast >= 2
+    transform_world((256, 64, 64), (1, 1), (170, 64, 64), "fft", "tff", single=single)
+    transform_world((128, 22, 18) if not single else (128, 64, 64), (1, 1), None, "fft", "tff", single=single)      # partial X tiles
+    transform_world((256, 64, 64), (2, 2), (170, 42, 64), "fft", "tff", single=single, p2p=True)
+    monkeypatch.delenv("P3DFFT_B200_XSTAGE")
+    transform_world((128, 64, 64), (2, 2), None, "fft", "tff", single=single, p2p=True)      # by rule: peer outputs
+    steps, _ = pb.load(single).plan_steps((2, 1), 128, 64, 64, 0, False, "fft", p2p=True)
+    assert steps[0].st.kind == 2 and any(steps[0].st.out.seg[g].peer >= 0 for g in range(steps[0].st.out.nseg))
