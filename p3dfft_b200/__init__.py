@@ -72,7 +72,9 @@ BUF_USER_IN, BUF_USER_OUT, BUF_A, BUF_B, BUF_C = 0, 1, 2, 3, 4
 
 
 def lib_path(single: bool = False) -> str:
-    return os.path.join(_HERE, "lib", "libp3dfft_single.so" if single else "libp3dfft.so")
+    # P3DFFT_B200_LIB_SUFFIX=_x selects lib/libp3dfft_x.so: experimental builds side by side with the product (tools/)
+    suf = os.environ.get("P3DFFT_B200_LIB_SUFFIX", "")
+    return os.path.join(_HERE, "lib", f"libp3dfft{'_single' if single else ''}{suf}.so")
 
 
 def _addr(x) -> int:

@@ -581,7 +581,8 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
       if (s.chunk < 0 || s.chunk + 1 == nchunks) L.dirty[s.ex.recvbuf] = true;
       slots.push_back(s.ex.timer); is_ex.push_back(1);
     } else {
-      if (!launch(s.st, st, s.chunk >= 0 ? sms - side_sms : 0)) return false;
+      // (the first producer chunk has no consumer beside it yet: it takes the whole GPU)
+      if (!launch(s.st, st, s.chunk > 0 ? sms - side_sms : 0)) return false;
       slots.push_back(s.st.timer); is_ex.push_back(0);
     }
   }
