@@ -59,7 +59,7 @@ def build_one(name: str, defines: list[str], verbose: bool = False, force: bool 
     if force or _newer(target, objs):
         # -Bsymbolic: references inside a library bind to its own definitions even when the double and the single library
         # (same symbol names, different real type) sit in one process loaded RTLD_GLOBAL
-        cmd = [NVCC, *ARCH, "-shared", "-Xlinker", "-Bsymbolic", "-o", target, *objs, "-ldl"]
+        cmd = [NVCC, *ARCH, "-shared", "-Xlinker", "-Bsymbolic", "-o", target, *objs, "-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

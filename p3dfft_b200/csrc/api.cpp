@@ -9,12 +9,15 @@
 #include <nccl.h>
 
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -211,6 +214,143 @@ bool is_device_ptr(const void* p) {
   cudaError_t e = cudaPointerGetAttributes(&a, p);
   if (e != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+
+// ------------------------------------------------------------------------------------
+// Host arrays.  The reference's callers pass ordinary heap memory (malloc in every sample driver, driver_sine.c:144-146).
+// Page-locked arrays (cudaHostAlloc / cudaHostRegister) are copied by one DMA; pageable ones go through a ring of
+// page-locked chunks filled (or drained) by a few copy threads while the previous chunk is on the PCIe bus, instead of
+// the driver's single-threaded bounce copy.  Nothing of the caller's memory is pinned or remembered between calls.
+// ------------------------------------------------------------------------------------
+class CopyPool {
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  char* dst_ = nullptr; const char* src_ = nullptr; size_t n_ = 0;
+  unsigned long gen_ = 0; int pending_ = 0; bool stop_ = false;
+  void work(int id, int nth) {
+    unsigned long seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> l(m_);
+      cv_.wait(l, [&] { return stop_ || gen_ != seen; });
+      if (stop_) return;
+      seen = gen_;
+      char* d = dst_; const char* s = src_; const size_t n = n_;
+      l.unlock();
+      const size_t per = ((n + nth - 1) / nth + 4095) / 4096 * 4096, a = std::min(n, per * id), b = std::min(n, a + per);
+      if (b > a) memcpy(d + a, s + a, b - a);
+      l.lock();
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+ public:
+  int threads() const { return (int)th_.size(); }
+  void start(int n) {
+    if (!th_.empty()) return;
+    for (int i = 0; i < n; i++) th_.emplace_back([this, i, n] { work(i, n); });
+  }
+  void copy(void* d, const void* s, size_t n) {      // returns when every slice has been copied
+    if (th_.empty() || n < (1u << 20)) { memcpy(d, s, n); return; }
+    std::unique_lock<std::mutex> l(m_);
+    dst_ = (char*)d; src_ = (const char*)s; n_ = n; pending_ = (int)th_.size(); gen_++;
+    cv_.notify_all();
+    done_.wait(l, [&] { return pending_ == 0; });
+  }
+  void shutdown() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+    th_.clear(); stop_ = false;
+  }
+};
+
+struct HostPipe {
+  static constexpr int NSLOT = 4;
+  size_t chunk = 32u << 20;
+  char* slot[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+  CopyPool pool;
+  bool ready = false, failed = false;
+  bool init() {
+    if (ready) return true;
+    if (failed) return false;
+    const char* ct = getenv("P3DFFT_B200_COPY_THREADS");
+    const char* ck = getenv("P3DFFT_B200_COPY_CHUNK_KB");      // (tests: small chunks so that small arrays take the ring)
+    if (ck && atoi(ck) > 0) chunk = (size_t)atoi(ck) << 10;
+    for (int i = 0; i < NSLOT; i++) {
+      if (cudaHostAlloc((void**)&slot[i], chunk, cudaHostAllocDefault) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); release(); failed = true; return false; }
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nth = ct ? atoi(ct) : (int)std::min<unsigned>(8, std::max<unsigned>(1, hw / 2));
+    if (nth > 1) pool.start(nth);
+    ready = true;
+    return true;
+  }
+  void release() {
+    pool.shutdown();
+    for (int i = 0; i < NSLOT; i++) {
+      if (slot[i]) { cudaFreeHost(slot[i]); slot[i] = nullptr; }
+      if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+    }
+    ready = false;
+  }
+} g_pipe;
+
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// host -> device on stream st; on return the host array may be reused by the caller
+bool copy_h2d(void* dev, const void* host, size_t bytes, cudaStream_t st) {
+  static const bool direct = getenv("P3DFFT_B200_HOSTPIPE") && atoi(getenv("P3DFFT_B200_HOSTPIPE")) == 0;
+  if (direct || is_pinned_host(host) || !g_pipe.init() || bytes < 2 * g_pipe.chunk) {
+    CUDA_OK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st));
+    return true;
+  }
+  bool used[HostPipe::NSLOT] = {false, false, false, false};
+  size_t off = 0;
+  for (int k = 0; off < bytes; k++) {
+    const int s = k % HostPipe::NSLOT;
+    const size_t n = std::min(g_pipe.chunk, bytes - off);
+    if (used[s]) CUDA_OK(cudaEventSynchronize(g_pipe.ev[s]));          // the DMA that read this slot has finished
+    g_pipe.pool.copy(g_pipe.slot[s], (const char*)host + off, n);
+    CUDA_OK(cudaMemcpyAsync((char*)dev + off, g_pipe.slot[s], n, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaEventRecord(g_pipe.ev[s], st));
+    used[s] = true;
+    off += n;
+  }
+  for (int s = 0; s < HostPipe::NSLOT; s++) if (used[s]) CUDA_OK(cudaEventSynchronize(g_pipe.ev[s]));   // slots are free for the next call
+  return true;
+}
+
+// device -> host on stream st.  Page-locked destination: asynchronous (the caller synchronises the stream); pageable: complete on return
+bool copy_d2h(void* host, const void* dev, size_t bytes, cudaStream_t st) {
+  static const bool direct = getenv("P3DFFT_B200_HOSTPIPE") && atoi(getenv("P3DFFT_B200_HOSTPIPE")) == 0;
+  if (direct || is_pinned_host(host) || !g_pipe.init() || bytes < 2 * g_pipe.chunk) {
+    CUDA_OK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
+    return true;
+  }
+  const size_t nchunk = (bytes + g_pipe.chunk - 1) / g_pipe.chunk;
+  auto issue = [&](size_t k) -> bool {
+    const int s = (int)(k % HostPipe::NSLOT);
+    const size_t off = k * g_pipe.chunk, n = std::min(g_pipe.chunk, bytes - off);
+    CUDA_OK(cudaMemcpyAsync(g_pipe.slot[s], (const char*)dev + off, n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaEventRecord(g_pipe.ev[s], st));
+    return true;
+  };
+  for (size_t k = 0; k < nchunk && k < (size_t)HostPipe::NSLOT; k++) if (!issue(k)) return false;
+  for (size_t k = 0; k < nchunk; k++) {
+    const int s = (int)(k % HostPipe::NSLOT);
+    const size_t off = k * g_pipe.chunk, n = std::min(g_pipe.chunk, bytes - off);
+    CUDA_OK(cudaEventSynchronize(g_pipe.ev[s]));
+    g_pipe.pool.copy((char*)host + off, g_pipe.slot[s], n);
+    if (k + HostPipe::NSLOT < nchunk && !issue(k + HostPipe::NSLOT)) return false;
+  }
+  return true;
 }
 
 const void* twiddle_table(int nfft) {
@@ -474,7 +614,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
       if (L.stage_in) cudaFree(L.stage_in);
       CUDA_OK(cudaMalloc(&L.stage_in, in_bytes)); L.stage_in_bytes = in_bytes;
     }
-    CUDA_OK(cudaMemcpyAsync(L.stage_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+    if (!copy_h2d(L.stage_in, in, in_bytes, st)) return false;
     din = L.stage_in;
   }
   if (!out_dev) {
@@ -603,7 +743,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     slots.push_back(8); is_ex.push_back(0);
   }
   if (timed) cudaEventRecord(get_event(nev++), st);
-  if (!out_dev) CUDA_OK(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+  if (!out_dev && !copy_d2h(out, dout, out_bytes, st)) return false;
   if (!L.async || !in_dev || !out_dev || exchange_ms) {
     CUDA_OK(cudaStreamSynchronize(st));
     if (timed) {
@@ -843,6 +983,7 @@ void p3dfft_clean(void) {
   for (int b = P3D_BUF_A; b <= P3D_BUF_C; b++) if (L.buf[b]) { cudaFree(L.buf[b]); L.buf[b] = nullptr; }
   if (L.stage_in) { cudaFree(L.stage_in); L.stage_in = nullptr; L.stage_in_bytes = 0; }
   if (L.stage_out) { cudaFree(L.stage_out); L.stage_out = nullptr; L.stage_out_bytes = 0; }
+  g_pipe.release();
   for (auto& kv : L.twiddles) cudaFree(kv.second);
   L.twiddles.clear();
   for (auto& kv : L.fast_twiddles) cudaFree(kv.second);
@@ -985,7 +1126,7 @@ void p3dfft_b200_spectrum(const void* B, double factor, double* E, int kmax) {
         L.stage_in = nullptr; L.stage_in_bytes = 0;
         CUDA_OK(cudaMalloc(&L.stage_in, cplx_bytes)); L.stage_in_bytes = cplx_bytes;
       }
-      CUDA_OK(cudaMemcpyAsync(L.stage_in, B, cplx_bytes, cudaMemcpyHostToDevice, st));
+      if (!copy_h2d(L.stage_in, B, cplx_bytes, st)) return false;
       dB = L.stage_in;
     }
     if (L.spec_bins < kmax + 1) {

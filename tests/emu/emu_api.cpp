@@ -42,6 +42,10 @@ cudaError_t cudaFree(void* p) {
   emu_mp::shm_release(p);
   return cudaSuccess;
 }
+// page-locked host memory: ordinary heap memory here (cudaPointerGetAttributes keeps calling it unregistered, so host arrays
+// of any size take the pageable path of api.cpp -- the ring of chunks and the copy threads)
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = malloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void* p) { emu_rt::sync_all(); free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { emu_rt::sync_legacy(); memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st) {
   emu_rt::enqueue(st, [=]() { memmove(d, s, n); });

@@ -301,3 +301,37 @@ def test_clean_releases_every_device_allocation(lib):
         assert lib.lib.emu_live_allocations(C.byref(nb)) > base
         lib.p3dfft_clean()
         assert lib.lib.emu_live_allocations(C.byref(nb)) == base, (cycle, nb.value)
+
+
+@pytest.mark.parametrize("threads", ["1", "3"])
+def test_pageable_host_arrays_take_the_chunk_ring(monkeypatch, threads):
+    """host arrays that are not page-locked go through a ring of page-locked chunks filled / drained by copy threads
+    (api.cpp copy_h2d / copy_d2h): forward, backward and in-place calls on arrays of many chunks, sizes that are no multiple
+    of the chunk -- in a fresh process, since the ring is sized once"""
+    import subprocess
+    import sys
+    code = ("import os, sys, numpy as np\n"
+            f"sys.path.insert(0, {ROOT!r})\n"
+            "import p3dfft_b200 as pb\n"
+            "from oracle import p3dfft_oracle as po\n"
+            f"lib = pb.P3DFFT(False, path={os.path.join(ROOT, 'tests', 'emu', 'lib', 'libp3dfft_emu.so')!r})\n"
+            "n = (64, 48, 40)\n"
+            "lib.p3dfft_setup((1, 1), *n, 0)\n"
+            "d = po.Decomp(*n, (1, 1), 0)\n"
+            "A = np.asfortranarray(np.random.default_rng(3).random(n))\n"
+            "F = np.zeros((d.nxhp, n[1], n[2]), dtype=np.complex128, order='F')\n"
+            "lib.p3dfft_ftran_r2c(A, F, 'fft')\n"
+            "e1 = po.rel_l2(F, po.local_forward(A, d, 'fft'))\n"
+            "B = np.zeros(n, order='F')\n"
+            "lib.p3dfft_btran_c2r(F, B, 'tff')\n"
+            "e2 = float(np.max(np.abs(B / A.size - A)))\n"
+            "mem = lib.p3dfft_setup and None\n"
+            "W = np.zeros(2 * d.nxhp * n[1] * n[2]); W[:A.size] = A.ravel(order='F')\n"
+            "lib.p3dfft_ftran_r2c(W, W, 'fft')\n"
+            "e3 = po.rel_l2(W.view(np.complex128), F.ravel(order='F'))\n"
+            "lib.p3dfft_clean()\n"
+            "print('errors', e1, e2, e3)\n"
+            "sys.exit(0 if max(e1, e3) < 1e-13 and e2 < 1e-13 else 1)\n")
+    env = dict(os.environ, P3DFFT_B200_COPY_CHUNK_KB="100", P3DFFT_B200_COPY_THREADS=threads)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
