@@ -51,9 +51,19 @@ typedef int MPI_Fint;
 typedef struct { int MPI_SOURCE, MPI_TAG, MPI_ERROR; } MPI_Status;
 
 #define MPI_SUCCESS 0
+#ifdef P3D_MPI_STUB_LIBRARY
+/* Built as a stand-alone shared library (tests/c/mpi_stub.c -> libmpi_stub.so): an "application's own MPI" with
+ * MPICH-family handle values, whose MPI_Comm_c2f knows nothing about the P3DFFT library -- the library then
+ * bootstraps itself from this MPI through dlsym (api.cpp, comm_from_mpi). */
+#define MPI_COMM_WORLD 0x44000000
+#define MPI_COMM_NULL 0x04000000
+enum { MPI_CHAR = 0x4c000101, MPI_BYTE = 0x4c00010d, MPI_INT = 0x4c000405, MPI_LONG = 0x4c000807, MPI_FLOAT = 0x4c00040a,
+       MPI_DOUBLE = 0x4c00080b, MPI_UNSIGNED = 0x4c000406, MPI_LONG_LONG = 0x4c000809 };
+#else
 #define MPI_COMM_WORLD 1
 #define MPI_COMM_NULL 0
 enum { MPI_CHAR = 1, MPI_BYTE, MPI_INT, MPI_LONG, MPI_FLOAT, MPI_DOUBLE, MPI_UNSIGNED, MPI_LONG_LONG };
+#endif
 #define MPI_REAL MPI_FLOAT
 #define MPI_DOUBLE_PRECISION MPI_DOUBLE
 #define MPI_INTEGER MPI_INT
@@ -261,6 +271,9 @@ static int MPI_Dims_create(int nnodes, int ndims, int* dims) {
 
 /* The "Fortran handle" p3dfft_setup receives is the library's communicator handle. */
 static MPI_Fint MPI_Comm_c2f(MPI_Comm c) {
+#ifdef P3D_MPI_STUB_LIBRARY
+  return (MPI_Fint)c;      /* an MPI of its own: the handle value, nothing else */
+#endif
   (void)c;
   if (!p3d_mpi_.init) MPI_Init(NULL, NULL);
   if (!p3d_mpi_.lib_comm) {

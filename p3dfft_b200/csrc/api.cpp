@@ -56,6 +56,9 @@ static const size_t CSIZE = 2 * sizeof(real_t);
 #define P3D_OVERLAP_MIN_BYTES (48ll << 20)
 #endif
 
+extern "C" int p3dfft_b200_get_unique_id(void* id128);
+extern "C" int p3dfft_b200_comm_create(int rank, int size, const void* id128, int device);
+
 namespace {
 
 // ------------------------------------------------------------------------------------
@@ -125,7 +128,7 @@ struct CommCtx {
   ncclComm_t world = nullptr;
 };
 std::map<int, CommCtx*> g_comms;
-int g_next_handle = 1;
+int g_next_handle = 0x50330001;      // 'P3' + counter: out of the way of small integers, which are Fortran MPI handles of some MPIs
 
 // ------------------------------------------------------------------------------------
 // the plan (module-global state of the reference)
@@ -799,6 +802,63 @@ bool run_rtran(int which, const void* src, void* dst, int* dstart, int* dend, in
   return true;
 }
 
+
+// ------------------------------------------------------------------------------------
+// A caller's own MPI.  The reference takes a Fortran MPI handle (MPI_Comm_c2f(MPI_COMM_WORLD), driver_sine.c:126;
+// setup.F90:178-261 builds its Cartesian communicators from it).  When `comm` is not a handle of
+// p3dfft_b200_comm_create and the process has an MPI loaded, the library borrows four entry points from it through
+// dlsym(RTLD_DEFAULT) -- MPI_Comm_f2c, MPI_Comm_rank, MPI_Comm_size, MPI_Bcast -- to learn rank and size and to
+// distribute the ncclUniqueId, then creates its own communicator.  Nothing else of MPI is used; the library does not link
+// it.  Handle types differ between MPI families: MPICH and its derivatives (Intel MPI, MVAPICH, Cray) use 32-bit
+// integers (MPI_BYTE = 0x4c00010d), Open MPI uses pointers to global objects (MPI_BYTE = &ompi_mpi_byte); both pass
+// through pointer-sized arguments here.
+// ------------------------------------------------------------------------------------
+std::map<int, int> g_mpi_comms;      // Fortran MPI handle -> library handle
+
+int local_device_for(int rank) {
+  const char* names[] = {"OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "SLURM_LOCALID", "LOCAL_RANK", nullptr};
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return -1; }
+  for (int i = 0; names[i]; i++)
+    if (const char* v = getenv(names[i])) return atoi(v) % ndev;
+  return rank % ndev;
+}
+
+// returns a library handle (> 0), 0 when no MPI is loaded, < 0 on failure
+int comm_from_mpi(int fhandle) {
+  auto it = g_mpi_comms.find(fhandle);
+  if (it != g_mpi_comms.end() && g_comms.count(it->second)) return it->second;
+  typedef uintptr_t (*f2c_t)(int);
+  typedef int (*rank_t)(uintptr_t, int*);
+  typedef int (*bcast_t)(void*, int, uintptr_t, int, uintptr_t);
+  typedef int (*inited_t)(int*);
+  f2c_t f2c = (f2c_t)dlsym(RTLD_DEFAULT, "MPI_Comm_f2c");
+  rank_t crank = (rank_t)dlsym(RTLD_DEFAULT, "MPI_Comm_rank"), csize = (rank_t)dlsym(RTLD_DEFAULT, "MPI_Comm_size");
+  bcast_t bcast = (bcast_t)dlsym(RTLD_DEFAULT, "MPI_Bcast");
+  inited_t inited = (inited_t)dlsym(RTLD_DEFAULT, "MPI_Initialized");
+  if (!f2c || !crank || !csize || !bcast) return 0;
+  int flag = 1;
+  if (inited && (inited(&flag) != 0 || !flag)) return 0;
+  void* ompi_byte = dlsym(RTLD_DEFAULT, "ompi_mpi_byte");
+  uintptr_t c = f2c(fhandle);
+  if (!ompi_byte) c &= 0xffffffffu;                                   // integer handles: only the low word is defined
+  const uintptr_t byte_t = ompi_byte ? (uintptr_t)ompi_byte : (uintptr_t)0x4c00010d;
+  int rank = -1, size = 0;
+  if (crank(c, &rank) != 0 || csize(c, &size) != 0 || size < 1 || rank < 0 || rank >= size) return -1;
+  unsigned char id[P3DFFT_B200_UNIQUE_ID_BYTES];
+  memset(id, 0, sizeof id);
+  if (size > 1) {
+    if (rank == 0 && p3dfft_b200_get_unique_id(id) != 0) memset(id, 0, sizeof id);      // all-zero id: the others fail with rank 0
+    if (bcast(id, (int)sizeof id, byte_t, 0, c) != 0) return -1;
+    bool zero = true;
+    for (unsigned char b : id) zero = zero && b == 0;
+    if (zero) return -1;
+  }
+  const int h = p3dfft_b200_comm_create(rank, size, id, local_device_for(rank));
+  if (h > 0) g_mpi_comms[fhandle] = h;
+  return h;
+}
+
 bool check_set() {
   if (!L.set) {
     // module.F90:231, ftran.F90:506-509: message and return
@@ -825,13 +885,20 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   }
   CommCtx* cc = nullptr;
   if (comm) { auto it = g_comms.find(*comm); if (it != g_comms.end()) cc = it->second; }
-  if (comm && *comm != 0 && !cc) {
-    // not a handle of p3dfft_b200_comm_create (0 is reserved for the implicit one-rank communicator): e.g. a real Fortran
-    // MPI handle from code that was not ported.  Running on as one rank would silently give every process its own
-    // full-size transform, so this is an error (INTEGRATION.md section 1 shows the four lines a real-MPI driver adds).
-    report(true, "P3DFFT(B200) setup error: communicator %d is not a handle created by p3dfft_b200_comm_create "
-                 "(a Fortran MPI handle is not understood by this build; see INTEGRATION.md)", *comm);
-    return;
+  if (comm && !cc) {
+    // Not a handle of p3dfft_b200_comm_create: with an MPI loaded in the process this is the Fortran MPI handle of an unmodified
+    // caller (MPI_Comm_c2f(MPI_COMM_WORLD): 0x44000000 with MPICH and its derivatives, 0 with Open MPI) and the library
+    // bootstraps itself from that MPI (comm_from_mpi).  Without one, 0 is the implicit one-rank communicator; any other value is
+    // an error: running on as a single rank would silently give every process of a job its own full-size transform.
+    const bool try_mpi = *comm != 0 || dlsym(RTLD_DEFAULT, "ompi_mpi_comm_world") != nullptr;
+    const int h = try_mpi ? comm_from_mpi(*comm) : 0;
+    if (h > 0) cc = g_comms[h];
+    else if (h < 0 || *comm != 0) {
+      report(true, "P3DFFT(B200) setup error: communicator %d is neither a handle of p3dfft_b200_comm_create nor a "
+                   "communicator of an MPI loaded in this process%s (see INTEGRATION.md)", *comm,
+             h < 0 ? " -- the bootstrap through that MPI failed" : "");
+      return;
+    }
   }
   const int rank = cc ? cc->rank : 0, ntasks = cc ? cc->size : 1;
   std::string err = L.d.init(*nx, *ny, *nz, dims[0], dims[1], rank, ntasks, nxc ? *nxc : *nx, nyc ? *nyc : *ny,
@@ -1032,6 +1099,7 @@ void p3dfft_get_mpi_info(int* taskid, int* ntasks, int* comm) {      // module.F
   *taskid = L.d.rank; *ntasks = L.d.numtasks;
   *comm = 0;
   for (auto& kv : g_comms) if (kv.second == L.comm) *comm = kv.first;
+  for (auto& kv : g_mpi_comms) if (kv.second == *comm) *comm = kv.first;      // the caller's own MPI handle, as the reference returns it
 }
 
 int p3dfft_b200_proc_id2coords(int id, int* ipid, int* jpid) {

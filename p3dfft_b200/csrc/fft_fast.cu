@@ -18,7 +18,9 @@ using namespace fast;
 
 namespace {
 
-bool c2c_len_ok(int n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048; }
+bool c2c_len_ok(int n) {
+  return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 384 || n == 768 || n == 1536 || n == 640 || n == 1280;
+}
 bool x_half_ok(int h) { return h == 32 || h == 64 || h == 128 || h == 256 || h == 512 || h == 1024; }
 
 template <class S>
@@ -66,6 +68,11 @@ bool dispatch_c(int n, F&& f) {
     case 512:  f(std::integral_constant<int, 512>{});  return true;
     case 1024: f(std::integral_constant<int, 1024>{}); return true;
     case 2048: f(std::integral_constant<int, 2048>{}); return true;
+    case 384:  f(std::integral_constant<int, 384>{});  return true;
+    case 768:  f(std::integral_constant<int, 768>{});  return true;
+    case 1536: f(std::integral_constant<int, 1536>{}); return true;
+    case 640:  f(std::integral_constant<int, 640>{});  return true;
+    case 1280: f(std::integral_constant<int, 1280>{}); return true;
     default: return false;
   }
 }

@@ -99,8 +99,26 @@ P3D_CCFG(float, 128, 128, P3D_RS(16, 8), 128, 8)
 P3D_CCFG(float, 256, 128, P3D_RS(16, 16), 256, 4)
 P3D_CCFG(float, 512, 128, P3D_RS(8, 8, 8), 256, 2)
 P3D_CCFG(float, 1024, 128, P3D_RS(16, 8, 8), 512, 1)
+// 3 * 2^k and 5 * 2^k: the odd radix comes FIRST, so that every later sub-transform length (the M of the XOR addressing in
+// twiddle_store / mid_pass) stays a power of two
+P3D_CCFG(double, 384, 64, P3D_RS(3, 16, 8), 128, 4)
+P3D_CCFG(double, 768, 64, P3D_RS(3, 16, 16), 256, 3)
+P3D_CCFG(double, 1536, 64, P3D_RS(6, 16, 16), 256, 2)
+P3D_CCFG(double, 640, 64, P3D_RS(5, 16, 8), 128, 4)
+P3D_CCFG(double, 1280, 64, P3D_RS(5, 16, 16), 256, 2)
+P3D_CCFG(double, 384, 128, P3D_RS(3, 16, 8), 256, 3)
+P3D_CCFG(double, 768, 128, P3D_RS(3, 16, 16), 256, 2)
+P3D_CCFG(double, 640, 128, P3D_RS(5, 16, 8), 256, 2)
+P3D_CCFG(float, 384, 64, P3D_RS(3, 16, 8), 256, 4)
+P3D_CCFG(float, 768, 64, P3D_RS(3, 16, 16), 256, 3)
+P3D_CCFG(float, 1536, 64, P3D_RS(6, 16, 16), 512, 2)
+P3D_CCFG(float, 640, 64, P3D_RS(5, 16, 8), 256, 4)
+P3D_CCFG(float, 1280, 64, P3D_RS(5, 16, 16), 512, 2)
+P3D_CCFG(float, 384, 128, P3D_RS(3, 16, 8), 256, 3)
+P3D_CCFG(float, 768, 128, P3D_RS(3, 16, 16), 512, 2)
+P3D_CCFG(float, 640, 128, P3D_RS(5, 16, 8), 512, 2)
 #undef P3D_CCFG
-// the 128-byte tile of a 2048-point transform (256 KB) does not fit in shared memory
+// the 128-byte tile of a transform longer than 1024 points does not fit in shared memory beside its tables (or only just)
 constexpr bool ccfg_exists(int n, int rb) { return rb == 64 || (rb == 128 && n <= 1024); }
 
 // Two-pass variants (opt-in, P3DFFT_B200_R32=1): 1024 = 32 x 32 and 512 = 16 x 32 instead of three passes, i.e. ONE round
@@ -170,6 +188,48 @@ template <typename T> struct Bfly<T, 2> {
 template <typename T> struct Bfly<T, 4> {
   using T2 = typename Cx<T>::type;
   __device__ __forceinline__ static void run(T2* v) { bf4(v[0], v[1], v[2], v[3]); }
+};
+// odd radices (lengths 3 * 2^k, 5 * 2^k: the DNS-typical sizes 384, 768, 1536, 640, 1280): forward DFT, natural order
+template <typename T> struct Bfly<T, 3> {
+  using T2 = typename Cx<T>::type;
+  __device__ __forceinline__ static void run(T2* v) {
+    const T s = (T)0.86602540378443864676, hf = (T)0.5;
+    const T2 t1 = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+    const T2 t2 = T2{v[0].x - hf * t1.x, v[0].y - hf * t1.y};
+    const T2 r = T2{s * d.y, -s * d.x};                         // -i s (v1 - v2)
+    v[0] = cadd(v[0], t1); v[1] = cadd(t2, r); v[2] = csub(t2, r);
+  }
+};
+template <typename T> struct Bfly<T, 5> {
+  using T2 = typename Cx<T>::type;
+  __device__ __forceinline__ static void run(T2* v) {
+    const T c1 = (T)0.30901699437494742410, c2 = (T)-0.80901699437494742410, s1 = (T)0.95105651629515357212, s2 = (T)0.58778525229247312917;
+    const T2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+    const T2 m1 = T2{v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y};
+    const T2 m2 = T2{v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y};
+    const T2 n1 = T2{s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y};
+    const T2 n2 = T2{s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y};
+    v[0] = T2{v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y};
+    v[1] = T2{m1.x + n1.y, m1.y - n1.x};                        // m1 - i n1
+    v[4] = T2{m1.x - n1.y, m1.y + n1.x};                        // m1 + i n1
+    v[2] = T2{m2.x + n2.y, m2.y - n2.x};
+    v[3] = T2{m2.x - n2.y, m2.y + n2.x};
+  }
+};
+template <typename T> struct Bfly<T, 6> {
+  using T2 = typename Cx<T>::type;
+  // X[k] = E[k mod 3] + W6^k O[k mod 3],  E = DFT3(v0, v2, v4), O = DFT3(v1, v3, v5)
+  __device__ __forceinline__ static void run(T2* v) {
+    const T s = (T)0.86602540378443864676, hf = (T)0.5;
+    T2 e[3] = {v[0], v[2], v[4]}, o[3] = {v[1], v[3], v[5]};
+    Bfly<T, 3>::run(e);
+    Bfly<T, 3>::run(o);
+    const T2 o1 = T2{hf * o[1].x + s * o[1].y, hf * o[1].y - s * o[1].x};        // O1 * W6^1 = O1 (1/2 - i s)
+    const T2 o2 = T2{-hf * o[2].x + s * o[2].y, -hf * o[2].y - s * o[2].x};      // O2 * W6^2 = O2 (-1/2 - i s)
+    v[0] = cadd(e[0], o[0]); v[3] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1);   v[4] = csub(e[1], o1);
+    v[2] = cadd(e[2], o2);   v[5] = csub(e[2], o2);
+  }
 };
 template <typename T> struct Bfly<T, 8> {
   using T2 = typename Cx<T>::type;

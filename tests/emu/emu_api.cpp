@@ -90,6 +90,7 @@ const char* cudaGetErrorName(cudaError_t) { return "cudaErrorEmulated"; }
 const char* cudaGetErrorString(cudaError_t) { return "error reported by the emulated runtime"; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }        // a 4-SM "GPU"
 cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 cudaError_t cudaCtxResetPersistingL2Cache(void) { return cudaSuccess; }

@@ -377,3 +377,19 @@ def test_emulated_staged_x_stores(monkeypatch, single):
     transform_world((128, 64, 64), (2, 2), None, "fft", "tff", single=single, p2p=True)      # by rule: peer outputs
     steps, _ = pb.load(single).plan_steps((2, 1), 128, 64, 64, 0, False, "fft", p2p=True)
     assert steps[0].st.kind == 2 and any(steps[0].st.out.seg[g].peer >= 0 for g in range(steps[0].st.out.nseg))
+
+
+@pytest.mark.parametrize("single", [False, True])
+@pytest.mark.parametrize("n", [384, 768, 1536, 640, 1280])
+def test_emulated_non_power_of_two_c2c(n, single):
+    """3 * 2^k and 5 * 2^k lengths on the specialised c2c kernels (odd radix first: 384 = 3.16.8, 768 = 3.16.16,
+    1536 = 6.16.16, 640 = 5.16.8, 1280 = 5.16.16): Y and Z stages, forward and backward, pruned, DCT-I of the matching odd
+    length, 2 x 2 with peer stores"""
+    nx = 64 if single else 16
+    fast, generic = transform_world((nx, n, nx), (1, 1), None, "fft", "tff", single=single)
+    assert fast >= 2
+    fast, generic = transform_world((nx, nx, n), (1, 1), (nx, nx, 2 * (n // 3)), "fft", "tff", single=single)
+    assert fast >= 2
+    if n <= 768 and not single:
+        transform_world((16, 16, n // 2 + 1), (1, 1), None, "ffc", "cff")          # DCT-I: nfft = 2 (nz - 1) = n
+        transform_world((32, n, 16), (2, 2), None, "fft", "tff", p2p=True)
