@@ -21,7 +21,9 @@ namespace {
 bool c2c_len_ok(int n) {
   return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 384 || n == 768 || n == 1536 || n == 640 || n == 1280;
 }
-bool x_half_ok(int h) { return h == 32 || h == 64 || h == 128 || h == 256 || h == 512 || h == 1024; }
+bool x_half_ok(int h) {
+  return h == 32 || h == 64 || h == 128 || h == 256 || h == 512 || h == 1024 || h == 192 || h == 384 || h == 768 || h == 320 || h == 640;
+}
 
 template <class S>
 void fill_pass_tables(long double n_total, std::vector<long double>& re, std::vector<long double>& im) {
@@ -85,6 +87,11 @@ bool dispatch_x(int h, F&& f) {
     case 256:  f(std::integral_constant<int, 256>{});  return true;
     case 512:  f(std::integral_constant<int, 512>{});  return true;
     case 1024: f(std::integral_constant<int, 1024>{}); return true;
+    case 192:  f(std::integral_constant<int, 192>{});  return true;
+    case 384:  f(std::integral_constant<int, 384>{});  return true;
+    case 768:  f(std::integral_constant<int, 768>{});  return true;
+    case 320:  f(std::integral_constant<int, 320>{});  return true;
+    case 640:  f(std::integral_constant<int, 640>{});  return true;
     default: return false;
   }
 }
@@ -102,7 +109,7 @@ static int row_bytes(const P3dStage& st) {
       aw = sd.seg[g].aw;
     }
   }
-  if (!aw) return st.nfft <= 1024 ? 128 : 64;
+  if (!aw) return ccfg_exists(st.nfft, 128) ? 128 : 64;
   return aw * 2 * (int)sizeof(T);
 }
 

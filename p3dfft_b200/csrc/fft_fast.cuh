@@ -109,6 +109,8 @@ P3D_CCFG(double, 1280, 64, P3D_RS(5, 16, 16), 256, 2)
 P3D_CCFG(double, 384, 128, P3D_RS(3, 16, 8), 256, 3)
 P3D_CCFG(double, 768, 128, P3D_RS(3, 16, 16), 256, 2)
 P3D_CCFG(double, 640, 128, P3D_RS(5, 16, 8), 256, 2)
+P3D_CCFG(double, 1280, 128, P3D_RS(5, 16, 16), 512, 1)
+P3D_CCFG(double, 1536, 128, P3D_RS(6, 16, 16), 512, 1)
 P3D_CCFG(float, 384, 64, P3D_RS(3, 16, 8), 256, 4)
 P3D_CCFG(float, 768, 64, P3D_RS(3, 16, 16), 256, 3)
 P3D_CCFG(float, 1536, 64, P3D_RS(6, 16, 16), 512, 2)
@@ -117,9 +119,12 @@ P3D_CCFG(float, 1280, 64, P3D_RS(5, 16, 16), 512, 2)
 P3D_CCFG(float, 384, 128, P3D_RS(3, 16, 8), 256, 3)
 P3D_CCFG(float, 768, 128, P3D_RS(3, 16, 16), 512, 2)
 P3D_CCFG(float, 640, 128, P3D_RS(5, 16, 8), 512, 2)
+P3D_CCFG(float, 1280, 128, P3D_RS(5, 16, 16), 512, 1)
+P3D_CCFG(float, 1536, 128, P3D_RS(6, 16, 16), 512, 1)
 #undef P3D_CCFG
-// the 128-byte tile of a transform longer than 1024 points does not fit in shared memory beside its tables (or only just)
-constexpr bool ccfg_exists(int n, int rb) { return rb == 64 || (rb == 128 && n <= 1024); }
+// the 128-byte tile of a 2048-point transform (256 KB) does not fit in shared memory; 1536 points (192 KB + 24 KB of row
+// tables) still do, with one CTA per SM
+constexpr bool ccfg_exists(int n, int rb) { return rb == 64 || (rb == 128 && n <= 1536); }
 
 // Two-pass variants (opt-in, P3DFFT_B200_R32=1): 1024 = 32 x 32 and 512 = 16 x 32 instead of three passes, i.e. ONE round
 // trip through shared memory per element instead of two (r1 ncu: the LSU pipe is busy ~55 % of a 1024-point stage, most
@@ -157,6 +162,19 @@ P3D_XCFG(float, 128, P3D_RS(4, 4, 8), 8, 128, 6, 3, 5)
 P3D_XCFG(float, 256, P3D_RS(8, 4, 8), 8, 256, 3, 5, 0)
 P3D_XCFG(float, 512, P3D_RS(8, 8, 8), 8, 256, 3, 6, 0)
 P3D_XCFG(float, 1024, P3D_RS(8, 16, 8), 8, 512, 2, 7, 0)
+// nx = 3 * 2^k, 5 * 2^k: the pair passes (first pass of c2r, last pass of r2c) need EVEN radices <= 8, the odd factor sits in
+// the middle (the X kernels address shared memory additively, so no pass needs a power-of-two sub-transform length).  The
+// swizzle shifts are not tuned for these lengths (some bank conflicts; correctness does not depend on them).
+P3D_XCFG(double, 192, P3D_RS(4, 6, 8), 4, 64, 8, 3, 5)
+P3D_XCFG(double, 384, P3D_RS(8, 6, 8), 4, 128, 4, 5, 0)
+P3D_XCFG(double, 768, P3D_RS(8, 3, 4, 8), 4, 256, 2, 6, 0)
+P3D_XCFG(double, 320, P3D_RS(8, 5, 8), 4, 128, 4, 5, 0)
+P3D_XCFG(double, 640, P3D_RS(8, 5, 2, 8), 4, 256, 2, 6, 0)
+P3D_XCFG(float, 192, P3D_RS(4, 6, 8), 8, 128, 6, 3, 5)
+P3D_XCFG(float, 384, P3D_RS(8, 6, 8), 8, 256, 3, 5, 0)
+P3D_XCFG(float, 768, P3D_RS(8, 3, 4, 8), 8, 512, 2, 6, 0)
+P3D_XCFG(float, 320, P3D_RS(8, 5, 8), 8, 256, 3, 5, 0)
+P3D_XCFG(float, 640, P3D_RS(8, 5, 2, 8), 8, 512, 2, 6, 0)
 #undef P3D_XCFG
 #undef P3D_RS
 #if defined(__CUDACC__) || defined(P3D_EMULATE)      // P3D_EMULATE: host emulation of the kernels (tests/emu, CPU tests)
@@ -1070,7 +1088,7 @@ __device__ __forceinline__ void xlast_bfly(const typename Cx<T>::type* s, int t,
 // returns log2(lanes along k)
 __device__ __forceinline__ int pair_lanes_log(int half) {
   int il = 32;
-  while (il > half) il >>= 1;
+  while (il > half || half % il) il >>= 1;      // a power of two that divides the pair count (24 pairs: 8 lanes along k)
   return 31 - __clz(il);
 }
 

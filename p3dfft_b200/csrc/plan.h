@@ -152,8 +152,11 @@ struct Decomp {
 // bytes: 128-byte rows unless the 128-byte tile of the longest Y/Z transform would not fit in shared
 // memory (fft_fast.cuh, CCfg); `force_row_bytes` (64 or 128) overrides the rule.
 inline int pick_W(int ny, int nz, int csize, int force_row_bytes = 0) {
-  const int rb = (force_row_bytes == 64 || force_row_bytes == 128) ? force_row_bytes
-                                                                   : ((ny <= 1024 && nz <= 1024) ? 128 : 64);
+  // 128-byte rows whenever the tile of the longest Y/Z transform fits on chip: up to 1024 points for any length (the
+  // any-length kernel then takes up to 8 lines), and the specialised 1280- and 1536-point kernels (160 / 192 KB tiles;
+  // measured at 1280^3: 64-byte rows 76.6 ms per pair, 2.6 TB/s -- the Z stages crawl on half-line accesses)
+  auto fits128 = [](int n) { return n <= 1024 || n == 1280 || n == 1536; };
+  const int rb = (force_row_bytes == 64 || force_row_bytes == 128) ? force_row_bytes : ((fits128(ny) && fits128(nz)) ? 128 : 64);
   return rb / csize;
 }
 

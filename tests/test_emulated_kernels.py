@@ -393,3 +393,19 @@ def test_emulated_non_power_of_two_c2c(n, single):
     if n <= 768 and not single:
         transform_world((16, 16, n // 2 + 1), (1, 1), None, "ffc", "cff")          # DCT-I: nfft = 2 (nz - 1) = n
         transform_world((32, n, 16), (2, 2), None, "fft", "tff", p2p=True)
+
+
+@pytest.mark.parametrize("single", [False, True])
+@pytest.mark.parametrize("nx", [384, 768, 1536, 640, 1280])
+def test_emulated_non_power_of_two_x_stage(nx, single):
+    """nx = 3 * 2^k, 5 * 2^k on the specialised X kernels (even radices in the pair passes, the odd factor in the middle:
+    192 = 4.6.8, 384 = 8.6.8, 768 = 8.3.4.8, 320 = 8.5.8, 640 = 8.5.2.8): r2c and c2r, pruned in x, partial tiles, staged
+    whole-row stores towards a peer"""
+    ny = 64 if single else 16
+    fast, generic = transform_world((nx, ny, ny), (1, 1), None, "fft", "tff", single=single)
+    assert fast >= 2 and (not single or generic == 0)
+    transform_world((nx, ny, ny), (1, 1), (2 * (nx // 3), ny, ny), "fft", "tff", single=single)
+    if not single:
+        transform_world((nx, 22, 18), (1, 1), None, "fft", "tff")                    # partial X tiles
+        if nx <= 768:
+            transform_world((nx, 32, 16), (2, 2), None, "fft", "tff", p2p=True)      # staged stores into the row peer

@@ -128,6 +128,22 @@ def test_fast_kernels_double(lib, n, cut):
         lib.force_generic(False)
 
 
+NONPOW2_CASES = [((384, 64, 64), None), ((768, 64, 128), None), ((1536, 64, 64), None), ((640, 128, 64), None), ((1280, 64, 64), None),
+                 ((64, 384, 64), None), ((64, 64, 768), None), ((64, 1536, 64), None), ((128, 640, 64), None), ((64, 64, 1280), None),
+                 ((384, 384, 384), None), ((768, 384, 640), (512, 256, 426)), ((64, 64, 385), None)]
+
+
+@pytest.mark.parametrize("n,cut", NONPOW2_CASES)
+def test_fast_kernels_non_power_of_two(lib, libf, n, cut):
+    """3 * 2^k and 5 * 2^k lengths (the DNS-typical 384, 768, 1536, 640, 1280) on the specialised kernels, every stage, double
+    and single precision; the last case is the DCT-I of length 385 (a 768-point transform)"""
+    ops = ("ffc", "cff") if n[2] % 2 else ("fft", "tff")
+    for L, single in ((lib, False), (libf, True)):
+        L.fast_launch_count(True)
+        _fwd_bwd(L, n, cut, single=single, device=True, opf=ops[0], opb=ops[1])
+        assert L.fast_launch_count() == 6
+
+
 @pytest.mark.parametrize("n,cut", [FAST_CASES[0], FAST_CASES[1], FAST_CASES[8], FAST_CASES[10], ((64, 1024, 1024), None)])
 def test_fast_kernels_row_bytes(lib, n, cut):
     """Both tile row widths of the internal layouts (64- and 128-byte rows) give the same transform."""
