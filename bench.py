@@ -523,6 +523,9 @@ def main():
                       else "grouped ncclSend/ncclRecv")),
         "clocks": clocks, "roundtrip_max_err": err,
     }
+    if world > 1:
+        line["roofline"]["note"] = ("N > 1: the stages that feed a transpose are bound by their NVLink peer stores, not by HBM (see "
+                                    "roofline_pair_*); consumer chunks of the pipelined group run on a side stream and are not in stages_ms")
     if variant:
         line["library_variant"] = variant
     if parity is not None:

@@ -60,15 +60,16 @@ void p3dfft_b200_force_generic(int on);
  * receive buffer over NVLink and the exchange step is only a barrier.  on = 0 keeps grouped
  * ncclSend/ncclRecv.  Must precede p3dfft_setup (also env P3DFFT_B200_P2P=0/1).               */
 void p3dfft_b200_set_p2p(int on);
-/* env P3DFFT_B200_OVERLAP=C (opt-in, experimental): the last two stages of a peer-to-peer transform run as C chunks, the
- * local consumer chunks on a second stream beside the NVLink-bound producer (P3DFFT_B200_OVERLAP_SMS = SMs left to them);
- * the per-stage timers then only cover the producer side.
+/* env P3DFFT_B200_OVERLAP=C (default 4; 0 or 1: off): the last stage-exchange-stage triple of a peer-to-peer transform runs as C
+ * chunks, the local consumer chunks on a second stream beside the NVLink-bound producer (P3DFFT_B200_OVERLAP_SMS = SMs left to
+ * them, default 74); the per-stage timers then only cover the producer side.
  * env P3DFFT_B200_R32 = 0 / 1 / unset: two-pass (radix-32) 512/1024-point c2c schedules never / wherever they exist / by the
  * measured rule (1024-point stages that write whole tiles contiguously).  P3DFFT_B200_BULK = 0 / 1 / unset: bulk asynchronous
  * (TMA, cp.async.bulk) tile stores never / wherever the output rows allow / for stages storing into a peer's memory.
  * Both are read at p3dfft_setup.                                                                                          */
-/* env P3DFFT_B200_FLAGBAR=1 (opt-in, experimental): the barrier that orders the peer-to-peer transposes becomes a
- * one-CTA kernel exchanging epoch flags through peer-mapped memory instead of a one-float NCCL all-reduce.         */
+/* env P3DFFT_B200_FLAGBAR=0: the barrier that orders the peer-to-peer transposes is a one-float NCCL all-reduce instead of the
+ * default one-CTA kernel exchanging epoch flags through peer-mapped memory.  P3DFFT_B200_SCOPED=0: every such barrier spans
+ * the world instead of signalling to all ranks and waiting only for the ranks of the exchange's row or column (default).  */
 int p3dfft_b200_p2p_active(void);
 /* on != 0: keep the reference's pack-buffer layouts and exact alltoallv counts in the
  * library's own work buffers instead of the tile-blocked B200 layouts (plan.h); results are

@@ -42,6 +42,9 @@ static const size_t CSIZE = 2 * sizeof(real_t);
 #ifndef P3D_DEFAULT_FLAGBAR
 #define P3D_DEFAULT_FLAGBAR 1
 #endif
+#ifndef P3D_DEFAULT_SCOPED
+#define P3D_DEFAULT_SCOPED 1
+#endif
 #ifndef P3D_DEFAULT_OVERLAP
 #define P3D_DEFAULT_OVERLAP 4
 #endif
@@ -167,6 +170,17 @@ struct Lib {
   std::vector<unsigned*> peer_flags;             // [world rank] mapped flag arrays (own entry = bar_flags)
   unsigned** peer_flags_dev = nullptr;           // the same table on the device
   unsigned bar_epoch = 0;
+  // Scoped synchronisation (flag barrier only, at most 64 ranks; P3DFFT_B200_SCOPED=0 keeps world barriers).  A flag is its
+  // owner's progress counter: every sync point of a plan (each exchange, each chunk of a pipelined group, the end of a
+  // transform) signals the next epoch to ALL ranks, but an exchange WAITS only for the ranks of its own row or column.
+  // The write-after-read rule becomes exact: release[b] is the epoch whose signal is stream-ordered behind this rank's
+  // last read of buffer b -- every rank runs the same step sequence, so it is also the epoch a PEER signals behind ITS last
+  // read of its copy of b.  A stage that stores into the peers' copies of b first waits for its target peers to have reached
+  // release[b], unless a wait already queued on this stream covers it (passed[c], per communicator).
+  bool want_scoped = true, scoped = false;
+  unsigned long long scope_mask[2] = {0, 0};      // world ranks of this rank's row / column (bit r)
+  unsigned release[5] = {0, 0, 0, 0, 0};
+  unsigned passed[2] = {0, 0};
   // dirty[b]: buffer b was the receive buffer of an exchange since the last world barrier, i.e. some rank may still
   // be reading it.  A peer-to-peer stage must not store into the peers' copies of such a buffer before another
   // barrier (run_plan).  Derived from the exchange steps only, so every rank takes the same decisions.
@@ -400,6 +414,7 @@ void close_peer_maps() {
     if (L.peer_flags[i] && (int)i != me) cudaIpcCloseMemHandle(L.peer_flags[i]);
   L.peer_flags.clear();
   L.flagbar = false;
+  L.scoped = false;
 }
 
 bool world_barrier(cudaStream_t st) {
@@ -407,6 +422,7 @@ bool world_barrier(cudaStream_t st) {
   if (L.flagbar) {
     CUDA_OK(p3d::launch_flag_barrier(L.peer_flags_dev, L.comm->rank, L.comm->size, ++L.bar_epoch, st));
     for (bool& d : L.dirty) d = false;
+    L.passed[0] = L.passed[1] = L.bar_epoch;      // every rank has reached this epoch
     return true;
   }
   if (!L.bar_scratch) { CUDA_OK(cudaMalloc(&L.bar_scratch, 256)); CUDA_OK(cudaMemset(L.bar_scratch, 0, 256)); }
@@ -425,6 +441,8 @@ bool open_flag_maps() {
     CUDA_OK(cudaMalloc(&L.bar_flags, bytes));
     CUDA_OK(cudaMemset(L.bar_flags, 0, bytes));
     L.bar_epoch = 0;
+    for (unsigned& r : L.release) r = 0;
+    L.passed[0] = L.passed[1] = 0;
   }
   if ((size_t)P * 128 > bytes) return false;
   cudaIpcMemHandle_t mine;
@@ -459,6 +477,13 @@ bool open_flag_maps() {
   if (!L.peer_flags_dev) CUDA_OK(cudaMalloc(&L.peer_flags_dev, sizeof(unsigned*) * 1024));
   CUDA_OK(cudaMemcpy(L.peer_flags_dev, L.peer_flags.data(), sizeof(unsigned*) * P, cudaMemcpyHostToDevice));
   L.flagbar = true;
+  L.scoped = L.want_scoped && P <= 64;
+  L.scope_mask[0] = L.scope_mask[1] = 0;
+  for (int r = 0; r < P && L.scoped; r++) {
+    const int ip = L.d.dims_c ? r / L.d.jproc : r % L.d.iproc, jp = L.d.dims_c ? r % L.d.jproc : r / L.d.iproc;
+    if (jp == L.d.jpid) L.scope_mask[0] |= 1ull << r;      // my row: same jpid
+    if (ip == L.d.ipid) L.scope_mask[1] |= 1ull << r;      // my column: same ipid
+  }
   return true;
 }
 
@@ -690,13 +715,55 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
   const int want_sms = L.overlap_sms_dir[dir] > 0 ? L.overlap_sms_dir[dir] : L.overlap_sms;
   const int side_sms = want_sms > 0 && want_sms < sms ? want_sms : sms / 2;
   bool pre_done = false;      // the barrier that protects the receive buffer of the NEXT exchange has been issued
+  // scoped synchronisation (see Lib::release): bookkeeping of this call
+  const bool scoped = L.scoped && L.flagbar;
+  std::vector<int> reads_main, reads_side;      // work buffers read by stages queued since the last signal (main stream) / on the side stream
+  bool any_p2p = false;
+  int group_comm = -1;
+  unsigned group_last_epoch = 0;
+  auto note_reads = [&](const P3dStage& stg, bool on_side) {
+    for (int g = 0; g < stg.in.nseg; g++) {
+      const int b = stg.in.seg[g].buf;
+      if (b >= P3D_BUF_A && b <= P3D_BUF_C) (on_side ? reads_side : reads_main).push_back(b);
+    }
+  };
+  auto assign_release = [&](unsigned e) {       // `e` has just been signalled on the main stream, behind everything in reads_main
+    for (int b : reads_main) L.release[b] = e;
+    reads_main.clear();
+  };
+  auto hazard_wait = [&](const P3dExchange& ex) -> bool {      // before a stage that stores into the peers' copies of ex.recvbuf
+    const unsigned need = L.release[ex.recvbuf];
+    if (need != 0 && (int)(need - L.passed[ex.comm]) > 0) {
+      CUDA_OK(p3d::launch_flag_sync_mask(L.peer_flags_dev, L.comm->rank, L.comm->size, 0u, 0, L.scope_mask[ex.comm], need, st));
+      L.passed[ex.comm] = need;
+    }
+    return true;
+  };
+  auto join_group = [&]() -> bool {
+    const bool was = used_side;
+    if (!join_side()) return false;
+    if (was && scoped) {
+      reads_main.insert(reads_main.end(), reads_side.begin(), reads_side.end());
+      reads_side.clear();
+      if (group_comm >= 0 && (int)(group_last_epoch - L.passed[group_comm]) > 0) L.passed[group_comm] = group_last_epoch;
+    }
+    return true;
+  };
   for (size_t i = 0; i < nsteps; i++) {
     auto& s = tp->steps[i];
-    if (s.chunk < 0 && used_side && !join_side()) return false;      // a step behind the pipelined group: the group is complete
+    if (s.chunk < 0 && used_side && !join_group()) return false;      // a step behind the pipelined group: the group is complete
     if (!s.is_exchange && s.side) {
       // consumer chunk: after every rank's producer chunk (flag wait on this stream, or the event behind the NCCL barrier)
       CUDA_OK(cudaStreamWaitEvent(L.side_stream, L.chunk_events[s.chunk], 0));      // this rank's own chunk (and signal) first
-      if (L.flagbar) CUDA_OK(p3d::launch_flag_wait(L.peer_flags_dev, L.comm->rank, L.comm->size, chunk_epoch[s.chunk], L.side_stream));
+      if (scoped) {
+        const P3dExchange& ge = tp->steps[i - 1].ex;      // the chunk's exchange step precedes its consumer
+        CUDA_OK(p3d::launch_flag_sync_mask(L.peer_flags_dev, L.comm->rank, L.comm->size, 0u, 0, L.scope_mask[ge.comm], chunk_epoch[s.chunk],
+                                           L.side_stream));
+        group_comm = ge.comm; group_last_epoch = chunk_epoch[s.chunk];
+        note_reads(s.st, true);
+      } else if (L.flagbar) {
+        CUDA_OK(p3d::launch_flag_wait(L.peer_flags_dev, L.comm->rank, L.comm->size, chunk_epoch[s.chunk], L.side_stream));
+      }
       if (!launch(s.st, L.side_stream, s.chunk + 1 < nchunks ? side_sms : 0)) return false;
       used_side = true;
       continue;
@@ -706,15 +773,29 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     // across ranks): barrier first.  Decided from the exchange steps alone, identically on every rank -- a rank
     // whose producing stage is empty issues the same barrier when it reaches the exchange.  (Chunks after the first
     // of a pipelined group store into other regions of the buffer their group was already cleared for.)
+    // With scoped synchronisation the rule is exact instead: wait for the target peers' release epoch of that buffer.
     const P3dExchange* nex = s.is_exchange ? &s.ex : (i + 1 < nsteps && tp->steps[i + 1].is_exchange ? &tp->steps[i + 1].ex : nullptr);
-    if (nex && nex->p2p && !pre_done && L.dirty[nex->recvbuf] && s.chunk <= 0) {
+    if (scoped) {
+      if (nex && nex->p2p && !s.is_exchange && s.chunk <= 0 && !hazard_wait(*nex)) return false;
+    } else if (nex && nex->p2p && !pre_done && L.dirty[nex->recvbuf] && s.chunk <= 0) {
       if (timed) { cudaEventRecord(get_event(nev++), st); slots.push_back(nex->timer); is_ex.push_back(1); }
       if (!world_barrier(st)) return false;
     }
     if (nex) pre_done = !s.is_exchange;
     if (timed) { cudaEventRecord(get_event(nev++), st); }
     if (s.is_exchange) {
-      if (s.chunk >= 0 && s.ex.p2p && L.flagbar) {
+      if (s.ex.p2p && scoped) {
+        any_p2p = true;
+        const unsigned e = ++L.bar_epoch;
+        if (s.chunk >= 0) {      // chunk of a pipelined group: signal only, the consumer waits on the side stream
+          chunk_epoch[s.chunk] = e;
+          CUDA_OK(p3d::launch_flag_signal(L.peer_flags_dev, L.comm->rank, L.comm->size, e, st));
+        } else {                 // signal to every rank, wait for the ranks of this exchange's communicator
+          CUDA_OK(p3d::launch_flag_sync_mask(L.peer_flags_dev, L.comm->rank, L.comm->size, e, 1, L.scope_mask[s.ex.comm], e, st));
+          L.passed[s.ex.comm] = e;
+        }
+        assign_release(e);
+      } else if (s.chunk >= 0 && s.ex.p2p && L.flagbar) {
         // chunk barrier, first half: tell every rank that this rank's producer chunk has been stored; the main stream goes
         // straight on to the next producer chunk, the consumer waits for all ranks' flags on the side stream
         chunk_epoch[s.chunk] = ++L.bar_epoch;
@@ -726,10 +807,17 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
     } else {
       // (the first producer chunk has no consumer beside it yet: it takes the whole GPU)
       if (!launch(s.st, st, s.chunk > 0 ? sms - side_sms : 0)) return false;
+      if (scoped) note_reads(s.st, false);
       slots.push_back(s.st.timer); is_ex.push_back(0);
     }
   }
-  if (!join_side()) return false;       // everything behind this point (epilogues, copies, the next call) is ordered after the side stream
+  if (!join_group()) return false;      // everything behind this point (epilogues, copies, the next call) is ordered after the side stream
+  if (scoped && any_p2p) {
+    // end of the transform: one more signal, so that every read of a work buffer in this call has a release epoch behind it
+    const unsigned e = ++L.bar_epoch;
+    CUDA_OK(p3d::launch_flag_signal(L.peer_flags_dev, L.comm->rank, L.comm->size, e, st));
+    assign_release(e);
+  }
   if (cheby) {
     // p3dfft_cheby epilogue, ftran.F90:408-451
     const double norm = 1.0 / ((double)d.nx * (double)d.ny * (double)(d.nzc - 1));
@@ -931,6 +1019,7 @@ void p3dfft_setup(int* dims, int* nx, int* ny, int* nz, int* comm, int* nxc, int
   L.want_p2p = env_int("P3DFFT_B200_P2P", L.api_p2p ? 1 : 0) != 0;
   if (getenv("P3DFFT_B200_ROWB")) L.force_row_bytes = atoi(getenv("P3DFFT_B200_ROWB"));
   L.want_flagbar = env_int("P3DFFT_B200_FLAGBAR", P3D_DEFAULT_FLAGBAR) != 0;
+  L.want_scoped = env_int("P3DFFT_B200_SCOPED", P3D_DEFAULT_SCOPED) != 0;
   L.overlap = env_int("P3DFFT_B200_OVERLAP", P3D_DEFAULT_OVERLAP);
   L.overlap_forced = getenv("P3DFFT_B200_OVERLAP") != nullptr;
   L.overlap_sms_dir[0] = env_int("P3DFFT_B200_OVERLAP_SMS_FWD", 0);

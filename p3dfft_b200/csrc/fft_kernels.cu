@@ -496,7 +496,44 @@ __global__ void flag_wait_kernel(unsigned* const* __restrict__ peers, int me, in
   __syncthreads();
 }
 
+// Scoped forms (api.cpp, scoped synchronisation): `signal` always goes to every rank -- a flag is the sender's progress counter --,
+// the wait covers only the ranks of `mask` (bit r = world rank r; at most 64 ranks).  One launch: optional signal, then wait.
+__global__ void flag_sync_mask_kernel(unsigned* const* __restrict__ peers, int me, int nrank, unsigned signal_epoch, int do_signal,
+                                      unsigned long long mask, unsigned wait_epoch) {
+  const int r = threadIdx.x;
+  if (r < nrank) {
+    if (do_signal) {
+      unsigned* dst = peers[r] + (size_t)me * 32;
+#ifndef P3D_EMULATE
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(signal_epoch) : "memory");
+#else
+      __atomic_store_n(dst, signal_epoch, __ATOMIC_RELEASE);
+#endif
+    }
+    if ((mask >> r) & 1ull) {
+      const unsigned* src = peers[me] + (size_t)r * 32;
+      unsigned v;
+#ifndef P3D_EMULATE
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+      } while ((int)(v - wait_epoch) < 0);
+#else
+      do { v = __atomic_load_n(src, __ATOMIC_ACQUIRE); } while ((int)(v - wait_epoch) < 0);
+#endif
+    }
+  }
+  __syncthreads();
+}
+
 static int flag_threads(int nrank) { return nrank <= 32 ? 32 : ((nrank + 31) / 32) * 32; }
+cudaError_t launch_flag_sync_mask(unsigned* const* peers, int me, int nrank, unsigned signal_epoch, int do_signal,
+                                  unsigned long long mask, unsigned wait_epoch, cudaStream_t stream) {
+  if (nrank > 64) return cudaErrorInvalidValue;
+  const int nt = flag_threads(nrank);
+  P3D_KLAUNCH(flag_sync_mask_kernel, 1, nt, 0, stream, peers, me, nrank, signal_epoch, do_signal, mask, wait_epoch);
+  return cudaGetLastError();
+}
 cudaError_t launch_flag_barrier(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream) {
   if (nrank > 1024) return cudaErrorInvalidValue;
   const int nt = flag_threads(nrank);

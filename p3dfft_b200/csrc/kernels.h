@@ -32,5 +32,9 @@ cudaError_t launch_flag_barrier(unsigned* const* peers, int me, int nrank, unsig
 // the barrier's two halves as separate launches (pipelined groups): store `epoch` into every rank's slot `me` / wait for all
 cudaError_t launch_flag_signal(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream);
 cudaError_t launch_flag_wait(unsigned* const* peers, int me, int nrank, unsigned epoch, cudaStream_t stream);
+// scoped form: optionally signal `signal_epoch` to every rank, then wait until the ranks of `mask` (bit r = world rank r, at most
+// 64 ranks) have signalled `wait_epoch`
+cudaError_t launch_flag_sync_mask(unsigned* const* peers, int me, int nrank, unsigned signal_epoch, int do_signal,
+                                  unsigned long long mask, unsigned wait_epoch, cudaStream_t stream);
 template <typename T> cudaError_t launch_spectrum(const void* B, const SpecJob& job, double* E, cudaStream_t stream);
 }  // namespace p3d

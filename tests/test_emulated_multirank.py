@@ -92,14 +92,18 @@ def test_real_transposes_and_queries(grid):
 
 
 @pytest.mark.parametrize("grid,env", [("1x2", {"P3D_EMU_DELAY": "1:3:2:250"}), ("1x4", {"P3D_EMU_DELAY": "2:3:2:250"}),
-                                      ("1x2", {"P3DFFT_B200_FLAGBAR": "1", "P3D_EMU_DELAY": "1:3:2:250"}),
-                                      ("2x2", {"P3DFFT_B200_FLAGBAR": "1"})])
+                                      ("2x2", {"P3D_EMU_DELAY": "3:3:2:250"}), ("2x1", {"P3D_EMU_DELAY": "1:3:2:250", "P3DFFT_B200_OVERLAP": "3"}),
+                                      ("1x2", {"P3DFFT_B200_SCOPED": "0", "P3D_EMU_DELAY": "1:3:2:250"}),
+                                      ("2x2", {"P3DFFT_B200_SCOPED": "0"}),
+                                      ("1x2", {"P3DFFT_B200_FLAGBAR": "0", "P3D_EMU_DELAY": "1:3:2:250"}),
+                                      ("1x4", {"P3DFFT_B200_FLAGBAR": "0", "P3D_EMU_DELAY": "2:3:2:250"})])
 def test_repeated_direction_hazard_rule(grid, env):
     """forward x3 then backward x3: on a one-dimensional grid the producing stage of call k+1 stores into the receive buffer a
     slower peer is still reading in the last stage of call k.  P3D_EMU_DELAY makes one rank's last stage slow (emu_runtime.inc),
-    so the executor's write-after-read barrier (and, opt-in, the flag barrier over peer-mapped memory) is what keeps the
-    results right: the same run against a build with that barrier rule removed fails with errors of order 1 (checked by
-    hand when the test was written: api.cpp run_plan, `L.dirty[nex->recvbuf]`)."""
+    so the executor's write-after-read rule is what keeps the results right -- in each of its three forms: the scoped flag
+    synchronisation (default: wait for the target peers' release epoch of the buffer, api.cpp `hazard_wait`), world flag
+    barriers (P3DFFT_B200_SCOPED=0) and NCCL barriers (P3DFFT_B200_FLAGBAR=0; both `L.dirty[nex->recvbuf]`).  Checked by hand
+    for each form: the same run against a build with the rule removed fails with errors of order 1."""
     check(grid, ["--suite", "none", "--repeat"], env)
 
 
