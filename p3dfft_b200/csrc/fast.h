@@ -39,7 +39,7 @@ struct FastSide {
 struct FastStage {
   int32_t na, nb, nc;    // batch extents; CTAs tile a
   int32_t n;             // logical length of the transform axis (nx, ny, nz)
-  int32_t mirror;        // 1: DCT-I -- FFT row r >= n reads logical row nfft - r
+  int32_t mirror;        // 1: DCT-I -- FFT row r >= n reads logical row nfft - r;  2: DST-I (odd extension, DST instantiation)
   int32_t prefetch;      // L2 prefetch of a CTA's next tile for inputs whose row pitch is <= this many bytes (0: off)
   int32_t bord;          // tile order: this many consecutive b are innermost (the tiles that share memory lines of a
                          // gathered input run on neighbouring CTAs at the same time), else 1

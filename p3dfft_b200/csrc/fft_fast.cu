@@ -126,8 +126,9 @@ bool fast_supported(const P3dStage& st) {
   if (st.scale != 1.0 && st.kind == P3D_R2C) return false;     // fused scaling: c2c / DCT stages and the X c2r stage
   if (st.in.nseg + 1 > P3D_MAXRUN || st.out.nseg + 1 > P3D_MAXRUN) return false;
   switch (st.kind) {
-    case P3D_C2C_FWD: case P3D_C2C_BWD: case P3D_DCT1: {
+    case P3D_C2C_FWD: case P3D_C2C_BWD: case P3D_DCT1: case P3D_DST1: {
       if (!c2c_len_ok(st.nfft)) return false;
+      if (st.kind == P3D_DST1 && (st.scale != 1.0 || st.nfft != 2 * (st.n + 1))) return false;      // no SCALED instantiation
       const int rb = row_bytes<T>(st);
       if ((rb != 64 && rb != 128) || !ccfg_exists(st.nfft, rb)) return false;
       const int tx = tile_lines<T>(st);
@@ -197,7 +198,7 @@ int fast_variant(const P3dStage& st) {
     for (int g = 0; g < st.out.nseg; g++) if (st.out.seg[g].peer >= 0) peer = true;
     return (sw.xstage > 0 || (sw.xstage < 0 && peer)) ? 16 : 0;
   }
-  if (is_x(st.kind) || st.out.nseg == 0 || st.in.nseg == 0) return 0;
+  if (is_x(st.kind) || st.kind == P3D_DST1 || st.out.nseg == 0 || st.in.nseg == 0) return 0;
   if (!(st.nfft == 1024 || st.nfft == 512) || row_bytes<T>(st) != 128) return 0;
   const int tx = 128 / (2 * (int)sizeof(T));
   // every output run: whole 128-byte tile rows, consecutive in memory (the writer-contiguous internal layouts)
@@ -280,7 +281,7 @@ void to_fast(const P3dStage& st, FastStage& f, size_t real_bytes, int variant) {
   const int tx = real_bytes == 4 ? tile_lines<float>(st, variant) : tile_lines<double>(st, variant);
   f.variant = variant;
   f.na = st.na; f.nb = st.nb; f.nc = st.nc; f.n = st.n;
-  f.mirror = st.kind == P3D_DCT1;
+  f.mirror = st.kind == P3D_DCT1 ? 1 : st.kind == P3D_DST1 ? 2 : 0;
   static const int pf = getenv("P3DFFT_B200_PREFETCH") ? atoi(getenv("P3DFFT_B200_PREFETCH")) : 131072;
   f.prefetch = pf;
   static const int bo = getenv("P3DFFT_B200_BORD") ? atoi(getenv("P3DFFT_B200_BORD")) : -1;
@@ -370,7 +371,9 @@ static cudaError_t launch_c(const P3dStage& st, const FastStage& f, cudaStream_t
   if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;      // 32-bit tile counters: the generic kernel takes over
   cudaError_t e;
   const bool scaled = f.scale != 1.0;
-  if (st.kind == P3D_C2C_BWD) {
+  if (st.kind == P3D_DST1) {
+    P3D_LAUNCH(cstage_kernel<T, NN, RB, false, false, CCfg<T, NN, RB>, false, true>);
+  } else if (st.kind == P3D_C2C_BWD) {
     if (scaled) P3D_LAUNCH(cstage_kernel<T, NN, RB, true, true>);
     else P3D_LAUNCH(cstage_kernel<T, NN, RB, true>);
   } else {
@@ -477,7 +480,7 @@ cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t str
     if (f.rowb == 64) err = launch_c<T, NN, 64>(st, f, stream);
     else if constexpr (NN == 1024) {
       const bool far_rows = f.in.nrun > 0 && f.in.run[0].ps * (long long)sizeof(T2) > (long long)(f.prefetch > 0 ? f.prefetch : 131072);
-      const bool split = split_env < 0 ? far_rows : split_env != 0;
+      const bool split = st.kind != P3D_DST1 && (split_env < 0 ? far_rows : split_env != 0);
       if (f.rowb == 128) err = split ? launch_split<T, NN>(st, f, stream) : launch_c<T, NN, 128>(st, f, stream);
     } else if constexpr (ccfg_exists(NN, 128)) { if (f.rowb == 128) err = launch_c<T, NN, 128>(st, f, stream); }
   });

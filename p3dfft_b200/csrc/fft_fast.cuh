@@ -484,11 +484,18 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { (void)*reinterpret_
 // ---------------------------------------------------------------------------------------
 constexpr long long ROW_NONE = -1;
 
-template <int NT, int ESZ>
+// DSTM (DST-I by odd extension, FFT length nrows = 2 (n + 1), n = nlogical): FFT row r holds logical row r - 1 for
+// 1 <= r <= n; rows 0 and n + 1 are zero; on the INPUT side (DSTM = 1) row r > n + 1 mirrors logical row nrows - r - 1
+// (the kernel negates it), on the OUTPUT side (DSTM = 2) only rows 1 .. n are stored.
+template <int NT, int ESZ, int DSTM = 0>
 __device__ __forceinline__ void build_rowent(const FastSide& sd, long long* ent, int nrows, int nlogical, int mirror_nfft) {
   for (int row = threadIdx.x; row < nrows; row += NT) {
     int k = row;
-    if (mirror_nfft && row >= nlogical) k = mirror_nfft - row;
+    if constexpr (DSTM != 0) {
+      if (row >= 1 && row <= nlogical) k = row - 1;
+      else if (DSTM == 1 && row > nlogical + 1) k = nrows - row - 1;
+      else k = -1;
+    } else if (mirror_nfft && row >= nlogical) k = mirror_nfft - row;
     long long e = ROW_NONE;
     for (int i = 0; i < sd.nrun; i++) {
       const FastRun& r = sd.run[i];
@@ -557,7 +564,11 @@ __device__ __forceinline__ void fill_tilebase(const FastStage& st, RunTab& rt, i
 // BULK (opt-in, P3DFFT_B200_BULK=1; 128-byte rows, outputs whose tile rows are contiguous per run -- every stage that
 // feeds an exchange): the last pass puts the tile back into shared memory in natural row order and ONE bulk asynchronous
 // copy per output run (per peer) moves it to HBM or over NVLink, instead of 16-byte stores from registers.
-template <typename T, int N, int RB, bool SWAP, bool SCALED = false, class C = CCfg<T, N, RB>, bool BULK = false>
+// DST (P3D_DST1, exec_strans_r2_complex_same, fft_exec.F90:866-921): the sine transform of n = N/2 - 1 points as an N-point
+// FFT of the odd extension (row r = 1 .. n holds input r - 1, rows N - r hold its negative, rows 0 and n + 1 are zero) --
+// the extension exists only in the row table and one sign at the load; output k is i * W[k + 1].  A separate
+// instantiation: the other kernels' code does not change.
+template <typename T, int N, int RB, bool SWAP, bool SCALED = false, class C = CCfg<T, N, RB>, bool BULK = false, bool DST = false>
 __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
   using S = typename C::S;
@@ -578,8 +589,14 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
   const long long lin = (long long)t * st.in.run[0].sa * (long long)sizeof(T2);     // line offsets inside a tile
   const long long lout = (long long)t * st.out.run[0].sa * (long long)sizeof(T2);
 
-  build_rowent<NT, sizeof(T2)>(st.in, ent_in, N, st.n, st.mirror ? N : 0);
-  build_rowent<NT, sizeof(T2)>(st.out, ent_out, N, N, 0);
+  static_assert(!DST || (!SWAP && !BULK), "the sine transform is its own inverse and stores from registers");
+  if constexpr (DST) {
+    build_rowent<NT, sizeof(T2), 1>(st.in, ent_in, N, st.n, 0);
+    build_rowent<NT, sizeof(T2), 2>(st.out, ent_out, N, st.n, 0);
+  } else {
+    build_rowent<NT, sizeof(T2)>(st.in, ent_in, N, st.n, st.mirror ? N : 0);
+    build_rowent<NT, sizeof(T2)>(st.out, ent_out, N, N, 0);
+  }
   for (int g = threadIdx.x; g < st.in.nrun; g += NT) {
     const long long psb = st.in.run[g].ps * (long long)sizeof(T2);
     rt->pfmode[g] = (st.prefetch && psb <= (long long)st.prefetch) ? (psb == 64 ? 2 : 1) : 0;
@@ -612,6 +629,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
             const long long e = ent_in[u + p * M];
             v[p] = (live && e >= 0) ? ldg_stream(reinterpret_cast<const T2*>(row_addr(e, tbi) + lin)) : T2{0, 0};
             if (SWAP) v[p] = cswap(v[p]);
+            if constexpr (DST) { if (u + p * M > st.n + 1) v[p] = T2{-v[p].x, -v[p].y}; }      // the mirrored half of the odd extension
           }
           Bfly<T, R>::run(v);
           if constexpr (BULK) {
@@ -629,7 +647,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
     // ---- L2 prefetch of the rows of this CTA's next tile ---------------------------------------
     if (has_next && st.prefetch) {
       char* const* tbn = rt->tb[slot ^ 1][0];
-      for (int row = threadIdx.x; row < (st.mirror ? st.n : N); row += NT) {
+      for (int row = threadIdx.x; row < (DST ? st.n + 1 : st.mirror ? st.n : N); row += NT) {
         const long long e = ent_in[row];
         if (e < 0) continue;
         const int pm = rt->pfmode[(int)e & 31];
@@ -650,6 +668,10 @@ __global__ void __launch_bounds__(C::NT, C::MINB) cstage_kernel(const __grid_con
           const T sc = (T)st.scale;
 #pragma unroll
           for (int q = 0; q < RL; q++) { v[q].x *= sc; v[q].y *= sc; }
+        }
+        if constexpr (DST) {
+#pragma unroll
+          for (int q = 0; q < RL; q++) v[q] = mul_pi(v[q]);      // Y[k] = i * W[k + 1]
         }
 #pragma unroll
         for (int q = 0; q < RL; q++) {

@@ -155,8 +155,11 @@ inline int pick_W(int ny, int nz, int csize, int force_row_bytes = 0) {
   // 128-byte rows whenever the tile of the longest Y/Z transform fits on chip: up to 1024 points for any length (the
   // any-length kernel then takes up to 8 lines), and the specialised 1280- and 1536-point kernels (160 / 192 KB tiles;
   // measured at 1280^3: 64-byte rows 76.6 ms per pair, 2.6 TB/s -- the Z stages crawl on half-line accesses)
+  // (nz = 1023 / 1025: the sine / cosine transform of the third dimension runs as a 2048-point FFT of the odd / even
+  // extension, which exists with 64-byte rows only; the plain c2c of such an nz belongs to the any-length kernel anyway)
   auto fits128 = [](int n) { return n <= 1024 || n == 1280 || n == 1536; };
-  const int rb = (force_row_bytes == 64 || force_row_bytes == 128) ? force_row_bytes : ((fits128(ny) && fits128(nz)) ? 128 : 64);
+  const bool zext2048 = nz == 1023 || nz == 1025;
+  const int rb = (force_row_bytes == 64 || force_row_bytes == 128) ? force_row_bytes : ((fits128(ny) && fits128(nz) && !zext2048) ? 128 : 64);
   return rb / csize;
 }
 

@@ -192,6 +192,22 @@ def test_emulated_kernels_chebyshev_and_stride1(n, cut, stride1):
     assert (fast, generic) == (6, 0)
 
 
+@pytest.mark.parametrize("n,cut,single,stride1", [((64, 64, 31), None, False, False), ((64, 64, 63), None, False, True),
+                                                  ((128, 64, 127), (64, 32, 64), False, False), ((64, 64, 63), None, True, False),
+                                                  ((64, 64, 191), None, False, False), ((64, 64, 1023), None, False, False)])
+def test_emulated_kernels_sine_transform(n, cut, single, stride1):
+    """DST-I (op letter 's', exec_strans_r2_complex_same, fft_exec.F90:866-921) as a 2 (nz + 1)-point FFT of the odd extension
+    through the c2c kernel's DST instantiation: nfft = 64 ... 2048 and 384 = 3.128, pruned z, STRIDE1, single precision.
+    nz = 1023 needs the 64-byte rows that pick_W chooses for it (the 128-byte tile of a 2048-point transform does not fit)."""
+    fast, generic = transform_world(n, (1, 1), cut, "ffs", "sff", single=single, stride1=stride1)
+    assert (fast, generic) == (6, 0)
+
+
+def test_emulated_kernels_sine_transform_multi_rank():
+    fast, generic = transform_world((64, 64, 63), (2, 2), None, "ffs", "sff", p2p=True)
+    assert (fast, generic) == (24, 0)
+
+
 def test_emulated_split_kernel(monkeypatch):
     """the two-half-tiles variant of the 1024-point c2c kernel (taken on the GPU for far-pitch inputs)"""
     monkeypatch.setenv("P3DFFT_B200_SPLIT", "1")

@@ -174,6 +174,23 @@ def test_fast_kernels_dct(lib, n, cut, stride1):
     assert lib.fast_launch_count() == 6
 
 
+@pytest.mark.parametrize("stride1", [False, True])
+@pytest.mark.parametrize("n,cut", [((64, 64, 31), None), ((128, 64, 63), None), ((64, 128, 127), (32, 64, 64)), ((64, 64, 511), None),
+                                   ((64, 64, 1023), None), ((64, 64, 383), None)])
+def test_fast_kernels_dst(lib, n, cut, stride1):
+    """Sine third dimension: DST-I of nz = 2^k - 1 (and 3 * 2^k - 1) points as an odd-extended FFT of length 2 (nz + 1) on the
+    specialised c2c kernel (fft_exec.F90:866-921); nz = 1023 takes 64-byte rows (2048-point tile)."""
+    lib.fast_launch_count(True)
+    _fwd_bwd(lib, n, cut, "ffs", "sff", stride1=stride1, device=True)
+    assert lib.fast_launch_count() == 6
+
+
+def test_fast_kernels_dst_single(libf):
+    libf.fast_launch_count(True)
+    _fwd_bwd(libf, (64, 128, 255), None, "ffs", "sff", single=True, device=True)
+    assert libf.fast_launch_count() == 6
+
+
 @pytest.mark.parametrize("n", [(64, 64, 64), (128, 64, 256)])
 def test_fast_kernels_stride1(lib, n):
     lib.fast_launch_count(True)
