@@ -246,9 +246,8 @@ class CopyPool {
   std::condition_variable cv_, done_;
   char* dst_ = nullptr; const char* src_ = nullptr; size_t n_ = 0;
   unsigned long gen_ = 0; int pending_ = 0; bool stop_ = false;
-  void work(int id, int nth) {
-    unsigned long seen = 0;
-    for (;;) {
+  void work(int id, int nth, unsigned long seen) {      // seen: the generation at start -- a pool restarted after p3dfft_clean
+    for (;;) {                                          // must not take the last job of its predecessor for a new one
       std::unique_lock<std::mutex> l(m_);
       cv_.wait(l, [&] { return stop_ || gen_ != seen; });
       if (stop_) return;
@@ -265,10 +264,12 @@ class CopyPool {
   int threads() const { return (int)th_.size(); }
   void start(int n) {
     if (!th_.empty()) return;
-    for (int i = 0; i < n; i++) th_.emplace_back([this, i, n] { work(i, n); });
+    unsigned long g0;
+    { std::lock_guard<std::mutex> l(m_); g0 = gen_; }
+    for (int i = 0; i < n; i++) th_.emplace_back([this, i, n, g0] { work(i, n, g0); });
   }
   void copy(void* d, const void* s, size_t n) {      // returns when every slice has been copied
-    if (th_.empty() || n < (1u << 20)) { memcpy(d, s, n); return; }
+    if (th_.empty() || n < (1u << 16)) { memcpy(d, s, n); return; }
     std::unique_lock<std::mutex> l(m_);
     dst_ = (char*)d; src_ = (const char*)s; n_ = n; pending_ = (int)th_.size(); gen_++;
     cv_.notify_all();

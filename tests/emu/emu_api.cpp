@@ -10,6 +10,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <sys/mman.h>
 
 #include <chrono>
 #include <cstdlib>
@@ -22,6 +23,7 @@
 
 namespace {
 std::map<char*, size_t> g_alloc;          // "device" allocations
+std::map<char*, size_t> g_hostalloc;      // page-locked host allocations (cudaHostAlloc)
 std::mutex g_mu;
 }  // namespace
 
@@ -44,8 +46,26 @@ cudaError_t cudaFree(void* p) {
 }
 // page-locked host memory: ordinary heap memory here (cudaPointerGetAttributes keeps calling it unregistered, so host arrays
 // of any size take the pageable path of api.cpp -- the ring of chunks and the copy threads)
-cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = malloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaFreeHost(void* p) { emu_rt::sync_all(); free(p); return cudaSuccess; }
+// (own mappings, unmapped at cudaFreeHost like the real runtime's: a late access -- a copy thread that outlives its ring --
+// faults here as it would on the GPU box instead of scribbling over recycled heap memory)
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
+  const size_t len = (n + 4095) / 4096 * 4096 + 4096;
+  void* m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (m == MAP_FAILED) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  std::lock_guard<std::mutex> l(g_mu);
+  g_hostalloc[(char*)m] = len;
+  *p = m;
+  return cudaSuccess;
+}
+cudaError_t cudaFreeHost(void* p) {
+  emu_rt::sync_all();
+  std::lock_guard<std::mutex> l(g_mu);
+  auto it = g_hostalloc.find((char*)p);
+  if (it == g_hostalloc.end()) return cudaErrorInvalidValue;
+  munmap(p, it->second);
+  g_hostalloc.erase(it);
+  return cudaSuccess;
+}
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { emu_rt::sync_legacy(); memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st) {
   emu_rt::enqueue(st, [=]() { memmove(d, s, n); });
