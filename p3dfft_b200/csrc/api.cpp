@@ -5,6 +5,7 @@
 // (build/module.F90:103-176), p3dfft_setup may be called again only after p3dfft_clean
 // (setup.F90:130-135), every rank calls every routine collectively.
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -285,7 +286,8 @@ class CopyPool {
 
 struct HostPipe {
   static constexpr int NSLOT = 4;
-  size_t chunk = 32u << 20;
+  size_t chunk = 8u << 20;       // measured on the B200 box (tools/ab_hostpipe.py, profiles/r2_ab_hostpipe.log): 8 MB chunks, 12 threads:
+                                 // 1024^3 pair 805 ms against 665 page-locked; 32 MB / 8 threads (the first setting): 940-1050
   char* slot[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
   CopyPool pool;
@@ -300,8 +302,13 @@ struct HostPipe {
       if (cudaHostAlloc((void**)&slot[i], chunk, cudaHostAllocDefault) != cudaSuccess ||
           cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); release(); failed = true; return false; }
     }
-    const unsigned hw = std::thread::hardware_concurrency();
-    const int nth = ct ? atoi(ct) : (int)std::min<unsigned>(8, std::max<unsigned>(1, hw / 2));
+    unsigned hw = std::thread::hardware_concurrency();
+#ifdef __linux__
+    cpu_set_t cs;      // the cores this process may use, not the machine's
+    if (sched_getaffinity(0, sizeof cs, &cs) == 0 && CPU_COUNT(&cs) > 0) hw = (unsigned)CPU_COUNT(&cs);
+#endif
+    const unsigned share = (unsigned)std::max(1, std::min(L.d.numtasks, 8));      // ranks of one box share its cores
+    const int nth = ct ? atoi(ct) : (int)std::min<unsigned>(12, std::max<unsigned>(1, hw * 3 / 4 / share));
     if (nth > 1) pool.start(nth);
     ready = true;
     return true;
