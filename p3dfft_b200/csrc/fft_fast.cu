@@ -109,7 +109,7 @@ static int row_bytes(const P3dStage& st) {
       aw = sd.seg[g].aw;
     }
   }
-  if (!aw) return ccfg_exists(st.nfft, 128) ? 128 : 64;
+  if (!aw) return (ccfg_exists(st.nfft, 128) && !csplit_only(st.nfft)) ? 128 : 64;
   return aw * 2 * (int)sizeof(T);
 }
 
@@ -131,6 +131,7 @@ bool fast_supported(const P3dStage& st) {
       if (st.kind == P3D_DST1 && (st.scale != 1.0 || st.nfft != 2 * (st.n + 1))) return false;      // no SCALED instantiation
       const int rb = row_bytes<T>(st);
       if ((rb != 64 && rb != 128) || !ccfg_exists(st.nfft, rb)) return false;
+      if (rb == 128 && csplit_only(st.nfft) && st.kind == P3D_DST1) return false;      // the split kernel has no DST instantiation
       const int tx = tile_lines<T>(st);
       for (int side = 0; side < 2; side++) {          // one line pitch per side (the kernels keep it in a register)
         const P3dSide& sd = side ? st.out : st.in;
@@ -478,6 +479,7 @@ cudaError_t launch_fast(const P3dStage& st, const FastStage& f, cudaStream_t str
     // writes above all.  P3DFFT_B200_SPLIT = 0 never / 1 always / unset: by that rule.
     static const int split_env = getenv("P3DFFT_B200_SPLIT") ? atoi(getenv("P3DFFT_B200_SPLIT")) : -1;
     if (f.rowb == 64) err = launch_c<T, NN, 64>(st, f, stream);
+    else if constexpr (csplit_only(NN)) { if (f.rowb == 128) err = launch_split<T, NN>(st, f, stream); }
     else if constexpr (NN == 1024) {
       const bool far_rows = f.in.nrun > 0 && f.in.run[0].ps * (long long)sizeof(T2) > (long long)(f.prefetch > 0 ? f.prefetch : 131072);
       const bool split = st.kind != P3D_DST1 && (split_env < 0 ? far_rows : split_env != 0);

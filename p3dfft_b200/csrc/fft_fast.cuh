@@ -121,10 +121,15 @@ P3D_CCFG(float, 768, 128, P3D_RS(3, 16, 16), 512, 2)
 P3D_CCFG(float, 640, 128, P3D_RS(5, 16, 8), 512, 2)
 P3D_CCFG(float, 1280, 128, P3D_RS(5, 16, 16), 512, 1)
 P3D_CCFG(float, 1536, 128, P3D_RS(6, 16, 16), 512, 1)
+// 2048 points with 128-byte rows: the tile is 256 KB and exists only for the SPLIT kernel (half of it in shared memory, the
+// other half waiting in registers); schedule and line count come from here, threads from SplitCfg
+P3D_CCFG(double, 2048, 128, P3D_RS(16, 16, 8), 512, 1)
+P3D_CCFG(float, 2048, 128, P3D_RS(16, 16, 8), 512, 1)
 #undef P3D_CCFG
 // the 128-byte tile of a 2048-point transform (256 KB) does not fit in shared memory; 1536 points (192 KB + 24 KB of row
 // tables) still do, with one CTA per SM
-constexpr bool ccfg_exists(int n, int rb) { return rb == 64 || (rb == 128 && n <= 1536); }
+constexpr bool csplit_only(int n) { return n == 2048; }
+constexpr bool ccfg_exists(int n, int rb) { return rb == 64 || (rb == 128 && (n <= 1536 || csplit_only(n))); }
 
 // Two-pass variants (opt-in, P3DFFT_B200_R32=1): 1024 = 32 x 32 and 512 = 16 x 32 instead of three passes, i.e. ONE round
 // trip through shared memory per element instead of two (r1 ncu: the LSU pipe is busy ~55 % of a 1024-point stage, most
@@ -733,6 +738,11 @@ template <typename T, int N> constexpr size_t cstage_r32_smem() {
 // ---------------------------------------------------------------------------------------
 template <typename T, int N> struct SplitCfg {
   static constexpr int NT = 256, MINB = 2;
+};
+// 2048 points: 128 KB of shared memory per CTA, hence one CTA per SM and 512 threads (the half tile that waits in registers
+// is 4 x 8 single or 2 x 8 double complex values per thread)
+template <typename T> struct SplitCfg<T, 2048> {
+  static constexpr int NT = 512, MINB = 1;
 };
 
 template <typename T, int N, bool SWAP, bool SCALED = false>

@@ -152,14 +152,19 @@ struct Decomp {
 // bytes: 128-byte rows unless the 128-byte tile of the longest Y/Z transform would not fit in shared
 // memory (fft_fast.cuh, CCfg); `force_row_bytes` (64 or 128) overrides the rule.
 inline int pick_W(int ny, int nz, int csize, int force_row_bytes = 0) {
-  // 128-byte rows whenever the tile of the longest Y/Z transform fits on chip: up to 1024 points for any length (the
-  // any-length kernel then takes up to 8 lines), and the specialised 1280- and 1536-point kernels (160 / 192 KB tiles;
-  // measured at 1280^3: 64-byte rows 76.6 ms per pair, 2.6 TB/s -- the Z stages crawl on half-line accesses)
-  // (nz = 1023 / 1025: the sine / cosine transform of the third dimension runs as a 2048-point FFT of the odd / even
-  // extension, which exists with 64-byte rows only; the plain c2c of such an nz belongs to the any-length kernel anyway)
-  auto fits128 = [](int n) { return n <= 1024 || n == 1280 || n == 1536; };
-  const bool zext2048 = nz == 1023 || nz == 1025;
-  const int rb = (force_row_bytes == 64 || force_row_bytes == 128) ? force_row_bytes : ((fits128(ny) && fits128(nz) && !zext2048) ? 128 : 64);
+  // 128-byte rows whenever a kernel exists for the 128-byte tile of the longest Y/Z transform: up to 1024 points for any length
+  // (the any-length kernel then takes up to 8 lines), the specialised 1280- and 1536-point kernels (160 / 192 KB tiles;
+  // measured at 1280^3: 64-byte rows 76.6 ms per pair, 2.6 TB/s -- the Z stages crawl on half-line accesses) and 2048 points
+  // through the split kernel (half of the 256 KB tile waits in registers; measured on one B200, profiles/
+  // r2_ab_1gpu_2048_rows.log: 256 x 2048 x 2048 double 33.2 -> 28.5 ms per pair, 512 x 2048 x 2048 single 31.1 -> 29.2: the Z
+  // stages gain 17-29 %, the single-precision Y stages, whose 64-byte-row tiles are contiguous, lose 4-11 %).
+  // nz = 1023: the sine transform of the third dimension runs as a 2048-point FFT of the odd extension, which exists with
+  // 64-byte rows only (the split kernel has no DST instantiation; the plain c2c of such an nz is the any-length kernel's)
+  auto fits128 = [](int n) { return n <= 1024 || n == 1280 || n == 1536 || n == 2048; };
+  // nz = 1025: the Chebyshev / cosine transform of the third dimension is a 2048-point FFT of the even extension (split kernel)
+  const bool zext2048 = nz == 1023;
+  const int rb = (force_row_bytes == 64 || force_row_bytes == 128) ? force_row_bytes
+               : ((fits128(ny) && (fits128(nz) || nz == 1025) && !zext2048) ? 128 : 64);
   return rb / csize;
 }
 

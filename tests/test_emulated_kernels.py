@@ -208,6 +208,27 @@ def test_emulated_kernels_sine_transform_multi_rank():
     assert (fast, generic) == (24, 0)
 
 
+@pytest.mark.parametrize("n,cut,single,stride1,ops", [((16, 16, 2048), None, False, False, ("fft", "tff")),
+                                                      ((64, 2048, 64), (64, 1364, 64), True, False, ("fft", "tff")),
+                                                      ((64, 64, 2048), None, True, True, ("fft", "tff")),
+                                                      ((16, 16, 1025), None, False, False, ("ffc", "cff"))])
+def test_emulated_2048_points_with_128_byte_rows(n, cut, single, stride1, ops):
+    """2048-point Y/Z stages take 128-byte rows through the split kernel (half of the 256 KB tile waits in registers): the
+    planner's rule (pick_W), double and single, pruned, STRIDE1, and the DCT-I of 1025 points (2048-point even extension)"""
+    L = pb.load(single)
+    _, inf = L.plan_steps((1, 1), *n, 0, False, ops[0], 1, *(cut or n), stride1=stride1)
+    st = [s.st for s in L.plan_steps((1, 1), *n, 0, False, ops[0], 1, *(cut or n), stride1=stride1)[0] if not s.is_exchange]
+    assert st[-1].inp.seg[0].aw == (16 if single else 8)       # the Z stage reads 128-byte rows
+    fast, generic = transform_world(n, (1, 1), cut, *ops, single=single, stride1=stride1)
+    long_stages = sum(1 for v in n if v >= 64 and v != 1025) + (1 if n[2] == 1025 else 0)
+    assert fast == 2 * long_stages and fast + generic == 6
+
+
+def test_emulated_2048_points_multi_rank_peer_stores():
+    fast, generic = transform_world((64, 2048, 64), (2, 2), None, "fft", "tff", p2p=True)
+    assert (fast, generic) == (24, 0)
+
+
 def test_emulated_split_kernel(monkeypatch):
     """the two-half-tiles variant of the 1024-point c2c kernel (taken on the GPU for far-pitch inputs)"""
     monkeypatch.setenv("P3DFFT_B200_SPLIT", "1")
