@@ -165,7 +165,7 @@ struct Lib {
   bool want_p2p = true, p2p = false;
   std::vector<void*> peer_buf;   // [world rank * 3 + (buffer id - P3D_BUF_A)], own entries = own buffers
   float* bar_scratch = nullptr;
-  // opt-in flag barrier over peer-mapped memory (P3DFFT_B200_FLAGBAR=1; not yet run on hardware -- default off)
+  // flag barrier over peer-mapped memory (the default since round 2, stress-tested on 2/4/8 B200s; P3DFFT_B200_FLAGBAR=0: NCCL all-reduce)
   bool want_flagbar = false, flagbar = false;
   unsigned* bar_flags = nullptr;                 // this rank's slots: one 128-byte slot per world rank, own 2 MiB allocation
   std::vector<unsigned*> peer_flags;             // [world rank] mapped flag arrays (own entry = bar_flags)
@@ -189,8 +189,8 @@ struct Lib {
   long long work_elems_alloc = 0;   // complex elements per work buffer
   bool rtran_sized = false;         // the buffers already cover rtran_work_elems()
   std::map<int, p3d::TransformPlan> aux_plans;     // r2c_1d (key 100) and rtran (key which*2 + p2p) plans
-  // opt-in pipelined tail of the peer-to-peer plans (P3DFFT_B200_OVERLAP=C chunks; plan.h split_for_overlap): the consumer
-  // chunks run on a side stream, on at most overlap_sms SMs while the producer keeps the rest (not yet run on hardware)
+  // pipelined tail of the peer-to-peer plans (P3DFFT_B200_OVERLAP=C chunks, default 4; plan.h split_for_overlap): the consumer
+  // chunks run on a side stream, on at most overlap_sms SMs while the producer keeps the rest (A/B on 2/4/8 B200s under profiles/)
   int overlap = P3D_DEFAULT_OVERLAP, overlap_sms = P3D_DEFAULT_OVERLAP_SMS;
   bool overlap_forced = false;   // P3DFFT_B200_OVERLAP given in the environment: also for small transforms (tests)
   int overlap_sms_dir[2] = {0, 0};      // per direction (forward, backward); 0: overlap_sms
@@ -439,7 +439,7 @@ bool world_barrier(cudaStream_t st) {
   return true;
 }
 
-// Opt-in flag barrier: maps every rank's flag array (collective over the world).  The arrays are zeroed before their
+// Flag barrier: maps every rank's flag array (collective over the world).  The arrays are zeroed before their
 // handles travel through the all-gather, so nobody can signal into an array that is still being initialised.
 bool open_flag_maps() {
   const int P = L.comm->size, me = L.comm->rank;
@@ -647,7 +647,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
   const void* din = in; void* dout = out;
   if (!in_dev) {
     if (L.stage_in_bytes < in_bytes) {
-      if (L.stage_in) cudaFree(L.stage_in);
+      if (L.stage_in) { cudaFree(L.stage_in); L.stage_in = nullptr; L.stage_in_bytes = 0; }      // (a failed allocation must not leave the old pointer behind)
       CUDA_OK(cudaMalloc(&L.stage_in, in_bytes)); L.stage_in_bytes = in_bytes;
     }
     if (!copy_h2d(L.stage_in, in, in_bytes, st)) return false;
@@ -655,7 +655,7 @@ bool run_plan(p3d::TransformPlan* tp, const void* in, void* out, size_t in_bytes
   }
   if (!out_dev) {
     if (L.stage_out_bytes < out_bytes) {
-      if (L.stage_out) cudaFree(L.stage_out);
+      if (L.stage_out) { cudaFree(L.stage_out); L.stage_out = nullptr; L.stage_out_bytes = 0; }
       CUDA_OK(cudaMalloc(&L.stage_out, out_bytes)); L.stage_out_bytes = out_bytes;
     }
     dout = L.stage_out;
