@@ -131,7 +131,6 @@ bool fast_supported(const P3dStage& st) {
       if (st.kind == P3D_DST1 && (st.scale != 1.0 || st.nfft != 2 * (st.n + 1))) return false;      // no SCALED instantiation
       const int rb = row_bytes<T>(st);
       if ((rb != 64 && rb != 128) || !ccfg_exists(st.nfft, rb)) return false;
-      if (rb == 128 && csplit_only(st.nfft) && st.kind == P3D_DST1) return false;      // the split kernel has no DST instantiation
       const int tx = tile_lines<T>(st);
       for (int side = 0; side < 2; side++) {          // one line pitch per side (the kernels keep it in a register)
         const P3dSide& sd = side ? st.out : st.in;
@@ -438,7 +437,10 @@ static cudaError_t launch_split(const P3dStage& st, const FastStage& f, cudaStre
   if (tiles >= (1LL << 31)) return cudaErrorMisalignedAddress;
   cudaError_t e;
   const bool scaled = f.scale != 1.0;
-  if (st.kind == P3D_C2C_BWD) {
+  if (st.kind == P3D_DST1) {
+    if constexpr (csplit_only(NN)) P3D_LAUNCH(cstage_split_kernel<T, NN, false, false, true>);
+    else return cudaErrorInvalidValue;
+  } else if (st.kind == P3D_C2C_BWD) {
     if (scaled) P3D_LAUNCH(cstage_split_kernel<T, NN, true, true>);
     else P3D_LAUNCH(cstage_split_kernel<T, NN, true>);
   } else {

@@ -745,7 +745,8 @@ template <typename T> struct SplitCfg<T, 2048> {
   static constexpr int NT = 512, MINB = 1;
 };
 
-template <typename T, int N, bool SWAP, bool SCALED = false>
+// DST: the sine transform by odd extension, as in cstage_kernel (only the 2048-point instantiation is built: nz = 1023)
+template <typename T, int N, bool SWAP, bool SCALED = false, bool DST = false>
 __global__ void __launch_bounds__(SplitCfg<T, N>::NT, SplitCfg<T, N>::MINB) cstage_split_kernel(const __grid_constant__ FastStage st) {
   using T2 = typename Cx<T>::type;
   using S = typename CCfg<T, N, 128>::S;
@@ -767,8 +768,14 @@ __global__ void __launch_bounds__(SplitCfg<T, N>::NT, SplitCfg<T, N>::MINB) csta
   const long long lin = (long long)t * st.in.run[0].sa * (long long)sizeof(T2);
   const long long lout = (long long)t * st.out.run[0].sa * (long long)sizeof(T2);
 
-  build_rowent<NT, sizeof(T2)>(st.in, ent_in, N, st.n, st.mirror ? N : 0);
-  build_rowent<NT, sizeof(T2)>(st.out, ent_out, N, N, 0);
+  static_assert(!DST || !SWAP, "the sine transform is its own inverse");
+  if constexpr (DST) {
+    build_rowent<NT, sizeof(T2), 1>(st.in, ent_in, N, st.n, 0);
+    build_rowent<NT, sizeof(T2), 2>(st.out, ent_out, N, st.n, 0);
+  } else {
+    build_rowent<NT, sizeof(T2)>(st.in, ent_in, N, st.n, st.mirror ? N : 0);
+    build_rowent<NT, sizeof(T2)>(st.out, ent_out, N, N, 0);
+  }
   for (int g = threadIdx.x; g < st.in.nrun; g += NT) {
     const long long psb = st.in.run[g].ps * (long long)sizeof(T2);
     rt->pfmode[g] = (st.prefetch && psb <= (long long)st.prefetch) ? (psb == 64 ? 2 : 1) : 0;
@@ -796,6 +803,7 @@ __global__ void __launch_bounds__(SplitCfg<T, N>::NT, SplitCfg<T, N>::MINB) csta
           const long long e = ent_in[u + p * M0];
           v[p] = (live && e >= 0) ? ldg_stream(reinterpret_cast<const T2*>(row_addr(e, tbi) + lin)) : T2{0, 0};
           if (SWAP) v[p] = cswap(v[p]);
+          if constexpr (DST) { if (u + p * M0 > st.n + 1) v[p] = T2{-v[p].x, -v[p].y}; }
         }
         Bfly<T, R0>::run(v);
         const T2* twp = tw + S::twoff(0) + u;
@@ -812,7 +820,7 @@ __global__ void __launch_bounds__(SplitCfg<T, N>::NT, SplitCfg<T, N>::MINB) csta
     // ---- L2 prefetch of the rows of this CTA's next tile ---------------------------------------
     if (has_next && st.prefetch) {
       char* const* tbn = rt->tb[slot ^ 1][0];
-      for (int row = threadIdx.x; row < (st.mirror ? st.n : N); row += NT) {
+      for (int row = threadIdx.x; row < (DST ? st.n + 1 : st.mirror ? st.n : N); row += NT) {
         const long long e = ent_in[row];
         if (e < 0) continue;
         const int pm = rt->pfmode[(int)e & 31];
@@ -849,6 +857,10 @@ __global__ void __launch_bounds__(SplitCfg<T, N>::NT, SplitCfg<T, N>::MINB) csta
             const T sc = (T)st.scale;
 #pragma unroll
             for (int q = 0; q < RL; q++) { v[q].x *= sc; v[q].y *= sc; }
+          }
+          if constexpr (DST) {
+#pragma unroll
+            for (int q = 0; q < RL; q++) v[q] = mul_pi(v[q]);      // Y[k] = i * W[k + 1]
           }
 #pragma unroll
           for (int q = 0; q < RL; q++) {

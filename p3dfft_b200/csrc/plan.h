@@ -158,13 +158,11 @@ inline int pick_W(int ny, int nz, int csize, int force_row_bytes = 0) {
   // through the split kernel (half of the 256 KB tile waits in registers; measured on one B200, profiles/
   // r2_ab_1gpu_2048_rows.log: 256 x 2048 x 2048 double 33.2 -> 28.5 ms per pair, 512 x 2048 x 2048 single 31.1 -> 29.2: the Z
   // stages gain 17-29 %, the single-precision Y stages, whose 64-byte-row tiles are contiguous, lose 4-11 %).
-  // nz = 1023: the sine transform of the third dimension runs as a 2048-point FFT of the odd extension, which exists with
-  // 64-byte rows only (the split kernel has no DST instantiation; the plain c2c of such an nz is the any-length kernel's)
+  // nz = 1023 / 1025: the sine / cosine (Chebyshev) transform of the third dimension is a 2048-point FFT of the odd / even
+  // extension (split kernel); the plain c2c of such an nz is the any-length kernel's
   auto fits128 = [](int n) { return n <= 1024 || n == 1280 || n == 1536 || n == 2048; };
-  // nz = 1025: the Chebyshev / cosine transform of the third dimension is a 2048-point FFT of the even extension (split kernel)
-  const bool zext2048 = nz == 1023;
   const int rb = (force_row_bytes == 64 || force_row_bytes == 128) ? force_row_bytes
-               : ((fits128(ny) && (fits128(nz) || nz == 1025) && !zext2048) ? 128 : 64);
+               : ((fits128(ny) && (fits128(nz) || nz == 1025)) ? 128 : 64);
   return rb / csize;
 }
 

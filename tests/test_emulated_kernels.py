@@ -197,8 +197,8 @@ def test_emulated_kernels_chebyshev_and_stride1(n, cut, stride1):
                                                   ((64, 64, 191), None, False, False), ((64, 64, 1023), None, False, False)])
 def test_emulated_kernels_sine_transform(n, cut, single, stride1):
     """DST-I (op letter 's', exec_strans_r2_complex_same, fft_exec.F90:866-921) as a 2 (nz + 1)-point FFT of the odd extension
-    through the c2c kernel's DST instantiation: nfft = 64 ... 2048 and 384 = 3.128, pruned z, STRIDE1, single precision.
-    nz = 1023 needs the 64-byte rows that pick_W chooses for it (the 128-byte tile of a 2048-point transform does not fit)."""
+    through the c2c kernel's DST instantiation: nfft = 64 ... 1024 and 384 = 3.128, pruned z, STRIDE1, single precision;
+    nz = 1023 (nfft = 2048) through the DST instantiation of the split kernel (128-byte rows)."""
     fast, generic = transform_world(n, (1, 1), cut, "ffs", "sff", single=single, stride1=stride1)
     assert (fast, generic) == (6, 0)
 

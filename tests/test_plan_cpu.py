@@ -205,7 +205,7 @@ def test_exchange_tables_equal_reference_byte_counts(lib):
 def test_tile_row_width_rule(single):
     """pick_W (plan.h): 128-byte rows wherever a kernel exists for the 128-byte tile of the longest Y/Z transform -- any length
     up to 1024, 1280, 1536 and, through the split kernel, 2048 (nz = 1025: the Chebyshev transform's 2048-point even
-    extension) -- and 64-byte rows otherwise (nz = 1023: the sine transform's 2048-point odd extension has no 128-byte kernel)."""
+    extension; nz = 1023: the sine transform's odd extension) -- and 64-byte rows otherwise."""
     L = pb.load(single)
     full = 16 if single else 8            # lines per 128-byte row
 
@@ -218,5 +218,5 @@ def test_tile_row_width_rule(single):
     assert width(1280, 64) == full and width(64, 1536) == full
     assert width(64, 2048) == full and width(2048, 2048) == full
     assert width(64, 1025, "ffc") == full
-    assert width(64, 1023, "ffs") == full // 2
+    assert width(64, 1023, "ffs") == full
     assert width(64, 4096) == full // 2 and width(1792, 64) == full // 2
