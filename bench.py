@@ -536,7 +536,7 @@ def main():
         line["cufft_comparison"] = cufft
     if e2e:
         line["e2e"] = e2e
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:             # (rank 0 at N = 1 only: the reference arm carries the CPU number at every N)
         from oracle import p3dfft_oracle as po     # CPU baseline leg (checker code, never on the GPU path)
         cores = cpu_cores()
         res = po.cpu_pair_measured(nx, ny, nz, dtype=args.dtype, op=args.op, workers=cores, budget_s=args.cpu_budget,
