@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call's worth of measurements.  Results under gpurun_out/ (copy what should be judged into profiles/).
-#   1 GPU :  gpurun --timeout 900 -- 'bash tools/gpu_session.sh tests|ab|sanitize|ncu|aux|bench'
+#   1 GPU :  gpurun --timeout 900 -- 'bash tools/gpu_session.sh tests|ab|sanitize|ncu|aux|bench|membench|hostpipe'
 #   N GPUs:  gpurun --gpus N --timeout 900 -- 'bash tools/gpu_session.sh mgpu N [parity] [stress] [ab] [refbin] [bench] [configs]'
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
@@ -39,6 +39,16 @@ if [[ $what == ncu ]]; then
       python tools/prof_pair.py --size 1024 --pairs 1 > gpurun_out/ncu_stages.log 2>&1
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-parity --no-cufft > gpurun_out/bench_under_ncu.log 2>&1
+fi
+
+if [[ $what == membench ]]; then
+  # access-pattern copies (no FFT arithmetic): the user layout's misaligned rows, flat tiles, store flavours
+  nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/membench tools/membench.cu 2>/dev/null
+  { ./tools/membench 128; ./tools/membench flat,half; } 2>&1 | tee gpurun_out/membench.log
+fi
+
+if [[ $what == hostpipe ]]; then
+  python tools/ab_hostpipe.py 2>&1 | tee gpurun_out/ab_hostpipe.log
 fi
 
 if [[ $what == aux ]]; then
