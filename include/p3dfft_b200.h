@@ -3,10 +3,20 @@
  * The reference library takes a Fortran MPI communicator handle in p3dfft_setup
  * (build/setup.F90:83-107) and relies on MPI for process bootstrap.  The B200 build runs
  * one process per GPU and moves data with NCCL / NVLink peer memory, so the `comm` integer
- * passed to p3dfft_setup is a handle returned by p3dfft_b200_comm_create() (a process that
- * never creates one gets a single-rank communicator whatever it passes).
+ * passed to p3dfft_setup is a handle returned by p3dfft_b200_comm_create(), or -- with an MPI
+ * loaded in the process -- the caller's own Fortran MPI handle, from which the library then
+ * bootstraps itself; 0 without an MPI is the single-rank
+ * communicator, any other value is an error.
  *
  * Everything here is plain C: pointers, ints and sizes only.
+ *
+ * Limits (sizes the reference accepts and this build refuses with a message through the error
+ * path below): a processor-grid dimension above 16; a transform length with a prime factor above
+ * 4096; a transform whose single line exceeds 200 KB of shared memory (double: ny, nz <= 12800,
+ * nx <= ~11000; single: twice that).  Specialised kernels exist for the lengths 64 ... 2048 in
+ * powers of two, 384, 768, 1536, 640, 1280 (nx: twice those; sine / cosine third dimension:
+ * nz = those / 2 -+ 1); every other length is correct on the any-length kernel at about three
+ * times the cost per byte (DESIGN.md sections 4 and 6).
  */
 #ifndef P3DFFT_B200_H
 #define P3DFFT_B200_H
